@@ -1,0 +1,188 @@
+/*
+ * scrubby_gpu.h -- C ABI of libscrubby_gpu.so: the B200 (sm_100a) depletion hot path.
+ *
+ * The reference (esteinig/scrubby 1.0.2, pure Rust) has no FFI of its own; the seams
+ * this library sits behind are the Rust functions cited on each entry point below
+ * (file:line under the reference's src/).  INTEGRATION.md shows the `extern "C"`
+ * block + build.rs a maintainer would add to call them from cleaner.rs /
+ * alignment.rs / classifier.rs / utils.rs.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every function returns an sgpu_status
+ *    (0 = ok); none aborts.  Would-be panics of the reference (fields[] index out of
+ *    bounds) are reported as SGPU_ERR_WOULD_PANIC.
+ *  - Buffers hold DECOMPRESSED bytes.  gz/bz2/xz sniffing and .gz writing stay in
+ *    the host stage (utils.rs:56-74, niffler), outside the timed region.
+ *  - `*_dev` variants take device pointers (cudaMalloc / torch tensors) on the
+ *    context's device and enqueue on the context's stream; the plain variants take
+ *    host pointers and perform the H2D / D2H copies themselves.
+ *  - A context belongs to one device (one process per GPU).  An idset is immutable
+ *    once built and may be shared by concurrent cleaners (cleaner.rs:238-248 runs
+ *    the two mate files on two threads against one &HashSet); calls on ONE context
+ *    are serialised by the library, so use one context per host thread for overlap.
+ *  - There is no CPU fallback: without a CUDA device sgpu_ctx_create fails with
+ *    SGPU_ERR_CUDA.
+ */
+#ifndef SCRUBBY_GPU_H
+#define SCRUBBY_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGPU_ABI_VERSION 1
+
+typedef enum {
+    SGPU_OK = 0,
+    SGPU_ERR_IO = 1,                    /* ScrubbyError::IoError (error.rs:14): invalid UTF-8 in BufRead::lines */
+    SGPU_ERR_NIFFLER = 2,               /* ScrubbyError::NifflerError (error.rs:20); host stage only */
+    SGPU_ERR_FASTQ_INVALID_START = 3,   /* NeedletailParseError (error.rs:23): record does not start with '@' */
+    SGPU_ERR_FASTQ_INVALID_SEPARATOR = 4, /* ... separator line does not start with '+' */
+    SGPU_ERR_FASTQ_UNEQUAL_LENGTHS = 5, /* ... sequence and quality lengths differ */
+    SGPU_ERR_FASTQ_UNEXPECTED_END = 6,  /* ... truncated last record */
+    SGPU_ERR_FASTQ_UNKNOWN_FORMAT = 7,  /* ... first byte is neither '@' nor '>' */
+    SGPU_ERR_RECORD_NAME_UTF8 = 8,      /* ScrubbyError::RecordNameUtf8Error (error.rs:41) from get_id */
+    SGPU_ERR_FASTQ_HEADER = 9,          /* ScrubbyError::NeedletailFastqHeader (error.rs:53) */
+    SGPU_ERR_PAF_INTEGER = 10,          /* ScrubbyError::PafRecordIntegerError (error.rs:47) */
+    SGPU_ERR_WOULD_PANIC = 11,          /* reference indexes a missing column: alignment.rs:248-259, classifier.rs:412-415,508-513 */
+    SGPU_ERR_KRAKEN_REPORT_READS = 12,  /* KrakenReportReadFieldConversion (error.rs:142) */
+    SGPU_ERR_KRAKEN_REPORT_DIRECT = 13, /* KrakenReportDirectReadFieldConversion (error.rs:144) */
+    SGPU_ERR_KRAKEN_REPORT_PARENT = 14, /* KrakenReportTaxonParent (error.rs:140) */
+    SGPU_ERR_FASTA_UNSUPPORTED = 15,    /* '>' input: needletail would switch to its FASTA reader; not built */
+    SGPU_ERR_CUDA = 16,                 /* CUDA runtime failure / no device; sgpu_last_cuda_error() has the text */
+    SGPU_ERR_NOMEM = 17,
+    SGPU_ERR_INVALID_ARG = 18,
+    SGPU_ERR_CAPACITY = 19,             /* an output buffer is too small; required sizes are returned */
+    SGPU_ERR_KEY_TOO_LONG = 20,         /* a read id of 16 MiB or more */
+    SGPU_ERR_HALO = 21                  /* shard: the last owned record does not end inside the buffer */
+} sgpu_status;
+
+typedef struct sgpu_ctx sgpu_ctx;     /* device, stream, scratch arena */
+typedef struct sgpu_idset sgpu_idset; /* exact read-id set (HashSet<String>) resident in HBM */
+
+typedef struct {
+    uint64_t reads_in;      /* records parsed from the input                                   */
+    uint64_t reads_out;     /* records written (clean) / records of the output file (diff)     */
+    uint64_t difference;    /* diff: input records whose id is absent from the output          */
+    uint64_t error_record;  /* 0-based record (FASTQ) or line (evidence) index of the error    */
+    uint32_t crlf;          /* 1: first record ends its header with CRLF, output uses CRLF     */
+    uint32_t empty_input;   /* 1: fewer than 5 bytes => "empty" (utils.rs:359-375); no output  */
+    uint32_t path;          /* 1: fused single-pass kernel produced the result, 2: general path */
+    uint32_t reserved;
+} sgpu_counts;
+
+/* ---- context ------------------------------------------------------------------- */
+sgpu_status sgpu_ctx_create(int device, sgpu_ctx **out);
+void sgpu_ctx_destroy(sgpu_ctx *);
+/* enqueue on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+sgpu_status sgpu_ctx_set_stream(sgpu_ctx *, void *cuda_stream);
+/* 0: auto (fused kernel when the input is canonical, else general); 1: force the general path */
+sgpu_status sgpu_ctx_set_mode(sgpu_ctx *, int mode);
+sgpu_status sgpu_ctx_sync(sgpu_ctx *);
+const char *sgpu_strerror(int status);
+const char *sgpu_last_cuda_error(void);
+int sgpu_abi_version(void);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+uint64_t sgpu_ctx_launch_count(const sgpu_ctx *);
+
+/* ---- evidence -> read-id set ---------------------------------------------------- */
+/* ReadAlignment::from_paf, alignment.rs:84-114 (+ PafRecord::from_str :244-263, predicate :102-104;
+ * same loop as cleaner.rs:669-678).  PAF and GAF share it (alignment.rs:41,49-50). */
+sgpu_status sgpu_idset_from_paf(sgpu_ctx *, const uint8_t *buf, size_t n, uint64_t min_len,
+                                double min_cov, uint8_t min_mapq, sgpu_idset **out,
+                                uint64_t *err_line);
+sgpu_status sgpu_idset_from_paf_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, uint64_t min_len,
+                                    double min_cov, uint8_t min_mapq, sgpu_idset **out,
+                                    uint64_t *err_line);
+/* ReadAlignment::from_txt, alignment.rs:60-82: every line verbatim */
+sgpu_status sgpu_idset_from_txt(sgpu_ctx *, const uint8_t *buf, size_t n, sgpu_idset **out,
+                                uint64_t *err_line);
+sgpu_status sgpu_idset_from_txt_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, sgpu_idset **out,
+                                    uint64_t *err_line);
+/* get_taxid_reads_kraken (style 0, classifier.rs:270-290) / get_taxid_reads_metabuli (style 1,
+ * :308-328).  `taxids` is the HashSet<String> returned by get_taxids_from_report
+ * (classifier.rs:124-252, computed on the host), passed as n_taxids byte strings. */
+sgpu_status sgpu_idset_from_reads(sgpu_ctx *, const uint8_t *buf, size_t n, int style,
+                                  const char *const *taxids, const size_t *taxid_lens,
+                                  size_t n_taxids, sgpu_idset **out, uint64_t *err_line);
+sgpu_status sgpu_idset_from_reads_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, int style,
+                                      const char *const *taxids, const size_t *taxid_lens,
+                                      size_t n_taxids, sgpu_idset **out, uint64_t *err_line);
+/* a caller-built HashSet<String> (the `read_ids: &HashSet<String>` argument of
+ * FastqCleaner::clean_reads, cleaner.rs:731): ids[i] has lens[i] bytes */
+sgpu_status sgpu_idset_from_ids(sgpu_ctx *, const char *const *ids, const size_t *lens, size_t n,
+                                sgpu_idset **out);
+sgpu_status sgpu_idset_new(sgpu_ctx *, sgpu_idset **out); /* empty set (diff accumulator) */
+uint64_t sgpu_idset_len(const sgpu_idset *);              /* HashSet::len */
+sgpu_status sgpu_idset_contains(sgpu_ctx *, const sgpu_idset *, const char *id, size_t len,
+                                int *found);
+/* sorted (bytewise) ids, each followed by '\n', in a malloc'ed buffer freed with sgpu_free */
+sgpu_status sgpu_idset_dump(sgpu_ctx *, const sgpu_idset *, uint8_t **out, size_t *n);
+void sgpu_idset_free(sgpu_idset *);
+void sgpu_free(void *);
+
+/* ---- FASTQ filter ---------------------------------------------------------------- */
+/* FastqCleaner::clean_reads, cleaner.rs:731-760 (loop :742-754) including needletail's
+ * framing and re-serialisation and get_id (utils.rs:91-103).
+ *   out_written : the bytes the reference writes to its output file
+ *                 (kept records when reverse == 0, matched records when reverse != 0)
+ *   out_other   : the complementary partition (may be NULL: not produced)
+ * cap_* are the buffer capacities; n_* receive the produced sizes.  On a parse error
+ * the records before the failing one are produced (the reference leaves them on disk)
+ * and the error class is returned with counts->error_record set. */
+sgpu_status sgpu_clean_fastq(sgpu_ctx *, const sgpu_idset *, const uint8_t *in, size_t n_in,
+                             int reverse, uint8_t *out_written, size_t cap_written,
+                             size_t *n_written, uint8_t *out_other, size_t cap_other,
+                             size_t *n_other, sgpu_counts *counts);
+sgpu_status sgpu_clean_fastq_dev(sgpu_ctx *, const sgpu_idset *, const uint8_t *d_in, size_t n_in,
+                                 int reverse, uint8_t *d_out_written, size_t cap_written,
+                                 size_t *n_written, uint8_t *d_out_other, size_t cap_other,
+                                 size_t *n_other, sgpu_counts *counts);
+
+/* One shard of a file cut at arbitrary byte offsets (multi-GPU).  The buffer holds
+ * the shard's own bytes [0, own_len) followed by a halo; the shard produces exactly the
+ * records that START inside [0, own_len).  `newlines_before` is the number of '\n' bytes in
+ * the file before this shard (allgathered by the caller), `crlf` the file-level line ending
+ * (decided by the first record, i.e. by shard 0), `is_last` marks the shard that holds EOF.
+ * Concatenating the shards' outputs in order is byte-identical to the unsharded call. */
+sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *, const sgpu_idset *, const uint8_t *d_in,
+                                       size_t n_in, size_t own_len, uint64_t newlines_before,
+                                       int is_first, int is_last, int crlf, int reverse,
+                                       uint8_t *d_out_written, size_t cap_written,
+                                       size_t *n_written, uint8_t *d_out_other, size_t cap_other,
+                                       size_t *n_other, sgpu_counts *counts);
+/* '\n' count of a device buffer (the per-shard figure that is allgathered) */
+sgpu_status sgpu_count_newlines_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, uint64_t *count);
+
+/* ---- diff / report counts -------------------------------------------------------- */
+/* ReadDifference::get_difference, utils.rs:250-285, for ONE (input, output) file pair:
+ * counts->{reads_in, reads_out, difference} are incremented (+=) and the ids absent from the
+ * output are inserted into *diff_ids (created when *diff_ids == NULL), so calling it once
+ * per pair reproduces the loop at utils.rs:256. */
+sgpu_status sgpu_diff(sgpu_ctx *, const uint8_t *in, size_t n_in, const uint8_t *out, size_t n_out,
+                      sgpu_counts *counts, sgpu_idset **diff_ids);
+sgpu_status sgpu_diff_dev(sgpu_ctx *, const uint8_t *d_in, size_t n_in, const uint8_t *d_out,
+                          size_t n_out, sgpu_counts *counts, sgpu_idset **diff_ids);
+
+/* ---- multi-GPU plumbing: replicate a set over NCCL ---------------------------------- */
+typedef struct {
+    void *d_table;        /* device pointer: capacity 16-byte slots           */
+    uint64_t table_bytes;
+    void *d_arena;        /* device pointer: key bytes of ids longer than 15  */
+    uint64_t arena_bytes;
+    uint64_t capacity;    /* slots (power of two)                             */
+    uint64_t count;       /* distinct ids                                     */
+    uint64_t has_empty;   /* the empty string is a member (txt blank line)    */
+} sgpu_idset_image;
+/* the set's device buffers (still owned by the set): broadcast them, then import */
+sgpu_status sgpu_idset_export(const sgpu_idset *, sgpu_idset_image *img);
+/* builds a set on this context's device by COPYING the image's device buffers */
+sgpu_status sgpu_idset_import(sgpu_ctx *, const sgpu_idset_image *img, sgpu_idset **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCRUBBY_GPU_H */

@@ -1,0 +1,290 @@
+"""Thin Python harness over the C ABI (include/scrubby_gpu.h) for tests, bench.py and the
+torch.distributed driver.  The drop-in host (CLI, report writer, taxon state machine) is the
+C++ code under scrubby_b200/host/; this module only moves bytes and handles.
+
+Every call goes to libscrubby_gpu.so -- there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+from . import _lib
+
+
+class ScrubbyGpuError(RuntimeError):
+    def __init__(self, status: int, index: int = 0, what: str = ""):
+        L = _lib.load()
+        msg = L.sgpu_strerror(status).decode()
+        if status == 16:
+            msg += ": " + L.sgpu_last_cuda_error().decode()
+        super().__init__(f"{_lib.STATUS.get(status, status)} ({msg}) {what} at record/line {index}")
+        self.status = status
+        self.code = status
+        self.index = index
+
+
+def _check(status: int, index: int = 0, what: str = ""):
+    if status != 0:
+        raise ScrubbyGpuError(status, index, what)
+
+
+def _host_ptr(buf):
+    """(address, nbytes, keepalive) of bytes / bytearray / numpy / torch CPU uint8"""
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        b = bytes(buf) if not isinstance(buf, bytes) else buf
+        arr = C.create_string_buffer(b, len(b)) if len(b) else C.create_string_buffer(1)
+        return C.cast(arr, C.c_void_p), len(b), arr
+    if hasattr(buf, "data_ptr"):  # torch tensor on the CPU
+        assert buf.device.type == "cpu" and buf.is_contiguous()
+        return C.c_void_p(buf.data_ptr()), buf.numel() * buf.element_size(), buf
+    import numpy as np
+
+    a = np.ascontiguousarray(buf, dtype=np.uint8)
+    return C.c_void_p(a.ctypes.data), a.size, a
+
+
+def _dev_ptr(t):
+    assert t.is_cuda and t.is_contiguous(), "device tensor expected"
+    return C.c_void_p(t.data_ptr()), t.numel() * t.element_size()
+
+
+class Context:
+    """sgpu_ctx: one per device / per host thread."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self.L = _lib.load()
+        self.h = C.c_void_p()
+        _check(self.L.sgpu_ctx_create(device, C.byref(self.h)), what="sgpu_ctx_create")
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        """stream: torch.cuda.Stream, raw cudaStream_t int, or None for an own stream"""
+        raw = getattr(stream, "cuda_stream", stream)
+        _check(self.L.sgpu_ctx_set_stream(self.h, C.c_void_p(raw) if raw else None))
+
+    def set_mode(self, mode: int):
+        _check(self.L.sgpu_ctx_set_mode(self.h, mode))
+
+    def sync(self):
+        _check(self.L.sgpu_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.sgpu_ctx_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.sgpu_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class IdSet:
+    """sgpu_idset: the HashSet<String> of read ids, resident in HBM."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle if isinstance(handle, C.c_void_p) else C.c_void_p(handle)
+
+    # -- constructors mirroring the reference's evidence parsers ---------------------------
+    @classmethod
+    def empty(cls, ctx):
+        h = C.c_void_p()
+        _check(ctx.L.sgpu_idset_new(ctx.h, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_ids(cls, ctx, ids):
+        bs = [i.encode() if isinstance(i, str) else bytes(i) for i in ids]
+        arr = (C.c_char_p * max(1, len(bs)))(*bs)
+        lens = (C.c_size_t * max(1, len(bs)))(*[len(b) for b in bs])
+        h = C.c_void_p()
+        _check(ctx.L.sgpu_idset_from_ids(ctx.h, arr, lens, len(bs), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_paf(cls, ctx, buf, min_len=0, min_cov=0.0, min_mapq=0):
+        """ReadAlignment::from_paf, alignment.rs:84-114"""
+        h, err = C.c_void_p(), C.c_uint64()
+        if hasattr(buf, "is_cuda") and buf.is_cuda:
+            p, n = _dev_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_paf_dev(ctx.h, p, n, min_len, min_cov, min_mapq, C.byref(h), C.byref(err))
+        else:
+            p, n, keep = _host_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_paf(ctx.h, p, n, min_len, min_cov, min_mapq, C.byref(h), C.byref(err))
+        _check(rc, err.value, "from_paf")
+        return cls(ctx, h)
+
+    @classmethod
+    def from_txt(cls, ctx, buf):
+        """ReadAlignment::from_txt, alignment.rs:60-82"""
+        h, err = C.c_void_p(), C.c_uint64()
+        if hasattr(buf, "is_cuda") and buf.is_cuda:
+            p, n = _dev_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_txt_dev(ctx.h, p, n, C.byref(h), C.byref(err))
+        else:
+            p, n, keep = _host_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_txt(ctx.h, p, n, C.byref(h), C.byref(err))
+        _check(rc, err.value, "from_txt")
+        return cls(ctx, h)
+
+    @classmethod
+    def from_reads(cls, ctx, buf, style: int, taxids):
+        """get_taxid_reads_kraken (style 0) / get_taxid_reads_metabuli (style 1), classifier.rs:270-328"""
+        bs = [t.encode() if isinstance(t, str) else bytes(t) for t in taxids]
+        arr = (C.c_char_p * max(1, len(bs)))(*bs)
+        lens = (C.c_size_t * max(1, len(bs)))(*[len(b) for b in bs])
+        h, err = C.c_void_p(), C.c_uint64()
+        if hasattr(buf, "is_cuda") and buf.is_cuda:
+            p, n = _dev_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_reads_dev(ctx.h, p, n, style, arr, lens, len(bs), C.byref(h), C.byref(err))
+        else:
+            p, n, keep = _host_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_reads(ctx.h, p, n, style, arr, lens, len(bs), C.byref(h), C.byref(err))
+        _check(rc, err.value, "from_reads")
+        return cls(ctx, h)
+
+    # -- HashSet surface ----------------------------------------------------------------------
+    def __len__(self):
+        return int(self.ctx.L.sgpu_idset_len(self.h))
+
+    def __contains__(self, key):
+        b = key.encode() if isinstance(key, str) else bytes(key)
+        found = C.c_int()
+        _check(self.ctx.L.sgpu_idset_contains(self.ctx.h, self.h, b, len(b), C.byref(found)))
+        return bool(found.value)
+
+    def sorted_ids(self) -> list[bytes]:
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(self.ctx.L.sgpu_idset_dump(self.ctx.h, self.h, C.byref(out), C.byref(n)))
+        raw = C.string_at(out, n.value)
+        self.ctx.L.sgpu_free(out)
+        return raw.split(b"\n")[:-1] if raw else []
+
+    def image(self) -> _lib.IdSetImage:
+        img = _lib.IdSetImage()
+        _check(self.ctx.L.sgpu_idset_export(self.h, C.byref(img)))
+        return img
+
+    @classmethod
+    def from_image(cls, ctx, img):
+        h = C.c_void_p()
+        _check(ctx.L.sgpu_idset_import(ctx.h, C.byref(img), C.byref(h)))
+        return cls(ctx, h)
+
+    def free(self):
+        if self.h:
+            self.ctx.L.sgpu_idset_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class CleanResult:
+    written: bytes
+    other: bytes
+    reads_in: int
+    reads_out: int
+    crlf: bool
+    empty_input: bool
+    path: int
+    error: int = 0
+    error_record: int = 0
+
+
+def clean_fastq(ctx: Context, ids: IdSet, buf, reverse: bool = False, want_other: bool = True,
+                raise_on_error: bool = True) -> CleanResult:
+    """FastqCleaner::clean_reads (cleaner.rs:731-760) on HOST bytes, copies included."""
+    import numpy as np
+
+    p, n, keep = _host_ptr(buf)
+    cap = 2 * n + 64
+    o1 = np.empty(cap, dtype=np.uint8)
+    o2 = np.empty(cap if want_other else 1, dtype=np.uint8)
+    n1, n2, c = C.c_size_t(), C.c_size_t(), _lib.Counts()
+    rc = ctx.L.sgpu_clean_fastq(ctx.h, ids.h, p, n, int(reverse), o1.ctypes.data, cap, C.byref(n1),
+                                o2.ctypes.data if want_other else None, cap if want_other else 0, C.byref(n2),
+                                C.byref(c))
+    if rc and (raise_on_error or rc >= 16):
+        raise ScrubbyGpuError(rc, c.error_record, "clean_fastq")
+    return CleanResult(o1[: n1.value].tobytes(), o2[: n2.value].tobytes() if want_other else b"", c.reads_in,
+                       c.reads_out, bool(c.crlf), bool(c.empty_input), c.path, rc, c.error_record)
+
+
+@dataclass
+class DevCleanResult:
+    n_written: int
+    n_other: int
+    reads_in: int
+    reads_out: int
+    crlf: bool
+    empty_input: bool
+    path: int
+
+
+def clean_fastq_dev(ctx: Context, ids: IdSet, d_in, n_in: int, d_out, d_other=None, reverse: bool = False
+                    ) -> DevCleanResult:
+    """same on device tensors (uint8, 16-byte aligned); outputs land in d_out / d_other"""
+    n1, n2, c = C.c_size_t(), C.c_size_t(), _lib.Counts()
+    rc = ctx.L.sgpu_clean_fastq_dev(
+        ctx.h, ids.h, C.c_void_p(d_in.data_ptr()), n_in, int(reverse), C.c_void_p(d_out.data_ptr()), d_out.numel(),
+        C.byref(n1), C.c_void_p(d_other.data_ptr()) if d_other is not None else None,
+        d_other.numel() if d_other is not None else 0, C.byref(n2), C.byref(c))
+    _check(rc, c.error_record, "clean_fastq_dev")
+    return DevCleanResult(n1.value, n2.value, c.reads_in, c.reads_out, bool(c.crlf), bool(c.empty_input), c.path)
+
+
+def clean_fastq_shard_dev(ctx: Context, ids: IdSet, d_in, n_in: int, own_len: int, newlines_before: int,
+                          is_first: bool, is_last: bool, crlf: bool, d_out, d_other=None, reverse: bool = False
+                          ) -> DevCleanResult:
+    n1, n2, c = C.c_size_t(), C.c_size_t(), _lib.Counts()
+    rc = ctx.L.sgpu_clean_fastq_shard_dev(
+        ctx.h, ids.h, C.c_void_p(d_in.data_ptr()), n_in, own_len, newlines_before, int(is_first), int(is_last),
+        int(crlf), int(reverse), C.c_void_p(d_out.data_ptr()), d_out.numel(), C.byref(n1),
+        C.c_void_p(d_other.data_ptr()) if d_other is not None else None,
+        d_other.numel() if d_other is not None else 0, C.byref(n2), C.byref(c))
+    _check(rc, c.error_record, "clean_fastq_shard_dev")
+    return DevCleanResult(n1.value, n2.value, c.reads_in, c.reads_out, bool(c.crlf), bool(c.empty_input), c.path)
+
+
+def count_newlines_dev(ctx: Context, d_buf, n: int) -> int:
+    out = C.c_uint64()
+    _check(ctx.L.sgpu_count_newlines_dev(ctx.h, C.c_void_p(d_buf.data_ptr()), n, C.byref(out)))
+    return int(out.value)
+
+
+def diff(ctx: Context, pairs, raise_on_error: bool = True):
+    """ReadDifference::get_difference (utils.rs:250-285) over [(input, output), ...] host or device buffers
+    -> (reads_in, reads_out, difference, IdSet of absent ids)"""
+    c = _lib.Counts()
+    h = C.c_void_p()
+    for fin, fout in pairs:
+        if hasattr(fin, "is_cuda") and fin.is_cuda:
+            p1, n1 = _dev_ptr(fin)
+            p2, n2 = _dev_ptr(fout)
+            rc = ctx.L.sgpu_diff_dev(ctx.h, p1, n1, p2, n2, C.byref(c), C.byref(h))
+        else:
+            p1, n1, k1 = _host_ptr(fin)
+            p2, n2, k2 = _host_ptr(fout)
+            rc = ctx.L.sgpu_diff(ctx.h, p1, n1, p2, n2, C.byref(c), C.byref(h))
+        if rc:
+            if h:
+                ctx.L.sgpu_idset_free(h)
+            if raise_on_error:
+                raise ScrubbyGpuError(rc, c.error_record, "diff")
+            return rc, c.error_record
+    ids = IdSet(ctx, h) if h else IdSet.empty(ctx)
+    return c.reads_in, c.reads_out, c.difference, ids

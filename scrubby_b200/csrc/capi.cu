@@ -1,0 +1,331 @@
+// capi.cu -- extern "C" entry points of libscrubby_gpu.so (see include/scrubby_gpu.h).
+#include <vector>
+
+#include "fastq_records.cuh"
+
+namespace sgpu {
+const char *last_cuda_error_text();
+// fastq_fused.cu: single-pass kernel; returns SGPU_OK with *used = 0 when the input is not canonical
+sgpu_status clean_fused(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, int reverse,
+                        uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
+                        sgpu_counts *counts, int *used);
+
+// ids of every record of a FASTQ buffer (diff): span + validity
+__global__ void __launch_bounds__(128)
+    fastq_ids_kernel(RecParams P, IdSetView probe, int want_absent, uint64_t *key_off, uint32_t *key_len, uint8_t *sel,
+                     unsigned long long *err_word, unsigned long long *counters) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool rec = false, pick = false;
+    if (k <= P.k_full) {
+        RecMeta m = {0, 0, 0, 0};
+        uint64_t start, p1, p3;
+        size_t id_off = 0, id_len = 0;
+        uint64_t off = 0;
+        uint32_t len = 0;
+        if (locate_record(P, k, &start, &p1, &p3, &m, &id_off, &id_len, err_word)) {
+            rec = true;
+            off = start + 1 + id_off;
+            len = (uint32_t)id_len;
+            if (want_absent)
+                pick = !(id_len <= IDSET_MAX_KEY && idset_contains(probe, P.in + off, len));
+            else
+                pick = true;
+        }
+        key_off[k] = off;
+        key_len[k] = len;
+        sel[k] = pick ? 1 : 0;
+    }
+    unsigned br = __ballot_sync(0xffffffffu, rec), bp = __ballot_sync(0xffffffffu, pick);
+    if ((threadIdx.x & 31) == 0) {
+        if (br) atomicAdd(&counters[0], (unsigned long long)__popc(br));
+        if (bp) atomicAdd(&counters[1], (unsigned long long)__popc(bp));
+    }
+}
+
+// needletail picks the parser from the first byte; niffler needs 5 bytes (utils.rs:359-383)
+static sgpu_status sniff(sgpu_ctx *c, const uint8_t *d_in, size_t n_in, bool *empty) {
+    *empty = n_in < 5;
+    if (*empty) return SGPU_OK;
+    SGPU_CUDA(cudaMemcpyAsync(c->h_pinned, d_in, 1, cudaMemcpyDeviceToHost, c->stream));
+    SGPU_CUDA(cudaStreamSynchronize(c->stream));
+    uint8_t b = *(uint8_t *)c->h_pinned;
+    if (b == '>') return SGPU_ERR_FASTA_UNSUPPORTED;
+    if (b != '@') return SGPU_ERR_FASTQ_UNKNOWN_FORMAT;
+    return SGPU_OK;
+}
+
+// one FASTQ buffer -> ids (all, or only those absent from `probe`) inserted into `into`
+static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, const sgpu_idset *probe,
+                                  int want_absent, sgpu_idset *into, uint64_t *n_records, uint64_t *n_picked,
+                                  uint64_t *err_record) {
+    *n_records = *n_picked = 0;
+    bool empty;
+    SGPU_TRY(sniff(c, d_buf, n, &empty));
+    if (empty) return SGPU_OK;
+    cudaStream_t st = c->stream;
+    DevBuf<uint64_t> nlpos, key_off, scratch;
+    DevBuf<uint32_t> key_len;
+    DevBuf<uint8_t> sel;
+    uint64_t n_nl;
+    SGPU_TRY(index_newlines(c, d_buf, n, nlpos, &n_nl));
+    RecParams P;
+    P.in = d_buf;
+    P.n_in = n;
+    P.own_len = n;
+    P.nlpos = nlpos.p;
+    P.is_last = 1;
+    P.reverse = 0;
+    P.crlf = 0;
+    P.set = view_of(nullptr);
+    setup_records(P, n_nl, 0, 1);
+    uint64_t n_thr = P.k_full + 1;
+    SGPU_TRY(key_off.alloc(n_thr, st));
+    SGPU_TRY(key_len.alloc(n_thr, st));
+    SGPU_TRY(sel.alloc(n_thr, st));
+    SGPU_TRY(scratch.alloc(4, st));
+    uint64_t init[4] = {~0ull, 0, 0, 0};
+    memcpy(c->h_pinned + 32, init, sizeof(init));
+    SGPU_CUDA(cudaMemcpyAsync(scratch.p, c->h_pinned + 32, sizeof(init), cudaMemcpyHostToDevice, st));
+    fastq_ids_kernel<<<(unsigned)ceil_div(n_thr, 128), 128, 0, st>>>(P, view_of(probe), want_absent, key_off.p,
+                                                                      key_len.p, sel.p, (unsigned long long *)scratch.p,
+                                                                      (unsigned long long *)(scratch.p + 1));
+    SGPU_LAUNCH(c);
+    uint64_t h[3];
+    SGPU_TRY(read_u64s(c, scratch.p, h, 3));
+    if (h[0] != ~0ull) {
+        if (err_record) *err_record = h[0] >> 8;
+        return (sgpu_status)(h[0] & 0xFF);
+    }
+    *n_records = h[1];
+    *n_picked = h[2];
+    if (into) SGPU_TRY(idset_insert_spans(c, into, d_buf, key_off.p, key_len.p, sel.p, n_thr));
+    return SGPU_OK;
+}
+
+static sgpu_status clean_dev_locked(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, int reverse,
+                                    uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o,
+                                    size_t *n_o, sgpu_counts *counts) {
+    memset(counts, 0, sizeof(*counts));
+    *n_w = 0;
+    if (n_o) *n_o = 0;
+    if (n_in && ((uintptr_t)d_in & 15)) return SGPU_ERR_INVALID_ARG;
+    bool empty;
+    SGPU_TRY(sniff(c, d_in, n_in, &empty));
+    if (empty) {
+        counts->empty_input = 1;
+        return SGPU_OK;
+    }
+    if (c->mode == 0) {
+        int used = 0;
+        SGPU_TRY(clean_fused(c, set, d_in, n_in, reverse, d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts, &used));
+        if (used) return SGPU_OK;
+        memset(counts, 0, sizeof(*counts));
+    }
+    return clean_general(c, set, d_in, n_in, n_in, 0, 1, 1, -1, reverse, d_out_w, cap_w, n_w, d_out_o, cap_o, n_o,
+                         counts);
+}
+
+}  // namespace sgpu
+
+using namespace sgpu;
+
+extern "C" {
+
+int sgpu_abi_version(void) { return SGPU_ABI_VERSION; }
+
+const char *sgpu_last_cuda_error(void) { return last_cuda_error_text(); }
+
+const char *sgpu_strerror(int s) {
+    switch (s) {
+    case SGPU_OK: return "ok";
+    case SGPU_ERR_IO: return "I/O error: stream did not contain valid UTF-8";
+    case SGPU_ERR_NIFFLER: return "compression sniffing failed";
+    case SGPU_ERR_FASTQ_INVALID_START: return "FASTQ record does not start with '@'";
+    case SGPU_ERR_FASTQ_INVALID_SEPARATOR: return "FASTQ separator line does not start with '+'";
+    case SGPU_ERR_FASTQ_UNEQUAL_LENGTHS: return "FASTQ sequence and quality lengths differ";
+    case SGPU_ERR_FASTQ_UNEXPECTED_END: return "FASTQ ended in the middle of a record";
+    case SGPU_ERR_FASTQ_UNKNOWN_FORMAT: return "input is neither FASTQ nor FASTA";
+    case SGPU_ERR_RECORD_NAME_UTF8: return "failed to parse record name from BAM";
+    case SGPU_ERR_FASTQ_HEADER: return "failed to extract a valid header of read";
+    case SGPU_ERR_PAF_INTEGER: return "failed to parse a valid integer from PAF";
+    case SGPU_ERR_WOULD_PANIC: return "record has too few columns (the reference panics here)";
+    case SGPU_ERR_KRAKEN_REPORT_READS: return "failed to convert the read field in the report from `Kraken2`";
+    case SGPU_ERR_KRAKEN_REPORT_DIRECT: return "failed to convert the direct read field in the report from `Kraken2`";
+    case SGPU_ERR_KRAKEN_REPORT_PARENT: return "failed to provide a parent taxon while parsing report from `Kraken2`";
+    case SGPU_ERR_FASTA_UNSUPPORTED: return "FASTA input is not supported by this build";
+    case SGPU_ERR_CUDA: return "CUDA error (see sgpu_last_cuda_error)";
+    case SGPU_ERR_NOMEM: return "out of memory";
+    case SGPU_ERR_INVALID_ARG: return "invalid argument";
+    case SGPU_ERR_CAPACITY: return "output buffer too small";
+    case SGPU_ERR_KEY_TOO_LONG: return "read id of 16 MiB or more";
+    case SGPU_ERR_HALO: return "shard halo too small: last owned record does not end inside the buffer";
+    default: return "unknown status";
+    }
+}
+
+sgpu_status sgpu_ctx_create(int device, sgpu_ctx **out) {
+    if (!out) return SGPU_ERR_INVALID_ARG;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        set_cuda_error(e != cudaSuccess ? e : cudaErrorNoDevice, __FILE__, __LINE__);
+        return SGPU_ERR_CUDA;  // no CPU fallback by design
+    }
+    SGPU_CUDA(cudaSetDevice(device));
+    sgpu_ctx *c = new (std::nothrow) sgpu_ctx();
+    if (!c) return SGPU_ERR_NOMEM;
+    c->device = device;
+    cudaDeviceProp prop;
+    SGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    SGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    SGPU_CUDA(cudaHostAlloc((void **)&c->h_pinned, 64 * 8, cudaHostAllocDefault));
+    // keep freed scratch in the pool: steady-state steps do not touch the driver allocator
+    cudaMemPool_t pool;
+    SGPU_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ull;
+    SGPU_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return SGPU_OK;
+}
+
+void sgpu_ctx_destroy(sgpu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    delete c;
+}
+
+sgpu_status sgpu_ctx_set_stream(sgpu_ctx *c, void *stream) {
+    if (!c) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    SGPU_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) {
+        cudaStreamDestroy(c->stream);
+        c->own_stream = false;
+    }
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        SGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return SGPU_OK;
+}
+
+sgpu_status sgpu_ctx_set_mode(sgpu_ctx *c, int mode) {
+    if (!c || (mode != 0 && mode != 1)) return SGPU_ERR_INVALID_ARG;
+    c->mode = mode;
+    return SGPU_OK;
+}
+
+sgpu_status sgpu_ctx_sync(sgpu_ctx *c) {
+    if (!c) return SGPU_ERR_INVALID_ARG;
+    SGPU_CUDA(cudaSetDevice(c->device));
+    SGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return SGPU_OK;
+}
+
+uint64_t sgpu_ctx_launch_count(const sgpu_ctx *c) { return c ? c->launches : 0; }
+
+sgpu_status sgpu_count_newlines_dev(sgpu_ctx *c, const uint8_t *d_buf, size_t n, uint64_t *count) {
+    if (!c || !count || (n && !d_buf)) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    return count_newlines(c, d_buf, n, count);
+}
+
+sgpu_status sgpu_clean_fastq_dev(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, int reverse,
+                                 uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o,
+                                 size_t *n_o, sgpu_counts *counts) {
+    if (!c || !set || !n_w || !counts || (n_in && !d_in) || (cap_w && !d_out_w)) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    return clean_dev_locked(c, set, d_in, n_in, reverse, d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
+}
+
+sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in,
+                                       size_t own_len, uint64_t newlines_before, int is_first, int is_last, int crlf,
+                                       int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o,
+                                       size_t cap_o, size_t *n_o, sgpu_counts *counts) {
+    if (!c || !set || !n_w || !counts || (n_in && !d_in) || own_len > n_in || (is_last && own_len != n_in) ||
+        (is_first && newlines_before != 0))
+        return SGPU_ERR_INVALID_ARG;
+    if (n_in && ((uintptr_t)d_in & 15)) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    memset(counts, 0, sizeof(*counts));
+    *n_w = 0;
+    if (n_o) *n_o = 0;
+    return clean_general(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, crlf ? 1 : 0, reverse,
+                         d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
+}
+
+sgpu_status sgpu_clean_fastq(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *in, size_t n_in, int reverse,
+                             uint8_t *out_w, size_t cap_w, size_t *n_w, uint8_t *out_o, size_t cap_o, size_t *n_o,
+                             sgpu_counts *counts) {
+    if (!c || !set || !n_w || !counts || (n_in && !in) || (cap_w && !out_w)) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    DevBuf<uint8_t> d_in, d_w, d_o;
+    SGPU_TRY(d_in.alloc(n_in + 16, st));
+    SGPU_TRY(d_w.alloc(cap_w + 16, st));
+    if (out_o) SGPU_TRY(d_o.alloc(cap_o + 16, st));
+    if (n_in) SGPU_CUDA(cudaMemcpyAsync(d_in.p, in, n_in, cudaMemcpyHostToDevice, st));
+    sgpu_status rc = clean_dev_locked(c, set, d_in.p, n_in, reverse, d_w.p, cap_w, n_w, out_o ? d_o.p : nullptr, cap_o,
+                                      n_o, counts);
+    if (rc == SGPU_ERR_CAPACITY || rc == SGPU_ERR_CUDA || rc == SGPU_ERR_NOMEM) return rc;
+    if (*n_w) SGPU_CUDA(cudaMemcpyAsync(out_w, d_w.p, *n_w, cudaMemcpyDeviceToHost, st));
+    if (out_o && n_o && *n_o) SGPU_CUDA(cudaMemcpyAsync(out_o, d_o.p, *n_o, cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+sgpu_status sgpu_diff_dev(sgpu_ctx *c, const uint8_t *d_in, size_t n_in, const uint8_t *d_out, size_t n_out,
+                          sgpu_counts *counts, sgpu_idset **diff_ids) {
+    if (!c || !counts || !diff_ids || (n_in && !d_in) || (n_out && !d_out)) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    if (!*diff_ids) SGPU_TRY(idset_create(c, diff_ids));
+    sgpu_idset *o_ids = nullptr;  // utils.rs:257 reads2_ids
+    SGPU_TRY(idset_create(c, &o_ids));
+    uint64_t n_rec = 0, n_pick = 0, err = 0;
+    sgpu_status rc = fastq_ids_into(c, d_out, n_out, nullptr, 0, o_ids, &n_rec, &n_pick, &err);  // :259-267
+    if (rc == SGPU_OK) {
+        counts->reads_out += n_rec;
+        rc = fastq_ids_into(c, d_in, n_in, o_ids, 1, *diff_ids, &n_rec, &n_pick, &err);  // :269-283
+        if (rc == SGPU_OK) {
+            counts->reads_in += n_rec;
+            counts->difference += n_pick;
+        }
+    }
+    if (rc != SGPU_OK) counts->error_record = err;
+    cudaStreamSynchronize(c->stream);
+    sgpu_idset_free(o_ids);
+    return rc;
+}
+
+sgpu_status sgpu_diff(sgpu_ctx *c, const uint8_t *in, size_t n_in, const uint8_t *out, size_t n_out,
+                      sgpu_counts *counts, sgpu_idset **diff_ids) {
+    if (!c || !counts || !diff_ids || (n_in && !in) || (n_out && !out)) return SGPU_ERR_INVALID_ARG;
+    DevBuf<uint8_t> d_in, d_out;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        SGPU_CUDA(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        SGPU_TRY(d_in.alloc(n_in + 16, st));
+        SGPU_TRY(d_out.alloc(n_out + 16, st));
+        if (n_in) SGPU_CUDA(cudaMemcpyAsync(d_in.p, in, n_in, cudaMemcpyHostToDevice, st));
+        if (n_out) SGPU_CUDA(cudaMemcpyAsync(d_out.p, out, n_out, cudaMemcpyHostToDevice, st));
+    }
+    sgpu_status rc = sgpu_diff_dev(c, d_in.p, n_in, d_out.p, n_out, counts, diff_ids);
+    cudaStreamSynchronize(c->stream);
+    return rc;
+}
+
+}  // extern "C"
