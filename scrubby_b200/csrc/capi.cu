@@ -125,6 +125,15 @@ static sgpu_status clean_dev_locked(sgpu_ctx *c, const sgpu_idset *set, const ui
                          counts);
 }
 
+void ctx_release(sgpu_ctx *c) {
+    if (c->refs.fetch_sub(1) != 1) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    delete c;
+}
+
 }  // namespace sgpu
 
 using namespace sgpu;
@@ -191,12 +200,7 @@ sgpu_status sgpu_ctx_create(int device, sgpu_ctx **out) {
 }
 
 void sgpu_ctx_destroy(sgpu_ctx *c) {
-    if (!c) return;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
-    if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    delete c;
+    if (c) ctx_release(c);
 }
 
 sgpu_status sgpu_ctx_set_stream(sgpu_ctx *c, void *stream) {

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "../../include/scrubby_gpu.h"
@@ -82,6 +83,7 @@ struct sgpu_ctx {
     int mode = 0;
     int sm_count = 148;
     uint64_t launches = 0;
+    std::atomic<int> refs{1};  // the handle itself + every live idset built on it
     std::mutex mu;
     // pinned staging for small D2H results
     uint64_t *h_pinned = nullptr;  // 64 x u64
@@ -311,6 +313,9 @@ sgpu_status index_newlines(sgpu_ctx *c, const uint8_t *d_buf, size_t n, DevBuf<u
 sgpu_status count_newlines(sgpu_ctx *c, const uint8_t *d_buf, size_t n, uint64_t *count);
 // d2h of a few u64 through the pinned staging buffer, synchronises the stream
 sgpu_status read_u64s(sgpu_ctx *c, const void *d_src, uint64_t *h_dst, size_t count);
+
+// capi.cu: drops one reference; the last one tears the context down
+void ctx_release(sgpu_ctx *c);
 
 // idset.cu
 sgpu_status idset_create(sgpu_ctx *c, sgpu_idset **out);

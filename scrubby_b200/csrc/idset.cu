@@ -140,6 +140,7 @@ sgpu_status idset_create(sgpu_ctx *c, sgpu_idset **out) {
     sgpu_idset *s = new (std::nothrow) sgpu_idset();
     if (!s) return SGPU_ERR_NOMEM;
     s->ctx = c;
+    c->refs.fetch_add(1);
     s->device = c->device;
     *out = s;
     return SGPU_OK;
@@ -234,9 +235,15 @@ uint64_t sgpu_idset_len(const sgpu_idset *s) { return s ? s->count + (s->has_emp
 
 void sgpu_idset_free(sgpu_idset *s) {
     if (!s) return;
-    cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
-    if (s->d_table) cudaFreeAsync(s->d_table, st);
-    if (s->d_arena) cudaFreeAsync(s->d_arena, st);
+    // the set holds a reference on its context, so the stream is still alive here
+    sgpu_ctx *c = s->ctx;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != s->device) cudaSetDevice(s->device);
+    if (s->d_table) cudaFreeAsync(s->d_table, c->stream);
+    if (s->d_arena) cudaFreeAsync(s->d_arena, c->stream);
+    if (dev >= 0 && dev != s->device) cudaSetDevice(dev);
+    ctx_release(c);
     delete s;
 }
 

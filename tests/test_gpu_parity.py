@@ -1,0 +1,324 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle: bit-exact bytes, id sets and counts.
+
+All tests here need a B200 (`-m gpu`).  Inputs are the hand-derived golden vectors, seeded synthetic
+data of the BASELINE.json shapes at sizes the oracle finishes in seconds, and adversarial FASTQ.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import B
+from oracle import oracle as orc
+from scrubby_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module", params=[0, 1], ids=["auto", "general"])
+def ctx_mode(request):
+    c = api.Context(0)
+    c.set_mode(request.param)
+    yield c
+    c.close()
+
+
+def _ids(lst):
+    return sorted(B(x) for x in lst)
+
+
+def _same_clean(ctx, buf: bytes, ids, reverse=False):
+    """GPU vs oracle on one buffer, both outputs + counts (+ identical error class / index)"""
+    o = orc.clean_fastq(buf, orc.OSet.from_ids(ids), reverse, raise_on_error=False)
+    g = api.clean_fastq(ctx, api.IdSet.from_ids(ctx, ids), buf, reverse, raise_on_error=False)
+    assert g.error == o.error, (g.error, o.error)
+    if o.error:
+        assert g.error_record == o.error_record
+    assert g.written == o.written
+    assert g.other == o.other
+    assert (g.reads_in, g.reads_out) == (o.reads_in, o.reads_out)
+    assert g.empty_input == o.empty_input
+    if not o.error and not o.empty_input:
+        assert g.crlf == o.crlf
+    return g
+
+
+# ---------------------------------------------------------------------------- golden vectors
+def test_golden_fastq_cases(ctx_mode, golden):
+    for c in golden["fastq_cases"]:
+        ids = [B(i) for i in c["ids"]]
+        g = api.clean_fastq(ctx_mode, api.IdSet.from_ids(ctx_mode, ids), B(c["buf"]), c["reverse"])
+        assert g.written == B(c["written"]), c["name"]
+        assert (g.reads_in, g.reads_out) == (c["reads_in"], c["reads_out"]), c["name"]
+        assert g.empty_input == c.get("empty_input", False), c["name"]
+        _same_clean(ctx_mode, B(c["buf"]), ids, c["reverse"])
+
+
+def test_golden_fastq_errors(ctx_mode, golden):
+    for c in golden["fastq_errors"]:
+        g = api.clean_fastq(ctx_mode, api.IdSet.empty(ctx_mode), B(c["buf"]), raise_on_error=False)
+        assert (g.error, g.error_record) == (c["error"], c["error_record"]), c["name"]
+        _same_clean(ctx_mode, B(c["buf"]), [])
+
+
+def test_golden_paf(ctx, golden):
+    for c in golden["paf_cases"]:
+        s = api.IdSet.from_paf(ctx, B(c["buf"]), c["min_len"], c["min_cov"], c["min_mapq"])
+        assert s.sorted_ids() == _ids(c["expect"]), c["name"]
+        assert len(s) == len(c["expect"])
+    for c in golden["paf_errors"]:
+        with pytest.raises(api.ScrubbyGpuError) as e:
+            api.IdSet.from_paf(ctx, B(c["buf"]))
+        assert e.value.status == c["error"], c["name"]
+        if "error_line" in c:
+            assert e.value.index == c["error_line"]
+
+
+def test_golden_reads_and_txt(ctx, golden):
+    for c in golden["reads_cases"]:
+        s = api.IdSet.from_reads(ctx, B(c["buf"]), c["style"], [B(t) for t in c["taxids"]])
+        assert s.sorted_ids() == _ids(c["expect"]), c["name"]
+    for c in golden["reads_errors"]:
+        with pytest.raises(api.ScrubbyGpuError) as e:
+            api.IdSet.from_reads(ctx, B(c["buf"]), c["style"], [])
+        assert e.value.status == c["error"], c["name"]
+    for c in golden["txt_cases"]:
+        s = api.IdSet.from_txt(ctx, B(c["buf"]))
+        assert s.sorted_ids() == _ids(c["expect"])
+        assert b"" in s and b"r2 " in s and b"r2" not in s
+
+
+def test_golden_diff(ctx, golden):
+    for c in golden["diff_cases"]:
+        pairs = [(B(a), B(b)) for a, b in c["pairs"]]
+        rin, rout, d, ids = api.diff(ctx, pairs)
+        assert (rin, rout, d) == (c["reads_in"], c["reads_out"], c["difference"]), c["name"]
+        assert ids.sorted_ids() == _ids(c["diff_ids"]), c["name"]
+
+
+# ---------------------------------------------------------------------------- id set
+def test_idset_inline_and_long_keys(ctx):
+    rng = random.Random(7)
+    keys = set()
+    for n in list(range(1, 40)) + [100, 1000, 5000]:
+        for _ in range(20):
+            keys.add(bytes(rng.randrange(33, 127) for _ in range(n)))
+    keys |= {b"a", b"a\x00", b"a\x00\x00", b"\x00", b"\xff" * 15, b"\xff" * 16, b"x" * 15, b"x" * 16, b"x" * 17}
+    keys = sorted(keys)
+    s = api.IdSet.from_ids(ctx, keys + keys[:50])  # duplicates offered
+    assert len(s) == len(keys)
+    assert s.sorted_ids() == keys
+    for k in keys[::37]:
+        assert k in s
+    assert b"a\x00\x00\x00" not in s and b"x" * 18 not in s and b"" not in s
+    # image round trip (what the NCCL broadcast carries)
+    s2 = api.IdSet.from_image(ctx, s.image())
+    assert s2.sorted_ids() == keys
+
+
+def test_idset_many_keys_matches_oracle(ctx):
+    txt = synth.gen_txt_ids(300_000).numpy().tobytes()
+    s = api.IdSet.from_txt(ctx, txt)
+    o = orc.set_from_txt(txt)
+    assert len(s) == len(o)
+    assert s.sorted_ids() == o.sorted_ids()
+
+
+# ---------------------------------------------------------------------------- synthetic configs (small)
+def test_c1_alignment_config_small(ctx_mode):
+    """config 1 shape: 2x150 pairs + PAF, -l 50 -c 0.5 -q 50, deplete and extract"""
+    n = 60_000
+    paf = synth.gen_paf(n).numpy().tobytes()
+    gs = api.IdSet.from_paf(ctx_mode, paf, 50, 0.5, 50)
+    os_ = orc.set_from_paf(paf, 50, 0.5, 50)
+    assert gs.sorted_ids() == os_.sorted_ids()
+    for mate in (1, 2):
+        fq = synth.gen_fastq(n, mate, start=7).numpy().tobytes()
+        for reverse in (False, True):
+            o = orc.clean_fastq(fq, os_, reverse)
+            g = api.clean_fastq(ctx_mode, gs, fq, reverse)
+            assert g.written == o.written and g.other == o.other
+            assert (g.reads_in, g.reads_out) == (o.reads_in, o.reads_out)
+            if ctx_mode is not None and reverse is False and mate == 1:
+                assert g.path in (1, 2)
+
+
+def test_c2_classifier_config_small(ctx):
+    """config 2 shape: Kraken2 reads + report, -T Chordata -D 9606 (taxids from the oracle's host stage)"""
+    n = 50_000
+    rep = synth.gen_kraken_report(500)
+    taxids = orc.taxids_from_report(rep, ["Chordata"], ["9606"]).sorted_ids()
+    kr = synth.gen_kraken_reads(n).numpy().tobytes()
+    gs = api.IdSet.from_reads(ctx, kr, 0, taxids)
+    os_ = orc.set_from_reads(kr, 0, orc.OSet.from_ids(taxids))
+    assert gs.sorted_ids() == os_.sorted_ids()
+    fq = synth.gen_fastq(n, 1).numpy().tobytes()
+    for reverse in (False, True):
+        o = orc.clean_fastq(fq, os_, reverse)
+        g = api.clean_fastq(ctx, gs, fq, reverse)
+        assert g.written == o.written and g.other == o.other
+
+
+def test_c3_ont_config_small(ctx_mode):
+    """config 3 shape: long reads, UUID ids (arena-resident keys), many PAF lines per read"""
+    n = 300
+    fq, lens, uu = synth.gen_ont_fastq(n, max_len=120_000)
+    fqb = fq.numpy().tobytes()
+    rng = random.Random(3)
+    lines = []
+    expect = set()
+    for i in range(n):
+        rid = bytes(uu[i].tolist()).decode()
+        k = 1 + min(40, int(rng.expovariate(1 / 8)))
+        passed = False
+        for j in range(k):
+            qlen = int(lens[i])
+            alen = rng.randrange(20, qlen)
+            mapq = rng.choice([0, 10, 49, 50, 60])
+            lines.append(f"{rid}\t{qlen}\t0\t{alen}\t+\tchr1\t1000000\t5\t{5 + alen}\t{alen}\t{alen}\t{mapq}\ttp:A:P")
+            if (alen >= 5000 or alen / qlen >= 0.5) and mapq >= 50:
+                passed = True
+        if passed:
+            expect.add(rid.encode())
+    paf = ("\n".join(lines) + "\n").encode()
+    gs = api.IdSet.from_paf(ctx_mode, paf, 5000, 0.5, 50)
+    os_ = orc.set_from_paf(paf, 5000, 0.5, 50)
+    assert gs.sorted_ids() == os_.sorted_ids() == sorted(expect)
+    for reverse in (False, True):
+        o = orc.clean_fastq(fqb, os_, reverse)
+        g = api.clean_fastq(ctx_mode, gs, fqb, reverse)
+        assert g.written == o.written and g.other == o.other
+        assert (g.reads_in, g.reads_out) == (o.reads_in, o.reads_out)
+
+
+def test_c5_diff_small(ctx):
+    n = 40_000
+    ids = orc.set_from_txt(synth.gen_txt_ids(n).numpy().tobytes())
+    gids = api.IdSet.from_txt(ctx, synth.gen_txt_ids(n).numpy().tobytes())
+    pairs = []
+    for mate in (1, 2):
+        fq = synth.gen_fastq(n, mate).numpy().tobytes()
+        out = api.clean_fastq(ctx, gids, fq).written
+        assert out == orc.clean_fastq(fq, ids).written
+        pairs.append((fq, out))
+    o = orc.diff(pairs)
+    g = api.diff(ctx, pairs)
+    assert g[:3] == o[:3]
+    assert g[3].sorted_ids() == o[3].sorted_ids()
+    assert g[2] == 2 * len(ids) and len(g[3]) == len(ids)
+
+
+# ---------------------------------------------------------------------------- adversarial framing
+def _rand_fastq(rng, n_rec, crlf_first=False, ids_pool=None):
+    out = bytearray()
+    for i in range(n_rec):
+        style = rng.randrange(8)
+        rid = rng.choice(ids_pool) if ids_pool else f"r{i}".encode()
+        desc = rng.choice([b"", b" d", b"\t1:N:0", b" a b c", b"\x0bvt", " ü".encode(), b" \r x"])
+        L = rng.choice([0, 1, 2, 15, 16, 17, 31, 64, 150, 151, 1000])
+        seq = bytes(rng.choice(b"ACGTN") for _ in range(L))
+        qual = bytes(rng.randrange(33, 74) for _ in range(L))
+        if L and style == 1:
+            qual = b"@" + qual[1:]
+        if L and style == 2:
+            qual = b"+" + qual[1:]
+        e = b"\r\n" if (crlf_first and i == 0) or style == 3 else b"\n"
+        sep = b"+" + (rid + desc if style == 4 else b"")
+        out += b"@" + rid + desc + e + seq + e + sep + e + qual + e
+    return bytes(out)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_adversarial_fastq(ctx_mode, seed):
+    rng = random.Random(seed)
+    pool = [f"id{k}".encode() for k in range(50)] + [b"x" * 15, b"x" * 16, b"y" * 40, "é1".encode()]
+    buf = _rand_fastq(rng, 400, crlf_first=bool(seed & 1), ids_pool=pool)
+    ids = rng.sample(pool, 20)
+    tails = [b"", b"\n", b"\n\n", b"\r\n", b"\r\n\n"]
+    for reverse in (False, True):
+        _same_clean(ctx_mode, buf + rng.choice(tails), ids, reverse)
+    # missing final newline
+    _same_clean(ctx_mode, buf[:-1] if buf.endswith(b"\n") else buf, ids)
+    # truncations and corruptions: same error class and index as the oracle
+    for _ in range(12):
+        cut = rng.randrange(1, len(buf))
+        _same_clean(ctx_mode, buf[:cut], ids)
+    for _ in range(12):
+        b2 = bytearray(buf)
+        pos = rng.randrange(len(b2))
+        b2[pos] = rng.choice(b"\n@+\rA\xff")
+        _same_clean(ctx_mode, bytes(b2), ids)
+
+
+def test_canonical_input_is_byte_copy(ctx_mode):
+    """for canonical input (LF, bare '+', final newline) output bytes == kept records' input bytes"""
+    fq = synth.gen_fastq(5000, 1).numpy().tobytes()
+    g = api.clean_fastq(ctx_mode, api.IdSet.empty(ctx_mode), fq)
+    assert g.written == fq and g.other == b"" and g.reads_out == 5000
+    g = api.clean_fastq(ctx_mode, api.IdSet.empty(ctx_mode), fq, reverse=True)
+    assert g.written == b"" and g.other == fq
+
+
+# ---------------------------------------------------------------------------- shards (multi-GPU unit of work)
+@pytest.mark.parametrize("k", [2, 3, 8])
+def test_sharded_concat_is_identical(ctx, k):
+    """cut the file at arbitrary byte offsets into k shards; concatenated outputs == unsharded output"""
+    n = 20_000
+    fq_t = synth.gen_fastq(n, 1, start=3)
+    fq = fq_t.numpy().tobytes()
+    ids_txt = synth.gen_txt_ids(n + 10).numpy().tobytes()
+    gs = api.IdSet.from_txt(ctx, ids_txt)
+    whole = api.clean_fastq(ctx, gs, fq)
+    rng = random.Random(k)
+    cuts = sorted(rng.randrange(1, len(fq)) for _ in range(k - 1))
+    bounds = [0] + cuts + [len(fq)]
+    halo = 4096
+    outs, others, rin, rout = [], [], 0, 0
+    nl_before = 0
+    for s in range(k):
+        a, b = bounds[s], bounds[s + 1]
+        end = len(fq) if s == k - 1 else min(len(fq), b + halo)
+        d_in = torch.zeros(end - a + 16, dtype=torch.uint8, device="cuda")
+        d_in[: end - a] = torch.frombuffer(bytearray(fq[a:end]), dtype=torch.uint8).cuda()
+        d_out = torch.empty(2 * (end - a) + 64, dtype=torch.uint8, device="cuda")
+        d_oth = torch.empty(2 * (end - a) + 64, dtype=torch.uint8, device="cuda")
+        r = api.clean_fastq_shard_dev(ctx, gs, d_in, end - a, b - a, nl_before, s == 0, s == k - 1, False, d_out,
+                                      d_oth)
+        assert nl_before == fq[:a].count(b"\n")
+        nl_before += api.count_newlines_dev(ctx, d_in, b - a)
+        outs.append(d_out[: r.n_written].cpu().numpy().tobytes())
+        others.append(d_oth[: r.n_other].cpu().numpy().tobytes())
+        rin += r.reads_in
+        rout += r.reads_out
+    assert b"".join(outs) == whole.written
+    assert b"".join(others) == whole.other
+    assert (rin, rout) == (whole.reads_in, whole.reads_out)
+
+
+def test_device_buffers_and_stream(ctx):
+    """the _dev entry point on torch tensors, enqueued on torch's current stream"""
+    n = 30_000
+    fq = synth.gen_fastq(n, 2, device="cuda")
+    ids = synth.gen_txt_ids(n, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ctx.set_stream(s)
+        gs = api.IdSet.from_txt(ctx, ids)
+        out = torch.empty(fq.numel() + 64, dtype=torch.uint8, device="cuda")
+        oth = torch.empty(fq.numel() + 64, dtype=torch.uint8, device="cuda")
+        r = api.clean_fastq_dev(ctx, gs, fq, fq.numel(), out, oth)
+    s.synchronize()
+    ctx.set_stream(None)
+    fqb = fq.cpu().numpy().tobytes()
+    o = orc.clean_fastq(fqb, orc.set_from_txt(ids.cpu().numpy().tobytes()))
+    assert out[: r.n_written].cpu().numpy().tobytes() == o.written
+    assert oth[: r.n_other].cpu().numpy().tobytes() == o.other
+    assert r.n_written + r.n_other == len(fqb)  # canonical input: a pure partition of the bytes
