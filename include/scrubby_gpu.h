@@ -77,7 +77,8 @@ typedef struct {
 /* ---- context ------------------------------------------------------------------- */
 sgpu_status sgpu_ctx_create(int device, sgpu_ctx **out);
 void sgpu_ctx_destroy(sgpu_ctx *);
-/* enqueue on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+/* enqueue on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream.
+ * The default stream is named by cudaStreamLegacy ((cudaStream_t)0x1). */
 sgpu_status sgpu_ctx_set_stream(sgpu_ctx *, void *cuda_stream);
 /* 0: auto (fused kernel when the input is canonical, else general); 1: force the general path */
 sgpu_status sgpu_ctx_set_mode(sgpu_ctx *, int mode);
@@ -87,6 +88,11 @@ const char *sgpu_last_cuda_error(void);
 int sgpu_abi_version(void);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 uint64_t sgpu_ctx_launch_count(const sgpu_ctx *);
+/* measurement aid: time every fused-kernel launch with CUDA events on the launching stream.
+ * sgpu_ctx_fused_stats synchronises, returns the summed device time, the launch count and the
+ * algorithmic bytes (input + every output byte produced) of those launches, and resets them. */
+sgpu_status sgpu_ctx_set_profiling(sgpu_ctx *, int on);
+sgpu_status sgpu_ctx_fused_stats(sgpu_ctx *, double *ms, uint64_t *launches, uint64_t *alg_bytes);
 
 /* ---- evidence -> read-id set ---------------------------------------------------- */
 /* ReadAlignment::from_paf, alignment.rs:84-114 (+ PafRecord::from_str :244-263, predicate :102-104;

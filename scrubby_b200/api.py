@@ -52,24 +52,44 @@ def _dev_ptr(t):
 class Context:
     """sgpu_ctx: one per device / per host thread."""
 
-    def __init__(self, device: int = 0, stream=None):
+    def __init__(self, device: int = 0, stream="torch"):
+        """stream: "torch" (default) enqueues on torch's current stream of `device`, so work is ordered
+        with the torch ops that produced the tensors; "own" uses a private non-blocking stream; a
+        torch.cuda.Stream / raw cudaStream_t is used as given."""
         self.L = _lib.load()
         self.h = C.c_void_p()
         _check(self.L.sgpu_ctx_create(device, C.byref(self.h)), what="sgpu_ctx_create")
         self.device = device
-        if stream is not None:
+        if stream == "torch":
+            import torch
+
+            self.set_stream(torch.cuda.current_stream(device))
+        elif stream != "own" and stream is not None:
             self.set_stream(stream)
 
     def set_stream(self, stream):
-        """stream: torch.cuda.Stream, raw cudaStream_t int, or None for an own stream"""
+        """stream: torch.cuda.Stream, raw cudaStream_t int, or None for an own stream.  torch's default
+        stream has handle 0; it is passed as cudaStreamLegacy (0x1), which names the same stream."""
+        if stream is None:
+            _check(self.L.sgpu_ctx_set_stream(self.h, None))
+            return
         raw = getattr(stream, "cuda_stream", stream)
-        _check(self.L.sgpu_ctx_set_stream(self.h, C.c_void_p(raw) if raw else None))
+        _check(self.L.sgpu_ctx_set_stream(self.h, C.c_void_p(raw if raw else 1)))
 
     def set_mode(self, mode: int):
         _check(self.L.sgpu_ctx_set_mode(self.h, mode))
 
     def sync(self):
         _check(self.L.sgpu_ctx_sync(self.h))
+
+    def set_profiling(self, on: bool):
+        _check(self.L.sgpu_ctx_set_profiling(self.h, int(on)))
+
+    def fused_stats(self):
+        """(device ms, launches, algorithmic bytes) of the fused-kernel launches since the last call"""
+        ms, n, b = C.c_double(), C.c_uint64(), C.c_uint64()
+        _check(self.L.sgpu_ctx_fused_stats(self.h, C.byref(ms), C.byref(n), C.byref(b)))
+        return ms.value, int(n.value), int(b.value)
 
     @property
     def launches(self) -> int:
@@ -288,3 +308,16 @@ def diff(ctx: Context, pairs, raise_on_error: bool = True):
             return rc, c.error_record
     ids = IdSet(ctx, h) if h else IdSet.empty(ctx)
     return c.reads_in, c.reads_out, c.difference, ids
+
+
+def clean_fastq_host(ctx: Context, ids: IdSet, h_in, n_in: int, h_out, h_other=None, reverse: bool = False
+                     ) -> DevCleanResult:
+    """sgpu_clean_fastq on caller-owned HOST tensors (pinned for full PCIe rate): the H2D copy of the
+    input and the D2H copy of the outputs happen inside the call.  This is bench.py's e2e path."""
+    n1, n2, c = C.c_size_t(), C.c_size_t(), _lib.Counts()
+    rc = ctx.L.sgpu_clean_fastq(
+        ctx.h, ids.h, C.c_void_p(h_in.data_ptr()), n_in, int(reverse), C.c_void_p(h_out.data_ptr()), h_out.numel(),
+        C.byref(n1), C.c_void_p(h_other.data_ptr()) if h_other is not None else None,
+        h_other.numel() if h_other is not None else 0, C.byref(n2), C.byref(c))
+    _check(rc, c.error_record, "clean_fastq")
+    return DevCleanResult(n1.value, n2.value, c.reads_in, c.reads_out, bool(c.crlf), bool(c.empty_input), c.path)

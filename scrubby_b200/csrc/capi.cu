@@ -131,6 +131,10 @@ void ctx_release(sgpu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto &e : c->prof_events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
     delete c;
 }
 
@@ -235,6 +239,31 @@ sgpu_status sgpu_ctx_sync(sgpu_ctx *c) {
 }
 
 uint64_t sgpu_ctx_launch_count(const sgpu_ctx *c) { return c ? c->launches : 0; }
+
+sgpu_status sgpu_ctx_set_profiling(sgpu_ctx *c, int on) {
+    if (!c) return SGPU_ERR_INVALID_ARG;
+    c->profiling = on != 0;
+    return SGPU_OK;
+}
+
+sgpu_status sgpu_ctx_fused_stats(sgpu_ctx *c, double *ms, uint64_t *launches, uint64_t *alg_bytes) {
+    if (!c || !ms || !launches || !alg_bytes) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    SGPU_CUDA(cudaStreamSynchronize(c->stream));
+    double total = 0;
+    for (size_t i = 0; i < c->prof_used; i++) {
+        float t = 0;
+        SGPU_CUDA(cudaEventElapsedTime(&t, c->prof_events[i].first, c->prof_events[i].second));
+        total += t;
+    }
+    *ms = total;
+    *launches = c->prof_used;
+    *alg_bytes = c->prof_alg_bytes;
+    c->prof_used = 0;
+    c->prof_alg_bytes = 0;
+    return SGPU_OK;
+}
 
 sgpu_status sgpu_count_newlines_dev(sgpu_ctx *c, const uint8_t *d_buf, size_t n, uint64_t *count) {
     if (!c || !count || (n && !d_buf)) return SGPU_ERR_INVALID_ARG;

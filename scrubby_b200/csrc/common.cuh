@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/scrubby_gpu.h"
 
@@ -87,6 +88,11 @@ struct sgpu_ctx {
     std::mutex mu;
     // pinned staging for small D2H results
     uint64_t *h_pinned = nullptr;  // 64 x u64
+    // optional timing of the dominant (fused) kernel with CUDA events on the launching stream
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    uint64_t prof_alg_bytes = 0;
 };
 
 struct Slot {

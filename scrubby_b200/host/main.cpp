@@ -1,0 +1,182 @@
+// main.cpp -- `scrubby` CLI host: same subcommands and flags as the reference's clap definition
+// (terminal.rs:8-50 App/Commands, :206-279 ClassifierArgs, :323-391 AlignmentArgs, :435-466 DiffArgs).
+// `reads` (external aligners / classifiers through `sh -c`, terminal.rs:57-157) is outside the hot
+// path and reports that instead of running.
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <map>
+
+#include "scrubby_host.hpp"
+
+using namespace scrubby;
+
+namespace {
+
+struct Flag {
+    char short_name;
+    const char *long_name;
+    int arity;  // 0 = switch, 1 = one value, 2 = zero or more values (num_args(0..))
+};
+
+struct Parsed {
+    std::map<std::string, std::vector<std::string>> values;
+    std::map<std::string, bool> seen;
+    bool has(const std::string &k) const { return seen.count(k) != 0; }
+    std::optional<std::string> one(const std::string &k) const {
+        auto it = values.find(k);
+        if (it == values.end() || it->second.empty()) return std::nullopt;
+        return it->second.back();
+    }
+    std::vector<std::string> many(const std::string &k) const {
+        auto it = values.find(k);
+        return it == values.end() ? std::vector<std::string>{} : it->second;
+    }
+};
+
+[[noreturn]] void usage_error(const std::string &msg) {
+    fprintf(stderr, "error: %s\n\nUsage: scrubby [--log-file <FILE>] <reads|classifier|alignment|diff> [OPTIONS]\n", msg.c_str());
+    exit(2);
+}
+
+Parsed parse(int argc, char **argv, int from, const std::vector<Flag> &flags) {
+    Parsed p;
+    const Flag *cur = nullptr;
+    for (int i = from; i < argc; i++) {
+        std::string a = argv[i];
+        const Flag *f = nullptr;
+        std::string inline_val;
+        bool has_inline = false;
+        if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+            std::string name = a.substr(2);
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) {
+                inline_val = name.substr(eq + 1);
+                name = name.substr(0, eq);
+                has_inline = true;
+            }
+            for (auto &fl : flags)
+                if (name == fl.long_name) f = &fl;
+            if (!f) usage_error("unexpected argument '" + a + "'");
+        } else if (a.size() == 2 && a[0] == '-' && a[1] != '-') {
+            for (auto &fl : flags)
+                if (fl.short_name == a[1]) f = &fl;  // on a short-flag collision the later definition wins
+            if (!f) usage_error("unexpected argument '" + a + "'");
+        }
+        if (f) {
+            p.seen[f->long_name] = true;
+            cur = f->arity ? f : nullptr;
+            if (has_inline) {
+                p.values[f->long_name].push_back(inline_val);
+                if (f->arity == 1) cur = nullptr;
+            }
+            continue;
+        }
+        if (!cur) usage_error("unexpected value '" + a + "'");
+        p.values[cur->long_name].push_back(a);
+        if (cur->arity == 1) cur = nullptr;
+    }
+    return p;
+}
+
+std::string join_args(int argc, char **argv) {  // std::env::args().join(" "), terminal.rs:300,412
+    std::string s;
+    for (int i = 0; i < argc; i++) s += (i ? " " : "") + std::string(argv[i]);
+    return s;
+}
+
+int device_from_env() {
+    const char *d = getenv("SCRUBBY_GPU_DEVICE");
+    return d ? atoi(d) : 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    try {
+        int i = 1;
+        while (i < argc && (!strcmp(argv[i], "-l") || !strcmp(argv[i], "--log-file"))) i += 2;  // terminal.rs:29-30
+        if (i >= argc) usage_error("a subcommand is required");
+        std::string cmd = argv[i++];
+        if (cmd == "--version" || cmd == "-V") {
+            printf("scrubby %s\n", CRATE_VERSION);
+            return 0;
+        }
+        if (cmd == "classifier") {
+            // note: in the reference both --reads and --json claim -j (terminal.rs:235,259); as in clap's
+            // release behaviour the later definition (json) wins for the short form, so use --reads.
+            std::vector<Flag> flags = {{'i', "input", 2}, {'o', "output", 2}, {'k', "report", 1}, {'j', "reads", 1},
+                                       {'c', "classifier", 1}, {'T', "taxa", 2}, {'D', "taxa-direct", 2}, {'j', "json", 1},
+                                       {'w', "workdir", 1}, {'r', "read-ids", 1}, {'e', "extract", 0}};
+            Parsed p = parse(argc, argv, i, flags);
+            if (!p.one("report")) usage_error("the following required arguments were not provided: --report <REPORT>");
+            if (!p.one("reads")) usage_error("the following required arguments were not provided: --reads <READS>");
+            if (!p.one("classifier")) usage_error("the following required arguments were not provided: --classifier <CLASSIFIER>");
+            auto cls = parse_classifier(*p.one("classifier"));
+            if (!cls) usage_error("invalid value '" + *p.one("classifier") + "' for '--classifier' [possible values: kraken2, metabuli]");
+            Scrubby s;
+            s.input = p.many("input");
+            s.output = p.many("output");
+            s.json = p.one("json");
+            s.workdir = p.one("workdir");
+            s.read_ids = p.one("read-ids");
+            s.extract = p.has("extract");
+            s.device = device_from_env();
+            s.config.command = join_args(argc, argv);
+            s.config.classifier = *cls;
+            s.config.reads = p.one("reads");
+            s.config.report = p.one("report");
+            s.config.taxa = p.many("taxa");
+            s.config.taxa_direct = p.many("taxa-direct");
+            build_classifier(s).clean();
+        } else if (cmd == "alignment") {
+            std::vector<Flag> flags = {{'i', "input", 2}, {'o', "output", 2}, {'a', "alignment", 1}, {'f', "format", 1},
+                                       {'l', "min-len", 1}, {'c', "min-cov", 1}, {'q', "min-mapq", 1}, {'j', "json", 1},
+                                       {'w', "workdir", 1}, {'r', "read-ids", 1}, {'e', "extract", 0}};
+            Parsed p = parse(argc, argv, i, flags);
+            if (!p.one("alignment")) usage_error("the following required arguments were not provided: --alignment <ALIGNMENT>");
+            Scrubby s;
+            s.input = p.many("input");
+            s.output = p.many("output");
+            s.json = p.one("json");
+            s.workdir = p.one("workdir");
+            s.read_ids = p.one("read-ids");
+            s.extract = p.has("extract");
+            s.device = device_from_env();
+            s.config.command = join_args(argc, argv);
+            s.config.alignment = p.one("alignment");
+            if (auto f = p.one("format")) {
+                auto fmt = parse_alignment_format(*f);
+                if (!fmt) usage_error("invalid value '" + *f + "' for '--format' [possible values: sam, bam, cram, paf, txt, gaf]");
+                s.config.alignment_format = fmt;
+            }
+            try {
+                s.config.min_query_length = std::stoull(p.one("min-len").value_or("0"));
+                s.config.min_query_coverage = std::stod(p.one("min-cov").value_or("0"));
+                unsigned long q = std::stoul(p.one("min-mapq").value_or("0"));
+                if (q > 255) throw std::out_of_range("u8");
+                s.config.min_mapq = (uint8_t)q;
+            } catch (const std::exception &) {
+                usage_error("invalid numeric value for --min-len / --min-cov / --min-mapq");
+            }
+            build_alignment(s).clean();
+        } else if (cmd == "diff") {
+            std::vector<Flag> flags = {{'i', "input", 2}, {'o', "output", 2}, {'j', "json", 1}, {'r', "read-ids", 1}};
+            Parsed p = parse(argc, argv, i, flags);
+            ReadDifference d = ReadDifference::build(p.many("input"), p.many("output"), p.one("json"), p.one("read-ids"));
+            d.device = device_from_env();
+            d.compute();
+        } else if (cmd == "reads") {
+            fprintf(stderr, "Error: `scrubby reads` runs external aligners/classifiers (bowtie2, minimap2, kraken2, ...) through the shell; "
+                            "that orchestration is outside this build. Run the tool yourself and pass its output to "
+                            "`scrubby alignment` or `scrubby classifier`.\n");
+            return 1;
+        } else {
+            usage_error("unrecognized subcommand '" + cmd + "'");
+        }
+    } catch (const ScrubbyError &e) {
+        fprintf(stderr, "Error: %s\n", e.what());  // anyhow-style: non-zero exit (main.rs:8,42)
+        return 1;
+    }
+    return 0;
+}

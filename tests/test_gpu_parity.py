@@ -316,9 +316,99 @@ def test_device_buffers_and_stream(ctx):
         oth = torch.empty(fq.numel() + 64, dtype=torch.uint8, device="cuda")
         r = api.clean_fastq_dev(ctx, gs, fq, fq.numel(), out, oth)
     s.synchronize()
-    ctx.set_stream(None)
+    ctx.set_stream(torch.cuda.current_stream())
     fqb = fq.cpu().numpy().tobytes()
     o = orc.clean_fastq(fqb, orc.set_from_txt(ids.cpu().numpy().tobytes()))
     assert out[: r.n_written].cpu().numpy().tobytes() == o.written
     assert oth[: r.n_other].cpu().numpy().tobytes() == o.other
     assert r.n_written + r.n_other == len(fqb)  # canonical input: a pure partition of the bytes
+
+
+# ---------------------------------------------------------------------------- fused single-pass kernel
+def test_fused_path_is_taken_and_matches_general(ctx):
+    """canonical input must run through the fused kernel (path 1) and equal the general path bit for bit"""
+    n = 200_000
+    ids = synth.gen_txt_ids(n).numpy().tobytes()
+    gs = api.IdSet.from_txt(ctx, ids)
+    os_ = orc.set_from_txt(ids)
+    for mate in (1, 2):
+        fq = synth.gen_fastq(n, mate, start=99_000).numpy().tobytes()
+        for reverse in (False, True):
+            ctx.set_mode(0)
+            f = api.clean_fastq(ctx, gs, fq, reverse)
+            ctx.set_mode(1)
+            g = api.clean_fastq(ctx, gs, fq, reverse)
+            ctx.set_mode(0)
+            assert f.path == 1 and g.path == 2
+            assert f.written == g.written and f.other == g.other
+            assert (f.reads_in, f.reads_out) == (g.reads_in, g.reads_out)
+            o = orc.clean_fastq(fq, os_, reverse)
+            assert f.written == o.written and f.other == o.other
+            assert (f.reads_in, f.reads_out) == (o.reads_in, o.reads_out)
+
+
+def test_fused_long_reads_straddle_many_tiles(ctx):
+    fq, lens, uu = synth.gen_ont_fastq(400, max_len=300_000)
+    fqb = fq.numpy().tobytes()
+    ids = [bytes(uu[i].tolist()) for i in range(0, 400, 3)]
+    gs = api.IdSet.from_ids(ctx, ids)
+    os_ = orc.OSet.from_ids(ids)
+    for reverse in (False, True):
+        f = api.clean_fastq(ctx, gs, fqb, reverse)
+        o = orc.clean_fastq(fqb, os_, reverse)
+        assert f.path == 1
+        assert f.written == o.written and f.other == o.other
+        assert (f.reads_in, f.reads_out) == (o.reads_in, o.reads_out)
+
+
+@pytest.mark.parametrize("n", [1, 2, 49, 50, 51, 3000])
+def test_fused_small_and_tile_edge_sizes(ctx, n):
+    """tiny inputs and inputs whose size lands around a 16 KiB tile edge"""
+    ids = [f"syn.{i}".encode() for i in range(0, n + 5, 2)]
+    gs = api.IdSet.from_ids(ctx, ids)
+    os_ = orc.OSet.from_ids(ids)
+    for rl in (150, 141, 142, 143):
+        fq = synth.gen_fastq(n, 1, read_len=rl).numpy().tobytes()
+        f = api.clean_fastq(ctx, gs, fq)
+        o = orc.clean_fastq(fq, os_)
+        assert f.path == 1
+        assert f.written == o.written and f.other == o.other
+
+
+def test_fused_falls_back_on_noncanonical(ctx):
+    fq = synth.gen_fastq(3000, 1).numpy().tobytes()
+    gs = api.IdSet.from_ids(ctx, [b"syn.5", b"syn.77"])
+    os_ = orc.OSet.from_ids([b"syn.5", b"syn.77"])
+    variants = {
+        "crlf_one_line": fq.replace(b"\n", b"\r\n", 1),
+        "crlf_late": fq[:500_000] + fq[500_000:].replace(b"\n", b"\r\n", 1),
+        "plus_id": fq.replace(b"\n+\n", b"\n+syn\n", 1),
+        "no_final_newline": fq[:-1],
+        "blank_tail": fq + b"\n",
+        "high_byte_header": fq.replace(b"ATCACG\n", "ATCACGé\n".encode(), 1),
+        "bad_len": fq[:700_000] + fq[700_000:].replace(b"A", b"", 1),
+    }
+    for name, buf in variants.items():
+        o = orc.clean_fastq(buf, os_, raise_on_error=False)
+        f = api.clean_fastq(ctx, gs, buf, raise_on_error=False)
+        assert f.path == 2, name
+        assert (f.error, f.error_record) == (o.error, o.error_record), name
+        assert f.written == o.written and f.other == o.other, name
+
+
+def test_fused_one_million_records(ctx):
+    """~331 MB per file: larger than L2, tens of thousands of tiles"""
+    n = 1_000_000
+    ids = synth.gen_txt_ids(n, device="cuda")
+    gs = api.IdSet.from_txt(ctx, ids)
+    os_ = orc.set_from_txt(ids.cpu().numpy().tobytes())
+    fq = synth.gen_fastq(n, 1, device="cuda", start=9_500_000)
+    out = torch.empty(fq.numel() + 64, dtype=torch.uint8, device="cuda")
+    oth = torch.empty(fq.numel() + 64, dtype=torch.uint8, device="cuda")
+    r = api.clean_fastq_dev(ctx, gs, fq, fq.numel(), out, oth)
+    assert r.path == 1
+    o = orc.clean_fastq(fq.cpu().numpy(), os_, want_bytes=False)
+    assert (r.reads_in, r.reads_out) == (o.reads_in, o.reads_out)
+    assert r.n_written == o.written.size and r.n_other == o.other.size
+    assert np.array_equal(out[: r.n_written].cpu().numpy(), o.written)
+    assert np.array_equal(oth[: r.n_other].cpu().numpy(), o.other)
