@@ -18,12 +18,16 @@
 //   so latency is hidden by several resident CTAs per SM rather than by prefetching tickets;
 //   P1  16-byte vector loads from smem -> '\n' bit masks (SWAR) + per-chunk counts, one packed
 //       block scan, decoupled look-back #1 over tile newline counts  => global line number;
-//   P2  every newline is classified by (line number mod 4): CR / "+\n" checks, record starts;
+//   P2  newline positions are compacted, then classified one thread per newline by
+//       (line number mod 4): CR / "+\n" checks, record starts;
 //   P3  one thread per record start: '@' check, id token, hash, exact probe of the id set,
 //       seq/qual length check; block scan of kept bytes; decoupled look-back #2 carries
 //       (kept bytes so far, keep-flag of the record that straddles the tile edge);
-//   P4  runs of kept / removed bytes are copied smem -> global by warps with 16-byte stores
-//       re-aligned to the destination (funnel shifts), long runs by the whole CTA.
+//   P4  destination-driven copy: each output stream of the tile is one contiguous global range;
+//       every 16-byte aligned destination chunk is owned by one thread (coalesced 16-byte
+//       stores), its source run found through a marker array + block max-scan, the source
+//       re-aligned with funnel shifts; the <=15 edge bytes of each run are written by the
+//       run's owner thread.
 // Records may straddle any number of tiles (ONT reads); only the id token must lie within the
 // post-halo of the tile where the record starts.
 #include <stdlib.h>
@@ -41,7 +45,6 @@ constexpr int HALO = 1024;                 // post-halo
 constexpr int BUF = PRE + TILE + HALO;     // bytes per smem stage
 constexpr int RMAX = 512;                  // record starts per tile
 constexpr int LMAX = 4 * RMAX + 8;         // newline list capacity per tile
-constexpr int LONG_RUN = 2048;             // runs at least this long are copied by the whole CTA
 
 constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
 constexpr uint64_t D2_START = 1ull << 61, D2_FLAG = 1ull << 60;
@@ -257,54 +260,18 @@ __device__ __forceinline__ void lookback_kept(unsigned long long *desc, uint64_t
     if (tid == 0) st_relaxed(desc + t, ST_INC | (out_flag ? D2_FLAG : 0) | incl);
 }
 
-// ------------------------------------------------------------------ smem -> global run copy
-// One warp copies n bytes from shared `src` to global `dst` (both arbitrarily aligned):
-// 16-byte stores on the destination's alignment, source re-aligned with funnel shifts.
-__device__ __forceinline__ void copy_run_lanes(uint8_t *dst, const uint8_t *src, uint32_t n, int lane, int nlanes) {
-    uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
-    if (head > n) head = n;
-    for (uint32_t i = lane; i < head; i += nlanes) dst[i] = src[i];
-    dst += head;
-    src += head;
-    n -= head;
-    const uint32_t nchunks = n >> 4;
-    const uint32_t sa = smem_u32(src);
-    const uint32_t q = sa & 15, qw = q >> 2, qb = (q & 3) * 8;
-    const uint8_t *sbase = src - q;  // 16-byte aligned
-    for (uint32_t i = lane; i < nchunks; i += nlanes) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(sbase + (size_t)i * 16);
-        uint4 o;
-        if (q == 0) {
-            o = a;
-        } else {
-            const uint4 b = *reinterpret_cast<const uint4 *>(sbase + (size_t)i * 16 + 16);
-            uint32_t w0, w1, w2, w3, w4;
-            switch (qw) {  // warp-uniform
-            case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
-            case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
-            case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
-            default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
-            }
-            o.x = __funnelshift_r(w0, w1, qb);
-            o.y = __funnelshift_r(w1, w2, qb);
-            o.z = __funnelshift_r(w2, w3, qb);
-            o.w = __funnelshift_r(w3, w4, qb);
-        }
-        st_global_v4(dst + (size_t)i * 16, o);
-    }
-    const uint32_t done = nchunks << 4;
-    for (uint32_t i = done + lane; i < n; i += nlanes) dst[i] = src[i];
-}
-
+// ------------------------------------------------------------------ shared memory
 struct __align__(16) FusedSmem {
     uint64_t bar;
     uint64_t scan[80];
     LookbackSmem lb;
-    uint32_t cur_lo, cur_hi, fallback, has_long;
+    uint32_t cur_lo, cur_hi, fallback, pad0;
+    uint32_t wmax[FT / 32];
     uint16_t nlp[LMAX];        // local positions of the tile's newlines
-    uint16_t rs[RMAX + 2];     // local positions of record starts
-    uint8_t rflag[RMAX + 2];   // 1: the record is written to out_w
-    uint32_t rkoff[RMAX + 2];  // exclusive kept-byte offsets of the records (relative to the tile)
+    uint16_t runS[RMAX + 4];   // run r starts at runS[r]; run 0 = carried-in head, run j+1 = record j; sentinel = tile_len
+    uint8_t runF[RMAX + 4];    // 1: the run goes to out_w
+    uint32_t runK[RMAX + 4];   // kept bytes of the records before run r (head excluded); sentinel = rest_total
+    __align__(16) uint16_t crun[TILE / 16];  // per destination chunk: 1 + index of the run it lies inside
     __align__(16) uint8_t buf[BUF];
 };
 
@@ -361,11 +328,128 @@ __device__ __forceinline__ void issue_tile_load(const FusedParams &P, FusedSmem 
     bulk_g2s(dst, P.in + src0, bytes, &S->bar);
 }
 
+// 16-bit mask (bit i <-> byte i) of the bytes equal to '\n' in a 16-byte chunk.
+// Per word: exact zero-byte test of (w ^ 0x0a0a0a0a), then the four flag bits (7,15,23,31) are
+// gathered into a nibble with one multiply: ((t >> 7) * 0x10204080) >> 28.
+__device__ __forceinline__ uint32_t nl_nibble(uint32_t w) {
+    const uint32_t x = w ^ 0x0a0a0a0au;
+    const uint32_t t = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    return ((t >> 7) * 0x10204080u) >> 28;
+}
+__device__ __forceinline__ uint32_t nl_mask16_fast(uint4 v) {
+    return nl_nibble(v.x) | (nl_nibble(v.y) << 4) | (nl_nibble(v.z) << 8) | (nl_nibble(v.w) << 12);
+}
+
+// 16 bytes from shared memory at an arbitrary byte address (two aligned 16-byte loads + funnel shifts)
+__device__ __forceinline__ uint4 lds_unaligned16(const uint8_t *src) {
+    const uint32_t sa = smem_u32(src);
+    const uint32_t q = sa & 15, qw = q >> 2, qb = (q & 3) * 8;
+    const uint8_t *sbase = src - q;
+    const uint4 a = *reinterpret_cast<const uint4 *>(sbase);
+    const uint4 b = *reinterpret_cast<const uint4 *>(sbase + 16);
+    // select the five consecutive words starting at word qw of {a, b}
+    const uint32_t w0 = qw == 0 ? a.x : qw == 1 ? a.y : qw == 2 ? a.z : a.w;
+    const uint32_t w1 = qw == 0 ? a.y : qw == 1 ? a.z : qw == 2 ? a.w : b.x;
+    const uint32_t w2 = qw == 0 ? a.z : qw == 1 ? a.w : qw == 2 ? b.x : b.y;
+    const uint32_t w3 = qw == 0 ? a.w : qw == 1 ? b.x : qw == 2 ? b.y : b.z;
+    const uint32_t w4 = qw == 0 ? b.x : qw == 1 ? b.y : qw == 2 ? b.z : b.w;
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, qb);
+    o.y = __funnelshift_r(w1, w2, qb);
+    o.z = __funnelshift_r(w2, w3, qb);
+    o.w = __funnelshift_r(w3, w4, qb);
+    return o;
+}
+
+// P4 for one output stream.  The stream's bytes of this tile form ONE contiguous global range
+// [base, base + total): run r contributes len_r bytes at offset off_r iff it belongs to the stream.
+//   WRITTEN = true : stream out_w, runs with flag set,   off_r = K_r (kept prefix)
+//   WRITTEN = false: stream out_o, runs with flag clear, off_r = S_r - K_r
+template <bool WRITTEN>
+__device__ __forceinline__ void emit_stream(FusedSmem *S, const uint8_t *tile, uint8_t *base, uint32_t total,
+                                            uint32_t n_starts, bool carry, uint32_t head_kept) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = FT / 32;
+    if (total == 0) return;  // uniform
+    const uintptr_t b0 = (uintptr_t)base;
+    const uintptr_t A0 = (b0 + 15) & ~(uintptr_t)15;            // first aligned chunk
+    const uintptr_t A1 = (b0 + total) & ~(uintptr_t)15;         // end of the last aligned chunk
+    const uint32_t n_chunks = A1 > A0 ? (uint32_t)((A1 - A0) >> 4) : 0u;
+    __syncthreads();  // the previous stream's chunk loop has finished reading crun[]
+    // clear this thread's 8 markers (blocked: chunks 8*tid .. 8*tid+7)
+    *reinterpret_cast<uint4 *>(&S->crun[8 * tid]) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // ---- owners: one thread per run writes the run's edge bytes and marks its first interior chunk
+    for (uint32_t r = tid; r <= n_starts; r += FT) {
+        const uint32_t s = S->runS[r], e = S->runS[r + 1];
+        const uint32_t len = e - s;
+        const bool fl = r ? (S->runF[r] != 0) : carry;
+        if (len == 0 || fl != WRITTEN) continue;
+        const uint32_t K = r ? head_kept + S->runK[r] : 0u;
+        const uint32_t off = WRITTEN ? K : s - K;
+        const uintptr_t a = b0 + off, b = a + len;
+        const uintptr_t a16 = (a + 15) & ~(uintptr_t)15, b16 = b & ~(uintptr_t)15;
+        const uint8_t *src = tile + s;
+        uint8_t *dst = base + off;
+        if (a16 < b16) {
+            S->crun[(a16 - A0) >> 4] = (uint16_t)(r + 1);
+            const uint32_t hn = (uint32_t)(a16 - a), tn = (uint32_t)(b - b16);
+            for (uint32_t i = 0; i < hn; i++) dst[i] = src[i];
+            for (uint32_t i = len - tn; i < len; i++) dst[i] = src[i];
+        } else {
+            for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+        }
+    }
+    __syncthreads();
+    // ---- propagate the markers: crun[c] = last marker at or before c (block-wide max-scan)
+    {
+        uint4 mk = *reinterpret_cast<const uint4 *>(&S->crun[8 * tid]);
+        uint32_t v[8] = {mk.x & 0xFFFF, mk.x >> 16, mk.y & 0xFFFF, mk.y >> 16,
+                         mk.z & 0xFFFF, mk.z >> 16, mk.w & 0xFFFF, mk.w >> 16};
+#pragma unroll
+        for (int i = 1; i < 8; i++) v[i] = max(v[i], v[i - 1]);
+        uint32_t inc = v[7];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc = max(inc, o);
+        }
+        if (lane == 31) S->wmax[warp] = inc;
+        uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NW; w++)
+            if (w < warp) excl = max(excl, S->wmax[w]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = max(v[i], excl);
+        mk.x = v[0] | (v[1] << 16);
+        mk.y = v[2] | (v[3] << 16);
+        mk.z = v[4] | (v[5] << 16);
+        mk.w = v[6] | (v[7] << 16);
+        *reinterpret_cast<uint4 *>(&S->crun[8 * tid]) = mk;
+    }
+    __syncthreads();
+    // ---- interior chunks: thread-per-chunk, interleaved so that a warp stores 512 contiguous bytes
+    for (uint32_t c = tid; c < n_chunks; c += FT) {
+        const uint32_t r1 = S->crun[c];
+        if (r1 == 0) continue;
+        const uint32_t r = r1 - 1;
+        const uint32_t s = S->runS[r], e = S->runS[r + 1];
+        const uint32_t K = r ? head_kept + S->runK[r] : 0u;
+        const uint32_t off = WRITTEN ? K : s - K;
+        const uint32_t x = (uint32_t)(A0 - b0) + (c << 4);  // stream offset of this chunk
+        if (x + 16 > off + (e - s)) continue;                // the chunk straddles the run's end: edge bytes
+        const uint4 o = lds_unaligned16(tile + s + (x - off));
+        st_global_v4(reinterpret_cast<void *>(A0 + ((uintptr_t)c << 4)), o);
+    }
+}
+
 __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FusedSmem *S = reinterpret_cast<FusedSmem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long my_reads_out = 0;
+    const int tid = threadIdx.x;
+    unsigned long long my_reads_out = 0;  // thread 0 only
     uint32_t phase = 0;
 
     if (tid == 0) {
@@ -382,7 +466,6 @@ __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParam
             S->cur_lo = (uint32_t)tn;
             S->cur_hi = (uint32_t)(tn >> 32);
             S->fallback = 0;
-            S->has_long = 0;
             if (tn < P.n_tiles) issue_tile_load(P, S, tn);
         }
         __syncthreads();
@@ -404,51 +487,53 @@ __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParam
         uint32_t m[FC];
         uint32_t hi_or = 0;
         uint64_t packed[2] = {0, 0};
+        if (tile_len == (uint32_t)TILE) {
 #pragma unroll
-        for (int k = 0; k < FC; k++) {
-            const uint32_t pos = (uint32_t)(k * FT + tid) * 16;
-            uint4 v = *reinterpret_cast<const uint4 *>(tile + pos);
-            uint32_t mm = nl_mask16(v);
-            if (pos + 16 > tile_len) {  // last tile: bytes past the end of the file are stale
-                if (pos >= tile_len) {
-                    mm = 0;
-                    v = make_uint4(0, 0, 0, 0);
-                } else {
-                    const uint32_t valid = tile_len - pos;
-                    mm &= (1u << valid) - 1u;
-                    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        const int rem = (int)valid - 4 * x;
-                        if (rem <= 0) w[x] = 0;
-                        else if (rem < 4) w[x] &= (1u << (8 * rem)) - 1u;
-                    }
-                    v = make_uint4(w[0], w[1], w[2], w[3]);
-                }
+            for (int k = 0; k < FC; k++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(tile + (uint32_t)(k * FT + tid) * 16);
+                m[k] = nl_mask16_fast(v);
+                hi_or |= (v.x | v.y | v.z | v.w);
+                packed[k >> 2] |= (uint64_t)__popc(m[k]) << (16 * (k & 3));
             }
-            m[k] = mm;
-            hi_or |= (v.x | v.y | v.z | v.w);
-            packed[k >> 2] |= (uint64_t)__popc(mm) << (16 * (k & 3));
+        } else {
+#pragma unroll
+            for (int k = 0; k < FC; k++) {  // last tile: bytes past the end of the file are stale
+                const uint32_t pos = (uint32_t)(k * FT + tid) * 16;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                uint32_t mm = 0;
+                if (pos < tile_len) {
+                    v = *reinterpret_cast<const uint4 *>(tile + pos);
+                    mm = nl_mask16_fast(v);
+                    const uint32_t valid = tile_len - pos;
+                    if (valid < 16) {
+                        mm &= (1u << valid) - 1u;
+                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                            const int rem = (int)valid - 4 * x;
+                            if (rem <= 0) w[x] = 0;
+                            else if (rem < 4) w[x] &= (1u << (8 * rem)) - 1u;
+                        }
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                m[k] = mm;
+                hi_or |= (v.x | v.y | v.z | v.w);
+                packed[k >> 2] |= (uint64_t)__popc(mm) << (16 * (k & 3));
+            }
         }
         if (hi_or & 0x80808080u) S->fallback = 1;  // reason 1: non-ASCII byte, Unicode rules needed
         uint64_t pre[2], tot[2];
         block_scan2(packed[0], packed[1], &pre[0], &pre[1], &tot[0], &tot[1], S->scan);
-        uint32_t row_base[FC];
         uint32_t n_nl = 0;
+        uint32_t row_base[FC];
 #pragma unroll
         for (int k = 0; k < FC; k++) {
             row_base[k] = n_nl + (uint32_t)((pre[k >> 2] >> (16 * (k & 3))) & 0xFFFF);
             n_nl += (uint32_t)((tot[k >> 2] >> (16 * (k & 3))) & 0xFFFF);
         }
-        // ---- look-back #1 (whole CTA): newlines before this tile
-        const uint64_t L0 = lookback_sum(P.desc1, t, n_nl, &S->lb);
         const bool dense = n_nl > (uint32_t)LMAX;
-        // position 0 starts a record iff 4k newlines precede it and the previous byte is one
-        const bool pos0_start = ((L0 & 3) == 0) && tile[-1] == '\n';
-        const uint32_t c0 = (uint32_t)(L0 & 3);
-
-        // ---- P2: classify every newline by its role (line number mod 4)
-        uint32_t bad = 0;  // fallback reason: 3 CRLF, 4 separator, 5 too many records
+        // ---- P2a: compact the newline positions (needs only the in-tile ranks)
         if (!dense) {
 #pragma unroll
             for (int k = 0; k < FC; k++) {
@@ -456,26 +541,41 @@ __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParam
                 uint32_t r = row_base[k];
                 const uint32_t pos = (uint32_t)(k * FT + tid) * 16;
                 while (mm) {
-                    const uint32_t p = pos + (uint32_t)(__ffs(mm) - 1);
+                    S->nlp[r++] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
                     mm &= mm - 1;
-                    S->nlp[r] = (uint16_t)p;
-                    const uint32_t role = (c0 + r) & 3;
+                }
+            }
+        }
+        // ---- look-back #1 (whole CTA): newlines before this tile (its barriers publish nlp[])
+        const uint64_t L0 = lookback_sum(P.desc1, t, n_nl, &S->lb);
+        // position 0 starts a record iff 4k newlines precede it and the previous byte is one
+        const bool pos0_start = ((L0 & 3) == 0) && tile[-1] == '\n';
+        const uint32_t c0 = (uint32_t)(L0 & 3);
+
+        // ---- P2b: one thread per newline: classify by role (line number mod 4)
+        {
+            uint32_t bad = 0;  // fallback reason: 3 CRLF, 4 separator, 5 too many records
+            if (!dense) {
+                for (uint32_t i = tid; i < n_nl; i += FT) {
+                    const uint32_t p = S->nlp[i];
+                    const uint32_t role = (c0 + i) & 3;
                     if (tile[(int)p - 1] == '\r') bad = 3;  // CRLF: not canonical
                     if (role == 1) {                        // end of the sequence line: "+\n" must follow
                         if (p + 2 >= avail) bad = 4;
                         else if (tile[p + 1] != '+' || tile[p + 2] != '\n') bad = 4;
-                    } else if (role == 3 && p + 1 < tile_len) {  // a record starts at p + 1
-                        const uint32_t j = (uint32_t)(((L0 + r) >> 2) - (L0 >> 2)) + (pos0_start ? 1u : 0u);
-                        if (j < (uint32_t)RMAX) S->rs[j] = (uint16_t)(p + 1);
+                    } else if (role == 3 && p + 1 < tile_len) {  // record j starts at p + 1 (run j + 1)
+                        const uint32_t j = (uint32_t)(((L0 + i) >> 2) - (L0 >> 2)) + (pos0_start ? 1u : 0u);
+                        if (j < (uint32_t)RMAX) S->runS[j + 1] = (uint16_t)(p + 1);
                         else bad = 5;
                     }
-                    r++;
                 }
             }
+            if (tid == 0) {
+                S->runS[0] = 0;
+                if (pos0_start) S->runS[1] = 0;
+            }
+            if (bad || dense) S->fallback = dense ? 2 : bad;
         }
-        if (tid == 0 && pos0_start) S->rs[0] = 0;
-        if (bad || dense) S->fallback = dense ? 2 : bad;
-        __syncthreads();
         // number of record starts inside the tile
         const uint32_t n_term = (uint32_t)(((L0 + n_nl) >> 2) - (L0 >> 2));
         uint32_t n_starts = n_term + (pos0_start ? 1u : 0u);
@@ -485,6 +585,8 @@ __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParam
             if ((uint32_t)S->nlp[r_last] + 1u >= tile_len) n_starts--;
         }
         if (dense || n_starts > (uint32_t)RMAX) n_starts = 0;  // (the fallback flag is already raised)
+        __syncthreads();
+        if (tid == 0) S->runS[n_starts + 1] = (uint16_t)tile_len;  // sentinel (TILE <= 32768 fits)
 
         // ---- P3: one thread per record start: '@', id token, exact probe, seq/qual length check
         uint64_t rest_total = 0;
@@ -493,8 +595,8 @@ __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParam
             uint32_t my_len = 0;
             bool my_flag = false;
             if (j < n_starts) {
-                const uint32_t s = S->rs[j];
-                const uint32_t e = (j + 1 < n_starts) ? S->rs[j + 1] : tile_len;
+                const uint32_t s = S->runS[j + 1];
+                const uint32_t e = (j + 1 < n_starts) ? S->runS[j + 2] : tile_len;
                 my_len = e - s;
                 uint32_t why = tile[s] == '@' ? 0u : 6u;  // 6 '@', 7 id token, 8 seq/qual lengths
                 // id token: skip leading blanks, run to the next blank / newline (ASCII: high bytes fell back)
@@ -514,22 +616,19 @@ __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParam
                     if (sgn != 0) why = why ? why : 8u;
                 }
                 if (why) S->fallback = why;
-                S->rflag[j] = my_flag ? 1 : 0;
-                if (my_len >= (uint32_t)LONG_RUN) S->has_long = 1;
+                S->runF[j + 1] = my_flag ? 1 : 0;
             }
-            uint64_t koff, dummy, round_total, dummy2;
-            block_scan2(my_flag ? my_len : 0u, 0, &koff, &dummy, &round_total, &dummy2, S->scan);
-            if (j < n_starts) S->rkoff[j] = (uint32_t)(rest_total + koff);
+            uint64_t koff, kcnt, round_total, round_cnt;
+            block_scan2(my_flag ? my_len : 0u, my_flag ? 1u : 0u, &koff, &kcnt, &round_total, &round_cnt, S->scan);
+            if (j < n_starts) S->runK[j + 1] = (uint32_t)(rest_total + koff);
             rest_total += round_total;
-            const unsigned kept_ballot = __ballot_sync(0xffffffffu, my_flag);
-            if (lane == 0) my_reads_out += __popc(kept_ballot);
+            my_reads_out += round_cnt;
         }
-        __syncthreads();  // rs / rflag / rkoff complete (also when the loop ran zero times)
-        const uint32_t head_len = n_starts ? (uint32_t)S->rs[0] : tile_len;
+        __syncthreads();  // runS / runF / runK complete (also when the loop ran zero times)
+        const uint32_t head_len = S->runS[1];  // == tile_len when no record starts in the tile
 
         // ---- the cross-tile length-check sums (one thread, before it joins the look-back)
         if (tid == 0) {
-            if (head_len >= (uint32_t)LONG_RUN) S->has_long = 1;
             // signed newline-position sums: -p1 +p2 +p3 -p4 per record must vanish
             long long head = 0, total = 0;
             const int r_first = (int)((3u - c0) & 3u);
@@ -567,70 +666,25 @@ __global__ void __launch_bounds__(FT, CTAS_PER_SM) fastq_fused_kernel(FusedParam
         uint64_t kept_before;
         bool carry;
         {
-            const bool last_flag = n_starts ? (S->rflag[n_starts - 1] != 0) : false;
+            const bool last_flag = n_starts ? (S->runF[n_starts] != 0) : false;
             lookback_kept(P.desc2, t, n_starts > 0, last_flag, head_len, (uint32_t)rest_total, &S->lb, &kept_before,
                           &carry);
         }
         if (tid == 0 && S->fallback) set_fallback(P.res, (int)S->fallback);
 
-        // ---- P4: copy runs.  run 0 = carried-in head, run j>=1 = record j-1's bytes inside the tile
+        // ---- P4: destination-driven copy of the tile's two byte streams
         {
-            const uint64_t head_kept = carry ? head_len : 0;
-            const uint32_t n_runs = n_starts + 1;
-            const uint64_t w_base = kept_before + head_kept;  // + rkoff[j]
-            const uint64_t o_base = g0 - kept_before;          // + (src - head_kept - rkoff[j])
-            const bool has_long = S->has_long != 0;
-            // short runs: one warp each
-            for (uint32_t r = warp; r < n_runs; r += FT / 32) {
-                uint32_t s, e, ko;
-                bool fl;
-                if (r == 0) {
-                    s = 0; e = head_len; fl = carry; ko = 0;
-                } else {
-                    s = S->rs[r - 1];
-                    e = (r < n_starts) ? S->rs[r] : tile_len;
-                    fl = S->rflag[r - 1] != 0;
-                    ko = S->rkoff[r - 1];
-                }
-                const uint32_t len = e - s;
-                if (len == 0 || len >= (uint32_t)LONG_RUN) continue;
-                if (fl) {
-                    const uint64_t d = (r == 0) ? kept_before : w_base + ko;
-                    copy_run_lanes(P.out_w + d, tile + s, len, lane, 32);
-                } else if (P.out_o) {
-                    const uint64_t d = (r == 0) ? o_base : o_base + (s - head_kept - ko);
-                    copy_run_lanes(P.out_o + d, tile + s, len, lane, 32);
-                }
-            }
-            // long runs (ONT-sized records): the whole CTA, one after another
-            if (has_long) {
-                for (uint32_t r = 0; r < n_runs; r++) {
-                    uint32_t s, e, ko;
-                    bool fl;
-                    if (r == 0) {
-                        s = 0; e = head_len; fl = carry; ko = 0;
-                    } else {
-                        s = S->rs[r - 1];
-                        e = (r < n_starts) ? S->rs[r] : tile_len;
-                        fl = S->rflag[r - 1] != 0;
-                        ko = S->rkoff[r - 1];
-                    }
-                    const uint32_t len = e - s;
-                    if (len < (uint32_t)LONG_RUN) continue;
-                    if (fl) {
-                        const uint64_t d = (r == 0) ? kept_before : w_base + ko;
-                        copy_run_lanes(P.out_w + d, tile + s, len, tid, FT);
-                    } else if (P.out_o) {
-                        const uint64_t d = (r == 0) ? o_base : o_base + (s - head_kept - ko);
-                        copy_run_lanes(P.out_o + d, tile + s, len, tid, FT);
-                    }
-                }
-            }
-            if (t + 1 == P.n_tiles && tid == 0) P.res->kept_total = kept_before + head_kept + rest_total;
+            const uint32_t head_kept = carry ? head_len : 0u;
+            const uint32_t tile_kept = head_kept + (uint32_t)rest_total;
+            emit_stream<true>(S, tile, P.out_w + kept_before, tile_kept, n_starts, carry, head_kept);
+            if (P.out_o)
+                emit_stream<false>(S, tile, P.out_o + (g0 - kept_before), tile_len - tile_kept, n_starts, carry,
+                                   head_kept);
+            if (t + 1 == P.n_tiles && tid == 0) P.res->kept_total = kept_before + tile_kept;
         }
         __syncthreads();  // all reads of the buffer are done before it is refilled
     }
-    if (lane == 0 && my_reads_out) atomicAdd(&P.res->reads_out, my_reads_out);
+    if (tid == 0 && my_reads_out) atomicAdd(&P.res->reads_out, my_reads_out);
 }
 
 // cross-tile seq/qual length check: prefix of the signed sums must vanish at every record end
