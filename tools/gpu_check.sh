@@ -1,0 +1,13 @@
+#!/bin/bash
+# one gpurun call: GPU parity tests, smoke, bench, ncu launch list, ncu full capture of the fused kernel
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; tail -2 gpurun_out/bench.log
+timeout 600 python bench.py --steps 5 --warmup 3 --split > gpurun_out/bench_split.log 2>&1; tail -1 gpurun_out/bench_split.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python tools/prof_step.py --pairs 2000000 --steps 2 > gpurun_out/launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:fastq_fused -s 1 -c 1 -f -o gpurun_out/fused python tools/prof_step.py --pairs 2000000 --steps 1 > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log

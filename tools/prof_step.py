@@ -33,6 +33,7 @@ else:
 d_out = [torch.empty(t.numel() + 64, dtype=torch.uint8, device=dev) for t in d_r]
 d_oth = [torch.empty(t.numel() + 64, dtype=torch.uint8, device=dev) if a.split else None for t in d_r]
 torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off: only the steps are captured
 for s in range(a.steps):
     ids = mk()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -44,3 +45,4 @@ for s in range(a.steps):
     nbytes = sum(t.numel() for t in d_r)
     print(f"step {s}: clean {e0.elapsed_time(e1):.3f} ms, {nbytes / e0.elapsed_time(e1) / 1e6:.1f} GB/s in, path {rs[0].path}, "
           f"reads {sum(r.reads_in for r in rs)} kept {sum(r.reads_out for r in rs)}")
+torch.cuda.profiler.stop()
