@@ -1,0 +1,198 @@
+"""Multi-GPU driver for the depletion path: one process per GPU, torch.distributed for the plumbing.
+
+SURVEY 8e: every FASTQ file is cut into `world` contiguous byte ranges (mate files independently -- the
+reference filters each file on its own ids against the same set, cleaner.rs:236-254).  The only exchanges
+are tiny or one-off:
+    all_gather  per-shard '\\n' counts        -> each shard's starting line number (line phase mod 4)
+    broadcast   file-level CRLF decision      (needletail decides on the FIRST record, i.e. on shard 0)
+    broadcast   id-set table + key arena      (set built once on rank 0, replicated over NVLink by NCCL)
+    all_reduce  report counters               (reads_in, reads_out)
+    all_gather  output sizes                  -> each rank's write offset in the concatenated output
+Outputs concatenated in rank order are byte-identical to the single-GPU output.
+
+The compute calls go through `ops` (default: the C ABI via scrubby_b200.api, i.e. the GPU; there is no CPU
+path in the product).  tests/test_dist_gloo.py passes a CPU stand-in built on the oracle to exercise this
+file's host logic with the gloo backend at world_size 2.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+@dataclass
+class Shard:
+    rank: int
+    start: int      # first owned byte of the file
+    own_len: int    # owned bytes [start, start + own_len)
+    buf_len: int    # bytes uploaded: owned bytes + halo, clipped to the file
+    is_first: bool
+    is_last: bool
+
+
+def plan_shards(n_bytes: int, world: int, halo: int = 1 << 20, align: int = 16) -> list[Shard]:
+    """`world` contiguous ranges covering [0, n_bytes); cuts are multiples of `align` so that every shard
+    buffer keeps the 16-byte alignment the kernels want when it is a view of one device buffer.
+    A shard may be empty (tiny files); the last shard always ends at EOF and carries no halo."""
+    assert world >= 1 and n_bytes >= 0
+    per = -(-n_bytes // world)
+    per = max(align, -(-per // align) * align)
+    out, eof_seen = [], False
+    for r in range(world):
+        a = min(n_bytes, r * per)
+        b = n_bytes if r == world - 1 else min(n_bytes, (r + 1) * per)
+        if eof_seen:  # ranks after the one that reaches EOF own nothing
+            out.append(Shard(r, n_bytes, 0, 0, False, False))
+            continue
+        is_last = b == n_bytes
+        eof_seen = is_last
+        end = n_bytes if is_last else min(n_bytes, b + halo)
+        out.append(Shard(r, a, b - a, end - a, r == 0, is_last))
+    return out
+
+
+class GpuOps:
+    """the product's compute: libscrubby_gpu.so on this rank's device"""
+
+    def __init__(self, ctx):
+        import torch
+
+        from . import api
+
+        self.torch, self.api, self.ctx = torch, api, ctx
+        self.device = torch.device("cuda", ctx.device)
+
+    def upload(self, host_bytes):
+        t = self.torch.frombuffer(bytearray(host_bytes), dtype=self.torch.uint8) if len(host_bytes) else \
+            self.torch.empty(0, dtype=self.torch.uint8)
+        d = self.torch.zeros(len(host_bytes) + 16, dtype=self.torch.uint8, device=self.device)
+        d[: len(host_bytes)].copy_(t)
+        return d
+
+    def count_newlines(self, d_buf, n):
+        return self.api.count_newlines_dev(self.ctx, d_buf, n) if n else 0
+
+    def first_line_crlf(self, d_buf, n):
+        head = bytes(d_buf[: min(n, 1 << 16)].cpu().numpy())
+        p = head.find(b"\n")
+        if p < 0 and n > len(head):
+            head = bytes(d_buf[:n].cpu().numpy())
+            p = head.find(b"\n")
+        return p > 0 and head[p - 1 : p] == b"\r"
+
+    def clean_shard(self, ids, d_buf, sh: Shard, newlines_before, crlf, reverse, want_other):
+        cap = 2 * sh.buf_len + 64
+        d_out = self.torch.empty(cap, dtype=self.torch.uint8, device=self.device)
+        d_oth = self.torch.empty(cap, dtype=self.torch.uint8, device=self.device) if want_other else None
+        r = self.api.clean_fastq_shard_dev(self.ctx, ids, d_buf, sh.buf_len, sh.own_len, newlines_before,
+                                           sh.is_first, sh.is_last, crlf, d_out, d_oth, reverse)
+        written = bytes(d_out[: r.n_written].cpu().numpy())
+        other = bytes(d_oth[: r.n_other].cpu().numpy()) if want_other else b""
+        return written, other, r.reads_in, r.reads_out
+
+    def replicate_set(self, ids, dist, src: int = 0):
+        """broadcast the table and the key arena of rank `src`'s set (NCCL over NVLink) and import them"""
+        torch, api = self.torch, self.api
+        rank = dist.get_rank()
+        meta = torch.zeros(5, dtype=torch.int64, device=self.device)
+        if rank == src:
+            img = ids.image()
+            meta = torch.tensor([img.table_bytes, img.arena_bytes, img.capacity, img.count, img.has_empty],
+                                dtype=torch.int64, device=self.device)
+        dist.broadcast(meta, src)
+        tb, ab, cap, cnt, he = (int(x) for x in meta.tolist())
+        table = torch.empty(max(tb, 16), dtype=torch.uint8, device=self.device)
+        arena = torch.empty(max(ab, 16), dtype=torch.uint8, device=self.device)
+        if rank == src:
+            if tb:
+                table[:tb].copy_(_as_tensor(torch, img.d_table, tb, self.device))
+            if ab:
+                arena[:ab].copy_(_as_tensor(torch, img.d_arena, ab, self.device))
+        if tb:
+            dist.broadcast(table, src)
+        if ab:
+            dist.broadcast(arena, src)
+        if rank == src:
+            return ids
+        from . import _lib
+
+        img = _lib.IdSetImage()
+        img.d_table, img.table_bytes = table.data_ptr() if tb else None, tb
+        img.d_arena, img.arena_bytes = arena.data_ptr() if ab else None, ab
+        img.capacity, img.count, img.has_empty = cap, cnt, he
+        torch.cuda.current_stream(self.device).synchronize()
+        return api.IdSet.from_image(self.ctx, img)  # copies: `table` / `arena` may be dropped afterwards
+
+
+class _DevMem:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _as_tensor(torch, ptr, n, device):
+    return torch.as_tensor(_DevMem(ptr, n), device=device)
+
+
+@dataclass
+class ShardedResult:
+    written: bytes          # this rank's part of the output file
+    other: bytes
+    offset_written: int     # where this rank's part starts in the concatenated output
+    offset_other: int
+    total_written: int
+    total_other: int
+    reads_in: int           # allreduced: whole file
+    reads_out: int
+    crlf: bool
+
+
+def clean_fastq_sharded(ops, ids, file_bytes, dist=None, reverse: bool = False, want_other: bool = False,
+                        halo: int = 1 << 20, max_halo: int = 1 << 30) -> ShardedResult:
+    """FastqCleaner::clean_reads (cleaner.rs:731-760) for ONE file across all ranks.  `file_bytes` is any
+    sliceable view of the decompressed file (bytes, memoryview, numpy memmap ...); every rank touches only
+    its own range + halo.  A record longer than the halo makes the owning shard report SGPU_ERR_HALO; all
+    ranks then retry with a larger halo (collective decision, so nobody deadlocks)."""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    n = len(file_bytes)
+    while True:
+        sh = plan_shards(n, world, halo)[rank]
+        d_buf = ops.upload(file_bytes[sh.start : sh.start + sh.buf_len])
+        own_nl = ops.count_newlines(d_buf, sh.own_len)
+        crlf = ops.first_line_crlf(d_buf, sh.buf_len) if rank == 0 else False
+        counts = _all_gather_ints(dist, [own_nl, int(crlf)], world)
+        newlines_before = sum(c[0] for c in counts[:rank])
+        crlf = bool(counts[0][1])
+        halo_short = 0
+        try:
+            if sh.own_len == 0:
+                w, o, rin, rout = b"", b"", 0, 0
+            else:
+                w, o, rin, rout = ops.clean_shard(ids, d_buf, sh, newlines_before, crlf, reverse, want_other)
+        except Exception as e:  # SGPU_ERR_HALO == 21
+            if getattr(e, "status", None) != 21:
+                raise
+            halo_short, w, o, rin, rout = 1, b"", b"", 0, 0
+        res = _all_gather_ints(dist, [halo_short, len(w), len(o), rin, rout], world)
+        if any(r[0] for r in res):
+            if halo >= max_halo:
+                raise RuntimeError("a record is longer than the maximum shard halo")
+            halo = min(max_halo, halo * 8)
+            continue
+        return ShardedResult(w, o, sum(r[1] for r in res[:rank]), sum(r[2] for r in res[:rank]),
+                             sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res),
+                             sum(r[4] for r in res), crlf)
+
+
+def _all_gather_ints(dist, vals, world):
+    """all_gather of a short list of non-negative ints (works on gloo and nccl)"""
+    if dist is None or world == 1:
+        return [list(vals)]
+    import torch
+
+    dev = "cpu"
+    if dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    t = torch.tensor(vals, dtype=torch.int64, device=dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [[int(x) for x in o.tolist()] for o in out]

@@ -1,0 +1,151 @@
+"""Host logic of the multi-GPU driver (scrubby_b200/dist.py) on CPU: gloo backend, world_size 2 and 3.
+
+The compute calls are served by a CPU stand-in built on the oracle (tests may use the oracle as the
+checker); what is under test is the sharding plan, the newline-count all_gather that fixes each shard's
+line phase, the collective halo retry, the counter reduction and the output offsets.
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from scrubby_b200 import synth  # noqa: E402
+from scrubby_b200.dist import Shard, clean_fastq_sharded, plan_shards  # noqa: E402
+
+
+class HaloError(Exception):
+    status = 21  # SGPU_ERR_HALO
+
+
+class OracleOps:
+    """CPU stand-in for GpuOps (TEST ONLY)"""
+
+    def upload(self, b):
+        return bytes(b)
+
+    def count_newlines(self, buf, n):
+        return buf[:n].count(b"\n")
+
+    def first_line_crlf(self, buf, n):
+        p = buf[:n].find(b"\n")
+        return p > 0 and buf[p - 1 : p] == b"\r"
+
+    def clean_shard(self, ids, buf, sh: Shard, newlines_before, crlf, reverse, want_other):
+        from oracle import oracle as orc
+
+        # records that START inside [0, own_len): a record starts after a newline whose global index is 3 mod 4
+        pos, line = 0, newlines_before
+        if not sh.is_first:
+            while line % 4 != 0:
+                p = buf.find(b"\n", pos)
+                if p < 0:
+                    return b"", b"", 0, 0
+                pos, line = p + 1, line + 1
+        start = pos
+        end = start
+        while end < sh.own_len:
+            e = end
+            for _ in range(4):
+                p = buf.find(b"\n", e)
+                if p < 0:
+                    if sh.is_last:
+                        e = len(buf)
+                        break
+                    raise HaloError()
+                e = p + 1
+            end = e
+        if start >= sh.own_len:
+            return b"", b"", 0, 0
+        r = orc.clean_fastq(buf[start:end], ids, reverse)
+        return r.written, (r.other if want_other else b""), r.reads_in, r.reads_out
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fq, ids_txt, reverse, halo, q):
+    from oracle import oracle as orc
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        ids = orc.set_from_txt(ids_txt)
+        r = clean_fastq_sharded(OracleOps(), ids, fq, dist, reverse=reverse, want_other=True, halo=halo)
+        q.put((rank, r.written, r.other, r.offset_written, r.offset_other, r.total_written, r.total_other,
+               r.reads_in, r.reads_out))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, fq, ids_txt, reverse=False, halo=4096):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, fq, ids_txt, reverse, halo, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def test_plan_shards_covers_file_exactly():
+    for n, w in [(0, 2), (5, 4), (100, 3), (1000, 8), (33, 2), (1 << 20, 8)]:
+        sh = plan_shards(n, w, halo=10)
+        assert len(sh) == w and sum(s.own_len for s in sh) == n
+        assert sum(s.is_last for s in sh) == 1 and sh[0].is_first
+        pos = 0
+        for s in sh:
+            if s.own_len:
+                assert s.start == pos and s.start % 16 == 0
+                assert s.buf_len >= s.own_len and s.start + s.buf_len <= n
+            pos += s.own_len
+
+
+@pytest.mark.parametrize("world,reverse", [(2, False), (2, True), (3, False)])
+def test_sharded_clean_matches_unsharded(world, reverse):
+    from oracle import oracle as orc
+
+    n = 3000
+    fq = synth.gen_fastq(n, 1, start=7).numpy().tobytes()
+    ids_txt = synth.gen_txt_ids(n + 10).numpy().tobytes()
+    whole = orc.clean_fastq(fq, orc.set_from_txt(ids_txt), reverse)
+    res = _run(world, fq, ids_txt, reverse)
+    assert b"".join(r[1] for r in res) == whole.written
+    assert b"".join(r[2] for r in res) == whole.other
+    off_w = off_o = 0
+    for r in res:
+        assert (r[3], r[4]) == (off_w, off_o)  # write offsets in the concatenated output
+        off_w += len(r[1])
+        off_o += len(r[2])
+        assert (r[5], r[6]) == (len(whole.written), len(whole.other))
+        assert (r[7], r[8]) == (whole.reads_in, whole.reads_out)  # counters reduced over ranks
+
+
+def test_halo_retry_is_collective():
+    """records longer than the first halo: every rank retries with a larger one and the result is unchanged"""
+    from oracle import oracle as orc
+
+    recs = []
+    for i in range(40):
+        L = 3000 + 37 * i
+        recs.append(b"@long.%d x\n" % i + b"A" * L + b"\n+\n" + b"I" * L + b"\n")
+    fq = b"".join(recs)
+    ids_txt = b"".join(b"long.%d\n" % i for i in range(0, 40, 3))
+    whole = orc.clean_fastq(fq, orc.set_from_txt(ids_txt))
+    res = _run(2, fq, ids_txt, halo=64)
+    assert b"".join(r[1] for r in res) == whole.written
+    assert res[0][7] == whole.reads_in and res[0][8] == whole.reads_out

@@ -412,3 +412,22 @@ def test_fused_one_million_records(ctx):
     assert r.n_written == o.written.size and r.n_other == o.other.size
     assert np.array_equal(out[: r.n_written].cpu().numpy(), o.written)
     assert np.array_equal(oth[: r.n_other].cpu().numpy(), o.other)
+
+
+# ---------------------------------------------------------------------------- multi-GPU driver pieces on one GPU
+def test_dist_driver_world1_and_set_image(ctx):
+    """scrubby_b200.dist with the GPU ops (world 1) + the export/import pair used to replicate the set"""
+    from scrubby_b200 import dist as sdist
+
+    n = 5000
+    fq = synth.gen_fastq(n, 2, start=11).numpy().tobytes()
+    ids_txt = synth.gen_txt_ids(n + 3).numpy().tobytes()
+    gs = api.IdSet.from_txt(ctx, ids_txt)
+    clone = api.IdSet.from_image(ctx, gs.image())  # what a non-source rank does after the NCCL broadcast
+    assert clone.sorted_ids() == gs.sorted_ids()
+    o = orc.clean_fastq(fq, orc.set_from_txt(ids_txt))
+    r = sdist.clean_fastq_sharded(sdist.GpuOps(ctx), clone, fq, None, want_other=True)
+    assert r.written == o.written and r.other == o.other
+    assert (r.reads_in, r.reads_out, r.offset_written, r.total_written) == (o.reads_in, o.reads_out, 0, len(o.written))
+    t = sdist._as_tensor(torch, gs.image().d_table, 64, torch.device("cuda", 0))  # raw device pointer as a tensor
+    assert t.is_cuda and t.numel() == 64
