@@ -9,6 +9,10 @@ const char *last_cuda_error_text();
 sgpu_status clean_fused(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, int reverse,
                         uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
                         sgpu_counts *counts, int *used);
+sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
+                              uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
+                              size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
+                              sgpu_counts *counts, int *used);
 
 // ids of every record of a FASTQ buffer (diff): span + validity
 __global__ void __launch_bounds__(128)
@@ -294,6 +298,15 @@ sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *c, const sgpu_idset *set, const
     memset(counts, 0, sizeof(*counts));
     *n_w = 0;
     if (n_o) *n_o = 0;
+    if (c->mode == 0 && !crlf && n_in >= 5) {
+        int used = 0;
+        SGPU_TRY(clean_fused_shard(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, reverse, d_out_w,
+                                   cap_w, n_w, d_out_o, cap_o, n_o, counts, &used));
+        if (used) return SGPU_OK;
+        memset(counts, 0, sizeof(*counts));
+        *n_w = 0;
+        if (n_o) *n_o = 0;
+    }
     return clean_general(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, crlf ? 1 : 0, reverse,
                          d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
 }

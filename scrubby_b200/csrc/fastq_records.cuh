@@ -35,7 +35,9 @@ __device__ __forceinline__ int locate_record(const RecParams &P, uint64_t k, uin
     uint64_t b = P.b0 + 4 * k;
     uint64_t start = (b == 0) ? 0 : P.nlpos[b - 1] + 1;
     const uint8_t *in = P.in;
-    if (start >= P.own_len) return 0;
+    // a record that starts exactly at own_len (the next shard's first byte) is owned HERE: the next shard
+    // cannot know that its byte 0 follows a newline
+    if (P.is_last ? start >= P.own_len : start > P.own_len) return 0;
     uint64_t p1 = 0, p2 = 0, p3 = 0, end = 0;
     bool have = false;
     if (k < P.k_full) {

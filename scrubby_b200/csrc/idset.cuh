@@ -108,6 +108,19 @@ __device__ __forceinline__ bool idset_contains(const IdSetView &v, const uint8_t
     }
 }
 
+// exact membership of an INLINE key (1..15 bytes) whose slot image (lo, hi) the caller has already built
+// (byte0 = len, bytes 1..15 = id, zero padded) -- identical to key_image() + idset_contains()
+__device__ __forceinline__ bool idset_contains_inline(const IdSetView &v, uint64_t lo, uint64_t hi) {
+    if (v.table == nullptr) return false;
+    uint64_t idx = mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL)) & v.mask;
+    while (true) {
+        const Slot s = load_slot(v.table + idx);
+        if ((s.lo | s.hi) == 0) return false;
+        if (s.lo == lo && s.hi == hi) return true;
+        idx = (idx + 1) & v.mask;
+    }
+}
+
 #endif  // __CUDACC__
 
 static inline IdSetView view_of(const sgpu_idset *s) {

@@ -27,6 +27,7 @@ def ctx():
 def ctx_mode(request):
     c = api.Context(0)
     c.set_mode(request.param)
+    c.mode = request.param
     yield c
     c.close()
 
@@ -268,9 +269,21 @@ def test_canonical_input_is_byte_copy(ctx_mode):
 
 
 # ---------------------------------------------------------------------------- shards (multi-GPU unit of work)
-@pytest.mark.parametrize("k", [2, 3, 8])
-def test_sharded_concat_is_identical(ctx, k):
-    """cut the file at arbitrary byte offsets into k shards; concatenated outputs == unsharded output"""
+def _record_starts(fq: bytes):
+    pos, out = 0, []
+    while pos < len(fq):
+        out.append(pos)
+        for _ in range(4):
+            pos = fq.index(b"\n", pos) + 1
+    return out
+
+
+@pytest.mark.parametrize("k,cut_mode", [(2, "random"), (3, "random"), (8, "random"), (4, "at_start"), (4, "after_start"),
+                                        (4, "before_start")])
+def test_sharded_concat_is_identical(ctx_mode, k, cut_mode):
+    """cut the file at arbitrary byte offsets into k shards (also exactly at / next to record starts);
+    concatenated outputs == unsharded output"""
+    ctx = ctx_mode
     n = 20_000
     fq_t = synth.gen_fastq(n, 1, start=3)
     fq = fq_t.numpy().tobytes()
@@ -278,7 +291,12 @@ def test_sharded_concat_is_identical(ctx, k):
     gs = api.IdSet.from_txt(ctx, ids_txt)
     whole = api.clean_fastq(ctx, gs, fq)
     rng = random.Random(k)
-    cuts = sorted(rng.randrange(1, len(fq)) for _ in range(k - 1))
+    if cut_mode == "random":
+        cuts = sorted(rng.randrange(1, len(fq)) for _ in range(k - 1))
+    else:
+        starts = _record_starts(fq)
+        d = {"at_start": 0, "after_start": 1, "before_start": -1}[cut_mode]
+        cuts = sorted(starts[rng.randrange(1, len(starts))] + d for _ in range(k - 1))
     bounds = [0] + cuts + [len(fq)]
     halo = 4096
     outs, others, rin, rout = [], [], 0, 0
@@ -293,6 +311,8 @@ def test_sharded_concat_is_identical(ctx, k):
         r = api.clean_fastq_shard_dev(ctx, gs, d_in, end - a, b - a, nl_before, s == 0, s == k - 1, False, d_out,
                                       d_oth)
         assert nl_before == fq[:a].count(b"\n")
+        if ctx.mode == 0 and b - a > 400:
+            assert r.path == 1, "canonical shards must run through the fused kernel"
         nl_before += api.count_newlines_dev(ctx, d_in, b - a)
         outs.append(d_out[: r.n_written].cpu().numpy().tobytes())
         others.append(d_oth[: r.n_other].cpu().numpy().tobytes())
@@ -431,3 +451,34 @@ def test_dist_driver_world1_and_set_image(ctx):
     assert (r.reads_in, r.reads_out, r.offset_written, r.total_written) == (o.reads_in, o.reads_out, 0, len(o.written))
     t = sdist._as_tensor(torch, gs.image().d_table, 64, torch.device("cuda", 0))  # raw device pointer as a tensor
     assert t.is_cuda and t.numel() == 64
+
+
+def test_sharded_long_reads_fused(ctx):
+    """ONT-like records that straddle many tiles, cut into shards at arbitrary offsets"""
+    n = 300
+    fq_t, lens, uu = synth.gen_ont_fastq(n, seed=9)
+    fq = fq_t.numpy().tobytes()
+    ids = [bytes(uu[i].tolist()) for i in range(0, n, 3)]
+    o = orc.clean_fastq(fq, orc.OSet.from_ids(ids))
+    gs = api.IdSet.from_ids(ctx, ids)
+    rng = random.Random(5)
+    k = 5
+    bounds = [0] + sorted(rng.randrange(1, len(fq)) for _ in range(k - 1)) + [len(fq)]
+    halo = 600_000
+    outs, others, rin, rout, nl_before = [], [], 0, 0, 0
+    for s in range(k):
+        a, b = bounds[s], bounds[s + 1]
+        end = len(fq) if s == k - 1 else min(len(fq), b + halo)
+        d_in = torch.zeros(end - a + 16, dtype=torch.uint8, device="cuda")
+        d_in[: end - a] = torch.frombuffer(bytearray(fq[a:end]), dtype=torch.uint8).cuda()
+        d_out = torch.empty(end - a + 64, dtype=torch.uint8, device="cuda")
+        d_oth = torch.empty(end - a + 64, dtype=torch.uint8, device="cuda")
+        r = api.clean_fastq_shard_dev(ctx, gs, d_in, end - a, b - a, nl_before, s == 0, s == k - 1, False, d_out, d_oth)
+        nl_before += api.count_newlines_dev(ctx, d_in, b - a)
+        outs.append(d_out[: r.n_written].cpu().numpy().tobytes())
+        others.append(d_oth[: r.n_other].cpu().numpy().tobytes())
+        rin += r.reads_in
+        rout += r.reads_out
+    assert b"".join(outs) == o.written
+    assert b"".join(others) == o.other
+    assert (rin, rout) == (o.reads_in, o.reads_out)
