@@ -7,6 +7,7 @@ The .so lands in scrubby_b200/lib/ (git-ignored, shipped to the GPU box by gpuru
 from __future__ import annotations
 
 import os
+import shlex
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -14,8 +15,12 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "lib", "obj")
-SO = os.path.join(LIBDIR, "libscrubby_gpu.so")
+# tuning / diagnostic builds: SGPU_VARIANT=name selects libscrubby_gpu_name.so, built with the extra nvcc
+# flags in SGPU_NVCC_FLAGS (e.g. "-DSGPU_FUSED_TIMING"); the default build has no variant
+VARIANT = os.environ.get("SGPU_VARIANT", "")
+_SUFFIX = f"_{VARIANT}" if VARIANT else ""
+OBJDIR = os.path.join(HERE, "lib", "obj" + _SUFFIX)
+SO = os.path.join(LIBDIR, f"libscrubby_gpu{_SUFFIX}.so")
 SOURCES = ["scan.cu", "idset.cu", "evidence.cu", "fastq_general.cu", "fastq_fused.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -39,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *shlex.split(os.environ.get("SGPU_NVCC_FLAGS", "") if VARIANT else ""), "-c",
+               os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -11,26 +11,28 @@
 // parse errors, pathological line density) raises the device `fallback` flag and the caller
 // re-runs the always-exact general path (fastq_general.cu); nothing is approximated.
 //
-// Structure: persistent CTAs of NT threads, several per SM, each looping over dynamically
-// ticketed TILE-byte tiles (tickets are taken in order, so every tile a look-back waits on is
-// owned by a running CTA).  All threads of a CTA run every phase of a tile; latency (TMA load,
-// set probes, look-back) is hidden by the other CTAs resident on the SM.
-//   load : one thread issues a TMA bulk copy (cp.async.bulk + mbarrier) of the tile + 16 B
-//          pre-halo + post-halo into shared memory and an L2 prefetch of the tile this CTA is
-//          likely to take next;
-//   P1   : 16-byte vector loads -> exact '\n' bit masks (SWAR + dp4a gather), counts, scan,
-//          newline positions compacted in order;
+// Structure (v3): persistent CTAs of 256 threads, several resident per SM, each looping over
+// dynamically ticketed 32 KiB tiles (tickets are taken in order, so every tile a look-back waits on is
+// owned by a running CTA).  One shared-memory tile buffer per CTA; the latency
+// of a tile's dependent steps (load, set probes, look-back) is hidden by the other resident CTAs.
+// The byte-level phases (P1, P4) run on all warps; the record-level phases run with one thread per
+// newline / per record, so only as many warps as there are records execute them.
+//   load : one thread issues a TMA bulk copy (cp.async.bulk + mbarrier) of the tile + 16 B pre-halo
+//          + post-halo into shared memory; tiles are pulled into L2 one generation of CTAs ahead;
+//   P1   : 16-byte vector loads -> exact '\n' bit masks (SWAR + dp4a gather), packed warp scan of
+//          the counts, newline positions scattered in order;
 //   phase: line number mod 4 SPECULATED from the first "\n+\n" in the tile and published at once
 //          (a tile without one does a real decoupled look-back over 2-bit phases);
 //   P2   : one thread per newline: CR / "+\n" checks by role, record starts;
 //   P3   : one thread per record start: '@', id token -> slot image straight from a 16-byte
-//          window, exact probe of the id set, seq/qual length check, block scan of kept bytes,
-//          tile aggregate published;
+//          window, exact probe of the id set, seq/qual length check, warp scans of kept bytes;
+//          runs of consecutive records with the same fate are found with ballots and cut into
+//          copy items (source, length, stream offset);
 //   scan : decoupled look-back by one warp over (kept bytes, state of the record that straddles
-//          the tile edge), 256 descriptors per round, combined as a 3-state transducer;
-//   P4   : destination-driven copy: every 16-byte aligned output chunk is owned by one thread
-//          (coalesced 16-byte stores), its source run found through a marker array + max-scan,
-//          the source re-aligned with funnel shifts.
+//          the tile edge), 32 * LBW descriptors per round, combined as a 3-state transducer;
+//   P4   : a warp per copy item: 16-byte destination-aligned stores, the source re-aligned from two
+//          16-byte shared loads with funnel shifts (the shift is uniform per item), edge bytes by
+//          one byte store per lane.
 // The speculated phases and the cross-tile seq/qual length sums are verified exactly by a tiny
 // follow-up kernel over per-tile metadata; any mismatch is a fallback, never a wrong answer.
 // Records may straddle any number of tiles (ONT reads); only the id token must lie within the
@@ -45,33 +47,44 @@
 
 namespace sgpu {
 
-#ifndef SGPU_FUSED_NT
-#define SGPU_FUSED_NT 256
-#endif
-#ifndef SGPU_FUSED_FC
-#define SGPU_FUSED_FC 4
-#endif
 #ifndef SGPU_FUSED_CTAS
 #define SGPU_FUSED_CTAS 4
 #endif
-constexpr int NT = SGPU_FUSED_NT;       // worker threads per CTA
-constexpr int NW = NT / 32;             // worker warps per CTA
-constexpr int NTHREADS = NT + 32;       // + the scan warp
-constexpr int FC = SGPU_FUSED_FC;       // 16-byte chunks per worker thread
-constexpr int PW = (FC + 3) / 4;        // 64-bit words of packed per-round counts
-constexpr int TILE = NT * FC * 16;      // 16 KiB
+#ifndef SGPU_FUSED_PIECE
+#define SGPU_FUSED_PIECE 1024
+#endif
+#ifndef SGPU_FUSED_HALO
+#define SGPU_FUSED_HALO 256
+#endif
+#ifndef SGPU_FUSED_LBW
+#define SGPU_FUSED_LBW 4
+#endif
+constexpr int NT = 256;                 // threads per CTA
+constexpr int NW = NT / 32;             // warps per CTA
+constexpr int NTHREADS = NT;
+constexpr int FC = 8;                   // 16-byte chunks per thread
+constexpr int TILE = NT * FC * 16;      // 32 KiB
 constexpr int PRE = 16;                 // pre-halo (previous 16 bytes)
-constexpr int HALO = 1024;              // post-halo
+constexpr int HALO = SGPU_FUSED_HALO;   // post-halo: id token of the last record start, "+\n" after the last newline
 constexpr int BUF = PRE + TILE + HALO;  // bytes of the tile buffer
-constexpr int RMAX = 256;               // record starts per tile
+constexpr int RMAX = 320;               // record starts per tile
 constexpr int LMAX = 4 * RMAX + 8;      // newline list capacity per tile
-constexpr int LBW = 16;                 // look-back descriptors per lane and round (window 32 * LBW tiles)
+constexpr int WCAP = 192;               // newlines per warp region (4 KiB)
+constexpr int PIECE = SGPU_FUSED_PIECE; // copy items are at most this long
+constexpr int IMAX = RMAX + 2 * (TILE / PIECE) + 8;  // copy items per tile
+#ifndef SGPU_FUSED_LOAD_PIECE
+#define SGPU_FUSED_LOAD_PIECE 4096
+#endif
+constexpr int LOAD_PIECE = SGPU_FUSED_LOAD_PIECE;  // bytes per bulk copy of a tile load
+constexpr int LBW = SGPU_FUSED_LBW;     // look-back descriptors per lane and round (window 32 * LBW tiles)
 constexpr int CTAS_PER_SM = SGPU_FUSED_CTAS;  // resident CTAs the kernel is sized for (registers, shared memory)
-static_assert(TILE <= 32768 && FC % 2 == 0 && FC <= 8, "tile offsets are 16-bit; markers are handled in pairs");
+static_assert(TILE <= 32768 && TILE / PIECE <= 32 && HALO % 16 == 0, "tile offsets are 16-bit; head pieces fit a warp");
 
 constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
 // run / carry states
-constexpr uint32_t F_OTHER = 0, F_KEPT = 1, F_NONE = 2;
+constexpr uint32_t F_OTHER = 0, F_KEPT = 1, F_NONE = 2, F_INVALID = 3;
+// copy item tags
+constexpr uint32_t TAG_KEPT = 0u << 30, TAG_OTHER = 1u << 30, TAG_HEAD = 2u << 30;
 
 struct FusedResult {
     unsigned long long fallback;    // != 0: input is not canonical, use the general path
@@ -97,6 +110,7 @@ struct FusedParams {
     long long *sum_total, *sum_head;    // per tile signed newline-position sums (length check)
     uint32_t *nl_count;                 // per tile newline count (phase verification)
     uint8_t *has_term, *phase_used;     // per tile: has a record end; line phase (mod 4) the tile assumed
+    uint64_t pf_dist;  // L2 prefetch distance in tiles (0 = off)
     FusedResult *res;
 };
 
@@ -142,17 +156,24 @@ __device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long 
 __device__ __forceinline__ void st_global_v4(void *p, uint4 v) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_global_u8(void *p, uint32_t v) {
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
 }
-// barrier over the worker warps only (id 1; id 0 is __syncthreads, which the scan warp never joins)
-__device__ __forceinline__ void work_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
 
 // ------------------------------------------------------------------ byte classification
 // flag byte (0x80 per matching byte) of the bytes of w equal to '\n'.  Exact for every byte value:
@@ -174,65 +195,33 @@ __device__ __forceinline__ uint32_t nl_mask16_v2(uint4 v) {
 __device__ __forceinline__ uint32_t le20_flags(uint32_t w) { return ~(w + 0x5f5f5f5fu) & 0x80808080u; }
 
 // ------------------------------------------------------------------ shared memory
-// one tile buffer with everything the copy needs once the tile is parsed; a CTA owns two and parses tile
-// n+1 BEFORE it looks back and copies tile n, so an aggregate is published a whole parse ahead of the
-// look-backs that need it (predecessors are then normally ready and the look-back does not wait)
-struct __align__(16) Stage {
+struct __align__(8) Item {
+    uint16_t src, len;  // source offset in the tile, bytes (1..PIECE)
+    uint32_t rel;       // tag | offset relative to the stream's base for this tile
+};
+
+struct __align__(128) CtaSmem {
     uint64_t full;         // mbarrier: tile load complete
-    uint64_t agg_ready;    // mbarrier: workers -> scan warp, the tile's aggregate is published
-    uint64_t scan_done;    // mbarrier: scan warp -> workers, kept_before / carry are valid
-    uint64_t tile;         // tile index (>= n_tiles: no more tiles)
+    uint64_t first_tile;   // the CTA's first ticket
+    uint64_t next_tile;    // the ticket after the tile in flight
     uint64_t kept_before;  // look-back #2 result
     uint32_t carry;        // state of the record carried into the tile
-    uint32_t n_starts, head_len, rest_total, tile_len;
+    uint32_t c0;           // newlines before the tile, mod 4 (only when the speculation found no "\n+\n")
+    uint32_t n_items;
     uint32_t last_flag;
     uint32_t none_pos;  // first record start of the tile that belongs to the next shard
     uint32_t none_cnt;
+    uint32_t warp_tot[NW];  // newlines of the warp's region | local index of its first "\n+\n" newline << 16
+    uint32_t scan_tot[NW];
+    uint16_t nlw[NW][WCAP];  // per warp region: newline positions (tile offsets), in order
     uint16_t runS[RMAX + 4];  // run r starts at runS[r]; run 0 = carried-in head, run j+1 = record j; sentinel = tile_len
-    uint8_t runF[RMAX + 4];   // F_OTHER / F_KEPT / F_NONE
-    uint32_t runK[RMAX + 4];  // kept bytes of the records before run r (head excluded)
-    // nlp[] (parse: local newline positions) and crun[] (copy: per destination chunk, 1 + index of
-    // the run it lies inside) are never live at the same time
-    union {
-        __align__(16) uint16_t nlp[LMAX];
-        __align__(16) uint16_t crun[TILE / 16];
-    };
+    __align__(16) uint16_t nlp[LMAX];  // newline positions of the tile, in order
+    Item items[IMAX];
     __align__(16) uint8_t buf[BUF];
-};
-
-struct __align__(16) CtaSmem {
-    uint32_t c0;           // newlines before the tile, mod 4
-    uint32_t early;        // the previous tile's prefix is already there: copy it between the parse halves
-    uint32_t pad[2];
-    uint32_t warp_tot[NW], scan_tot[NW], wmax[NW];
-    Stage st[2];
 };
 
 __device__ __forceinline__ void set_fallback(FusedResult *res, int reason) {
     if (atomicExch(&res->fallback, 1ull) == 0ull) res->reason = (unsigned long long)reason;
-}
-
-// CTA-wide exclusive scan of one u32 per thread; two barriers
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total, uint32_t *sm, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += x;
-    }
-    if (lane == 31) sm[warp] = inc;
-    work_sync();
-    uint32_t base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-        const uint32_t x = sm[w];
-        if (w < warp) base += x;
-        tot += x;
-    }
-    work_sync();
-    *total = tot;
-    return base + inc - v;
 }
 
 // ------------------------------------------------------------------ look-back #1 (rare): line phase
@@ -262,7 +251,9 @@ __device__ __forceinline__ uint32_t lookback_phase_warp(unsigned long long *desc
 // inclusive:  [60:59] state carried out of the tile              [58:0] kept bytes up to and including the tile
 // A tile is a transducer on the carried state c: it keeps (c == KEPT ? head_len : 0) + rest bytes and
 // carries out (has_start ? last : c).  A run of tiles composes into {P: bytes kept iff c == KEPT, K: bytes
-// kept regardless, has, out}; composition is associative, so a warp reduces 256 descriptors per round.
+// kept regardless, has, out}; composition is associative.  A warp looks at 32 descriptors at a time (one per
+// lane): with ballots every lane finds the state carried into its tile, two warp reductions give the
+// window's composite; LBW windows are loaded per round.
 struct Comp {
     uint32_t P, K, has, out;
 };
@@ -282,88 +273,64 @@ __device__ __forceinline__ Comp compose(const Comp A /*earlier*/, const Comp B /
     }
     return R;
 }
-__device__ __forceinline__ uint64_t comp_pack(const Comp c) {
-    return (uint64_t)c.P | ((uint64_t)c.K << 26) | ((uint64_t)c.has << 52) | ((uint64_t)c.out << 53);
-}
-__device__ __forceinline__ Comp comp_unpack(uint64_t v) {
-    Comp c;
-    c.P = (uint32_t)(v & 0x3FFFFFFu);
-    c.K = (uint32_t)((v >> 26) & 0x3FFFFFFu);
-    c.has = (uint32_t)((v >> 52) & 1u);
-    c.out = (uint32_t)((v >> 53) & 3u);
-    return c;
-}
 
 __device__ __forceinline__ void lookback_kept_warp(unsigned long long *desc, uint64_t t, bool has_start,
                                                    uint32_t last_flag, uint32_t head_len, uint32_t rest, int lane,
                                                    uint64_t *kept_before, uint32_t *carry) {
-    Comp acc_all = comp_identity();  // composite of every tile visited so far (nearer rounds are later)
+    Comp acc_all = comp_identity();  // composite of every window visited so far (nearer windows are later)
     uint64_t inc_total = 0;
-    int64_t base = (int64_t)t - 1 - (int64_t)lane * LBW;  // nearest descriptor of this lane
+    int64_t base = (int64_t)t - 1;  // nearest tile of the round; lane l of window k looks at tile base - 32k - l
+    const uint64_t virt = ST_INC | ((uint64_t)F_NONE << 59);  // before the buffer: nothing kept, nothing carried
     while (true) {
         unsigned long long d[LBW];
-        int fi, zi;  // first inclusive / first not-ready descriptor of this lane
-        unsigned binc;
-        int L;
 #pragma unroll
         for (int k = 0; k < LBW; k++) {
-            const int64_t idx = base - k;
-            // virtual tiles before the buffer: nothing kept, nothing carried in
-            d[k] = idx >= 0 ? ld_relaxed(desc + idx) : (ST_INC | ((uint64_t)F_NONE << 59));
+            const int64_t idx = base - 32 * k - lane;
+            d[k] = idx >= 0 ? ld_relaxed(desc + idx) : virt;
         }
-        while (true) {
-            fi = LBW;
-            zi = LBW;
+        bool done = false;
 #pragma unroll
-            for (int k = LBW - 1; k >= 0; k--) {
-                const uint64_t s = d[k] & ST_MASK;
-                if (s == ST_INC) fi = k;
-                if (s == 0) zi = k;
+        for (int k = 0; k < LBW; k++) {
+            if (done) break;  // uniform
+            const int64_t idx = base - 32 * k - lane;
+            unsigned long long x = d[k];
+            int L;
+            // every descriptor up to the nearest inclusive one must be there
+            while (true) {
+                const uint32_t st = (uint32_t)(x >> 62);
+                const unsigned binc = __ballot_sync(0xffffffffu, st == 2u);
+                const unsigned bzero = __ballot_sync(0xffffffffu, st == 0u);
+                L = binc ? __ffs(binc) - 1 : 32;
+                const unsigned upto = L < 31 ? (2u << L) - 1u : 0xffffffffu;  // lanes <= L
+                if ((bzero & upto) == 0) break;
+                if (st == 0u && lane <= L) x = ld_relaxed(desc + idx);
             }
-            binc = __ballot_sync(0xffffffffu, fi < LBW);
-            L = binc ? __ffs(binc) - 1 : 32;
-            const int rk = lane < L ? LBW : (lane == L ? fi : 0);  // descriptors of this lane that matter
-            const bool need = zi < rk;
-            if (!__any_sync(0xffffffffu, need)) break;
-            if (need) {
-                // only the missing descriptors are polled again (an idle scan warp must not flood L2)
-                __nanosleep(200);
-#pragma unroll
-                for (int k = 0; k < LBW; k++)
-                    if (k < rk && (d[k] & ST_MASK) == 0) d[k] = ld_relaxed(desc + (base - k));
+            const bool agg = lane < L, isL = lane == L;
+            const uint32_t fl = (uint32_t)(x >> 59) & 3u;
+            const bool has = isL || (agg && ((x >> 61) & 1ull));
+            const uint32_t hl = agg ? (uint32_t)(x >> 30) & 0x1FFFFFFFu : 0u;
+            const uint32_t rs = agg ? (uint32_t)x & 0x3FFFFFFFu : 0u;
+            const unsigned has_m = __ballot_sync(0xffffffffu, has);
+            const unsigned kept_m = __ballot_sync(0xffffffffu, has && fl == F_KEPT);
+            // the state carried into my tile = state of the nearest earlier tile with a record start:
+            // the lowest set bit of has_m strictly above my lane
+            const unsigned hm = has_m & (0xFFFFFFFEu << lane);
+            const bool found = hm != 0u;
+            const bool in_kept = found && ((kept_m >> (__ffs(hm) - 1)) & 1u);
+            const uint32_t sumK = __reduce_add_sync(0xffffffffu, rs + (in_kept ? hl : 0u));
+            const uint32_t sumP = __reduce_add_sync(0xffffffffu, found ? 0u : hl);
+            Comp W;
+            W.P = sumP;
+            W.K = sumK;
+            W.has = has_m != 0u;
+            W.out = __shfl_sync(0xffffffffu, fl, has_m ? __ffs(has_m) - 1 : 0);
+            acc_all = compose(W, acc_all);
+            if (L < 32) {
+                inc_total = __shfl_sync(0xffffffffu, x, L) & ((1ull << 59) - 1);
+                done = true;
             }
         }
-        const int rk = lane < L ? LBW : (lane == L ? fi : 0);
-        Comp acc = comp_identity();
-        uint64_t my_total = 0;
-        if (lane == L) {
-            uint64_t di = d[0];
-#pragma unroll
-            for (int k = 1; k < LBW; k++)
-                if (k == fi) di = d[k];
-            acc = Comp{0u, 0u, 1u, (uint32_t)((di >> 59) & 3u)};
-            my_total = di & ((1ull << 59) - 1);
-        }
-#pragma unroll
-        for (int k = LBW - 1; k >= 0; k--) {  // file order: farthest first
-            if (k < rk) {
-                const uint64_t x = d[k];
-                const Comp a = Comp{(uint32_t)((x >> 30) & 0x1FFFFFFFu), (uint32_t)(x & 0x3FFFFFFFu),
-                                    (uint32_t)((x >> 61) & 1u), (uint32_t)((x >> 59) & 3u)};
-                acc = compose(acc, a);
-            }
-        }
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {  // lane l+s holds earlier tiles than lane l
-            const uint64_t o = __shfl_down_sync(0xffffffffu, comp_pack(acc), s);
-            if (lane + s < 32) acc = compose(comp_unpack(o), acc);
-        }
-        const uint64_t w = __shfl_sync(0xffffffffu, comp_pack(acc), 0);
-        acc_all = compose(comp_unpack(w), acc_all);
-        if (L < 32) {
-            inc_total = __shfl_sync(0xffffffffu, my_total, L);
-            break;
-        }
+        if (done) break;
         base -= 32 * LBW;
     }
     // acc_all starts with the inclusive descriptor (has == 1, P == 0)
@@ -374,131 +341,32 @@ __device__ __forceinline__ void lookback_kept_warp(unsigned long long *desc, uin
     if (lane == 0) st_relaxed(desc + t, ST_INC | ((uint64_t)out_flag << 59) | incl);
 }
 
-// ------------------------------------------------------------------ P4 for one output stream
-// The stream's bytes of this tile form ONE contiguous global range [base, base + total): run r
-// contributes len_r bytes at offset off_r iff it belongs to the stream.
-//   WRITTEN = true : stream out_w, runs in state KEPT,  off_r = K_r (kept prefix)
-//   WRITTEN = false: stream out_o, runs in state OTHER, off_r = S_r - K_r - none_prefix
-template <bool WRITTEN>
-__device__ __forceinline__ void emit_stream(Stage *S, uint32_t *wmax, const uint8_t *tile, uint8_t *base,
-                                            uint32_t total, uint32_t n_starts, uint32_t carry, uint32_t head_kept,
-                                            uint32_t none_prefix, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr uint32_t WANT = WRITTEN ? F_KEPT : F_OTHER;
-    if (total == 0) return;  // uniform
-    const uintptr_t b0 = (uintptr_t)base;
-    const uintptr_t A0 = (b0 + 15) & ~(uintptr_t)15;     // first aligned chunk
-    const uintptr_t A1 = (b0 + total) & ~(uintptr_t)15;  // end of the last aligned chunk
-    const uint32_t n_chunks = A1 > A0 ? (uint32_t)((A1 - A0) >> 4) : 0u;
-    work_sync();  // the previous user of crun[] / nlp[] is done
-    // clear this thread's FC markers (blocked: chunks FC*tid .. FC*tid+FC-1)
-    uint32_t *const my_marks = reinterpret_cast<uint32_t *>(&S->crun[FC * tid]);
-#pragma unroll
-    for (int i = 0; i < FC / 2; i++) my_marks[i] = 0;
-    work_sync();
-    // ---- owners: one thread per run writes the run's edge bytes and marks its first interior chunk
-    for (uint32_t r = tid; r <= n_starts; r += NT) {
-        const uint32_t s = S->runS[r], e = S->runS[r + 1];
-        const uint32_t len = e - s;
-        const uint32_t fl = r ? (uint32_t)S->runF[r] : carry;
-        if (len == 0 || fl != WANT) continue;
-        const uint32_t K = r ? head_kept + S->runK[r] : 0u;
-        const uint32_t off = WRITTEN ? K : s - K - none_prefix;
-        const uintptr_t a = b0 + off, b = a + len;
-        const uintptr_t a16 = (a + 15) & ~(uintptr_t)15, b16 = b & ~(uintptr_t)15;
-        const uint8_t *src = tile + s;
-        uint8_t *dst = base + off;
-        if (a16 < b16) {
-            S->crun[(a16 - A0) >> 4] = (uint16_t)(r + 1);
-            const uint32_t hn = (uint32_t)(a16 - a), tn = (uint32_t)(b - b16);
-            for (uint32_t i = 0; i < hn; i++) dst[i] = src[i];
-            for (uint32_t i = len - tn; i < len; i++) dst[i] = src[i];
-        } else {
-            for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
-        }
-    }
-    work_sync();
-    // ---- propagate the markers: crun[c] = last marker at or before c (max-scan over the workers)
-    {
-        uint32_t v[FC];
-#pragma unroll
-        for (int i = 0; i < FC / 2; i++) {
-            const uint32_t w = my_marks[i];
-            v[2 * i] = w & 0xFFFF;
-            v[2 * i + 1] = w >> 16;
-        }
-#pragma unroll
-        for (int i = 1; i < FC; i++) v[i] = max(v[i], v[i - 1]);
-        uint32_t inc = v[FC - 1];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc = max(inc, o);
-        }
-        if (lane == 31) wmax[warp] = inc;
-        uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) excl = 0;
-        work_sync();
-#pragma unroll
-        for (int w = 0; w < NW; w++)
-            if (w < warp) excl = max(excl, wmax[w]);
-#pragma unroll
-        for (int i = 0; i < FC; i++) v[i] = max(v[i], excl);
-#pragma unroll
-        for (int i = 0; i < FC / 2; i++) my_marks[i] = v[2 * i] | (v[2 * i + 1] << 16);
-    }
-    work_sync();
-    // ---- interior chunks: thread per chunk, interleaved so that a warp stores 512 contiguous bytes
-    const uint32_t tile_s = smem_u32(tile);
-    for (uint32_t c = tid; c < n_chunks; c += NT) {
-        const uint32_t r1 = S->crun[c];
-        if (r1 == 0) continue;
-        const uint32_t r = r1 - 1;
-        const uint32_t s = S->runS[r], e = S->runS[r + 1];
-        const uint32_t K = r ? head_kept + S->runK[r] : 0u;
-        const uint32_t off = WRITTEN ? K : s - K - none_prefix;
-        const uint32_t x = (uint32_t)(A0 - b0) + (c << 4);  // stream offset of this chunk
-        if (x + 16 > off + (e - s)) continue;                // the chunk straddles the run's end: edge bytes
-        // 16 source bytes at an arbitrary address: five aligned words + funnel shifts
-        const uint32_t sa = tile_s + s + (x - off);
-        const uint32_t wa = sa & ~3u, sh = (sa & 3u) * 8u;
-        const uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4), w2 = lds_u32(wa + 8), w3 = lds_u32(wa + 12),
-                       w4 = lds_u32(wa + 16);
-        uint4 o;
-        o.x = __funnelshift_r(w0, w1, sh);
-        o.y = __funnelshift_r(w1, w2, sh);
-        o.z = __funnelshift_r(w2, w3, sh);
-        o.w = __funnelshift_r(w3, w4, sh);
-        st_global_v4(reinterpret_cast<void *>(A0 + ((uintptr_t)c << 4)), o);
-    }
-}
-
 // ------------------------------------------------------------------ tile load (one thread)
-__device__ __forceinline__ void take_ticket_and_load(const FusedParams &P, Stage *st) {
-    const unsigned long long t = atomicAdd(&P.res->ticket, 1ull);
-    st->tile = t;
-    st->none_pos = 0xFFFFFFFFu;
-    st->none_cnt = 0;
-    if (t >= P.n_tiles) return;
+__device__ __forceinline__ void issue_load(const FusedParams &P, CtaSmem *S, uint64_t t) {
     // bytes [t*TILE - PRE, t*TILE + TILE + HALO) clipped to the buffer, rounded up to 16
     const uint64_t g0 = t * (uint64_t)TILE;
     const uint64_t src0 = t ? g0 - PRE : 0;
     uint64_t end = g0 + TILE + HALO;
     if (end > P.n_in) end = P.n_in;
     const uint32_t bytes = (uint32_t)(((end - src0) + 15) & ~15ull);
-    // the buffer was read through the generic proxy; order those reads before the async-proxy writes
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&st->full, bytes);
-    bulk_g2s(st->buf + (t ? 0 : PRE), P.in + src0, bytes, &st->full);
-    // the tile this CTA will most likely take next: pull it into L2 now
-    const uint64_t tn = t + gridDim.x;
-    if (tn < P.n_tiles) {
-        const uint64_t p0 = tn * (uint64_t)TILE;
-        uint64_t pe = p0 + TILE;
-        if (pe > P.n_in) pe = P.n_in;
-        const uint32_t pb = (uint32_t)((pe - p0) & ~15ull);
-        if (pb) bulk_prefetch_l2(P.in + p0, pb);
+    // (the reads of the buffer through the generic proxy are ordered before this point by the CTA barrier
+    // the caller has just passed; like the usual consumer-release -> TMA producer hand-over, no proxy fence)
+    mbar_expect_tx(&S->full, bytes);
+    // several smaller bulk copies: they are fetched concurrently
+    uint8_t *dst = S->buf + (t ? 0 : PRE);
+    const uint8_t *src = P.in + src0;
+    for (uint32_t o = 0; o < bytes; o += LOAD_PIECE) {
+        const uint32_t nb = bytes - o < (uint32_t)LOAD_PIECE ? bytes - o : (uint32_t)LOAD_PIECE;
+        bulk_g2s(dst + o, src + o, nb, &S->full);
     }
+}
+__device__ __forceinline__ void prefetch_tile(const FusedParams &P, uint64_t t) {
+    if (t >= P.n_tiles) return;
+    const uint64_t p0 = t * (uint64_t)TILE;
+    uint64_t pe = p0 + TILE;
+    if (pe > P.n_in) pe = P.n_in;
+    const uint32_t pb = (uint32_t)((pe - p0) & ~15ull);
+    if (pb) bulk_prefetch_l2(P.in + p0, pb);
 }
 
 // ------------------------------------------------------------------ per-record helpers (P3)
@@ -545,8 +413,8 @@ __device__ __forceinline__ uint64_t inline_home(uint64_t lo, uint64_t hi) {
     return mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL));
 }
 // general token scan + probe: skip leading blanks, run to the next blank / newline
-__device__ __forceinline__ bool record_probe_slow(const IdSetView &set, const uint8_t *tile, uint32_t sp,
-                                                  uint32_t avail, uint32_t *why) {
+__device__ __noinline__ bool record_probe_slow(const IdSetView &set, const uint8_t *tile, uint32_t sp, uint32_t avail,
+                                               uint32_t *why) {
     uint32_t a = sp + 1;
     while (a < avail && is_ws_ascii(tile[a]) && tile[a] != '\n') a++;
     uint32_t q = a;
@@ -557,469 +425,574 @@ __device__ __forceinline__ bool record_probe_slow(const IdSetView &set, const ui
     }
     return idset_contains(set, tile + a, q - a);
 }
-
-// what a thread carries from the first half of the parse (probe issued) to the second (probe consumed)
-struct ParseState {
-    uint32_t fb, c0, n_nl, n_starts, n_term;
-    bool pos0_start, dense;
-    uint32_t mode;  // 0: nothing pending; 1: inline probe in flight (`first` holds the home slot)
-    uint32_t why;
-    uint64_t lo, hi;
-    Slot first;
+// the home bucket of an inline key: four slots, one 64-byte burst, four independent loads
+struct Bucket {
+    Slot s[IDSET_BUCKET];
 };
-
-// ------------------------------------------------------------------ parse: P1, phase, P2, P3, aggregate
-// first half: everything up to the ISSUE of the set probes (one per record start)
-__device__ __forceinline__ ParseState parse_a(const FusedParams &P, CtaSmem *C, Stage *S, uint32_t parity, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const uint64_t t = S->tile;
-    uint8_t *buf = S->buf;
-    const uint8_t *tile = buf + PRE;  // tile[-16 .. avail)
-    if (warp == 0) {
-        while (!mbar_try_wait(&S->full, parity)) {
-        }
-    }
-    if (t == 0 && tid < PRE) buf[tid] = '\n';  // no predecessor: the pre-halo reads as a newline
-    work_sync();
-    while (!mbar_try_wait(&S->full, parity)) {  // passes at once: every thread observes the completed phase
-    }
-
-    const uint64_t g0 = t * (uint64_t)TILE;
-    const uint32_t tile_len = (uint32_t)((P.n_in - g0) < (uint64_t)TILE ? (P.n_in - g0) : (uint64_t)TILE);
-    const uint32_t avail =
-        (uint32_t)((P.n_in - g0) < (uint64_t)(TILE + HALO) ? (P.n_in - g0) : (uint64_t)(TILE + HALO));
-    const uint32_t lead_t = t == 0 ? P.lead : 0u;
-    uint32_t fb = 0;  // this thread's fallback reason (0 = none)
-
-    // ---- P1: newline masks and counts.  Warp w owns chunks [w*FC*32, (w+1)*FC*32); lane l takes
-    //      chunk k*32 + l of them in round k (conflict-free 16-byte shared loads)
-    uint32_t m[FC];
-    uint32_t hi_or = 0;
-    const uint32_t cbase = (uint32_t)warp * (FC * 32) + (uint32_t)lane;
-    if (tile_len == (uint32_t)TILE) {
+__device__ __forceinline__ Bucket load_bucket(const IdSetView &set, uint64_t lo, uint64_t hi) {
+    const Slot *bp = set.table + home_slot(inline_home(lo, hi), set.mask);
+    Bucket B;
 #pragma unroll
-        for (int k = 0; k < FC; k++) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(tile + (cbase + k * 32) * 16);
-            m[k] = nl_mask16_v2(v);
-            hi_or |= (v.x | v.y | v.z | v.w);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < FC; k++) {  // last tile: bytes past the end of the buffer are stale
-            const uint32_t pos = (cbase + k * 32) * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (pos < tile_len) {
-                v = *reinterpret_cast<const uint4 *>(tile + pos);
-                const uint32_t valid = tile_len - pos;
-                if (valid < 16) {
-                    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        const int rem = (int)valid - 4 * x;
-                        if (rem <= 0) w[x] = 0;
-                        else if (rem < 4) w[x] &= (1u << (8 * rem)) - 1u;
-                    }
-                    v = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-            m[k] = nl_mask16_v2(v);  // zero bytes are never newlines
-            hi_or |= (v.x | v.y | v.z | v.w);
-        }
-    }
-    if (lead_t && tid == 0) m[0] &= ~((1u << lead_t) - 1u);  // the previous shard's bytes
-    uint64_t packed[PW];
-#pragma unroll
-    for (int q = 0; q < PW; q++) packed[q] = 0;
-#pragma unroll
-    for (int k = 0; k < FC; k++) packed[k >> 2] |= (uint64_t)__popc(m[k]) << (16 * (k & 3));
-    if (hi_or & 0x80808080u) fb = 1;  // reason 1: non-ASCII byte, Unicode rules needed
-    // inclusive warp scan of the per-round counts (four 16-bit fields per word)
-    uint64_t inc[PW];
-#pragma unroll
-    for (int q = 0; q < PW; q++) inc[q] = packed[q];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-        for (int q = 0; q < PW; q++) {
-            const uint64_t x = __shfl_up_sync(0xffffffffu, inc[q], d);
-            if (lane >= d) inc[q] += x;
-        }
-    }
-    uint32_t row_base[FC];
-    uint32_t wtot = 0;
-#pragma unroll
-    for (int q = 0; q < PW; q++) {
-        const uint64_t rt = __shfl_sync(0xffffffffu, inc[q], 31);
-        const uint64_t ex = inc[q] - packed[q];  // exclusive within the round
-#pragma unroll
-        for (int k = 4 * q; k < 4 * q + 4 && k < FC; k++) {
-            row_base[k] = wtot + (uint32_t)((ex >> (16 * (k & 3))) & 0xFFFF);
-            wtot += (uint32_t)((rt >> (16 * (k & 3))) & 0xFFFF);
-        }
-    }
-    if (lane == 0) C->warp_tot[warp] = wtot;
-    work_sync();
-    uint32_t n_nl = 0, wbase = 0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-        const uint32_t x = C->warp_tot[w];
-        if (w < warp) wbase += x;
-        n_nl += x;
-    }
-    const bool dense = n_nl > (uint32_t)LMAX;
-    // ---- compact the newline positions in order
-    if (!dense) {
-#pragma unroll
-        for (int k = 0; k < FC; k++) {
-            uint32_t mm = m[k];
-            uint32_t r = wbase + row_base[k];
-            const uint32_t pos = (cbase + k * 32) * 16;
-            while (mm) {
-                S->nlp[r++] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
-                mm &= mm - 1;
-            }
-        }
-    }
-    work_sync();
-    // ---- line phase (warp 0): the first newline followed by "+\n" ends a sequence line (role 1)
-    if (warp == 0) {
-        uint32_t c0 = 0;
-        if (t == 0) {
-            if (lane == 0) st_relaxed(P.desc1 + t, ST_INC | (n_nl & 3));
-        } else {
-            bool hit = false;
-            if (!dense && (uint32_t)lane < n_nl) {
-                const uint32_t p = S->nlp[lane];
-                hit = p + 2 < avail && tile[p + 1] == '+' && tile[p + 2] == '\n';
-            }
-            const unsigned b = __ballot_sync(0xffffffffu, hit);
-            if (b) {
-                c0 = (1u - (uint32_t)(__ffs(b) - 1)) & 3u;  // role(first) = (c0 + first) & 3 == 1
-                if (lane == 0) st_relaxed(P.desc1 + t, ST_INC | ((c0 + n_nl) & 3));
-            } else {
-                c0 = lookback_phase_warp(P.desc1, t, n_nl, lane);
-            }
-        }
-        if (lane == 0) C->c0 = c0;
-    }
-    work_sync();
-    const uint32_t c0 = C->c0;
-    // the first byte of the tile starts a record iff 4k newlines precede it and the previous byte is one;
-    // tile 0 starts with a record by construction (at `lead`)
-    const bool pos0_start = t == 0 || ((c0 == 0) && tile[-1] == '\n');
-
-    // ---- P2: one thread per newline: classify by role (line number mod 4)
-    if (!dense) {
-        for (uint32_t i = tid; i < n_nl; i += NT) {
-            const uint32_t p = S->nlp[i];
-            const uint32_t role = (c0 + i) & 3;
-            if (tile[(int)p - 1] == '\r') fb = 3;  // CRLF: not canonical
-            if (role == 1) {                       // end of the sequence line: "+\n" must follow
-                if (p + 2 >= avail) fb = 4;
-                else if (tile[p + 1] != '+' || tile[p + 2] != '\n') fb = 4;
-            } else if (role == 3 && p + 1 < tile_len) {  // record j starts at p + 1 (run j + 1)
-                const uint32_t j = ((c0 + i) >> 2) + (pos0_start ? 1u : 0u);
-                if (j < (uint32_t)RMAX) S->runS[j + 1] = (uint16_t)(p + 1);
-                else fb = 5;
-            }
-        }
-    } else {
-        fb = 2;
-    }
-    if (tid == 0) {
-        S->runS[0] = 0;
-        if (pos0_start) S->runS[1] = (uint16_t)lead_t;
-    }
-    // number of record starts inside the tile
-    const uint32_t n_term = (c0 + n_nl) >> 2;
-    uint32_t n_starts = n_term + (pos0_start ? 1u : 0u);
-    if (n_term > 0 && !dense) {
-        // the last terminating newline may sit on the tile's final byte: its record belongs to the next tile
-        const uint32_t r_last = ((3u - c0) & 3u) + 4u * (n_term - 1);
-        if ((uint32_t)S->nlp[r_last] + 1u >= tile_len) n_starts--;
-    }
-    if (dense || n_starts > (uint32_t)RMAX) n_starts = 0;  // (a fallback reason is already raised)
-    work_sync();
-    if (tid == 0) S->runS[n_starts + 1] = (uint16_t)tile_len;  // sentinel (TILE <= 32768 fits)
-    work_sync();
-
-    // ---- P3a: one thread per record start (first NT records): id token -> slot image, probe issued
-    ParseState Z;
-    Z.fb = fb;
-    Z.c0 = c0;
-    Z.n_nl = n_nl;
-    Z.n_starts = n_starts;
-    Z.n_term = n_term;
-    Z.pos0_start = pos0_start;
-    Z.dense = dense;
-    Z.mode = 0;
-    Z.why = 0;
-    Z.lo = Z.hi = 0;
-    Z.first.lo = Z.first.hi = 0;
-    if ((uint32_t)tid < n_starts) {
-        const uint32_t sp = S->runS[tid + 1];
-        if (P.is_last || (g0 + sp <= P.own_len)) {
-            Z.why = tile[sp] == '@' ? 0u : 6u;  // 6 '@', 7 id token, 8 seq/qual lengths
-            const RecPrep R = record_prepare(smem_u32(tile), sp, avail);
-            Z.mode = R.mode;
-            Z.lo = R.lo;
-            Z.hi = R.hi;
-            if (R.mode == 1 && !Z.why && P.set.table != nullptr)
-                Z.first = load_slot(P.set.table + (inline_home(R.lo, R.hi) & P.set.mask));
-        }
-    }
-    return Z;
+    for (int q = 0; q < (int)IDSET_BUCKET; q++) B.s[q] = load_slot(bp + q);
+    return B;
 }
-
-// second half: probes consumed, seq/qual length check, block scan of kept bytes, aggregate published.
-// Adds (thread 0 only) the number of owned / kept records to *reads_in / *reads_out
-__device__ __forceinline__ void parse_b(const FusedParams &P, CtaSmem *C, Stage *S, const ParseState &Z, int tid,
-                                        unsigned long long *reads_in, unsigned long long *reads_out) {
-    const uint64_t t = S->tile;
-    const uint8_t *tile = S->buf + PRE;
-    const uint64_t g0 = t * (uint64_t)TILE;
-    const uint32_t tile_len = (uint32_t)((P.n_in - g0) < (uint64_t)TILE ? (P.n_in - g0) : (uint64_t)TILE);
-    const uint32_t avail =
-        (uint32_t)((P.n_in - g0) < (uint64_t)(TILE + HALO) ? (P.n_in - g0) : (uint64_t)(TILE + HALO));
-    uint32_t fb = Z.fb;
-    const uint32_t c0 = Z.c0, n_nl = Z.n_nl, n_starts = Z.n_starts, n_term = Z.n_term;
-    const bool pos0_start = Z.pos0_start, dense = Z.dense;
-    uint32_t rest_total = 0, kept_recs = 0;
-    for (uint32_t jb = 0; jb < n_starts; jb += NT) {
-        const uint32_t j = jb + tid;
-        uint32_t my_len = 0, my_flag = F_OTHER;
-        if (j < n_starts) {
-            const uint32_t sp = S->runS[j + 1];
-            const uint32_t e = S->runS[j + 2];
-            my_len = e - sp;
-            const bool owned = P.is_last || (g0 + sp <= P.own_len);
-            if (!owned) {
-                my_flag = F_NONE;
-                atomicMin(&S->none_pos, sp);
-                atomicAdd(&S->none_cnt, 1u);
-            } else {
-                uint32_t why, mode;
-                uint64_t lo, hi;
-                Slot first;
-                if (jb == 0) {  // prepared (and probed) by parse_a
-                    why = Z.why;
-                    mode = Z.mode;
-                    lo = Z.lo;
-                    hi = Z.hi;
-                    first = Z.first;
-                } else {
-                    why = tile[sp] == '@' ? 0u : 6u;
-                    const RecPrep R = record_prepare(smem_u32(tile), sp, avail);
-                    mode = R.mode;
-                    lo = R.lo;
-                    hi = R.hi;
-                    first.lo = first.hi = 0;
-                    if (mode == 1 && !why && P.set.table != nullptr)
-                        first = load_slot(P.set.table + (inline_home(lo, hi) & P.set.mask));
-                }
-                bool hit = false;
-                if (!why) {
-                    if (mode == 1) {
-                        // linear probing from the home slot (already loaded)
-                        Slot sl = first;
-                        if ((sl.lo | sl.hi) != 0) {
-                            if (sl.lo == lo && sl.hi == hi) {
-                                hit = true;
-                            } else {
-                                uint64_t idx = inline_home(lo, hi) & P.set.mask;
-                                while (true) {
-                                    idx = (idx + 1) & P.set.mask;
-                                    sl = load_slot(P.set.table + idx);
-                                    if ((sl.lo | sl.hi) == 0) break;
-                                    if (sl.lo == lo && sl.hi == hi) {
-                                        hit = true;
-                                        break;
-                                    }
-                                }
-                            }
-                        }
-                    } else {
-                        hit = record_probe_slow(P.set, tile, sp, avail, &why);
-                    }
-                }
-                if (!why) my_flag = (P.reverse ? hit : !hit) ? F_KEPT : F_OTHER;
-                // seq/qual length equality for records whose four newlines are inside the tile
-                const int r0 = pos0_start ? 4 * (int)j - 1 : (int)((3u - c0) & 3u) + 4 * (int)j;
-                if (r0 + 4 < (int)n_nl) {
-                    const int sgn = -(int)S->nlp[r0 + 1] + (int)S->nlp[r0 + 2] + (int)S->nlp[r0 + 3] -
-                                    (int)S->nlp[r0 + 4];
-                    if (sgn != 0) why = why ? why : 8u;
-                }
-                if (why) fb = why;
-            }
-            S->runF[j + 1] = (uint8_t)my_flag;
-        }
-        uint32_t round_total;
-        const uint32_t koff =
-            block_excl_scan(my_flag == F_KEPT ? (my_len | (1u << 16)) : 0u, &round_total, C->scan_tot, tid);
-        if (j < n_starts) S->runK[j + 1] = rest_total + (koff & 0xFFFFu);
-        rest_total += round_total & 0xFFFFu;
-        kept_recs += round_total >> 16;
+// exact membership given the home bucket; the probe sequence only leaves it when all four slots are taken
+// by other keys (< 1 % of the lookups at load <= 0.2)
+__device__ __forceinline__ bool probe_bucket(const IdSetView &set, const Bucket &B, uint64_t lo, uint64_t hi) {
+    bool hit = false, open = false;
+#pragma unroll
+    for (int q = 0; q < (int)IDSET_BUCKET; q++) {
+        hit |= B.s[q].lo == lo && B.s[q].hi == hi;
+        open |= (B.s[q].lo | B.s[q].hi) == 0;
     }
-    if (fb) set_fallback(P.res, (int)fb);
-    work_sync();  // runS / runF / runK complete (also when the loop ran zero times)
-
-    if (tid == 0) {
-        const uint32_t head_len = S->runS[1];  // == tile_len when no record starts in the tile
-        const uint32_t last_flag = n_starts ? (uint32_t)S->runF[n_starts] : F_OTHER;
-        // aggregate for look-back #2, visible to every later tile from here on
-        st_relaxed(P.desc2 + t, ST_AGG | (n_starts ? (1ull << 61) : 0ull) | ((uint64_t)last_flag << 59) |
-                                    ((uint64_t)head_len << 30) | rest_total);
-        S->n_starts = n_starts;
-        S->head_len = head_len;
-        S->rest_total = rest_total;
-        S->tile_len = tile_len;
-        S->last_flag = last_flag;
-        *reads_in += n_starts - S->none_cnt;
-        *reads_out += kept_recs;
-        if (S->none_pos != 0xFFFFFFFFu) atomicMin(&P.res->owned_end, (unsigned long long)(g0 + S->none_pos));
-        mbar_arrive(&S->agg_ready);  // the scan warp may look back for this tile now
-    }
-    if (tid == 32) {
-        // signed newline-position sums: -p1 +p2 +p3 -p4 per record must vanish
-        long long head = 0, total = 0;
-        const int r_first = (int)((3u - c0) & 3u);
-        if (!dense) {
-            if (n_term == 0) {
-                for (uint32_t r = 0; r < n_nl; r++) {
-                    const uint32_t role = (c0 + r) & 3;
-                    const long long pp = (long long)(g0 + S->nlp[r]);
-                    total += (role == 0 || role == 3) ? -pp : pp;
-                }
-            } else {
-                for (int r = 0; r <= r_first; r++) {
-                    const uint32_t role = (c0 + r) & 3;
-                    const long long pp = (long long)(g0 + S->nlp[r]);
-                    head += (role == 0 || role == 3) ? -pp : pp;
-                }
-                total = head;
-                for (uint32_t r = (uint32_t)r_first + 4u * (n_term - 1) + 1u; r < n_nl; r++) {
-                    const uint32_t role = (c0 + r) & 3;
-                    const long long pp = (long long)(g0 + S->nlp[r]);
-                    total += (role == 0 || role == 3) ? -pp : pp;
-                }
-            }
-        }
-        P.sum_total[t] = total;
-        P.sum_head[t] = head;
-        P.has_term[t] = n_term > 0 ? 1 : 0;
-        P.nl_count[t] = n_nl;
-        P.phase_used[t] = (uint8_t)c0;
-        // end-of-file condition of canonical input (the line count is checked by the follow-up kernel)
-        if (P.is_last && t + 1 == P.n_tiles && tile[tile_len - 1] != '\n') set_fallback(P.res, 9);
+    if (hit || open) return hit;
+    uint64_t idx = home_slot(inline_home(lo, hi), set.mask) + (IDSET_BUCKET - 1);
+    while (true) {
+        idx = (idx + 1) & set.mask;
+        const Slot sl = load_slot(set.table + idx);
+        if ((sl.lo | sl.hi) == 0) return false;
+        if (sl.lo == lo && sl.hi == hi) return true;
     }
 }
 
-// ------------------------------------------------------------------ P4 of a parsed tile (workers)
-__device__ __forceinline__ void copy_tile(const FusedParams &P, CtaSmem *C, Stage *S, uint32_t parity, int tid) {
-    const int warp = tid >> 5;
-    if (warp == 0) {
-        while (!mbar_try_wait(&S->scan_done, parity)) {
+// ------------------------------------------------------------------ P3: runs -> copy items (one warp)
+// Lanes hold consecutive records: flag, source start sp, end e, kept bytes before the record Kx.  A run is a
+// maximal group of consecutive lanes with flag == WANT (its bytes are contiguous in the tile AND in the
+// stream); the lane that ends a run cuts it into items of at most PIECE bytes.
+template <uint32_t WANT>
+__device__ __forceinline__ void emit_runs(CtaSmem *S, uint32_t flag, uint32_t sp, uint32_t e, uint32_t Kx,
+                                          uint32_t head_len, int lane) {
+    const unsigned km = __ballot_sync(0xffffffffu, flag == WANT);
+    if (km == 0) return;  // warp-uniform
+    const unsigned below = ~km & ((1u << lane) - 1u);
+    const int start_lane = below ? 32 - __clz(below) : 0;
+    const uint32_t s_src = __shfl_sync(0xffffffffu, sp, start_lane);
+    const uint32_t s_K = __shfl_sync(0xffffffffu, Kx, start_lane);
+    const bool mine = (km >> lane) & 1u;
+    const bool nxt = lane < 31 ? ((km >> (lane + 1)) & 1u) != 0 : false;
+    if (mine && !nxt) {
+        const uint32_t run_len = e - s_src;
+        const uint32_t rel = WANT == F_KEPT ? s_K : s_src - head_len - s_K;
+        const uint32_t np = (run_len + PIECE - 1) / PIECE;
+        const uint32_t slot = atomicAdd(&S->n_items, np);
+        for (uint32_t q = 0; q < np; q++) {
+            const uint32_t o = q * PIECE;
+            const uint32_t l = run_len - o < (uint32_t)PIECE ? run_len - o : (uint32_t)PIECE;
+            if (slot + q < (uint32_t)IMAX) {
+                Item it;
+                it.src = (uint16_t)(s_src + o);
+                it.len = (uint16_t)l;
+                it.rel = (WANT == F_KEPT ? TAG_KEPT : TAG_OTHER) | (rel + o);
+                S->items[slot + q] = it;
+            }
         }
     }
-    work_sync();  // (also: the stage's parse results written by thread 0 are visible)
-    while (!mbar_try_wait(&S->scan_done, parity)) {  // passes at once: every thread observes the phase
-    }
-    const uint64_t t = S->tile;
-    const uint64_t g0 = t * (uint64_t)TILE;
-    const uint32_t n_starts = S->n_starts, head_len = S->head_len, rest_total = S->rest_total,
-                   tile_len = S->tile_len, none_pos = S->none_pos;
-    const uint8_t *tile = S->buf + PRE;
-    const uint64_t kept_before = S->kept_before;
-    const uint32_t carry = S->carry;
-    const uint32_t head_kept = carry == F_KEPT ? head_len : 0u;
-    const uint32_t tile_kept = head_kept + rest_total;
-    const uint32_t none_prefix = carry == F_NONE ? head_len : 0u;
-    emit_stream<true>(S, C->wmax, tile, P.out_w + kept_before, tile_kept, n_starts, carry, head_kept, none_prefix,
-                      tid);
-    if (P.out_o) {
-        const uint32_t own_end = none_pos < tile_len ? none_pos : tile_len;
-        const uint32_t other_total = own_end > none_prefix + tile_kept ? own_end - none_prefix - tile_kept : 0u;
-        // bytes of the other stream before this tile = owned bytes before it - kept bytes before it
-        const uint64_t other_before = t == 0 ? 0 : (g0 - P.lead) - kept_before;
-        emit_stream<false>(S, C->wmax, tile, P.out_o + other_before, other_total, n_starts, carry, head_kept,
-                           none_prefix, tid);
-    }
-    if (t + 1 == P.n_tiles && tid == 0) P.res->kept_total = kept_before + tile_kept;
 }
 
-// ------------------------------------------------------------------ the scan warp
-// Runs the decoupled look-back of every tile this CTA parses, as soon as the workers have published the
-// tile's aggregate, and hands (kept_before, carry) back through the stage.  While it waits on predecessors
-// the workers are already parsing the next tile, so the inclusive prefix of a tile is normally published
-// long before anybody needs it and look-backs stay short.
-__device__ __forceinline__ void scan_warp_loop(const FusedParams &P, CtaSmem *C, int lane) {
-    for (uint32_t it = 0;; it++) {
-        Stage *S = &C->st[it & 1];
-        while (!mbar_try_wait(&S->agg_ready, (it >> 1) & 1)) __nanosleep(256);
-        const uint64_t t = S->tile;
-        if (t >= P.n_tiles) return;
-        uint64_t kept_before;
-        uint32_t carry;
-        lookback_kept_warp(P.desc2, t, S->n_starts > 0, S->last_flag, S->head_len, S->rest_total, lane, &kept_before,
-                           &carry);
-        if (lane == 0) {
-            S->kept_before = kept_before;
-            S->carry = carry;
-            mbar_arrive(&S->scan_done);
-        }
-        __syncwarp();
+// ------------------------------------------------------------------ P4: one copy item (one warp)
+// 16-byte chunks of the destination, each built from two aligned 16-byte shared loads; WS = word part of
+// the source misalignment (uniform over the item), bsh = byte part * 8
+template <int WS>
+__device__ __forceinline__ void copy_body(uint32_t sa0, uint32_t bsh, uint8_t *d0, uint32_t nfull, int lane) {
+    const uint32_t al = sa0 & ~15u;
+    for (uint32_t i = lane; i < nfull; i += 32) {
+        const uint4 A = lds_v4(al + (i << 4)), B = lds_v4(al + (i << 4) + 16);
+        const uint32_t x[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+        uint4 o;
+        o.x = __funnelshift_r(x[WS], x[WS + 1], bsh);
+        o.y = __funnelshift_r(x[WS + 1], x[WS + 2], bsh);
+        o.z = __funnelshift_r(x[WS + 2], x[WS + 3], bsh);
+        o.w = __funnelshift_r(x[WS + 3], x[WS + 4], bsh);
+        st_global_v4(d0 + ((size_t)i << 4), o);
     }
 }
+__device__ __forceinline__ void copy_piece(uint32_t src_s, uint32_t len, uint8_t *dst, int lane) {
+    const uint32_t a = (uint32_t)(uintptr_t)dst & 15u;
+    uint32_t hn = (16u - a) & 15u;  // bytes before the first aligned chunk
+    if (hn > len) hn = len;
+    const uint32_t body = len - hn;
+    const uint32_t nfull = body >> 4, tn = body & 15u;
+    const uint32_t sa0 = src_s + hn;
+    const uint32_t bsh = (sa0 & 3u) * 8u;
+    switch ((sa0 >> 2) & 3u) {  // warp-uniform
+        case 0: copy_body<0>(sa0, bsh, dst + hn, nfull, lane); break;
+        case 1: copy_body<1>(sa0, bsh, dst + hn, nfull, lane); break;
+        case 2: copy_body<2>(sa0, bsh, dst + hn, nfull, lane); break;
+        default: copy_body<3>(sa0, bsh, dst + hn, nfull, lane); break;
+    }
+    // edge bytes: lanes 0..14 the head, lanes 16..30 the tail
+    if ((uint32_t)lane < hn) {
+        st_global_u8(dst + lane, lds_u8(src_s + lane));
+    } else if (lane >= 16 && (uint32_t)(lane - 16) < tn) {
+        const uint32_t off = hn + (nfull << 4) + (uint32_t)(lane - 16);
+        st_global_u8(dst + off, lds_u8(src_s + off));
+    }
+}
+
+// ------------------------------------------------------------------ phase timing (diagnostics, -DSGPU_FUSED_TIMING)
+#ifdef SGPU_FUSED_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long *g_trace;  // per tile: ticket, loaded, agg, inc, done (globaltimer ns), smid
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+__device__ __forceinline__ uint32_t smid() {
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
+#define TRACE(t, slot)                                                  \
+    do {                                                                \
+        if (g_trace) g_trace[(t) * 8 + (slot)] = gtime();               \
+    } while (0)
+#else
+#define TRACE(t, slot) \
+    do {               \
+    } while (0)
+#endif
+#ifdef SGPU_FUSED_TIMING
+#define PHASE_MARK(i)                                  \
+    do {                                               \
+        if (tid == 0) {                                \
+            const long long now_ = clock64();          \
+            ph_acc[i] += (unsigned long long)(now_ - ph_last); \
+            ph_last = now_;                            \
+        }                                              \
+    } while (0)
+#else
+#define PHASE_MARK(i) \
+    do {              \
+    } while (0)
+#endif
 
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(FusedParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    CtaSmem *C = reinterpret_cast<CtaSmem *>(smem_raw);
-    const int tid = threadIdx.x;
+    CtaSmem *S = reinterpret_cast<CtaSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *buf = S->buf;
+    const uint8_t *tile = buf + PRE;  // tile[-16 .. avail)
+    const uint32_t tile_s = smem_u32(tile);
     if (tid == 0) {
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&C->st[s].full, 1);
-            mbar_init(&C->st[s].agg_ready, 1);
-            mbar_init(&C->st[s].scan_done, 1);
-        }
+        mbar_init(&S->full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        C->st[1].tile = ~0ull;
-        take_ticket_and_load(P, &C->st[0]);
-    }
-    __syncthreads();  // the only CTA-wide barrier: the scan warp goes its own way from here
-    if (tid >= NT) {
-        scan_warp_loop(P, C, tid & 31);
-        return;
-    }
-    unsigned long long my_reads_out = 0, my_reads_in = 0;  // thread 0 only
-    // software pipeline: parse tile n+1 up to the issue of its set probes, copy tile n while they fly,
-    // finish tile n+1 (aggregate published, scan warp notified), then start the load of tile n+2
-    for (uint32_t it = 0;; it++) {
-        Stage *cur = &C->st[it & 1], *prv = &C->st[(it & 1) ^ 1];
-        work_sync();  // cur->tile is visible; nobody still reads what the next writes overwrite
-        const bool have_cur = cur->tile < P.n_tiles;
-        ParseState Z;
-        if (have_cur) Z = parse_a(P, C, cur, (it >> 1) & 1, tid);
-        else if (tid == 0) mbar_arrive(&cur->agg_ready);  // releases the scan warp: it sees the end ticket
-        const bool have_prv = it > 0 && prv->tile < P.n_tiles;
-        const uint32_t prv_parity = ((it - 1) >> 1) & 1;
-        // The aggregate of cur must never wait on anybody (later tiles look back on it), so the copy of prv
-        // goes between the two halves of the parse -- where it hides the probe latency -- only when the scan
-        // warp has already delivered prv's prefix; otherwise cur is finished first.
-        bool early = false;
-        if (have_prv && have_cur) {
-            if (tid == 0) C->early = mbar_try_wait(&prv->scan_done, prv_parity) ? 1u : 0u;
-            work_sync();
-            early = C->early != 0;
+        const unsigned long long t0 = atomicAdd(&P.res->ticket, 1ull);
+        S->first_tile = t0;
+        if (t0 < P.n_tiles) {
+            TRACE(t0, 0);
+            issue_load(P, S, t0);
         }
-        if (have_prv && (early || !have_cur)) copy_tile(P, C, prv, prv_parity, tid);
-        if (!have_cur) break;
-        parse_b(P, C, cur, Z, tid, &my_reads_in, &my_reads_out);
-        if (have_prv && !early) copy_tile(P, C, prv, prv_parity, tid);
-        work_sync();  // every read of prv's buffer is done
-        if (tid == 0) take_ticket_and_load(P, prv);
     }
+    __syncthreads();
+    uint64_t t = S->first_tile;
+    unsigned long long my_reads_in = 0, my_reads_out = 0;  // thread 0 only
+#ifdef SGPU_FUSED_TIMING
+    unsigned long long ph_acc[12] = {0};
+    long long ph_last = clock64();
+#endif
+    for (uint32_t it = 0; t < P.n_tiles; it++) {
+        // the tile some CTA will take one generation from now: pull it into L2
+        if (tid == 0 && P.pf_dist) prefetch_tile(P, t + P.pf_dist);
+        while (!mbar_try_wait(&S->full, it & 1)) {
+        }
+        PHASE_MARK(0);  // load wait
+        if (tid == 0) {
+            TRACE(t, 1);
+#ifdef SGPU_FUSED_TIMING
+            if (g_trace) g_trace[t * 8 + 5] = smid();
+#endif
+        }
+        const uint64_t g0 = t * (uint64_t)TILE;
+        const uint32_t tile_len = (uint32_t)((P.n_in - g0) < (uint64_t)TILE ? (P.n_in - g0) : (uint64_t)TILE);
+        const uint32_t avail =
+            (uint32_t)((P.n_in - g0) < (uint64_t)(TILE + HALO) ? (P.n_in - g0) : (uint64_t)(TILE + HALO));
+        const uint32_t lead_t = t == 0 ? P.lead : 0u;
+        uint32_t fb = 0;                           // this thread's fallback reason (0 = none)
+        if (t == 0 && tid < PRE) buf[tid] = '\n';  // no predecessor: the pre-halo reads as a newline
+
+        // ---- P1: newline masks and counts.  Warp w owns chunks [w*FC*32, (w+1)*FC*32); lane l takes
+        //      chunk k*32 + l of them in round k (conflict-free 16-byte shared loads)
+        uint32_t m[FC];
+        uint32_t hi_or = 0;
+        const uint32_t cbase = (uint32_t)warp * (FC * 32) + (uint32_t)lane;
+        if (tile_len == (uint32_t)TILE) {
+#pragma unroll
+            for (int k = 0; k < FC; k++) {
+                const uint4 v = lds_v4(tile_s + (cbase + k * 32) * 16);
+                m[k] = nl_mask16_v2(v);
+                hi_or |= (v.x | v.y | v.z | v.w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < FC; k++) {  // last tile: bytes past the end of the buffer are stale
+                const uint32_t pos = (cbase + k * 32) * 16;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (pos < tile_len) {
+                    v = lds_v4(tile_s + pos);
+                    const uint32_t valid = tile_len - pos;
+                    if (valid < 16) {
+                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                            const int rem = (int)valid - 4 * x;
+                            if (rem <= 0) w[x] = 0;
+                            else if (rem < 4) w[x] &= (1u << (8 * rem)) - 1u;
+                        }
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                m[k] = nl_mask16_v2(v);  // zero bytes are never newlines
+                hi_or |= (v.x | v.y | v.z | v.w);
+            }
+        }
+        if (lead_t && tid == 0) m[0] &= ~((1u << lead_t) - 1u);  // the previous shard's bytes
+        if (hi_or & 0x80808080u) fb = 1;                         // reason 1: non-ASCII byte, Unicode rules needed
+        // inclusive warp scan of the per-round counts: three 10-bit fields per word (a round has <= 512 newlines)
+        constexpr int PW = (FC + 2) / 3;
+        uint32_t pk[PW], inc[PW];
+#pragma unroll
+        for (int q = 0; q < PW; q++) pk[q] = 0;
+#pragma unroll
+        for (int k = 0; k < FC; k++) pk[k / 3] |= (uint32_t)__popc(m[k]) << (10 * (k % 3));
+#pragma unroll
+        for (int q = 0; q < PW; q++) inc[q] = pk[q];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int q = 0; q < PW; q++) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, inc[q], d);
+                if (lane >= d) inc[q] += x;
+            }
+        }
+        uint32_t row_base[FC];
+        uint32_t wtot = 0;
+#pragma unroll
+        for (int q = 0; q < PW; q++) {
+            const uint32_t rt = __shfl_sync(0xffffffffu, inc[q], 31);
+            const uint32_t ex = inc[q] - pk[q];  // exclusive within the round
+#pragma unroll
+            for (int k = 3 * q; k < 3 * q + 3 && k < FC; k++) {
+                row_base[k] = wtot + ((ex >> (10 * (k % 3))) & 1023u);
+                wtot += (rt >> (10 * (k % 3))) & 1023u;
+            }
+        }
+        // ---- the warp's newline positions, in order, into its own list (no other warp is involved)
+        uint16_t *const my_nl = S->nlw[warp];
+        if (wtot <= (uint32_t)WCAP) {
+#pragma unroll
+            for (int k = 0; k < FC; k++) {
+                uint32_t mm = m[k];
+                if (mm) {  // almost always one or two newlines per 16 bytes ("\n+\n")
+                    uint32_t r = row_base[k];
+                    const uint32_t pos = (cbase + k * 32) * 16;
+                    my_nl[r] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
+                    mm &= mm - 1;
+                    if (mm) {
+                        my_nl[r + 1] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
+                        mm &= mm - 1;
+                        r += 2;
+                        while (mm) {
+                            my_nl[r++] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
+                            mm &= mm - 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- line phase candidate: the first newline of the region that is followed by "+\n" ends a
+        //      sequence line (role 1)
+        uint32_t cand = 0xFFFFu;
+        {
+            bool hit = false;
+            if (wtot <= (uint32_t)WCAP && (uint32_t)lane < wtot) {
+                const uint32_t p = my_nl[lane];
+                hit = p + 2 < avail && tile[p + 1] == '+' && tile[p + 2] == '\n';
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (b) cand = (uint32_t)(__ffs(b) - 1);
+        }
+        if (lane == 0) S->warp_tot[warp] = wtot | (cand << 16);
+        if (tid == 0) {
+            S->n_items = 0;
+            S->none_pos = 0xFFFFFFFFu;
+            S->none_cnt = 0;
+        }
+        PHASE_MARK(1);    // P1 own work
+        __syncthreads();  // B1
+        PHASE_MARK(2);    // B1 wait
+        // ---- every thread: newlines before its region, line phase from the first candidate (all candidates
+        //      must agree)
+        uint32_t n_nl = 0, wbase = 0, c0 = 4u;
+        bool dense = false, incons = false;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const uint32_t x = S->warp_tot[w];
+            const uint32_t cnt = x & 0xFFFFu, cd = x >> 16;
+            if (w == warp) wbase = n_nl;
+            if (cd != 0xFFFFu) {
+                const uint32_t c = (1u - (n_nl + cd)) & 3u;  // role(candidate) = (c0 + index) & 3 == 1
+                if (c0 == 4u) c0 = c;
+                else if (c != c0) incons = true;
+            }
+            if (cnt > (uint32_t)WCAP) dense = true;
+            n_nl += cnt;
+        }
+        if (n_nl > (uint32_t)LMAX) dense = true;
+        if (dense) fb = 2;
+        if (t == 0) {
+            if (c0 != 4u && c0 != 0u) incons = true;
+            c0 = 0;
+            if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | (n_nl & 3));
+        } else if (c0 != 4u) {
+            if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | ((c0 + n_nl) & 3));
+        } else {  // no "\n+\n" in the whole tile (CTA-uniform): a real look-back over the newline counts
+            if (warp == 0) {
+                c0 = lookback_phase_warp(P.desc1, t, n_nl, lane);
+                if (lane == 0) S->c0 = c0;
+            }
+            __syncthreads();
+            c0 = S->c0;
+        }
+        if (incons) fb = 4;
+        // the first byte of the tile starts a record iff 4k newlines precede it and the previous byte is one;
+        // tile 0 starts with a record by construction (at `lead`)
+        const bool pos0_start = t == 0 || ((c0 == 0) && tile[-1] == '\n');
+
+        // ---- P2: one thread per newline of the warp's own region: classify by role (line number mod 4),
+        //      file it under its index in the tile
+        if (!dense) {
+            for (uint32_t l = lane; l < wtot; l += 32) {
+                const uint32_t p = my_nl[l];
+                const uint32_t i = wbase + l;
+                const uint32_t role = (c0 + i) & 3;
+                S->nlp[i] = (uint16_t)p;
+                if (tile[(int)p - 1] == '\r') fb = 3;  // CRLF: not canonical
+                if (role == 1) {                       // end of the sequence line: "+\n" must follow
+                    if (p + 2 >= avail) fb = 4;
+                    else if (tile[p + 1] != '+' || tile[p + 2] != '\n') fb = 4;
+                } else if (role == 3 && p + 1 < tile_len) {  // record j starts at p + 1 (run j + 1)
+                    const uint32_t j = ((c0 + i) >> 2) + (pos0_start ? 1u : 0u);
+                    if (j < (uint32_t)RMAX) S->runS[j + 1] = (uint16_t)(p + 1);
+                    else fb = 5;
+                }
+            }
+        }
+        if (tid == 0) {
+            S->runS[0] = 0;
+            if (pos0_start) S->runS[1] = (uint16_t)lead_t;
+        }
+        __syncthreads();  // B3: nlp / runS complete
+        PHASE_MARK(4);    // phase + P2 + B3
+        // number of record starts inside the tile
+        const uint32_t n_term = (c0 + n_nl) >> 2;
+        uint32_t n_starts = n_term + (pos0_start ? 1u : 0u);
+        if (n_term > 0 && !dense) {
+            // the last terminating newline may sit on the tile's final byte: its record belongs to the next tile
+            const uint32_t r_last = ((3u - c0) & 3u) + 4u * (n_term - 1);
+            if ((uint32_t)S->nlp[r_last] + 1u >= tile_len) n_starts--;
+        }
+        if (dense || n_starts > (uint32_t)RMAX) n_starts = 0;  // (a fallback reason is already raised)
+
+        // ---- P3: one thread per record start: '@', id token -> exact probe, seq/qual length check, kept
+        //      bytes scanned per warp, runs cut into copy items.  NT records per round (almost always one)
+        const uint32_t head_len = n_starts ? S->runS[1] : tile_len;  // the carried-in record's bytes
+        uint32_t rest_total = 0, kept_recs = 0;
+        const uint32_t n_rounds = n_starts > (uint32_t)NT ? (n_starts + NT - 1) / NT : 1u;
+        for (uint32_t round = 0; round < n_rounds; round++) {
+            const uint32_t jb = round * NT;
+            const uint32_t j = jb + (uint32_t)tid;
+            const bool warp_active = jb + (uint32_t)warp * 32u < n_starts;
+            uint32_t flag = F_INVALID, sp = 0, e = 0, v = 0, inc = 0;
+            if (warp_active) {
+                if (j < n_starts) {
+                    sp = S->runS[j + 1];
+                    e = j + 1 < n_starts ? S->runS[j + 2] : tile_len;
+                    const bool owned = P.is_last || (g0 + sp <= P.own_len);
+                    if (!owned) {
+                        flag = F_NONE;
+                        atomicMin(&S->none_pos, sp);
+                        atomicAdd(&S->none_cnt, 1u);
+                    } else {
+                        uint32_t why = tile[sp] == '@' ? 0u : 6u;  // 6 '@', 7 id token, 8 seq/qual lengths
+                        const RecPrep R = record_prepare(tile_s, sp, avail);
+                        const bool inl = R.mode == 1 && !why && P.set.table != nullptr;
+                        Bucket first;
+#pragma unroll
+                        for (int q = 0; q < (int)IDSET_BUCKET; q++) first.s[q].lo = first.s[q].hi = 0;
+                        if (inl) first = load_bucket(P.set, R.lo, R.hi);
+                        // seq/qual length equality for records whose four newlines are inside the tile
+                        const int r0 = pos0_start ? 4 * (int)j - 1 : (int)((3u - c0) & 3u) + 4 * (int)j;
+                        if (r0 + 4 < (int)n_nl) {
+                            const int sgn = -(int)S->nlp[r0 + 1] + (int)S->nlp[r0 + 2] + (int)S->nlp[r0 + 3] -
+                                            (int)S->nlp[r0 + 4];
+                            if (sgn != 0) why = why ? why : 8u;
+                        }
+                        bool hit = false;
+                        if (!why) {
+                            if (R.mode == 1) hit = inl && probe_bucket(P.set, first, R.lo, R.hi);
+                            else hit = record_probe_slow(P.set, tile, sp, avail, &why);
+                        }
+                        flag = (P.reverse ? hit : !hit) ? F_KEPT : F_OTHER;
+                        if (why) {
+                            fb = why;
+                            flag = F_OTHER;
+                        }
+                    }
+                    if (j == n_starts - 1) S->last_flag = flag;
+                }
+                v = flag == F_KEPT ? ((e - sp) | (1u << 16)) : 0u;  // kept bytes | kept records << 16
+                inc = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += x;
+                }
+            }
+            if (lane == 31) S->scan_tot[warp] = inc;
+            PHASE_MARK(5);    // P3 own work (probe included)
+            __syncthreads();  // B4
+            PHASE_MARK(6);    // B4 wait
+            uint32_t base = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const uint32_t x = S->scan_tot[w];
+                if (w < warp) base += x;
+                tot += x;
+            }
+            if (warp_active) {
+                const uint32_t Kx = rest_total + ((base + inc - v) & 0xFFFFu);  // kept bytes of the records before
+                emit_runs<F_KEPT>(S, flag, sp, e, Kx, head_len, lane);
+                if (P.out_o) emit_runs<F_OTHER>(S, flag, sp, e, Kx, head_len, lane);
+            }
+            rest_total += tot & 0xFFFFu;
+            kept_recs += tot >> 16;
+            if (round + 1 < n_rounds) __syncthreads();  // scan_tot is reused
+        }
+        if (fb) set_fallback(P.res, (int)fb);
+
+        if (warp == NW - 1) {
+            // ---- look-back #2 (one warp): aggregate first -- every later tile may be waiting for it
+            const uint32_t last_flag = n_starts ? S->last_flag : F_OTHER;
+            if (lane == 0) TRACE(t, 2);
+            if (lane == 0)
+                st_relaxed(P.desc2 + t, ST_AGG | (n_starts ? (1ull << 61) : 0ull) | ((uint64_t)last_flag << 59) |
+                                            ((uint64_t)head_len << 30) | rest_total);
+            // the carried-in head as copy items (its fate is known after the look-back); the `lead` bytes of
+            // tile 0 belong to the previous shard
+            const uint32_t nph = t == 0 ? 0u : (head_len + PIECE - 1) / PIECE;
+            if (nph) {
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(&S->n_items, nph);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if ((uint32_t)lane < nph && slot + lane < (uint32_t)IMAX) {
+                    const uint32_t o = (uint32_t)lane * PIECE;
+                    Item itm;
+                    itm.src = (uint16_t)o;
+                    itm.len = (uint16_t)(head_len - o < (uint32_t)PIECE ? head_len - o : (uint32_t)PIECE);
+                    itm.rel = TAG_HEAD | o;
+                    S->items[slot + lane] = itm;
+                }
+            }
+            uint64_t kept_before;
+            uint32_t carry;
+            lookback_kept_warp(P.desc2, t, n_starts > 0, last_flag, head_len, rest_total, lane, &kept_before, &carry);
+            if (lane == 0) {
+                TRACE(t, 3);
+                S->kept_before = kept_before;
+                S->carry = carry;
+            }
+        } else if (tid == 0) {
+            my_reads_in += n_starts - S->none_cnt;
+            my_reads_out += kept_recs;
+            if (S->none_pos != 0xFFFFFFFFu) atomicMin(&P.res->owned_end, (unsigned long long)(g0 + S->none_pos));
+        } else if (tid == NT - 64) {
+            // per-tile metadata for the verification kernel.  Signed newline-position sums: -p1 +p2 +p3 -p4
+            // per record must vanish
+            long long head = 0, total = 0;
+            const int r_first = (int)((3u - c0) & 3u);
+            if (!dense) {
+                if (n_term == 0) {
+                    for (uint32_t r = 0; r < n_nl; r++) {
+                        const uint32_t role = (c0 + r) & 3;
+                        const long long pp = (long long)(g0 + S->nlp[r]);
+                        total += (role == 0 || role == 3) ? -pp : pp;
+                    }
+                } else {
+                    for (int r = 0; r <= r_first; r++) {
+                        const uint32_t role = (c0 + r) & 3;
+                        const long long pp = (long long)(g0 + S->nlp[r]);
+                        head += (role == 0 || role == 3) ? -pp : pp;
+                    }
+                    total = head;
+                    for (uint32_t r = (uint32_t)r_first + 4u * (n_term - 1) + 1u; r < n_nl; r++) {
+                        const uint32_t role = (c0 + r) & 3;
+                        const long long pp = (long long)(g0 + S->nlp[r]);
+                        total += (role == 0 || role == 3) ? -pp : pp;
+                    }
+                }
+            }
+            P.sum_total[t] = total;
+            P.sum_head[t] = head;
+            P.has_term[t] = n_term > 0 ? 1 : 0;
+            P.nl_count[t] = n_nl;
+            P.phase_used[t] = (uint8_t)c0;
+            // end-of-file condition of canonical input (the line count is checked by the follow-up kernel)
+            if (P.is_last && t + 1 == P.n_tiles && tile[tile_len - 1] != '\n') set_fallback(P.res, 9);
+        }
+        PHASE_MARK(7);    // emit
+        __syncthreads();  // B5: kept_before / carry / every copy item are there
+        PHASE_MARK(8);    // B5 wait (look-back)
+
+        // ---- P4: a warp per copy item.  The next ticket is taken only now: a ticket held while this tile
+        //      still waits on its look-back would stall every later tile behind this CTA
+        unsigned long long nt = 0;
+        if (tid == 0) nt = atomicAdd(&P.res->ticket, 1ull);
+        {
+            const uint64_t kept_before = S->kept_before;
+            const uint32_t carry = S->carry;
+            uint32_t n_items = S->n_items;
+            if (n_items > (uint32_t)IMAX) n_items = IMAX;
+            const uint32_t head_kept = carry == F_KEPT ? head_len : 0u;
+            uint8_t *const base_w = P.out_w + kept_before;  // the head goes here when it is kept
+            // bytes of the other stream before this tile = owned bytes before it - kept bytes before it
+            uint8_t *const base_o = P.out_o ? P.out_o + (t == 0 ? 0 : (g0 - P.lead) - kept_before) : nullptr;
+            const uint32_t head_other = carry == F_OTHER ? head_len : 0u;
+            for (uint32_t i = warp; i < n_items; i += NW) {
+                const Item itm = S->items[i];
+                const uint32_t tag = itm.rel & (3u << 30), rel = itm.rel & 0x3FFFFFFFu;
+                uint8_t *dst;
+                if (tag == TAG_KEPT) {
+                    dst = base_w + head_kept + rel;
+                } else if (tag == TAG_OTHER) {
+                    dst = base_o + head_other + rel;
+                } else {
+                    if (carry == F_KEPT) dst = base_w + rel;
+                    else if (carry == F_OTHER && base_o) dst = base_o + rel;
+                    else continue;
+                }
+                copy_piece(tile_s + itm.src, itm.len, dst, lane);
+            }
+            if (t + 1 == P.n_tiles && tid == 0) P.res->kept_total = kept_before + head_kept + rest_total;
+        }
+        PHASE_MARK(9);  // copy own work
+        if (tid == 0) {
+            TRACE(t, 4);
+            if (nt < P.n_tiles) TRACE(nt, 0);
+        }
+        if (tid == 0) S->next_tile = nt;
+        __syncthreads();  // B6: every read of the tile buffer and the lists is done
+        PHASE_MARK(10);  // ticket + B6 wait
+        const uint64_t next_t = S->next_tile;
+        if (tid == 0 && next_t < P.n_tiles) issue_load(P, S, next_t);
+        t = next_t;
+    }
+#ifdef SGPU_FUSED_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 12; i++) atomicAdd(&g_phase_cycles[i], ph_acc[i]);
+#endif
     if (tid == 0) {
         if (my_reads_out) atomicAdd(&P.res->reads_out, my_reads_out);
         if (my_reads_in) atomicAdd(&P.res->reads_in, my_reads_in);
@@ -1106,6 +1079,9 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     }
     uint64_t grid = (uint64_t)c->sm_count * occ[c->device & 63];  // persistent: every CTA is resident
     if (grid > n_tiles) grid = n_tiles;
+    // tiles are pulled into L2 one generation of CTAs ahead (SGPU_FUSED_PF scales the distance, 0 = off)
+    static const double pf_factor = getenv("SGPU_FUSED_PF") ? atof(getenv("SGPU_FUSED_PF")) : 1.0;
+    P.pf_dist = (uint64_t)((double)grid * pf_factor);
     if (c->profiling) {
         if (c->prof_used == c->prof_events.size()) {
             cudaEvent_t a, b;
@@ -1115,6 +1091,14 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
         }
         SGPU_CUDA(cudaEventRecord(c->prof_events[c->prof_used].first, st));
     }
+#ifdef SGPU_FUSED_TIMING
+    unsigned long long *d_trace = nullptr;
+    if (getenv("SGPU_FUSED_TRACE")) {
+        cudaMalloc((void **)&d_trace, n_tiles * 64);
+        cudaMemset(d_trace, 0, n_tiles * 64);
+    }
+    cudaMemcpyToSymbol(g_trace, &d_trace, sizeof(d_trace));
+#endif
     fastq_fused_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(P);
     SGPU_LAUNCH(c);
     if (c->profiling) SGPU_CUDA(cudaEventRecord(c->prof_events[c->prof_used++].second, st));
@@ -1127,6 +1111,30 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     SGPU_CUDA(cudaGetLastError());
     FusedResult h;
     SGPU_TRY(read_u64s(c, res.p, (uint64_t *)&h, sizeof(FusedResult) / 8));
+#ifdef SGPU_FUSED_TIMING
+    {
+        unsigned long long ph[16], zero[16] = {0};
+        cudaMemcpyFromSymbol(ph, g_phase_cycles, sizeof(ph));
+        cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
+        static const char *names[11] = {"load wait", "P1", "B1 wait", "scatter+B2", "phase+P2+B3", "P3 own", "B4 wait",
+                                        "emit", "B5 wait (look-back)", "copy", "ticket+B6"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 11; i++) tot += ph[i];
+        fprintf(stderr, "[sgpu] fused phases, thread 0, cycles per tile (%llu tiles):", (unsigned long long)n_tiles);
+        for (int i = 0; i < 11; i++) fprintf(stderr, " %s=%.0f", names[i], (double)ph[i] / (double)n_tiles);
+        fprintf(stderr, " total=%.0f\n", (double)tot / (double)n_tiles);
+        if (d_trace) {
+            std::vector<unsigned long long> tr(n_tiles * 8);
+            cudaMemcpy(tr.data(), d_trace, n_tiles * 64, cudaMemcpyDeviceToHost);
+            cudaFree(d_trace);
+            FILE *f = fopen(getenv("SGPU_FUSED_TRACE"), "wb");
+            if (f) {
+                fwrite(tr.data(), 8, tr.size(), f);
+                fclose(f);
+            }
+        }
+    }
+#endif
     // a shard must have seen the start of a foreign record: only then is its last owned record complete
     if (!h.fallback && !is_last && h.owned_end == ~0ull) {
         h.fallback = 1;

@@ -70,7 +70,7 @@ __global__ void idset_insert_kernel(Slot *table, uint64_t mask, const uint8_t *a
             const bool is_inline = L <= IDSET_INLINE_MAX;
             if (!is_inline) hi = ((arena_base + arena_off[i]) << 24) | L;
             unsigned __int128 mine = pack128(lo, hi);
-            uint64_t idx = home & mask;
+            uint64_t idx = home_slot(home, mask);
             while (true) {
                 unsigned __int128 old =
                     atomicCAS(reinterpret_cast<unsigned __int128 *>(table + idx), (unsigned __int128)0, mine);
@@ -100,7 +100,7 @@ __global__ void idset_rehash_kernel(const Slot *old_table, uint64_t old_cap, Slo
     Slot s = old_table[i];
     if ((s.lo | s.hi) == 0) return;
     unsigned __int128 mine = pack128(s.lo, s.hi);
-    uint64_t idx = slot_home(s.lo, s.hi) & mask;
+    uint64_t idx = home_slot(slot_home(s.lo, s.hi), mask);
     while (atomicCAS(reinterpret_cast<unsigned __int128 *>(table + idx), (unsigned __int128)0, mine) != 0)
         idx = (idx + 1) & mask;
 }
@@ -148,7 +148,7 @@ sgpu_status idset_create(sgpu_ctx *c, sgpu_idset **out) {
 
 static sgpu_status idset_reserve(sgpu_ctx *c, sgpu_idset *s, uint64_t n_new, uint64_t new_long_bytes) {
     cudaStream_t st = c->stream;
-    uint64_t need = next_pow2(std::max<uint64_t>(1024, 2 * (s->count + n_new)));
+    uint64_t need = next_pow2(std::max<uint64_t>(1024, IDSET_INV_LOAD * (s->count + n_new)));
     if (need > s->capacity) {
         Slot *nt = nullptr;
         cudaError_t e = cudaMallocAsync((void **)&nt, need * sizeof(Slot), st);

@@ -34,6 +34,8 @@ d_out = [torch.empty(t.numel() + 64, dtype=torch.uint8, device=dev) for t in d_r
 d_oth = [torch.empty(t.numel() + 64, dtype=torch.uint8, device=dev) if a.split else None for t in d_r]
 torch.cuda.synchronize()
 torch.cuda.profiler.start()  # ncu --profile-from-start off: only the steps are captured
+ctx.set_profiling(True)
+ctx.fused_stats()
 for s in range(a.steps):
     ids = mk()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -43,6 +45,9 @@ for s in range(a.steps):
     torch.cuda.synchronize()
     ids.free()
     nbytes = sum(t.numel() for t in d_r)
+    f_ms, f_n, f_bytes = ctx.fused_stats()
+    if f_n:
+        print(f"step {s}: fused kernel {f_n} launches, avg {f_ms / f_n:.3f} ms, {f_bytes / f_ms / 1e6:.1f} GB/s algorithmic")
     print(f"step {s}: clean {e0.elapsed_time(e1):.3f} ms, {nbytes / e0.elapsed_time(e1) / 1e6:.1f} GB/s in, path {rs[0].path}, "
           f"reads {sum(r.reads_in for r in rs)} kept {sum(r.reads_out for r in rs)}")
 torch.cuda.profiler.stop()
