@@ -29,7 +29,8 @@
 //          runs of consecutive records with the same fate are found with ballots and cut into
 //          copy items (source, length, stream offset);
 //   scan : decoupled look-back by one warp over (kept bytes, state of the record that straddles
-//          the tile edge), 32 * LBW descriptors per round, combined as a 3-state transducer;
+//          the tile edge), 32 descriptors per round, combined as a 3-state transducer; it starts
+//          before the tile's own records are done (it only needs the tiles before);
 //   P4   : a warp per copy item: 16-byte destination-aligned stores, the source re-aligned from two
 //          16-byte shared loads with funnel shifts (the shift is uniform per item), edge bytes by
 //          one byte store per lane.
@@ -56,9 +57,6 @@ namespace sgpu {
 #ifndef SGPU_FUSED_HALO
 #define SGPU_FUSED_HALO 256
 #endif
-#ifndef SGPU_FUSED_LBW
-#define SGPU_FUSED_LBW 4
-#endif
 constexpr int NT = 256;                 // threads per CTA
 constexpr int NW = NT / 32;             // warps per CTA
 constexpr int NTHREADS = NT;
@@ -69,14 +67,21 @@ constexpr int HALO = SGPU_FUSED_HALO;   // post-halo: id token of the last recor
 constexpr int BUF = PRE + TILE + HALO;  // bytes of the tile buffer
 constexpr int RMAX = 320;               // record starts per tile
 constexpr int LMAX = 4 * RMAX + 8;      // newline list capacity per tile
-constexpr int WCAP = 192;               // newlines per warp region (4 KiB)
 constexpr int PIECE = SGPU_FUSED_PIECE; // copy items are at most this long
 constexpr int IMAX = RMAX + 2 * (TILE / PIECE) + 8;  // copy items per tile
+#ifndef SGPU_FUSED_DSTRIDE
+#define SGPU_FUSED_DSTRIDE 4
+#endif
+#ifndef SGPU_FUSED_POLL_NS
+#define SGPU_FUSED_POLL_NS 500
+#endif
 #ifndef SGPU_FUSED_LOAD_PIECE
 #define SGPU_FUSED_LOAD_PIECE 4096
 #endif
+// 64-bit words between the look-back #2 descriptors of two tiles: one 32-byte sector each, so that the
+// hundreds of polling warps do not all hit the same few L2 lines (measured: 1.18 -> 1.06 ms per 1.65 GB)
+constexpr int DSTRIDE = SGPU_FUSED_DSTRIDE;
 constexpr int LOAD_PIECE = SGPU_FUSED_LOAD_PIECE;  // bytes per bulk copy of a tile load
-constexpr int LBW = SGPU_FUSED_LBW;     // look-back descriptors per lane and round (window 32 * LBW tiles)
 constexpr int CTAS_PER_SM = SGPU_FUSED_CTAS;  // resident CTAs the kernel is sized for (registers, shared memory)
 static_assert(TILE <= 32768 && TILE / PIECE <= 32 && HALO % 16 == 0, "tile offsets are 16-bit; head pieces fit a warp");
 
@@ -135,10 +140,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep in hardware, do not spin
         : "memory");
     return ok != 0;
 }
@@ -208,13 +213,13 @@ struct __align__(128) CtaSmem {
     uint32_t carry;        // state of the record carried into the tile
     uint32_t c0;           // newlines before the tile, mod 4 (only when the speculation found no "\n+\n")
     uint32_t n_items;
-    uint32_t last_flag;
-    uint32_t none_pos;  // first record start of the tile that belongs to the next shard
+    uint32_t last_flag;    // fate of the last record that starts in the tile
+    uint32_t head_len;     // bytes of the carried-in record (== tile_len when no record starts in the tile)
+    uint32_t rest_total;   // kept bytes of the records that start in the tile
+    uint32_t none_pos;     // first record start of the tile that belongs to the next shard
     uint32_t none_cnt;
-    uint32_t warp_tot[NW];  // newlines of the warp's region | local index of its first "\n+\n" newline << 16
+    uint32_t warp_tot[NW];  // newlines of the warp's region (bit 31: a 16-byte chunk with more than two)
     uint32_t scan_tot[NW];
-    uint16_t nlw[NW][WCAP];  // per warp region: newline positions (tile offsets), in order
-    uint16_t runS[RMAX + 4];  // run r starts at runS[r]; run 0 = carried-in head, run j+1 = record j; sentinel = tile_len
     __align__(16) uint16_t nlp[LMAX];  // newline positions of the tile, in order
     Item items[IMAX];
     __align__(16) uint8_t buf[BUF];
@@ -253,7 +258,8 @@ __device__ __forceinline__ uint32_t lookback_phase_warp(unsigned long long *desc
 // carries out (has_start ? last : c).  A run of tiles composes into {P: bytes kept iff c == KEPT, K: bytes
 // kept regardless, has, out}; composition is associative.  A warp looks at 32 descriptors at a time (one per
 // lane): with ballots every lane finds the state carried into its tile, two warp reductions give the
-// window's composite; LBW windows are loaded per round.
+// window's composite.  The look-back only needs the tiles BEFORE t, so it runs while the CTA's other warps
+// are still busy with the records of tile t.
 struct Comp {
     uint32_t P, K, has, out;
 };
@@ -274,71 +280,68 @@ __device__ __forceinline__ Comp compose(const Comp A /*earlier*/, const Comp B /
     return R;
 }
 
-__device__ __forceinline__ void lookback_kept_warp(unsigned long long *desc, uint64_t t, bool has_start,
-                                                   uint32_t last_flag, uint32_t head_len, uint32_t rest, int lane,
+// (kept bytes before tile t, state carried into it) from the descriptors of the tiles before t
+__device__ __forceinline__ void lookback_pred_warp(const unsigned long long *desc, uint64_t t, int lane,
                                                    uint64_t *kept_before, uint32_t *carry) {
     Comp acc_all = comp_identity();  // composite of every window visited so far (nearer windows are later)
     uint64_t inc_total = 0;
-    int64_t base = (int64_t)t - 1;  // nearest tile of the round; lane l of window k looks at tile base - 32k - l
+    int64_t base = (int64_t)t - 1;  // nearest tile of the window; lane l looks at tile base - l
     const uint64_t virt = ST_INC | ((uint64_t)F_NONE << 59);  // before the buffer: nothing kept, nothing carried
     while (true) {
-        unsigned long long d[LBW];
-#pragma unroll
-        for (int k = 0; k < LBW; k++) {
-            const int64_t idx = base - 32 * k - lane;
-            d[k] = idx >= 0 ? ld_relaxed(desc + idx) : virt;
+        const int64_t idx = base - lane;
+        unsigned long long x = idx >= 0 ? ld_relaxed(desc + idx * DSTRIDE) : virt;
+        int L;
+        // every descriptor up to the nearest inclusive one must be there
+        while (true) {
+            const uint32_t st = (uint32_t)(x >> 62);
+            const unsigned binc = __ballot_sync(0xffffffffu, st == 2u);
+            const unsigned bzero = __ballot_sync(0xffffffffu, st == 0u);
+            L = binc ? __ffs(binc) - 1 : 32;
+            const unsigned upto = L < 31 ? (2u << L) - 1u : 0xffffffffu;  // lanes <= L
+            if ((bzero & upto) == 0) break;
+            // a predecessor is still parsing (microseconds away): poll slowly, the issue slots belong to the
+            // warps that work
+            __nanosleep(SGPU_FUSED_POLL_NS);
+            if (st == 0u && lane <= L) x = ld_relaxed(desc + idx * DSTRIDE);
         }
-        bool done = false;
-#pragma unroll
-        for (int k = 0; k < LBW; k++) {
-            if (done) break;  // uniform
-            const int64_t idx = base - 32 * k - lane;
-            unsigned long long x = d[k];
-            int L;
-            // every descriptor up to the nearest inclusive one must be there
-            while (true) {
-                const uint32_t st = (uint32_t)(x >> 62);
-                const unsigned binc = __ballot_sync(0xffffffffu, st == 2u);
-                const unsigned bzero = __ballot_sync(0xffffffffu, st == 0u);
-                L = binc ? __ffs(binc) - 1 : 32;
-                const unsigned upto = L < 31 ? (2u << L) - 1u : 0xffffffffu;  // lanes <= L
-                if ((bzero & upto) == 0) break;
-                if (st == 0u && lane <= L) x = ld_relaxed(desc + idx);
-            }
-            const bool agg = lane < L, isL = lane == L;
-            const uint32_t fl = (uint32_t)(x >> 59) & 3u;
-            const bool has = isL || (agg && ((x >> 61) & 1ull));
-            const uint32_t hl = agg ? (uint32_t)(x >> 30) & 0x1FFFFFFFu : 0u;
-            const uint32_t rs = agg ? (uint32_t)x & 0x3FFFFFFFu : 0u;
-            const unsigned has_m = __ballot_sync(0xffffffffu, has);
-            const unsigned kept_m = __ballot_sync(0xffffffffu, has && fl == F_KEPT);
-            // the state carried into my tile = state of the nearest earlier tile with a record start:
-            // the lowest set bit of has_m strictly above my lane
-            const unsigned hm = has_m & (0xFFFFFFFEu << lane);
-            const bool found = hm != 0u;
-            const bool in_kept = found && ((kept_m >> (__ffs(hm) - 1)) & 1u);
-            const uint32_t sumK = __reduce_add_sync(0xffffffffu, rs + (in_kept ? hl : 0u));
-            const uint32_t sumP = __reduce_add_sync(0xffffffffu, found ? 0u : hl);
-            Comp W;
-            W.P = sumP;
-            W.K = sumK;
-            W.has = has_m != 0u;
-            W.out = __shfl_sync(0xffffffffu, fl, has_m ? __ffs(has_m) - 1 : 0);
-            acc_all = compose(W, acc_all);
-            if (L < 32) {
-                inc_total = __shfl_sync(0xffffffffu, x, L) & ((1ull << 59) - 1);
-                done = true;
-            }
+        const bool agg = lane < L, isL = lane == L;
+        const uint32_t fl = (uint32_t)(x >> 59) & 3u;
+        const bool has = isL || (agg && ((x >> 61) & 1ull));
+        const uint32_t hl = agg ? (uint32_t)(x >> 30) & 0x1FFFFFFFu : 0u;
+        const uint32_t rs = agg ? (uint32_t)x & 0x3FFFFFFFu : 0u;
+        const unsigned has_m = __ballot_sync(0xffffffffu, has);
+        const unsigned kept_m = __ballot_sync(0xffffffffu, has && fl == F_KEPT);
+        // the state carried into my tile = state of the nearest earlier tile with a record start:
+        // the lowest set bit of has_m strictly above my lane
+        const unsigned hm = has_m & (0xFFFFFFFEu << lane);
+        const bool found = hm != 0u;
+        const bool in_kept = found && ((kept_m >> (__ffs(hm) - 1)) & 1u);
+        const uint32_t sumK = __reduce_add_sync(0xffffffffu, rs + (in_kept ? hl : 0u));
+        const uint32_t sumP = __reduce_add_sync(0xffffffffu, found ? 0u : hl);
+        Comp W;
+        W.P = sumP;
+        W.K = sumK;
+        W.has = has_m != 0u;
+        W.out = __shfl_sync(0xffffffffu, fl, has_m ? __ffs(has_m) - 1 : 0);
+        acc_all = compose(W, acc_all);
+        if (L < 32) {
+            inc_total = __shfl_sync(0xffffffffu, x, L) & ((1ull << 59) - 1);
+            break;
         }
-        if (done) break;
-        base -= 32 * LBW;
+        base -= 32;
     }
     // acc_all starts with the inclusive descriptor (has == 1, P == 0)
     *kept_before = inc_total + acc_all.K;
     *carry = acc_all.out;
-    const uint64_t incl = *kept_before + (acc_all.out == F_KEPT ? head_len : 0u) + rest;
-    const uint32_t out_flag = has_start ? last_flag : acc_all.out;
-    if (lane == 0) st_relaxed(desc + t, ST_INC | ((uint64_t)out_flag << 59) | incl);
+}
+__device__ __forceinline__ unsigned long long agg_desc(bool has_start, uint32_t last_flag, uint32_t head_len,
+                                                       uint32_t rest) {
+    return ST_AGG | (has_start ? (1ull << 61) : 0ull) | ((uint64_t)last_flag << 59) | ((uint64_t)head_len << 30) | rest;
+}
+__device__ __forceinline__ unsigned long long inc_desc(bool has_start, uint32_t last_flag, uint32_t head_len,
+                                                       uint32_t rest, uint64_t kept_before, uint32_t carry) {
+    const uint64_t incl = kept_before + (carry == F_KEPT ? head_len : 0u) + rest;
+    return ST_INC | ((uint64_t)(has_start ? last_flag : carry) << 59) | incl;
 }
 
 // ------------------------------------------------------------------ tile load (one thread)
@@ -568,6 +571,21 @@ __device__ __forceinline__ uint32_t smid() {
 #endif
 
 // ------------------------------------------------------------------ the kernel
+// named barriers: 0 = the whole CTA; 1 = the records' scan (B4); 2 = totals handed to the look-back warp
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+
+// CR / "+\n" checks of one newline by its role (the newlines of whole records are checked by the record's thread)
+__device__ __forceinline__ uint32_t check_newline(const uint8_t *tile, uint32_t p, uint32_t role, uint32_t avail) {
+    uint32_t fb = 0;
+    if (tile[(int)p - 1] == '\r') fb = 3;  // CRLF: not canonical
+    if (role == 1) {                       // end of the sequence line: "+\n" must follow
+        if (p + 2 >= avail) fb = 4;
+        else if (tile[p + 1] != '+' || tile[p + 2] != '\n') fb = 4;
+    }
+    return fb;
+}
+
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(FusedParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     CtaSmem *S = reinterpret_cast<CtaSmem *>(smem_raw);
@@ -595,8 +613,11 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
     for (uint32_t it = 0; t < P.n_tiles; it++) {
         // the tile some CTA will take one generation from now: pull it into L2
         if (tid == 0 && P.pf_dist) prefetch_tile(P, t + P.pf_dist);
-        while (!mbar_try_wait(&S->full, it & 1)) {
+        if (lane == 0) {
+            while (!mbar_try_wait(&S->full, it & 1)) {
+            }
         }
+        __syncwarp();
         PHASE_MARK(0);  // load wait
         if (tid == 0) {
             TRACE(t, 1);
@@ -609,53 +630,42 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
         const uint32_t avail =
             (uint32_t)((P.n_in - g0) < (uint64_t)(TILE + HALO) ? (P.n_in - g0) : (uint64_t)(TILE + HALO));
         const uint32_t lead_t = t == 0 ? P.lead : 0u;
-        uint32_t fb = 0;                           // this thread's fallback reason (0 = none)
-        if (t == 0 && tid < PRE) buf[tid] = '\n';  // no predecessor: the pre-halo reads as a newline
+        uint32_t fb = 0;  // this thread's fallback reason (0 = none)
+        if (t == 0 || tile_len < (uint32_t)TILE) {  // (CTA-uniform) first / last tile of the buffer
+            // every thread observes the completed load, then the edges are patched
+            while (!mbar_try_wait(&S->full, it & 1)) {
+            }
+            if (t == 0 && tid < PRE) buf[tid] = '\n';  // no predecessor: the pre-halo reads as a newline
+            // bytes past the end of the buffer are stale: zero them (never a newline, ASCII)
+            for (uint32_t o = tile_len + tid; o < (uint32_t)TILE; o += NT) buf[PRE + o] = 0;
+            __syncthreads();
+        }
 
         // ---- P1: newline masks and counts.  Warp w owns chunks [w*FC*32, (w+1)*FC*32); lane l takes
         //      chunk k*32 + l of them in round k (conflict-free 16-byte shared loads)
         uint32_t m[FC];
         uint32_t hi_or = 0;
         const uint32_t cbase = (uint32_t)warp * (FC * 32) + (uint32_t)lane;
-        if (tile_len == (uint32_t)TILE) {
 #pragma unroll
-            for (int k = 0; k < FC; k++) {
-                const uint4 v = lds_v4(tile_s + (cbase + k * 32) * 16);
-                m[k] = nl_mask16_v2(v);
-                hi_or |= (v.x | v.y | v.z | v.w);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < FC; k++) {  // last tile: bytes past the end of the buffer are stale
-                const uint32_t pos = (cbase + k * 32) * 16;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (pos < tile_len) {
-                    v = lds_v4(tile_s + pos);
-                    const uint32_t valid = tile_len - pos;
-                    if (valid < 16) {
-                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int x = 0; x < 4; x++) {
-                            const int rem = (int)valid - 4 * x;
-                            if (rem <= 0) w[x] = 0;
-                            else if (rem < 4) w[x] &= (1u << (8 * rem)) - 1u;
-                        }
-                        v = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-                m[k] = nl_mask16_v2(v);  // zero bytes are never newlines
-                hi_or |= (v.x | v.y | v.z | v.w);
-            }
+        for (int k = 0; k < FC; k++) {
+            const uint4 v = lds_v4(tile_s + (cbase + k * 32) * 16);
+            m[k] = nl_mask16_v2(v);
+            hi_or |= (v.x | v.y | v.z | v.w);
         }
         if (lead_t && tid == 0) m[0] &= ~((1u << lead_t) - 1u);  // the previous shard's bytes
         if (hi_or & 0x80808080u) fb = 1;                         // reason 1: non-ASCII byte, Unicode rules needed
         // inclusive warp scan of the per-round counts: three 10-bit fields per word (a round has <= 512 newlines)
         constexpr int PW = (FC + 2) / 3;
         uint32_t pk[PW], inc[PW];
+        uint32_t many = 0;  // a chunk with more than two newlines: lines shorter than the fast path handles
 #pragma unroll
         for (int q = 0; q < PW; q++) pk[q] = 0;
 #pragma unroll
-        for (int k = 0; k < FC; k++) pk[k / 3] |= (uint32_t)__popc(m[k]) << (10 * (k % 3));
+        for (int k = 0; k < FC; k++) {
+            const uint32_t c = (uint32_t)__popc(m[k]);
+            many |= (c + 1u) >> 2;  // != 0 iff c >= 3
+            pk[k / 3] |= c << (10 * (k % 3));
+        }
 #pragma unroll
         for (int q = 0; q < PW; q++) inc[q] = pk[q];
 #pragma unroll
@@ -678,43 +688,8 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                 wtot += (rt >> (10 * (k % 3))) & 1023u;
             }
         }
-        // ---- the warp's newline positions, in order, into its own list (no other warp is involved)
-        uint16_t *const my_nl = S->nlw[warp];
-        if (wtot <= (uint32_t)WCAP) {
-#pragma unroll
-            for (int k = 0; k < FC; k++) {
-                uint32_t mm = m[k];
-                if (mm) {  // almost always one or two newlines per 16 bytes ("\n+\n")
-                    uint32_t r = row_base[k];
-                    const uint32_t pos = (cbase + k * 32) * 16;
-                    my_nl[r] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
-                    mm &= mm - 1;
-                    if (mm) {
-                        my_nl[r + 1] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
-                        mm &= mm - 1;
-                        r += 2;
-                        while (mm) {
-                            my_nl[r++] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
-                            mm &= mm - 1;
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- line phase candidate: the first newline of the region that is followed by "+\n" ends a
-        //      sequence line (role 1)
-        uint32_t cand = 0xFFFFu;
-        {
-            bool hit = false;
-            if (wtot <= (uint32_t)WCAP && (uint32_t)lane < wtot) {
-                const uint32_t p = my_nl[lane];
-                hit = p + 2 < avail && tile[p + 1] == '+' && tile[p + 2] == '\n';
-            }
-            const unsigned b = __ballot_sync(0xffffffffu, hit);
-            if (b) cand = (uint32_t)(__ffs(b) - 1);
-        }
-        if (lane == 0) S->warp_tot[warp] = wtot | (cand << 16);
+        const bool many_w = __any_sync(0xffffffffu, many != 0u);
+        if (lane == 0) S->warp_tot[warp] = wtot | (many_w ? 0x80000000u : 0u);
         if (tid == 0) {
             S->n_items = 0;
             S->none_pos = 0xFFFFFFFFu;
@@ -723,163 +698,88 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
         PHASE_MARK(1);    // P1 own work
         __syncthreads();  // B1
         PHASE_MARK(2);    // B1 wait
-        // ---- every thread: newlines before its region, line phase from the first candidate (all candidates
-        //      must agree)
-        uint32_t n_nl = 0, wbase = 0, c0 = 4u;
-        bool dense = false, incons = false;
+        // newlines before the warp's region / in the tile: lane w holds warp w's count
+        uint32_t n_nl, wbase;
+        bool dense;
+        {
+            const uint32_t x = lane < NW ? S->warp_tot[lane] : 0u;
+            const uint32_t cnt = x & 0x7FFFFFFFu;
+            uint32_t ic = cnt;
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-            const uint32_t x = S->warp_tot[w];
-            const uint32_t cnt = x & 0xFFFFu, cd = x >> 16;
-            if (w == warp) wbase = n_nl;
-            if (cd != 0xFFFFu) {
-                const uint32_t c = (1u - (n_nl + cd)) & 3u;  // role(candidate) = (c0 + index) & 3 == 1
-                if (c0 == 4u) c0 = c;
-                else if (c != c0) incons = true;
+            for (int d = 1; d < NW; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ic, d);
+                if (lane >= d) ic += y;
             }
-            if (cnt > (uint32_t)WCAP) dense = true;
-            n_nl += cnt;
+            n_nl = __shfl_sync(0xffffffffu, ic, NW - 1);
+            wbase = __shfl_sync(0xffffffffu, ic - cnt, warp);
+            dense = __any_sync(0xffffffffu, (x >> 31) != 0u) || n_nl > (uint32_t)LMAX;
         }
-        if (n_nl > (uint32_t)LMAX) dense = true;
-        if (dense) fb = 2;
+        // ---- the newline positions, in order (at most two per 16-byte chunk here: "\n+\n")
+        if (!dense) {
+#pragma unroll
+            for (int k = 0; k < FC; k++) {
+                uint32_t mm = m[k];
+                if (mm) {
+                    const uint32_t r = wbase + row_base[k];
+                    const uint32_t pos = (cbase + k * 32) * 16;
+                    S->nlp[r] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
+                    mm &= mm - 1;
+                    if (mm) S->nlp[r + 1] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
+                }
+            }
+        } else {
+            fb = 2;
+        }
+        __syncthreads();  // B2
+        PHASE_MARK(3);    // scatter + B2
+        // ---- line phase: the first newline followed by "+\n" ends a sequence line (role 1).  Every warp
+        //      evaluates the same 32 candidates, so the outcome is CTA-uniform without a barrier.
+        uint32_t c0 = 0;
         if (t == 0) {
-            if (c0 != 4u && c0 != 0u) incons = true;
-            c0 = 0;
             if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | (n_nl & 3));
-        } else if (c0 != 4u) {
-            if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | ((c0 + n_nl) & 3));
-        } else {  // no "\n+\n" in the whole tile (CTA-uniform): a real look-back over the newline counts
-            if (warp == 0) {
-                c0 = lookback_phase_warp(P.desc1, t, n_nl, lane);
-                if (lane == 0) S->c0 = c0;
+        } else {
+            bool hit = false;
+            if (!dense && (uint32_t)lane < n_nl) {
+                const uint32_t p = S->nlp[lane];
+                hit = p + 2 < avail && tile[p + 1] == '+' && tile[p + 2] == '\n';
             }
-            __syncthreads();
-            c0 = S->c0;
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (b) {
+                c0 = (1u - (uint32_t)(__ffs(b) - 1)) & 3u;  // role(first) = (c0 + first) & 3 == 1
+                if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | ((c0 + n_nl) & 3));
+            } else {
+                if (warp == 0) {
+                    c0 = lookback_phase_warp(P.desc1, t, n_nl, lane);
+                    if (lane == 0) S->c0 = c0;
+                }
+                __syncthreads();
+                c0 = S->c0;
+            }
         }
-        if (incons) fb = 4;
         // the first byte of the tile starts a record iff 4k newlines precede it and the previous byte is one;
         // tile 0 starts with a record by construction (at `lead`)
         const bool pos0_start = t == 0 || ((c0 == 0) && tile[-1] == '\n');
-
-        // ---- P2: one thread per newline of the warp's own region: classify by role (line number mod 4),
-        //      file it under its index in the tile
-        if (!dense) {
-            for (uint32_t l = lane; l < wtot; l += 32) {
-                const uint32_t p = my_nl[l];
-                const uint32_t i = wbase + l;
-                const uint32_t role = (c0 + i) & 3;
-                S->nlp[i] = (uint16_t)p;
-                if (tile[(int)p - 1] == '\r') fb = 3;  // CRLF: not canonical
-                if (role == 1) {                       // end of the sequence line: "+\n" must follow
-                    if (p + 2 >= avail) fb = 4;
-                    else if (tile[p + 1] != '+' || tile[p + 2] != '\n') fb = 4;
-                } else if (role == 3 && p + 1 < tile_len) {  // record j starts at p + 1 (run j + 1)
-                    const uint32_t j = ((c0 + i) >> 2) + (pos0_start ? 1u : 0u);
-                    if (j < (uint32_t)RMAX) S->runS[j + 1] = (uint16_t)(p + 1);
-                    else fb = 5;
-                }
-            }
-        }
-        if (tid == 0) {
-            S->runS[0] = 0;
-            if (pos0_start) S->runS[1] = (uint16_t)lead_t;
-        }
-        __syncthreads();  // B3: nlp / runS complete
-        PHASE_MARK(4);    // phase + P2 + B3
+        const uint32_t r3 = (3u - c0) & 3u;  // index of the first newline that ends a record
         // number of record starts inside the tile
         const uint32_t n_term = (c0 + n_nl) >> 2;
         uint32_t n_starts = n_term + (pos0_start ? 1u : 0u);
         if (n_term > 0 && !dense) {
             // the last terminating newline may sit on the tile's final byte: its record belongs to the next tile
-            const uint32_t r_last = ((3u - c0) & 3u) + 4u * (n_term - 1);
-            if ((uint32_t)S->nlp[r_last] + 1u >= tile_len) n_starts--;
+            if ((uint32_t)S->nlp[r3 + 4u * (n_term - 1)] + 1u >= tile_len) n_starts--;
         }
-        if (dense || n_starts > (uint32_t)RMAX) n_starts = 0;  // (a fallback reason is already raised)
+        if (n_starts > (uint32_t)RMAX) fb = 5;
+        if (dense || n_starts > (uint32_t)RMAX) n_starts = 0;  // (a fallback reason is raised)
+        // the carried-in record's bytes
+        const uint32_t head_len =
+            n_starts ? (pos0_start ? lead_t : (uint32_t)S->nlp[r3] + 1u) : tile_len;
+        // the look-back only needs the tiles before this one: when the last warp has no record to look after,
+        // it runs the look-back while the others work on the records (CTA-uniform)
+        const bool early = n_starts <= (uint32_t)(NT - 32);
 
-        // ---- P3: one thread per record start: '@', id token -> exact probe, seq/qual length check, kept
-        //      bytes scanned per warp, runs cut into copy items.  NT records per round (almost always one)
-        const uint32_t head_len = n_starts ? S->runS[1] : tile_len;  // the carried-in record's bytes
         uint32_t rest_total = 0, kept_recs = 0;
-        const uint32_t n_rounds = n_starts > (uint32_t)NT ? (n_starts + NT - 1) / NT : 1u;
-        for (uint32_t round = 0; round < n_rounds; round++) {
-            const uint32_t jb = round * NT;
-            const uint32_t j = jb + (uint32_t)tid;
-            const bool warp_active = jb + (uint32_t)warp * 32u < n_starts;
-            uint32_t flag = F_INVALID, sp = 0, e = 0, v = 0, inc = 0;
-            if (warp_active) {
-                if (j < n_starts) {
-                    sp = S->runS[j + 1];
-                    e = j + 1 < n_starts ? S->runS[j + 2] : tile_len;
-                    const bool owned = P.is_last || (g0 + sp <= P.own_len);
-                    if (!owned) {
-                        flag = F_NONE;
-                        atomicMin(&S->none_pos, sp);
-                        atomicAdd(&S->none_cnt, 1u);
-                    } else {
-                        uint32_t why = tile[sp] == '@' ? 0u : 6u;  // 6 '@', 7 id token, 8 seq/qual lengths
-                        const RecPrep R = record_prepare(tile_s, sp, avail);
-                        const bool inl = R.mode == 1 && !why && P.set.table != nullptr;
-                        Bucket first;
-#pragma unroll
-                        for (int q = 0; q < (int)IDSET_BUCKET; q++) first.s[q].lo = first.s[q].hi = 0;
-                        if (inl) first = load_bucket(P.set, R.lo, R.hi);
-                        // seq/qual length equality for records whose four newlines are inside the tile
-                        const int r0 = pos0_start ? 4 * (int)j - 1 : (int)((3u - c0) & 3u) + 4 * (int)j;
-                        if (r0 + 4 < (int)n_nl) {
-                            const int sgn = -(int)S->nlp[r0 + 1] + (int)S->nlp[r0 + 2] + (int)S->nlp[r0 + 3] -
-                                            (int)S->nlp[r0 + 4];
-                            if (sgn != 0) why = why ? why : 8u;
-                        }
-                        bool hit = false;
-                        if (!why) {
-                            if (R.mode == 1) hit = inl && probe_bucket(P.set, first, R.lo, R.hi);
-                            else hit = record_probe_slow(P.set, tile, sp, avail, &why);
-                        }
-                        flag = (P.reverse ? hit : !hit) ? F_KEPT : F_OTHER;
-                        if (why) {
-                            fb = why;
-                            flag = F_OTHER;
-                        }
-                    }
-                    if (j == n_starts - 1) S->last_flag = flag;
-                }
-                v = flag == F_KEPT ? ((e - sp) | (1u << 16)) : 0u;  // kept bytes | kept records << 16
-                inc = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += x;
-                }
-            }
-            if (lane == 31) S->scan_tot[warp] = inc;
-            PHASE_MARK(5);    // P3 own work (probe included)
-            __syncthreads();  // B4
-            PHASE_MARK(6);    // B4 wait
-            uint32_t base = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                const uint32_t x = S->scan_tot[w];
-                if (w < warp) base += x;
-                tot += x;
-            }
-            if (warp_active) {
-                const uint32_t Kx = rest_total + ((base + inc - v) & 0xFFFFu);  // kept bytes of the records before
-                emit_runs<F_KEPT>(S, flag, sp, e, Kx, head_len, lane);
-                if (P.out_o) emit_runs<F_OTHER>(S, flag, sp, e, Kx, head_len, lane);
-            }
-            rest_total += tot & 0xFFFFu;
-            kept_recs += tot >> 16;
-            if (round + 1 < n_rounds) __syncthreads();  // scan_tot is reused
-        }
-        if (fb) set_fallback(P.res, (int)fb);
-
-        if (warp == NW - 1) {
-            // ---- look-back #2 (one warp): aggregate first -- every later tile may be waiting for it
-            const uint32_t last_flag = n_starts ? S->last_flag : F_OTHER;
-            if (lane == 0) TRACE(t, 2);
-            if (lane == 0)
-                st_relaxed(P.desc2 + t, ST_AGG | (n_starts ? (1ull << 61) : 0ull) | ((uint64_t)last_flag << 59) |
-                                            ((uint64_t)head_len << 30) | rest_total);
+        if (early && warp == NW - 1) {
+            if (lane == 0) S->scan_tot[warp] = 0;
+            bar_arrive(1);  // B4: nothing to contribute
             // the carried-in head as copy items (its fate is known after the look-back); the `lead` bytes of
             // tile 0 belong to the previous shard
             const uint32_t nph = t == 0 ? 0u : (head_len + PIECE - 1) / PIECE;
@@ -898,50 +798,198 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
             }
             uint64_t kept_before;
             uint32_t carry;
-            lookback_kept_warp(P.desc2, t, n_starts > 0, last_flag, head_len, rest_total, lane, &kept_before, &carry);
+#ifdef SGPU_ABL_NOLB  // ablation (timing only, output is garbage): no in-order commit
+            kept_before = g0 / 2;
+            carry = F_OTHER;
+#else
+            lookback_pred_warp(P.desc2, t, lane, &kept_before, &carry);
+#endif
+            bar_sync(2);  // the workers' totals are in shared memory (and the aggregate is published)
             if (lane == 0) {
                 TRACE(t, 3);
+                st_relaxed(P.desc2 + t * DSTRIDE,
+                           inc_desc(n_starts > 0, S->last_flag, head_len, S->rest_total, kept_before, carry));
                 S->kept_before = kept_before;
                 S->carry = carry;
             }
-        } else if (tid == 0) {
-            my_reads_in += n_starts - S->none_cnt;
-            my_reads_out += kept_recs;
-            if (S->none_pos != 0xFFFFFFFFu) atomicMin(&P.res->owned_end, (unsigned long long)(g0 + S->none_pos));
-        } else if (tid == NT - 64) {
-            // per-tile metadata for the verification kernel.  Signed newline-position sums: -p1 +p2 +p3 -p4
-            // per record must vanish
-            long long head = 0, total = 0;
-            const int r_first = (int)((3u - c0) & 3u);
-            if (!dense) {
-                if (n_term == 0) {
-                    for (uint32_t r = 0; r < n_nl; r++) {
-                        const uint32_t role = (c0 + r) & 3;
-                        const long long pp = (long long)(g0 + S->nlp[r]);
-                        total += (role == 0 || role == 3) ? -pp : pp;
+        } else {
+            // ---- P3: one thread per record start: checks of the record's lines, '@', id token -> exact probe,
+            //      kept bytes scanned per warp, runs cut into copy items.  NT records per round (almost
+            //      always one round)
+            const uint32_t n_rounds = n_starts > (uint32_t)NT ? (n_starts + NT - 1) / NT : 1u;
+            for (uint32_t round = 0; round < n_rounds; round++) {
+                const uint32_t jb = round * NT;
+                const uint32_t j = jb + (uint32_t)tid;
+                const bool warp_active = jb + (uint32_t)warp * 32u < n_starts;
+                uint32_t flag = F_INVALID, sp = 0, e = 0, v = 0, inc = 0;
+                if (warp_active) {
+                    if (j < n_starts) {
+                        // index of the newline before the record (-1: the record starts the tile)
+                        const int s_idx = pos0_start ? 4 * (int)j - 1 : (int)r3 + 4 * (int)j;
+                        sp = s_idx >= 0 ? (uint32_t)S->nlp[s_idx] + 1u : lead_t;
+                        const bool whole = s_idx + 4 < (int)n_nl;  // its four newlines are inside the tile
+                        uint32_t why = tile[sp] == '@' ? 0u : 6u;  // 6 '@', 7 id token, 8 seq/qual lengths
+                        e = tile_len;
+                        if (whole) {
+                            const uint32_t p1 = S->nlp[s_idx + 1], p2 = S->nlp[s_idx + 2], p3 = S->nlp[s_idx + 3],
+                                           p4 = S->nlp[s_idx + 4];
+                            if (j + 1 < n_starts) e = p4 + 1;
+                            if (tile[p1 - 1] == '\r' || tile[p2 - 1] == '\r' || tile[p4 - 1] == '\r') fb = 3;
+                            if (p3 != p2 + 2 || tile[p2 + 1] != '+') fb = 4;
+                            if (p2 - p1 != p4 - p3) why = why ? why : 8u;
+                        }
+                        const bool owned = P.is_last || (g0 + sp <= P.own_len);
+                        if (!owned) {
+                            flag = F_NONE;
+                            atomicMin(&S->none_pos, sp);
+                            atomicAdd(&S->none_cnt, 1u);
+                        } else {
+                            const RecPrep R = record_prepare(tile_s, sp, avail);
+                            const bool inl = R.mode == 1 && !why && P.set.table != nullptr;
+                            Bucket first;
+#pragma unroll
+                            for (int q = 0; q < (int)IDSET_BUCKET; q++) first.s[q].lo = first.s[q].hi = 0;
+#ifndef SGPU_ABL_NOPROBE
+                            if (inl) first = load_bucket(P.set, R.lo, R.hi);
+#endif
+                            bool hit = false;
+                            if (!why) {
+#ifdef SGPU_ABL_NOPROBE  // ablation (timing only): no memory access for the lookup
+                                if (R.mode == 1) hit = (R.lo >> 20) & 1;
+#else
+                                if (R.mode == 1) hit = inl && probe_bucket(P.set, first, R.lo, R.hi);
+#endif
+                                else hit = record_probe_slow(P.set, tile, sp, avail, &why);
+                            }
+                            flag = (P.reverse ? hit : !hit) ? F_KEPT : F_OTHER;
+                            if (why) {
+                                fb = why;
+                                flag = F_OTHER;
+                            }
+                        }
+                        if (j == n_starts - 1) S->last_flag = flag;
                     }
-                } else {
-                    for (int r = 0; r <= r_first; r++) {
-                        const uint32_t role = (c0 + r) & 3;
-                        const long long pp = (long long)(g0 + S->nlp[r]);
-                        head += (role == 0 || role == 3) ? -pp : pp;
-                    }
-                    total = head;
-                    for (uint32_t r = (uint32_t)r_first + 4u * (n_term - 1) + 1u; r < n_nl; r++) {
-                        const uint32_t role = (c0 + r) & 3;
-                        const long long pp = (long long)(g0 + S->nlp[r]);
-                        total += (role == 0 || role == 3) ? -pp : pp;
+                    v = flag == F_KEPT ? ((e - sp) | (1u << 16)) : 0u;  // kept bytes | kept records << 16
+                    inc = v;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+                        if (lane >= d) inc += x;
                     }
                 }
+                if (lane == 31) S->scan_tot[warp] = inc;
+                PHASE_MARK(5);  // P3 own work (probe included)
+                bar_sync(1);    // B4
+                PHASE_MARK(6);  // B4 wait
+                uint32_t base = 0, tot = 0;
+                {
+                    const uint32_t x = lane < NW ? S->scan_tot[lane] : 0u;
+                    uint32_t ic = x;
+#pragma unroll
+                    for (int d = 1; d < NW; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, ic, d);
+                        if (lane >= d) ic += y;
+                    }
+                    tot = __shfl_sync(0xffffffffu, ic, NW - 1);
+                    base = __shfl_sync(0xffffffffu, ic - x, warp);
+                }
+                const uint32_t Kx = rest_total + ((base + inc - v) & 0xFFFFu);  // kept bytes of the records before
+                rest_total += tot & 0xFFFFu;
+                kept_recs += tot >> 16;
+                if (round + 1 == n_rounds && tid == 0) {
+                    // the aggregate: every later tile may be waiting for it
+                    const uint32_t last_flag = n_starts ? S->last_flag : F_OTHER;
+                    TRACE(t, 2);
+                    st_relaxed(P.desc2 + t * DSTRIDE, agg_desc(n_starts > 0, last_flag, head_len, rest_total));
+                    S->rest_total = rest_total;
+                    if (!n_starts) S->last_flag = F_OTHER;
+                }
+                if (round + 1 == n_rounds && early) bar_arrive(2);  // totals handed to the look-back warp
+                if (warp_active) {
+                    emit_runs<F_KEPT>(S, flag, sp, e, Kx, head_len, lane);
+                    if (P.out_o) emit_runs<F_OTHER>(S, flag, sp, e, Kx, head_len, lane);
+                }
+                if (round + 1 < n_rounds) __syncthreads();  // scan_tot is reused
             }
-            P.sum_total[t] = total;
-            P.sum_head[t] = head;
-            P.has_term[t] = n_term > 0 ? 1 : 0;
-            P.nl_count[t] = n_nl;
-            P.phase_used[t] = (uint8_t)c0;
-            // end-of-file condition of canonical input (the line count is checked by the follow-up kernel)
-            if (P.is_last && t + 1 == P.n_tiles && tile[tile_len - 1] != '\n') set_fallback(P.res, 9);
+            if (tid == 0) {
+                my_reads_in += n_starts - S->none_cnt;
+                my_reads_out += kept_recs;
+                if (S->none_pos != 0xFFFFFFFFu) atomicMin(&P.res->owned_end, (unsigned long long)(g0 + S->none_pos));
+            }
+            if (tid == NT - 64) {
+                // per-tile metadata for the verification kernel, and the checks of the newlines that do not
+                // belong to a whole record of this tile.  Signed newline-position sums: -p1 +p2 +p3 -p4 per
+                // record must vanish
+                long long head = 0, total = 0;
+                if (!dense) {
+                    if (n_term == 0) {
+                        for (uint32_t r = 0; r < n_nl; r++) {
+                            const uint32_t role = (c0 + r) & 3, p = S->nlp[r];
+                            const long long pp = (long long)(g0 + p);
+                            total += (role == 0 || role == 3) ? -pp : pp;
+                            const uint32_t f = check_newline(tile, p, role, avail);
+                            if (f) fb = f;
+                        }
+                    } else {
+                        for (uint32_t r = 0; r <= r3; r++) {
+                            const uint32_t role = (c0 + r) & 3, p = S->nlp[r];
+                            const long long pp = (long long)(g0 + p);
+                            head += (role == 0 || role == 3) ? -pp : pp;
+                            const uint32_t f = check_newline(tile, p, role, avail);
+                            if (f) fb = f;
+                        }
+                        total = head;
+                        for (uint32_t r = r3 + 4u * (n_term - 1) + 1u; r < n_nl; r++) {
+                            const uint32_t role = (c0 + r) & 3, p = S->nlp[r];
+                            const long long pp = (long long)(g0 + p);
+                            total += (role == 0 || role == 3) ? -pp : pp;
+                            const uint32_t f = check_newline(tile, p, role, avail);
+                            if (f) fb = f;
+                        }
+                    }
+                }
+                P.sum_total[t] = total;
+                P.sum_head[t] = head;
+                P.has_term[t] = n_term > 0 ? 1 : 0;
+                P.nl_count[t] = n_nl;
+                P.phase_used[t] = (uint8_t)c0;
+                // end-of-file condition of canonical input (the line count is checked by the follow-up kernel)
+                if (P.is_last && t + 1 == P.n_tiles && tile[tile_len - 1] != '\n') set_fallback(P.res, 9);
+            }
+            if (!early && warp == NW - 1) {
+                // (rare) the last warp had records of its own: head items and look-back only now
+                const uint32_t nph = t == 0 ? 0u : (head_len + PIECE - 1) / PIECE;
+                if (nph) {
+                    uint32_t slot = 0;
+                    if (lane == 0) slot = atomicAdd(&S->n_items, nph);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if ((uint32_t)lane < nph && slot + lane < (uint32_t)IMAX) {
+                        const uint32_t o = (uint32_t)lane * PIECE;
+                        Item itm;
+                        itm.src = (uint16_t)o;
+                        itm.len = (uint16_t)(head_len - o < (uint32_t)PIECE ? head_len - o : (uint32_t)PIECE);
+                        itm.rel = TAG_HEAD | o;
+                        S->items[slot + lane] = itm;
+                    }
+                }
+                uint64_t kept_before;
+                uint32_t carry;
+#ifdef SGPU_ABL_NOLB
+                kept_before = g0 / 2;
+                carry = F_OTHER;
+#else
+                lookback_pred_warp(P.desc2, t, lane, &kept_before, &carry);
+#endif
+                if (lane == 0) {
+                    TRACE(t, 3);
+                    st_relaxed(P.desc2 + t * DSTRIDE, inc_desc(n_starts > 0, n_starts ? S->last_flag : F_OTHER, head_len,
+                                                     rest_total, kept_before, carry));
+                    S->kept_before = kept_before;
+                    S->carry = carry;
+                }
+            }
         }
+        if (fb) set_fallback(P.res, (int)fb);
         PHASE_MARK(7);    // emit
         __syncthreads();  // B5: kept_before / carry / every copy item are there
         PHASE_MARK(8);    // B5 wait (look-back)
@@ -973,9 +1021,11 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                     else if (carry == F_OTHER && base_o) dst = base_o + rel;
                     else continue;
                 }
+#ifndef SGPU_ABL_NOCOPY  // ablation (timing only): nothing is written
                 copy_piece(tile_s + itm.src, itm.len, dst, lane);
+#endif
             }
-            if (t + 1 == P.n_tiles && tid == 0) P.res->kept_total = kept_before + head_kept + rest_total;
+            if (t + 1 == P.n_tiles && tid == 0) P.res->kept_total = kept_before + head_kept + S->rest_total;
         }
         PHASE_MARK(9);  // copy own work
         if (tid == 0) {
@@ -984,7 +1034,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
         }
         if (tid == 0) S->next_tile = nt;
         __syncthreads();  // B6: every read of the tile buffer and the lists is done
-        PHASE_MARK(10);  // ticket + B6 wait
+        PHASE_MARK(10);   // ticket + B6 wait
         const uint64_t next_t = S->next_tile;
         if (tid == 0 && next_t < P.n_tiles) issue_load(P, S, next_t);
         t = next_t;
@@ -1039,13 +1089,13 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     DevBuf<uint32_t> nl_count;
     DevBuf<uint8_t> bytes;
     DevBuf<FusedResult> res;
-    SGPU_TRY(desc.alloc(2 * n_tiles, st));
+    SGPU_TRY(desc.alloc((1 + DSTRIDE) * n_tiles, st));
     SGPU_TRY(sums.alloc(2 * n_tiles, st));
     SGPU_TRY(prefix.alloc(2 * n_tiles, st));
     SGPU_TRY(nl_count.alloc(n_tiles, st));
     SGPU_TRY(bytes.alloc(2 * n_tiles, st));
     SGPU_TRY(res.alloc(1, st));
-    SGPU_CUDA(cudaMemsetAsync(desc.p, 0, 2 * n_tiles * 8, st));
+    SGPU_CUDA(cudaMemsetAsync(desc.p, 0, (1 + DSTRIDE) * n_tiles * 8, st));
     FusedResult init;
     memset(&init, 0, sizeof(init));
     init.owned_end = ~0ull;
