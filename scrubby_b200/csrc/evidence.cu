@@ -43,8 +43,14 @@ __device__ __forceinline__ bool line_span(const LineParams &P, uint64_t i, uint6
 // BufRead::lines: validates UTF-8 (InvalidData otherwise) and strips "\n" / "\r\n"
 __device__ __forceinline__ bool line_content(const LineParams &P, uint64_t i, uint64_t s, uint64_t *e, bool *high) {
     const uint8_t *in = P.in;
-    bool h = false;
-    for (uint64_t k = s; k < *e; k++) h |= in[k] >= 0x80;
+    // any byte with its high bit set?  (bytes up to a 4-byte boundary, aligned words, tail bytes)
+    uint32_t acc = 0;
+    uint64_t k = s;
+    const uint64_t end = *e;
+    while (k < end && ((uintptr_t)(in + k) & 3)) acc |= in[k++];
+    for (; k + 4 <= end; k += 4) acc |= *reinterpret_cast<const uint32_t *>(in + k);
+    while (k < end) acc |= in[k++];
+    const bool h = (acc & 0x80808080u) != 0;
     *high = h;
     if (h && !utf8_valid(in + s, *e - s)) return false;
     if (i < P.n_nl && *e > s && in[*e - 1] == '\r') (*e)--;

@@ -49,7 +49,7 @@
 namespace sgpu {
 
 #ifndef SGPU_FUSED_CTAS
-#define SGPU_FUSED_CTAS 4
+#define SGPU_FUSED_CTAS 5
 #endif
 #ifndef SGPU_FUSED_PIECE
 #define SGPU_FUSED_PIECE 1024
@@ -60,7 +60,10 @@ namespace sgpu {
 constexpr int NT = 256;                 // threads per CTA
 constexpr int NW = NT / 32;             // warps per CTA
 constexpr int NTHREADS = NT;
-constexpr int FC = 8;                   // 16-byte chunks per thread
+#ifndef SGPU_FUSED_FC
+#define SGPU_FUSED_FC 8
+#endif
+constexpr int FC = SGPU_FUSED_FC;       // 16-byte chunks per thread
 constexpr int TILE = NT * FC * 16;      // 32 KiB
 constexpr int PRE = 16;                 // pre-halo (previous 16 bytes)
 constexpr int HALO = SGPU_FUSED_HALO;   // post-halo: id token of the last record start, "+\n" after the last newline

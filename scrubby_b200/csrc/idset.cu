@@ -34,14 +34,23 @@ __global__ void idset_measure_kernel(const uint32_t *len, const uint8_t *sel, si
         if (s && L > IDSET_MAX_KEY) st->too_long = 1;
         if (s && L == 0) st->has_empty = 1;
     }
+    // one pair of atomics per block (all blocks add to the same two words)
+    __shared__ unsigned long long s_cnt, s_lb;
+    if (threadIdx.x == 0) s_cnt = s_lb = 0;
+    __syncthreads();
     unsigned long long cnt = s ? 1 : 0, lb = l;
     for (int d = 16; d; d >>= 1) {
         cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         lb += __shfl_xor_sync(0xffffffffu, lb, d);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (cnt) atomicAdd(&st->n_sel, cnt);
-        if (lb) atomicAdd(&st->long_bytes, lb);
+        if (cnt) atomicAdd(&s_cnt, cnt);
+        if (lb) atomicAdd(&s_lb, lb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt) atomicAdd(&st->n_sel, s_cnt);
+        if (s_lb) atomicAdd(&st->long_bytes, s_lb);
     }
 }
 
@@ -71,14 +80,22 @@ __global__ void idset_insert_kernel(Slot *table, uint64_t mask, const uint8_t *a
             if (!is_inline) hi = ((arena_base + arena_off[i]) << 24) | L;
             unsigned __int128 mine = pack128(lo, hi);
             uint64_t idx = home_slot(home, mask);
+            // Read first (an L2 load brings the 64-byte bucket in from DRAM without occupying the L2 atomic
+            // unit for the whole miss), walk occupied slots without atomics, and issue the 128-bit CAS only
+            // on a slot that was seen empty.
             while (true) {
-                unsigned __int128 old =
-                    atomicCAS(reinterpret_cast<unsigned __int128 *>(table + idx), (unsigned __int128)0, mine);
-                if (old == 0) {
-                    fresh = true;
-                    break;
+                const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2 *>(table + idx));
+                uint64_t olo = cur.x, ohi = cur.y;
+                if ((olo | ohi) == 0) {
+                    unsigned __int128 old =
+                        atomicCAS(reinterpret_cast<unsigned __int128 *>(table + idx), (unsigned __int128)0, mine);
+                    if (old == 0) {
+                        fresh = true;
+                        break;
+                    }
+                    olo = (uint64_t)old;
+                    ohi = (uint64_t)(old >> 64);
                 }
-                uint64_t olo = (uint64_t)old, ohi = (uint64_t)(old >> 64);
                 if (olo == lo) {
                     if (is_inline) {
                         if (ohi == hi) break;  // duplicate
@@ -90,8 +107,13 @@ __global__ void idset_insert_kernel(Slot *table, uint64_t mask, const uint8_t *a
             }
         }
     }
+    __shared__ unsigned int s_fresh;
+    if (threadIdx.x == 0) s_fresh = 0;
+    __syncthreads();
     unsigned b = __ballot_sync(0xffffffffu, fresh);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&st->inserted, (unsigned long long)__popc(b));
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_fresh, (unsigned)__popc(b));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_fresh) atomicAdd(&st->inserted, (unsigned long long)s_fresh);
 }
 
 __global__ void idset_rehash_kernel(const Slot *old_table, uint64_t old_cap, Slot *table, uint64_t mask) {
