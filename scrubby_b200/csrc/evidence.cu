@@ -245,6 +245,345 @@ __global__ void __launch_bounds__(128)
     sel[i] = ok;
 }
 
+// ------------------------------------------------------------------ tile kernel for order-free evidence
+// Kraken2 / Metabuli per-read lines and TXT id lists do not need a global line index: a line is decided on
+// its own and the set does not care about insertion order.  One CTA per 16 KiB tile: 16-byte loads -> '\n'
+// masks -> the tile's newline positions in shared memory -> one thread per line that STARTS in the tile
+// (it reads on past the tile's end if the line does) -> selected (offset, length) spans compacted into a
+// candidate list with one global atomic per CTA.  Replaces nl_count + scan + nl_emit + reads_parse_kernel /
+// txt_lines_kernel (same per-line semantics); PAF keeps the indexed path (its segmented OR needs line order).
+constexpr int LT_NT = 256, LT_FC = 4, LT_TILE = LT_NT * LT_FC * 16, LT_LMAX = 1024, LT_HALO = 1024, LT_SMAX = 5120;
+
+struct TileOut {
+    uint64_t *cand_off;
+    uint32_t *cand_len;
+    uint64_t cap;
+    unsigned long long *n_cand;   // candidates found (may exceed cap: the caller retries with more room)
+    unsigned long long *err_word; // (line start offset << 8) | code, smallest wins
+    unsigned long long *dense;    // a tile with more than LT_LMAX lines: use the indexed path
+};
+
+// one line [s, e_raw) of the buffer (e_raw = position of its '\n', or n for an unterminated last line):
+// returns 1 and the key span if the line offers a key, 0 if not, and reports errors.
+// One pass over the line's aligned 4-byte words finds the high-bit bytes (UTF-8 screening) and the tabs.
+__device__ __forceinline__ int evidence_line(const uint8_t *in, uint64_t s, uint64_t e_raw, bool has_nl, int mode,
+                                             const TaxSet &T, int need_fields, uint64_t *koff, uint32_t *klen,
+                                             unsigned long long *err_word, uint64_t err_base) {
+    uint64_t e = e_raw;
+    uint32_t acc = 0;
+    int f = 0;  // fields closed so far
+    uint64_t fs = s, f1s = 0, f1e = 0, f2s = 0, f2e = 0;
+    {
+        const uintptr_t base = (uintptr_t)in;
+        uint64_t w0 = (base + s) & ~(uintptr_t)3;         // address of the first word
+        const uint64_t w1 = (base + e + 3) & ~(uintptr_t)3;  // one past the last word
+        for (uint64_t a = w0; a < w1; a += 4) {
+            uint32_t w = *reinterpret_cast<const uint32_t *>(a);
+            // bytes outside [s, e) read as zero (neither tab nor high)
+            const int64_t lo = (int64_t)(base + s) - (int64_t)a, hi = (int64_t)(base + e) - (int64_t)a;
+            if (lo > 0) w &= 0xFFFFFFFFu << (8 * lo);
+            if (hi < 4) w &= hi <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - hi)));
+            acc |= w;
+            if (mode == 0 && f < need_fields) {
+                uint32_t t = eq_mask4(w, 0x09090909u);
+                while (t) {
+                    const uint64_t pos = (a - base) + (uint64_t)(__ffs(t) - 1);
+                    t &= t - 1;
+                    if (f == 1) { f1s = fs; f1e = pos; }
+                    if (f == 2) { f2s = fs; f2e = pos; }
+                    f++;
+                    fs = pos + 1;
+                    if (f >= need_fields) break;
+                }
+            }
+        }
+    }
+    // BufRead::lines: UTF-8 check, strip "\n" / "\r\n"
+    const bool high = (acc & 0x80808080u) != 0;
+    if (high && !utf8_valid(in + s, e - s)) {
+        report_error(err_word, err_base + s, SGPU_ERR_IO);
+        return 0;
+    }
+    if (has_nl && e > s && in[e - 1] == '\r') e--;
+    if (mode == 1) {  // TXT: the line is the id, verbatim (alignment.rs:72-75)
+        *koff = s;
+        *klen = (uint32_t)(e - s);
+        return 1;
+    }
+    if (f < need_fields) {  // the end of the line closes the last field (a stripped '\r' is not part of it)
+        if (f == 1) { f1s = fs; f1e = e; }
+        if (f == 2) { f2s = fs; f2e = e; }
+        f++;
+    }
+    if (f < need_fields) {
+        report_error(err_word, err_base + s, SGPU_ERR_WOULD_PANIC);  // classifier.rs:412-415 / :508-513
+        return 0;
+    }
+    // a field that ended at the raw end of a "\r\n" line: the '\r' was stripped by lines()
+    if (f1e > e) f1e = e;
+    if (f2e > e) f2e = e;
+    // str::trim (Unicode White_Space) on read id and taxid
+    if (high) {
+        size_t b, t;
+        utf8_trim(in + f1s, f1e - f1s, &b, &t);
+        f1e = f1s + t;
+        f1s += b;
+        utf8_trim(in + f2s, f2e - f2s, &b, &t);
+        f2e = f2s + t;
+        f2s += b;
+    } else {
+        while (f1s < f1e && is_ws_ascii(in[f1s])) f1s++;
+        while (f1e > f1s && is_ws_ascii(in[f1e - 1])) f1e--;
+        while (f2s < f2e && is_ws_ascii(in[f2s])) f2s++;
+        while (f2e > f2s && is_ws_ascii(in[f2e - 1])) f2e--;
+    }
+    if (!taxid_member(T, in + f2s, (uint32_t)(f2e - f2s))) return 0;
+    *koff = f1s;
+    *klen = (uint32_t)(f1e - f1s);
+    return 1;
+}
+
+// 16-bit masks of the '\n' and '\t' bytes of a 16-byte chunk
+__device__ __forceinline__ void sep_masks16(uint4 v, bool want_tabs, uint32_t *m_nl, uint32_t *m_tab) {
+    *m_nl = nl_mask16(v);
+    const uint32_t c = 0x09090909u;
+    *m_tab = want_tabs ? (eq_mask4(v.x, c) | (eq_mask4(v.y, c) << 4) | (eq_mask4(v.z, c) << 8) | (eq_mask4(v.w, c) << 12))
+                       : 0u;
+}
+
+// The tile kernel proper.  P1 turns every 16-byte chunk of the tile (+ halo) into '\n' / '\t' masks and
+// scatters the separator positions, in order, into one list (bit 15 = newline) plus the list index of every
+// newline; a line's fields are then consecutive list entries -- no per-line scanning.  Tiles with a
+// non-ASCII byte and lines that run past the halo take the scanning routine (evidence_line) instead.
+__global__ void __launch_bounds__(LT_NT)
+    lines_tile_kernel(const uint8_t *in, uint64_t n, TaxSet T, int need_fields, int mode, TileOut O) {
+    constexpr int NWARP = LT_NT / 32;
+    constexpr int ROWS = LT_FC + 1;  // LT_FC rounds over the tile + one over the halo (warps 0 and 1)
+    __shared__ __align__(16) uint8_t tile[LT_TILE + LT_HALO];
+    __shared__ uint16_t seps[LT_SMAX];   // separator positions (tile offsets), bit 15: it is a newline
+    __shared__ uint16_t nl_idx[LT_LMAX]; // list index of the i-th newline
+    __shared__ uint32_t warp_tot[NWARP], warp_cand[NWARP], halo_tot[2];
+    __shared__ unsigned long long cand_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t g0 = (uint64_t)blockIdx.x * LT_TILE;
+    const uint32_t tile_len = (uint32_t)((n - g0) < (uint64_t)LT_TILE ? (n - g0) : (uint64_t)LT_TILE);
+    // bytes of the halo that exist (whole 16-byte chunks only)
+    const uint32_t halo_len =
+        tile_len < (uint32_t)LT_TILE ? 0u
+                                     : (uint32_t)(((n - g0 - LT_TILE) < (uint64_t)LT_HALO ? (n - g0 - LT_TILE) : (uint64_t)LT_HALO) & ~15ull);
+    const bool want_tabs = mode == 0;
+    // ---- P1: masks.  Warp w owns tile chunks [w*128, w*128+128): lane l takes chunk k*32 + l in round k;
+    //      round LT_FC is the halo (64 chunks: warps 0 and 1)
+    uint32_t mn[ROWS], mt[ROWS];
+    uint32_t hi_or = 0;
+    uint64_t pk = 0;  // per round: separators (low 8 bits... 6 used) | newlines << 8, 16 bits per round
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+        uint32_t pos, limit;
+        bool mine;
+        if (k < LT_FC) {
+            pos = ((uint32_t)warp * (LT_FC * 32) + (uint32_t)lane + k * 32) * 16;
+            limit = tile_len;
+            mine = true;
+        } else {
+            pos = (uint32_t)LT_TILE + ((uint32_t)warp * 32 + (uint32_t)lane) * 16;
+            limit = (uint32_t)LT_TILE + halo_len;
+            mine = warp < 2;
+        }
+        uint32_t a = 0, b = 0;
+        if (mine && pos + 16 <= limit) {
+            const uint4 v = ld_nc_u4(in + g0 + pos);
+            *reinterpret_cast<uint4 *>(tile + pos) = v;
+            sep_masks16(v, want_tabs, &a, &b);
+            hi_or |= v.x | v.y | v.z | v.w;
+        } else if (mine && pos < limit) {  // the buffer's last, partial chunk
+            for (uint32_t q = 0; pos + q < limit; q++) {
+                const uint8_t ch = in[g0 + pos + q];
+                tile[pos + q] = ch;
+                a |= (ch == '\n' ? 1u : 0u) << q;
+                b |= (want_tabs && ch == '\t' ? 1u : 0u) << q;
+                hi_or |= ch;
+            }
+        }
+        mn[k] = a;
+        mt[k] = b;
+        if (k < LT_FC) pk |= ((uint64_t)__popc(a | b) | ((uint64_t)__popc(a) << 8)) << (16 * k);
+    }
+    const bool high_w = __any_sync(0xffffffffu, (hi_or & 0x80808080u) != 0);
+    // ---- ranks: inclusive warp scan of the packed per-round counts (a round of 32 chunks has <= 512
+    //      separators: the 8-bit fields may carry into each other, so scan the two kinds separately)
+    uint64_t pk_s = 0, pk_n = 0;
+#pragma unroll
+    for (int k = 0; k < LT_FC; k++) {
+        pk_s |= (uint64_t)__popc(mn[k] | mt[k]) << (16 * k);
+        pk_n |= (uint64_t)__popc(mn[k]) << (16 * k);
+    }
+    (void)pk;
+    uint64_t inc_s = pk_s, inc_n = pk_n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t x = __shfl_up_sync(0xffffffffu, inc_s, d), y = __shfl_up_sync(0xffffffffu, inc_n, d);
+        if (lane >= d) {
+            inc_s += x;
+            inc_n += y;
+        }
+    }
+    const uint64_t rt_s = __shfl_sync(0xffffffffu, inc_s, 31), rt_n = __shfl_sync(0xffffffffu, inc_n, 31);
+    const uint64_t ex_s = inc_s - pk_s, ex_n = inc_n - pk_n;
+    uint32_t base_s[LT_FC], base_n[LT_FC], wtot_s = 0, wtot_n = 0;
+#pragma unroll
+    for (int k = 0; k < LT_FC; k++) {
+        base_s[k] = wtot_s + (uint32_t)((ex_s >> (16 * k)) & 0xFFFF);
+        base_n[k] = wtot_n + (uint32_t)((ex_n >> (16 * k)) & 0xFFFF);
+        wtot_s += (uint32_t)((rt_s >> (16 * k)) & 0xFFFF);
+        wtot_n += (uint32_t)((rt_n >> (16 * k)) & 0xFFFF);
+    }
+    // the halo round (warps 0, 1): ranks within the halo
+    uint32_t h_s = 0, h_ex = 0;
+    {
+        const uint32_t c = (uint32_t)__popc(mn[LT_FC] | mt[LT_FC]);
+        uint32_t ic = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, ic, d);
+            if (lane >= d) ic += x;
+        }
+        h_ex = ic - c;
+        h_s = __shfl_sync(0xffffffffu, ic, 31);
+    }
+    if (lane == 0) {
+        warp_tot[warp] = wtot_s | (wtot_n << 16) | (high_w ? 0x80000000u : 0u);
+        if (warp < 2) halo_tot[warp] = h_s;
+    }
+    __syncthreads();
+    uint32_t n_sep = 0, n_nl = 0, wb_s = 0, wb_n = 0, high_seen = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; w++) {
+        const uint32_t x = warp_tot[w];
+        if (w == warp) {
+            wb_s = n_sep;
+            wb_n = n_nl;
+        }
+        n_sep += x & 0xFFFF;
+        n_nl += (x >> 16) & 0x7FFF;
+        high_seen |= x >> 31;
+    }
+    const uint32_t n_halo = halo_tot[0] + halo_tot[1];
+    if (n_sep + n_halo > (uint32_t)LT_SMAX || n_nl > (uint32_t)LT_LMAX) {  // (uniform) pathological density
+        if (tid == 0) atomicExch(O.dense, 1ull);
+        return;
+    }
+    // ---- scatter, in order
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+        uint32_t mm = mn[k] | mt[k];
+        if (mm == 0) continue;
+        uint32_t pos, r, rn = 0;
+        if (k < LT_FC) {
+            pos = ((uint32_t)warp * (LT_FC * 32) + (uint32_t)lane + k * 32) * 16;
+            r = wb_s + base_s[k];
+            rn = wb_n + base_n[k];
+        } else {
+            pos = (uint32_t)LT_TILE + ((uint32_t)warp * 32 + (uint32_t)lane) * 16;
+            r = n_sep + (warp == 1 ? halo_tot[0] : 0u) + h_ex;
+        }
+        while (mm) {
+            const uint32_t bit = (uint32_t)(__ffs(mm) - 1);
+            mm &= mm - 1;
+            const bool is_nl = (mn[k] >> bit) & 1u;
+            seps[r] = (uint16_t)((pos + bit) | (is_nl ? 0x8000u : 0u));
+            if (is_nl && k < LT_FC) nl_idx[rn++] = (uint16_t)r;
+            r++;
+        }
+    }
+    __syncthreads();
+    const uint32_t n_all = n_sep + n_halo;  // list entries (the halo's come last)
+    const bool high = high_seen != 0;
+    // ---- one thread per line that starts in the tile
+    const bool first_ok = g0 == 0 || in[g0 - 1] == '\n';  // the tile's first byte starts a line
+    const uint32_t n_lines = n_nl + (first_ok ? 1u : 0u);  // candidates (the last may start at tile_len: skipped)
+    for (uint32_t qb = 0; qb < n_lines; qb += LT_NT) {  // (uniform trip count)
+        const uint32_t q = qb + (uint32_t)tid;
+        int sel = 0;
+        uint64_t koff = 0;
+        uint32_t klen = 0;
+        if (q < n_lines) {
+            const int pi = (int)q - (first_ok ? 1 : 0);  // which newline precedes the line, -1: it starts the tile
+            const int i0 = pi >= 0 ? (int)nl_idx[pi] : -1;  // its list index
+            const uint32_t s = pi >= 0 ? ((uint32_t)seps[i0] & 0x7FFFu) + 1u : 0u;
+            if (s < tile_len) {
+                // the line's own newline: the next newline entry of the list
+                bool fast = !high;
+                uint32_t e_nl = 0;  // tile offset of the line's '\n'
+                if (mode == 1) {
+                    // TXT: the next list entry is the line's newline
+                    if ((uint32_t)(i0 + 1) < n_all) e_nl = (uint32_t)seps[i0 + 1] & 0x7FFFu;
+                    else fast = false;
+                    if (fast) {
+                        uint32_t e = e_nl;
+                        if (e > s && tile[e - 1] == '\r') e--;
+                        koff = g0 + s;
+                        klen = e - s;
+                        sel = 1;
+                    }
+                } else if (fast) {
+                    // fields 1 and 2 end at tabs 2 and 3; the line must have need_fields - 1 tabs
+                    const uint32_t need_tabs = (uint32_t)need_fields - 1u;
+                    if ((uint32_t)i0 + need_tabs < n_all) {
+                        uint32_t any_nl = 0;
+                        for (uint32_t x = 1; x <= need_tabs; x++) any_nl |= seps[i0 + x];
+                        if (any_nl & 0x8000u) {
+                            report_error(O.err_word, g0 + s, SGPU_ERR_WOULD_PANIC);  // classifier.rs:412-415 / :508-513
+                        } else {
+                            uint32_t f1s = ((uint32_t)seps[i0 + 1]) + 1u, f1e = seps[i0 + 2];
+                            uint32_t f2s = f1e + 1u, f2e = seps[i0 + 3];
+                            // str::trim on read id and taxid (ASCII tile)
+                            while (f1s < f1e && is_ws_ascii(tile[f1s])) f1s++;
+                            while (f1e > f1s && is_ws_ascii(tile[f1e - 1])) f1e--;
+                            while (f2s < f2e && is_ws_ascii(tile[f2s])) f2s++;
+                            while (f2e > f2s && is_ws_ascii(tile[f2e - 1])) f2e--;
+                            if (taxid_member(T, tile + f2s, f2e - f2s)) {
+                                sel = 1;
+                                koff = g0 + f1s;
+                                klen = f1e - f1s;
+                            }
+                        }
+                    } else {
+                        fast = false;  // the list ends inside the line: it runs past the halo (or the buffer ends)
+                    }
+                }
+                if (!fast) {
+                    // scanning routine over the buffer: non-ASCII tile, or a line that leaves the halo
+                    uint64_t e = g0 + s;
+                    while (e < n && in[e] != '\n') e++;
+                    sel = evidence_line(in, g0 + s, e, e < n, mode, T, need_fields, &koff, &klen, O.err_word, 0);
+                }
+            }
+        }
+        // ---- compaction: order does not matter, one global atomic per CTA and round
+        const unsigned b = __ballot_sync(0xffffffffu, sel != 0);
+        if (lane == 0) warp_cand[warp] = (uint32_t)__popc(b);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) {
+            const uint32_t x = warp_cand[w];
+            if (w < warp) before += x;
+            total += x;
+        }
+        if (tid == 0 && total) cand_base = atomicAdd(O.n_cand, (unsigned long long)total);
+        __syncthreads();
+        if (sel) {
+            const uint64_t slot = cand_base + before + (uint32_t)__popc(b & ((1u << lane) - 1u));
+            if (slot < O.cap) {
+                O.cand_off[slot] = koff;
+                O.cand_len[slot] = klen;
+            }
+        }
+        __syncthreads();  // cand_base / warp_cand are reused
+    }
+}
+
 enum EvidenceKind { EV_PAF, EV_TXT, EV_READS };
 
 static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t *d_buf, size_t n, PafParams F,
@@ -257,7 +596,52 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
         return SGPU_OK;
     }
     sgpu_status rc = SGPU_OK;
-    do {
+    bool done = false;
+    if (kind != EV_PAF && ((uintptr_t)d_buf & 15) == 0) {
+        // ---- order-free evidence: the tile kernel, no newline index
+        do {
+            DevBuf<uint64_t> cand_off, ctr;
+            DevBuf<uint32_t> cand_len;
+            uint64_t cap = n / 32 + 4096;
+            const TaxSet none{nullptr, 0, nullptr, nullptr, 0};
+            for (int attempt = 0; attempt < 2 && rc == SGPU_OK; attempt++) {
+                if ((rc = cand_off.alloc(cap, st)) != SGPU_OK) break;
+                if ((rc = cand_len.alloc(cap, st)) != SGPU_OK) break;
+                if ((rc = ctr.alloc(3, st)) != SGPU_OK) break;
+                const uint64_t init[3] = {0, ~0ull, 0};
+                memcpy(c->h_pinned + 40, init, sizeof(init));
+                cudaMemcpyAsync(ctr.p, c->h_pinned + 40, sizeof(init), cudaMemcpyHostToDevice, st);
+                TileOut O{cand_off.p, cand_len.p, cap, (unsigned long long *)ctr.p, (unsigned long long *)ctr.p + 1,
+                          (unsigned long long *)ctr.p + 2};
+                lines_tile_kernel<<<(unsigned)ceil_div(n, (size_t)LT_TILE), LT_NT, 0, st>>>(
+                    d_buf, (uint64_t)n, T ? *T : none, need_fields, kind == EV_TXT ? 1 : 0, O);
+                SGPU_LAUNCH(c);
+                uint64_t h[3];
+                if ((rc = read_u64s(c, ctr.p, h, 3)) != SGPU_OK) break;
+                if (h[2]) break;  // pathological line density: the indexed path below
+                if (h[1] != ~0ull) {
+                    rc = (sgpu_status)(h[1] & 0xFF);
+                    if (err_line) {  // the line number of the offending line = newlines before its start
+                        uint64_t off = h[1] >> 8, before = 0;
+                        // count over the 16-byte aligned prefix, the remaining bytes on the host side are
+                        // not available: count_newlines handles any length
+                        if (off && count_newlines(c, d_buf, (size_t)off, &before) != SGPU_OK) before = 0;
+                        *err_line = before;
+                    }
+                    done = true;
+                    break;
+                }
+                if (h[0] > cap) {  // more candidates than room: once more with the exact count
+                    cap = h[0];
+                    continue;
+                }
+                if (h[0]) rc = idset_insert_spans(c, set, d_buf, cand_off.p, cand_len.p, nullptr, (size_t)h[0]);
+                done = true;
+                break;
+            }
+        } while (0);
+    }
+    if (!done && rc == SGPU_OK) do {
         DevBuf<uint64_t> nlpos, key_off, errw;
         DevBuf<uint32_t> key_len;
         DevBuf<uint8_t> sel, pass, head;

@@ -482,3 +482,97 @@ def test_sharded_long_reads_fused(ctx):
     assert b"".join(outs) == o.written
     assert b"".join(others) == o.other
     assert (rin, rout) == (o.reads_in, o.reads_out)
+
+
+# ---------------------------------------------------------------------------- evidence tile kernel
+def _reads_vs_oracle(ctx, buf: bytes, style: int, taxids):
+    ot = orc.OSet.from_ids([t if isinstance(t, bytes) else t.encode() for t in taxids])
+    try:
+        o = orc.set_from_reads(buf, style, ot)
+        oerr = None
+    except orc.OracleError as e:
+        o, oerr = None, (e.code, e.index)
+    try:
+        g = api.IdSet.from_reads(ctx, buf, style, taxids)
+        gerr = None
+    except api.ScrubbyGpuError as e:
+        g, gerr = None, (e.status, e.index)
+    assert gerr == oerr, (gerr, oerr)
+    if o is not None:
+        assert g.sorted_ids() == o.sorted_ids()
+
+
+def _txt_vs_oracle(ctx, buf: bytes):
+    try:
+        o = orc.set_from_txt(buf)
+        oerr = None
+    except orc.OracleError as e:
+        o, oerr = None, (e.code, e.index)
+    try:
+        g = api.IdSet.from_txt(ctx, buf)
+        gerr = None
+    except api.ScrubbyGpuError as e:
+        g, gerr = None, (e.status, e.index)
+    assert gerr == oerr, (gerr, oerr)
+    if o is not None:
+        assert g.sorted_ids() == o.sorted_ids()
+        assert len(g) == len(o)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_reads_tile_kernel_edge_cases(ctx, seed):
+    """Kraken2 / Metabuli lines across tile (16 KiB) and halo (1 KiB) edges, CRLF, whitespace to trim, non-ASCII
+    lines, very long lines, a missing final newline -- all against the oracle."""
+    rng = random.Random(1000 + seed)
+    taxids = ["9606", "7711", "0", "123456", "x9"]
+    style = seed & 1
+    lines = []
+    for i in range(3000):
+        tid = rng.choice(["9606", "562", "7711", " 9606", "9606 ", "09606", "+9606", "0", "123456", "x9", ""])
+        rid = rng.choice([f"r{i}", f" r{i} ", f"r{i}/1", f"read.{i}.{'x' * rng.randint(0, 40)}", f"ré{i}", f"r{i} "])
+        kmer = " ".join(f"{rng.randint(0, 9999)}:{rng.randint(1, 30)}" for _ in range(rng.choice([0, 1, 3, 8, 40, 400])))
+        if style == 0:
+            f = ["C", rid, tid, "150|150", kmer]
+        else:
+            f = ["1", rid, tid, "100", "80.5", "genus", kmer]
+        if rng.random() < 0.05:
+            f += ["extra", "fields"]
+        eol = "\r\n" if rng.random() < 0.1 else "\n"
+        lines.append("\t".join(f) + eol)
+    body = "".join(lines)
+    for tail in ("", "C\tlast\t9606\t1\tx" if style == 0 else "1\tlast\t9606\t1\t2\tg\tx"):
+        _reads_vs_oracle(ctx, (body + tail).encode(), style, taxids)
+    # a line longer than tile + halo, and tiles without any newline
+    long_line = ("C\tlong\t9606\t1\t" if style == 0 else "1\tlong\t9606\t1\t2\tg\t") + "k" * 50000 + "\n"
+    _reads_vs_oracle(ctx, (body + long_line + body).encode(), style, taxids)
+
+
+def test_reads_tile_kernel_errors(ctx):
+    """too few fields (the reference panics) and invalid UTF-8 report the reference's error class and line"""
+    good = "".join(f"C\tr{i}\t9606\t150\tk\n" for i in range(2000))
+    for bad, at in (("C\tr\t9606\t150\n", 700), ("\n", 1500), ("C\tr\n", 0), ("only one field", 2000)):
+        ls = good.splitlines(keepends=True)
+        ls.insert(at, bad)
+        _reads_vs_oracle(ctx, "".join(ls).encode(), 0, ["9606"])
+    raw = bytearray(good.encode())
+    raw[30000] = 0xFF  # invalid UTF-8 in some line
+    _reads_vs_oracle(ctx, bytes(raw), 0, ["9606"])
+    two = good.splitlines(keepends=True)
+    two.insert(100, "C\tr\n")
+    two.insert(1900, "x\n")
+    _reads_vs_oracle(ctx, "".join(two).encode(), 0, ["9606"])  # the first error wins
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_txt_tile_kernel_edge_cases(ctx, seed):
+    rng = random.Random(2000 + seed)
+    lines = []
+    for i in range(5000):
+        lines.append(rng.choice([f"id{i}", f"id{i} ", "", f"id{i % 50}", "x" * rng.randint(1, 60), f"é{i}",
+                                 "y" * rng.choice([15, 16, 17, 300, 5000])]) + rng.choice(["\n", "\n", "\r\n"]))
+    body = "".join(lines)
+    _txt_vs_oracle(ctx, body.encode())
+    _txt_vs_oracle(ctx, (body + "last-without-newline").encode())
+    _txt_vs_oracle(ctx, (body + "z" * 40000 + "\n" + body).encode())
+    _txt_vs_oracle(ctx, b"\n")
+    _txt_vs_oracle(ctx, b"a")
