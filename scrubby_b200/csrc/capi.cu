@@ -134,6 +134,8 @@ void ctx_release(sgpu_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &e : c->prof_events) {
         cudaEventDestroy(e.first);
@@ -285,6 +287,11 @@ sgpu_status sgpu_clean_fastq_dev(sgpu_ctx *c, const sgpu_idset *set, const uint8
     return clean_dev_locked(c, set, d_in, n_in, reverse, d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
 }
 
+static sgpu_status clean_shard_locked(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in,
+                                      size_t own_len, uint64_t newlines_before, int is_first, int is_last, int crlf,
+                                      int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o,
+                                      size_t cap_o, size_t *n_o, sgpu_counts *counts);
+
 sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in,
                                        size_t own_len, uint64_t newlines_before, int is_first, int is_last, int crlf,
                                        int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o,
@@ -295,6 +302,15 @@ sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *c, const sgpu_idset *set, const
     if (n_in && ((uintptr_t)d_in & 15)) return SGPU_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     SGPU_CUDA(cudaSetDevice(c->device));
+    return clean_shard_locked(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, crlf, reverse, d_out_w,
+                              cap_w, n_w, d_out_o, cap_o, n_o, counts);
+}
+
+// shard body shared by sgpu_clean_fastq_shard_dev and the pipelined host path (context locked, device set)
+static sgpu_status clean_shard_locked(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in,
+                                      size_t own_len, uint64_t newlines_before, int is_first, int is_last, int crlf,
+                                      int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o,
+                                      size_t cap_o, size_t *n_o, sgpu_counts *counts) {
     memset(counts, 0, sizeof(*counts));
     *n_w = 0;
     if (n_o) *n_o = 0;
@@ -311,6 +327,133 @@ sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *c, const sgpu_idset *set, const
                          d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
 }
 
+// Host buffers, large input: the file goes through the GPU in chunks (shards of one device) so that the
+// host->device copy of chunk k+1.., the kernels of chunk k and the device->host copy of chunk k-1 overlap on
+// three streams -- the end-to-end time approaches the PCIe time of the larger direction instead of the sum.
+// Results are identical to the one-shot path (the same shard logic the multi-GPU driver uses: line phase
+// from the running newline count, the record that straddles a cut belongs to the chunk where it starts).
+// *done = 0: not applicable here (small input, halo too small for a record ...), take the one-shot path.
+static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *in, size_t n_in, int reverse,
+                                        uint8_t *out_w, size_t cap_w, size_t *n_w, uint8_t *out_o, size_t cap_o,
+                                        size_t *n_o, sgpu_counts *counts, int *done) {
+    *done = 0;
+    // (environment knobs so that tests can drive the chunk logic with small inputs)
+    const size_t CHUNK = getenv("SGPU_PIPE_CHUNK") ? (size_t)atoll(getenv("SGPU_PIPE_CHUNK")) & ~(size_t)15
+                                                   : (size_t)128 << 20;
+    const size_t HALO = getenv("SGPU_PIPE_HALO") ? (size_t)atoll(getenv("SGPU_PIPE_HALO")) : (size_t)8 << 20;
+    if (CHUNK < 4096 || n_in < 2 * CHUNK || c->mode != 0) return SGPU_OK;
+    if (in[0] != '@') return SGPU_OK;  // FASTA / unknown format: the one-shot path reports it
+    // needletail decides the line ending on the first record's first line
+    const uint8_t *nl = (const uint8_t *)memchr(in, '\n', n_in);
+    const int crlf = nl && nl > in && nl[-1] == '\r';
+    if (!c->s_in) {
+        SGPU_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        SGPU_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    }
+    cudaStream_t st = c->stream;
+    const size_t K = ceil_div(n_in, CHUNK);
+    const size_t obuf = CHUNK + HALO + 64;
+    DevBuf<uint8_t> d_in, d_w[2], d_o[2];
+    SGPU_TRY(d_in.alloc(n_in + 16, st));
+    for (int r = 0; r < 2; r++) {
+        SGPU_TRY(d_w[r].alloc(obuf, st));
+        if (out_o) SGPU_TRY(d_o[r].alloc(obuf, st));
+    }
+    SGPU_CUDA(cudaStreamSynchronize(st));  // the allocations are stream-ordered on `st`; the copy streams use them
+    std::vector<cudaEvent_t> ev_in(K);
+    cudaEvent_t ev_k[2], ev_out[2];
+    for (size_t k = 0; k < K; k++) SGPU_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+    for (int r = 0; r < 2; r++) {
+        SGPU_CUDA(cudaEventCreateWithFlags(&ev_k[r], cudaEventDisableTiming));
+        SGPU_CUDA(cudaEventCreateWithFlags(&ev_out[r], cudaEventDisableTiming));
+    }
+    auto upload = [&](size_t k) -> cudaError_t {
+        const size_t a = k * CHUNK, len = std::min(CHUNK, n_in - a);
+        cudaError_t e = cudaMemcpyAsync(d_in.p + a, in + a, len, cudaMemcpyHostToDevice, c->s_in);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(ev_in[k], c->s_in);
+    };
+    sgpu_status rc = SGPU_OK;
+    size_t off_w = 0, off_o = 0;
+    uint64_t newlines_before = 0;
+    bool bail = false;
+    sgpu_counts total;
+    memset(&total, 0, sizeof(total));
+    total.path = 1;
+    cudaError_t ce = cudaSuccess;
+    for (size_t k = 0; k < std::min<size_t>(K, 3) && ce == cudaSuccess; k++) ce = upload(k);
+    for (size_t k = 0; k < K && ce == cudaSuccess && rc == SGPU_OK && !bail; k++) {
+        if (k + 3 < K) ce = upload(k + 3);  // keep the copy engine three chunks ahead
+        const int r = (int)(k & 1);
+        const size_t a = k * CHUNK, own = std::min(CHUNK, n_in - a);
+        const int is_last = k + 1 == K;
+        const size_t buf_len = is_last ? own : std::min(n_in - a, own + HALO);
+        // the chunk and its halo (inside the next chunks) are on the device; the output buffer is free again
+        for (size_t j = k; j < K && j * CHUNK < a + buf_len; j++) cudaStreamWaitEvent(st, ev_in[j], 0);
+        if (k >= 2) cudaStreamWaitEvent(st, ev_out[r], 0);
+        size_t nw = 0, no = 0;
+        sgpu_counts ck;
+        rc = clean_shard_locked(c, set, d_in.p + a, buf_len, own, newlines_before, k == 0, is_last, crlf, reverse,
+                                d_w[r].p, obuf, &nw, out_o ? d_o[r].p : nullptr, obuf, &no, &ck);
+        if (getenv("SGPU_DEBUG"))
+            fprintf(stderr, "[sgpu] pipe chunk %zu/%zu a=%zu own=%zu buf=%zu nlb=%llu -> rc=%d nw=%zu no=%zu in=%llu out=%llu path=%u\n",
+                    k, K, a, own, buf_len, (unsigned long long)newlines_before, (int)rc, nw, no,
+                    (unsigned long long)ck.reads_in, (unsigned long long)ck.reads_out, ck.path);
+        if (rc == SGPU_ERR_HALO) {  // a record longer than the halo: the one-shot path handles any length
+            rc = SGPU_OK;
+            bail = true;
+            break;
+        }
+        if (rc == SGPU_ERR_CAPACITY || rc == SGPU_ERR_CUDA || rc == SGPU_ERR_NOMEM) break;
+        const sgpu_status parse_rc = rc;  // a parse error: like the one-shot path (and the reference, which
+        rc = SGPU_OK;                     // leaves the records before the error on disk) the output so far stays
+        if (parse_rc != SGPU_OK) total.error_record = ck.error_record + total.reads_in;  // earlier chunks come first
+        if (off_w + nw > cap_w || (out_o && off_o + no > cap_o)) {
+            rc = SGPU_ERR_CAPACITY;
+            break;
+        }
+        cudaEventRecord(ev_k[r], st);
+        cudaStreamWaitEvent(c->s_out, ev_k[r], 0);
+        if (nw) ce = cudaMemcpyAsync(out_w + off_w, d_w[r].p, nw, cudaMemcpyDeviceToHost, c->s_out);
+        if (out_o && no && ce == cudaSuccess)
+            ce = cudaMemcpyAsync(out_o + off_o, d_o[r].p, no, cudaMemcpyDeviceToHost, c->s_out);
+        cudaEventRecord(ev_out[r], c->s_out);
+        off_w += nw;
+        off_o += no;
+        total.reads_in += ck.reads_in;
+        total.reads_out += ck.reads_out;
+        total.crlf = ck.crlf ? 1 : total.crlf;
+        if (ck.path != 1) total.path = ck.path;
+        if (parse_rc != SGPU_OK) {
+            rc = parse_rc;
+            break;
+        }
+        if (!is_last) {
+            uint64_t cnt = 0;
+            rc = count_newlines(c, d_in.p + a, own, &cnt);
+            newlines_before += cnt;
+        }
+    }
+    cudaStreamSynchronize(c->s_in);
+    cudaStreamSynchronize(c->s_out);
+    cudaStreamSynchronize(st);
+    for (size_t k = 0; k < K; k++) cudaEventDestroy(ev_in[k]);
+    for (int r = 0; r < 2; r++) {
+        cudaEventDestroy(ev_k[r]);
+        cudaEventDestroy(ev_out[r]);
+    }
+    if (ce != cudaSuccess) {
+        set_cuda_error(ce, __FILE__, __LINE__);
+        return SGPU_ERR_CUDA;
+    }
+    if (bail) return SGPU_OK;  // *done stays 0
+    *done = 1;
+    *counts = total;
+    *n_w = off_w;
+    if (n_o) *n_o = out_o ? off_o : 0;
+    return rc;
+}
+
 sgpu_status sgpu_clean_fastq(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *in, size_t n_in, int reverse,
                              uint8_t *out_w, size_t cap_w, size_t *n_w, uint8_t *out_o, size_t cap_o, size_t *n_o,
                              sgpu_counts *counts) {
@@ -318,6 +461,12 @@ sgpu_status sgpu_clean_fastq(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *
     std::lock_guard<std::mutex> lk(c->mu);
     SGPU_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
+    {
+        int done = 0;
+        sgpu_status prc =
+            clean_host_pipelined(c, set, in, n_in, reverse, out_w, cap_w, n_w, out_o, cap_o, n_o, counts, &done);
+        if (done || prc != SGPU_OK) return prc;
+    }
     DevBuf<uint8_t> d_in, d_w, d_o;
     SGPU_TRY(d_in.alloc(n_in + 16, st));
     SGPU_TRY(d_w.alloc(cap_w + 16, st));

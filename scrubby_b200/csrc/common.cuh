@@ -88,6 +88,8 @@ struct sgpu_ctx {
     std::mutex mu;
     // pinned staging for small D2H results
     uint64_t *h_pinned = nullptr;  // 64 x u64
+    // copy streams of the pipelined host-buffer path (created on first use)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
     // optional timing of the dominant (fused) kernel with CUDA events on the launching stream
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;

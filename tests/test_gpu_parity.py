@@ -576,3 +576,49 @@ def test_txt_tile_kernel_edge_cases(ctx, seed):
     _txt_vs_oracle(ctx, (body + "z" * 40000 + "\n" + body).encode())
     _txt_vs_oracle(ctx, b"\n")
     _txt_vs_oracle(ctx, b"a")
+
+
+# ---------------------------------------------------------------------------- pipelined host-buffer path
+@pytest.fixture()
+def small_pipeline_chunks(monkeypatch):
+    monkeypatch.setenv("SGPU_PIPE_CHUNK", str(256 * 1024))
+    monkeypatch.setenv("SGPU_PIPE_HALO", str(8 * 1024))
+
+
+def test_host_pipeline_matches_oracle(ctx, small_pipeline_chunks):
+    """sgpu_clean_fastq on host buffers cut into chunks (H2D / kernels / D2H overlapped): same bytes and counts
+    as the oracle, deplete, extract and split"""
+    n = 12000
+    fq = synth.gen_fastq(n, 1).numpy().tobytes()  # ~4 MB -> 16 chunks
+    ids = [b"syn.%d" % i for i in range(0, n, 3)]
+    for reverse in (False, True):
+        g = _same_clean(ctx, fq, ids, reverse)
+        assert g.path == 1
+    # no final newline, and a cut that falls right after a newline
+    _same_clean(ctx, fq[:-1], ids)
+    # a cut that falls exactly on a record boundary: a filler record pads the first chunk to 256 KiB
+    b = fq.rindex(b"\n@syn.", 0, 256 * 1024 - 100) + 1
+    room = 256 * 1024 - b
+    name = b"@pad" if (room - 9) % 2 == 0 else b"@padd"
+    L = (room - len(name) - 5) // 2
+    filler = name + b"\n" + b"A" * L + b"\n+\n" + b"I" * L + b"\n"
+    assert len(filler) == room
+    _same_clean(ctx, fq[:b] + filler + fq[b:], ids)
+    # a malformed join in a late chunk: same error, same records before it
+    cut = fq.index(b"\n", 3 * 256 * 1024 + 77) + 1
+    _same_clean(ctx, fq[:cut - 40] + fq[cut:], ids)
+
+
+def test_host_pipeline_crlf_errors_and_long_records(ctx, small_pipeline_chunks):
+    n = 6000
+    fq = synth.gen_fastq(n, 2).numpy().tobytes()
+    ids = [b"syn.%d" % i for i in range(1, n, 2)]
+    _same_clean(ctx, fq.replace(b"\n", b"\r\n"), ids)  # CRLF: every chunk on the general path
+    bad = bytearray(fq)
+    p = fq.index(b"\n@syn.4000 ") + 1
+    bad[p] = ord("X")  # invalid record start in a late chunk: same error class and record index
+    _same_clean(ctx, bytes(bad), ids)
+    # a record longer than the halo: the pipelined path steps aside for the one-shot path
+    long_rec = b"@long\n" + b"A" * 20000 + b"\n+\n" + b"I" * 20000 + b"\n"
+    k = fq.index(b"\n@syn.900 ") + 1
+    _same_clean(ctx, fq[:k] + long_rec + fq[k:], ids + [b"long"])
