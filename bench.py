@@ -23,9 +23,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -34,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "reads_per_s_depleted"
 UNIT = "reads/s"
+WORKLOAD = "classifier: synthetic 10M 2x150 pairs + Kraken2 reads/report, -T Chordata -D 9606, deplete"
 
 
 def peaks():
@@ -45,52 +44,60 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (a thread polling every
+    millisecond: the timed region of the device arm is only tens of milliseconds long)"""
 
     def __init__(self, device: int):
-        self.path = tempfile.mktemp(suffix=".csv")
-        self.proc = None
         self.device = device
+        self.sm, self.reasons = [], set()
+        self.mx = None
+        self._stop = threading.Event()
+        self.th = None
+        self.err = None
+
+    def _run(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            if self._stop.wait(0.001):
+                return
 
     def start(self):
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=self.f,
-                                         stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.device
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.device])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._run, args=(nv, h), daemon=True)
+            self.th.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if c[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.path)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.th:
+            self.th.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [f"nvml unavailable: {self.err}"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 def taxids_for_config():
@@ -133,14 +140,42 @@ def cpu_sample_run(pairs: int):
     return dt, reads, int(fq[0].size + fq[1].size)
 
 
+def cpu_sample_loop(pairs: int, min_seconds: float, max_reps: int = 200):
+    """repeats the bounded sample until `min_seconds` of CPU work have been timed; returns the totals"""
+    tot_t, tot_reads, tot_bytes, reps = 0.0, 0, 0, 0
+    while reps < max_reps and (tot_t < min_seconds or reps == 0):
+        dt, reads, nbytes = cpu_sample_run(pairs)
+        tot_t += dt
+        tot_reads += reads
+        tot_bytes += nbytes
+        reps += 1
+    return tot_t, tot_reads, tot_bytes, reps
+
+
+def fused_traffic(pairs: int, split: bool):
+    """DRAM bytes per launch of the fused kernel from the committed `ncu --set full` capture of this workload
+    (profiles/fused_traffic.json, written by tools/ncu_summary.py); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    try:
+        with open(p) as f:
+            j = json.load(f)
+        if j.get("pairs") == pairs and bool(j.get("split")) == bool(split):
+            return j["dram_bytes_read"] + j["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sample = args.cpu_pairs
     times = []
+    reps = 1
     for i in range(args.warmup + args.steps):
-        dt, reads, nbytes = cpu_sample_run(sample)
+        # one step = the bounded sample repeated for about args.cpu_step_seconds of CPU work
+        dt, reads, nbytes, reps = cpu_sample_loop(sample, args.cpu_step_seconds if i >= args.warmup else 0.0)
         if i >= args.warmup:
             times.append(dt)
     t = sum(times) / len(times)
@@ -149,10 +184,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "classifier: Kraken2 reads/report -T Chordata -D 9606, 2x150 pairs, deplete",
-                   "pairs_per_step": sample, "fastq_gb_per_s": nbytes / t / 1e9},
+        "config": {"workload": WORKLOAD, "sample_pairs_per_step": sample * reps,
+                   "outputs": "kept (reference-equivalent single output)", "fastq_gb_per_s": nbytes / t / 1e9},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 2, "kind": "port",
-                         "sample": f"{sample} pairs ({nbytes / 1e9:.2f} GB FASTQ) + {sample} Kraken2 lines per step; "
+                         "sample": f"{reps} x ({sample} pairs + {sample} Kraken2 lines) = {nbytes / 1e9:.2f} GB FASTQ per step; "
                                    "C oracle structured like the reference (evidence on 1 thread, one thread per "
                                    "mate file); the Rust reference itself cannot be built here (no cargo/rustc)",
                          "cores_available": os.cpu_count()},
@@ -212,11 +247,13 @@ def run_ours(args):
     sampler.start()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # `ncu --profile-from-start off` lists exactly the timed launches
     e0.record()
     for _ in range(args.steps):
         res = step_dev()
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (ctx.launches - l0)
@@ -270,10 +307,11 @@ def run_ours(args):
         achieved = f_bytes / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0
         cpu = None
         if world == 1 or True:
-            dt, creads, cbytes = cpu_sample_run(args.cpu_pairs)
+            cpu_sample_run(args.cpu_pairs)  # warm the page cache / allocator
+            dt, creads, cbytes, reps = cpu_sample_loop(args.cpu_pairs, args.cpu_seconds)
             cpu = {"value": creads / dt, "unit": UNIT, "cores": 2, "kind": "port",
-                   "sample": f"{args.cpu_pairs} pairs ({cbytes / 1e9:.2f} GB FASTQ) + {args.cpu_pairs} Kraken2 lines, "
-                             f"{dt:.2f} s; C oracle structured like the reference (1 thread evidence, 1 thread per "
+                   "sample": f"{reps} x ({args.cpu_pairs} pairs + {args.cpu_pairs} Kraken2 lines) = "
+                             f"{cbytes / 1e9:.2f} GB FASTQ, {dt:.2f} s; C oracle structured like the reference (1 thread evidence, 1 thread per "
                              "mate file)", "cores_available": os.cpu_count(),
                    "fastq_gb_per_s": cbytes / dt / 1e9}
         line = {
@@ -281,8 +319,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": "classifier: synthetic 10M 2x150 pairs + Kraken2 reads/report, -T Chordata -D 9606, deplete"
-                            if pairs == 10_000_000 else f"classifier: synthetic {pairs} 2x150 pairs + Kraken2 reads/report",
+                "workload": WORKLOAD if pairs == 10_000_000 else f"classifier: synthetic {pairs} 2x150 pairs + Kraken2 reads/report",
                 "pairs_per_gpu": pairs, "fastq_bytes_per_gpu": sum(n_r), "kraken_bytes_per_gpu": n_k,
                 "outputs": "kept+removed" if args.split else "kept (reference-equivalent single output)",
                 "fraction_kept": kept_all / reads_all, "parallelism": f"chunk-sharded x{world}",
@@ -295,7 +332,7 @@ def run_ours(args):
                               "buffers, stream synchronised"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": fused_traffic(pairs, args.split),
                          "kernel": "fastq_fused_kernel", "launches": f_n, "avg_ms": f_ms / f_n if f_n else None,
                          "algorithmic_bytes_per_launch": f_bytes / f_n if f_n else None, "peak_source": peak_src,
                          "share_of_step": f_ms / (ms * args.steps) if ms else None},
@@ -315,6 +352,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU (10M = BASELINE configs[1])")
     ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="bounded CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work timed for cpu_baseline")
+    ap.add_argument("--cpu-step-seconds", type=float, default=3.0, help="--impl reference: CPU work per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--split", action="store_true", help="also write the removed records (kept + removed)")
     args = ap.parse_args()
