@@ -191,6 +191,14 @@ sgpu_status sgpu_ctx_create(int device, sgpu_ctx **out) {
         return SGPU_ERR_CUDA;  // no CPU fallback by design
     }
     SGPU_CUDA(cudaSetDevice(device));
+    if (const char *g = getenv("SGPU_L2_FETCH")) {  // tuning: L2 fetch granularity in bytes (32 / 64 / 128)
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[sgpu] L2 fetch granularity %zu -> %zu\n", before, after);
+        cudaGetLastError();
+    }
     sgpu_ctx *c = new (std::nothrow) sgpu_ctx();
     if (!c) return SGPU_ERR_NOMEM;
     c->device = device;

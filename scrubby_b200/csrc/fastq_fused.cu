@@ -12,7 +12,7 @@
 // re-runs the always-exact general path (fastq_general.cu); nothing is approximated.
 //
 // Structure (v3): persistent CTAs of 256 threads, several resident per SM, each looping over
-// dynamically ticketed 32 KiB tiles (tickets are taken in order, so every tile a look-back waits on is
+// dynamically ticketed 36 KiB tiles (tickets are taken in order, so every tile a look-back waits on is
 // owned by a running CTA).  One shared-memory tile buffer per CTA; the latency
 // of a tile's dependent steps (load, set probes, look-back) is hidden by the other resident CTAs.
 // The byte-level phases (P1, P4) run on all warps; the record-level phases run with one thread per
@@ -52,7 +52,7 @@ namespace sgpu {
 #define SGPU_FUSED_CTAS 5
 #endif
 #ifndef SGPU_FUSED_PIECE
-#define SGPU_FUSED_PIECE 1024
+#define SGPU_FUSED_PIECE 2048
 #endif
 #ifndef SGPU_FUSED_HALO
 #define SGPU_FUSED_HALO 256
@@ -60,29 +60,22 @@ namespace sgpu {
 constexpr int NT = 256;                 // threads per CTA
 constexpr int NW = NT / 32;             // warps per CTA
 constexpr int NTHREADS = NT;
+// Throughput = tile bytes resident in shared memory / time a tile stays there (load .. copy-out, ~15 us of
+// which ~6 us are the in-order wait and the load): the tile is as large as five CTAs per SM allow.
 #ifndef SGPU_FUSED_FC
-#define SGPU_FUSED_FC 8
+#define SGPU_FUSED_FC 9
 #endif
 constexpr int FC = SGPU_FUSED_FC;       // 16-byte chunks per thread
-constexpr int TILE = NT * FC * 16;      // 32 KiB
+constexpr int TILE = NT * FC * 16;      // 36 KiB
 constexpr int PRE = 16;                 // pre-halo (previous 16 bytes)
 constexpr int HALO = SGPU_FUSED_HALO;   // post-halo: id token of the last record start, "+\n" after the last newline
 constexpr int BUF = PRE + TILE + HALO;  // bytes of the tile buffer
-constexpr int RMAX = 320;               // record starts per tile
+constexpr int RMAX = TILE / 1024 * 10;  // record starts per tile (>= 102 bytes per record on average)
 constexpr int LMAX = 4 * RMAX + 8;      // newline list capacity per tile
 constexpr int PIECE = SGPU_FUSED_PIECE; // copy items are at most this long
 constexpr int IMAX = RMAX + 2 * (TILE / PIECE) + 8;  // copy items per tile
-#ifndef SGPU_FUSED_SEQ_K
-#define SGPU_FUSED_SEQ_K 4
-#endif
-// when a tile's kept records are copied out (P4):
-//   0  from the shared-memory tile, before the CTA's next tile is loaded (the CTA idles through the in-order wait);
-//   1  from global memory (the tile is still in L2), after the next tile's load has been issued;
-//   2  like 1 but one tile later: the in-order wait of tile i is hidden behind the parse of tile i + 1;
-//   3  like 1 but the next ticket is only taken once the tile's prefix has arrived (a ticket held through
-//      an in-order wait delays every later tile).
-#ifndef SGPU_FUSED_DEFER
-#define SGPU_FUSED_DEFER 2
+#ifndef SGPU_FUSED_DSTRIDE
+#define SGPU_FUSED_DSTRIDE 4
 #endif
 #ifndef SGPU_FUSED_POLL_NS
 #define SGPU_FUSED_POLL_NS 500
@@ -90,17 +83,12 @@ constexpr int IMAX = RMAX + 2 * (TILE / PIECE) + 8;  // copy items per tile
 #ifndef SGPU_FUSED_LOAD_PIECE
 #define SGPU_FUSED_LOAD_PIECE 4096
 #endif
-// L2 eviction-priority hints (bit mask): 1 tile loads + prefetches evict_last, 2 set probes evict_first,
-// 4 output stores evict_first, 8 the copy's re-read of the tile evict_first
-#ifndef SGPU_FUSED_HINTS
-#define SGPU_FUSED_HINTS 0
-#endif
-constexpr int HINTS = SGPU_FUSED_HINTS;
-constexpr int DEFER = SGPU_FUSED_DEFER;
-constexpr int NSLOT = DEFER == 2 ? 2 : 1;  // item lists kept per CTA
+// 64-bit words between the look-back #2 descriptors of two tiles: one 32-byte sector each, so that the
+// hundreds of polling warps do not all hit the same few L2 lines (measured: 1.18 -> 1.06 ms per 1.65 GB)
+constexpr int DSTRIDE = SGPU_FUSED_DSTRIDE;
 constexpr int LOAD_PIECE = SGPU_FUSED_LOAD_PIECE;  // bytes per bulk copy of a tile load
 constexpr int CTAS_PER_SM = SGPU_FUSED_CTAS;  // resident CTAs the kernel is sized for (registers, shared memory)
-static_assert(TILE <= 32768 && TILE / PIECE <= 32 && HALO % 16 == 0, "tile offsets are 16-bit; head pieces fit a warp");
+static_assert(TILE + HALO < 65536 && TILE / PIECE <= 32 && HALO % 16 == 0, "tile offsets are 16-bit; head pieces fit a warp");
 
 constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
 // run / carry states
@@ -115,7 +103,7 @@ struct FusedResult {
     unsigned long long ticket;      // dynamic tile counter
     unsigned long long reason;      // first fallback reason (diagnostics)
     unsigned long long owned_end;   // end of the last owned record (shards); ~0 when no foreign record was seen
-    unsigned long long role;        // the first CTA to arrive runs the sequencer
+    unsigned long long pad;
 };
 
 struct FusedParams {
@@ -128,8 +116,7 @@ struct FusedParams {
     uint8_t *out_w, *out_o;
     int reverse;
     IdSetView set;
-    unsigned long long *desc1;          // per tile line-phase look-back descriptors (zero initialised)
-    unsigned long long *agg, *pref;     // per tile aggregate / exclusive prefix (zero initialised), see the sequencer
+    unsigned long long *desc1, *desc2;  // per tile look-back descriptors (zero initialised)
     long long *sum_total, *sum_head;    // per tile signed newline-position sums (length check)
     uint32_t *nl_count;                 // per tile newline count (phase verification)
     uint8_t *has_term, *phase_used;     // per tile: has a record end; line phase (mod 4) the tile assumed
@@ -151,43 +138,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-    if (HINTS & 1) {
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes),
-                     "l"(policy_evict_last())
-                     : "memory");
-    } else {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-    }
-}
-__device__ __forceinline__ uint4 ld_nc_u4_hint(const void *p, uint64_t pol) {
-    uint4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void st_global_v4_hint(void *p, uint4 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-                 "r"(v.w), "l"(pol)
-                 : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -212,16 +164,7 @@ __device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long 
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_global_v4(void *p, uint4 v) {
-    if (HINTS & 4) {
-        st_global_v4_hint(p, v, policy_evict_first());
-        return;
-    }
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// the copy's re-read of the tile: the line is dead afterwards
-__device__ __forceinline__ uint4 ld_tile_u4(const void *p) {
-    if (HINTS & 8) return ld_nc_u4_hint(p, policy_evict_first());
-    return ld_nc_u4(p);
 }
 __device__ __forceinline__ void st_global_u8(void *p, uint32_t v) {
     asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -271,17 +214,19 @@ struct __align__(128) CtaSmem {
     uint64_t full;         // mbarrier: tile load complete
     uint64_t first_tile;   // the CTA's first ticket
     uint64_t next_tile;    // the ticket after the tile in flight
-    uint32_t is_seq;       // this CTA runs the sequencer
+    uint64_t kept_before;  // look-back #2 result
+    uint32_t carry;        // state of the record carried into the tile
     uint32_t c0;           // newlines before the tile, mod 4 (only when the speculation found no "\n+\n")
-    uint32_t n_items[NSLOT];
-    uint32_t head_len[NSLOT];  // bytes of the carried-in record (== tile_len when no record starts in the tile)
+    uint32_t n_items;
     uint32_t last_flag;    // fate of the last record that starts in the tile
+    uint32_t head_len;     // bytes of the carried-in record (== tile_len when no record starts in the tile)
+    uint32_t rest_total;   // kept bytes of the records that start in the tile
     uint32_t none_pos;     // first record start of the tile that belongs to the next shard
     uint32_t none_cnt;
     uint32_t warp_tot[NW];  // newlines of the warp's region (bit 31: a 16-byte chunk with more than two)
     uint32_t scan_tot[NW];
     __align__(16) uint16_t nlp[LMAX];  // newline positions of the tile, in order
-    Item items[NSLOT][IMAX];
+    Item items[IMAX];
     __align__(16) uint8_t buf[BUF];
 };
 
@@ -311,71 +256,97 @@ __device__ __forceinline__ uint32_t lookback_phase_warp(unsigned long long *desc
     return acc & 3;
 }
 
-// ------------------------------------------------------------------ in-order commit: the sequencer
-// aggregate (one 64-bit word per tile, written by the tile's CTA once its records are decided):
-//   [63:62] != 0 ready  [61] has_start  [60:59] state of the last record  [58:30] head_len  [29:0] rest_kept
-// prefix (one 64-bit word per tile, written by the sequencer):
-//   [63] ready  [60:59] state carried into the tile  [58:0] kept bytes before the tile
+// ------------------------------------------------------------------ look-back #2: kept bytes + carried state
+// aggregate:  [61] has_start  [60:59] state of the last record  [58:30] head_len  [29:0] rest_kept
+// inclusive:  [60:59] state carried out of the tile              [58:0] kept bytes up to and including the tile
 // A tile is a transducer on the carried state c: it keeps (c == KEPT ? head_len : 0) + rest bytes and
-// carries out (has_start ? last : c).  ONE warp of one CTA (the first CTA to arrive) walks the aggregates in
-// tile order, 32 per step, and writes every tile's exclusive prefix; the tiles' CTAs never walk the
-// descriptors themselves (v3.1's per-tile look-back cost 29 % of all issued instructions and ~2 us of chain
-// lag per tile: 740 concurrent walkers, each reading the same few hundred descriptors window by window).
-// Aggregates never depend on a prefix of a LATER ticket, tickets are taken in order by running CTAs and the
-// sequencer is resident before any of them, so the chain always makes progress.
-constexpr uint64_t PREF_READY = 1ull << 63;
+// carries out (has_start ? last : c).  A run of tiles composes into {P: bytes kept iff c == KEPT, K: bytes
+// kept regardless, has, out}; composition is associative.  A warp looks at 32 descriptors at a time (one per
+// lane): with ballots every lane finds the state carried into its tile, two warp reductions give the
+// window's composite.  The look-back only needs the tiles BEFORE t, so it runs while the CTA's other warps
+// are still busy with the records of tile t.
+struct Comp {
+    uint32_t P, K, has, out;
+};
+__device__ __forceinline__ Comp comp_identity() { return Comp{0u, 0u, 0u, 0u}; }
+__device__ __forceinline__ Comp compose(const Comp A /*earlier*/, const Comp B /*later*/) {
+    Comp R;
+    if (!A.has) {
+        R.P = A.P + B.P;
+        R.K = B.K;
+        R.has = B.has;
+        R.out = B.out;
+    } else {
+        R.P = A.P;
+        R.K = A.K + B.K + (A.out == F_KEPT ? B.P : 0u);
+        R.has = 1u;
+        R.out = B.has ? B.out : A.out;
+    }
+    return R;
+}
+
+// (kept bytes before tile t, state carried into it) from the descriptors of the tiles before t
+__device__ __forceinline__ void lookback_pred_warp(const unsigned long long *desc, uint64_t t, int lane,
+                                                   uint64_t *kept_before, uint32_t *carry) {
+    Comp acc_all = comp_identity();  // composite of every window visited so far (nearer windows are later)
+    uint64_t inc_total = 0;
+    int64_t base = (int64_t)t - 1;  // nearest tile of the window; lane l looks at tile base - l
+    const uint64_t virt = ST_INC | ((uint64_t)F_NONE << 59);  // before the buffer: nothing kept, nothing carried
+    while (true) {
+        const int64_t idx = base - lane;
+        unsigned long long x = idx >= 0 ? ld_relaxed(desc + idx * DSTRIDE) : virt;
+        int L;
+        // every descriptor up to the nearest inclusive one must be there
+        while (true) {
+            const uint32_t st = (uint32_t)(x >> 62);
+            const unsigned binc = __ballot_sync(0xffffffffu, st == 2u);
+            const unsigned bzero = __ballot_sync(0xffffffffu, st == 0u);
+            L = binc ? __ffs(binc) - 1 : 32;
+            const unsigned upto = L < 31 ? (2u << L) - 1u : 0xffffffffu;  // lanes <= L
+            if ((bzero & upto) == 0) break;
+            // a predecessor is still parsing (microseconds away): poll slowly, the issue slots belong to the
+            // warps that work
+            __nanosleep(SGPU_FUSED_POLL_NS);
+            if (st == 0u && lane <= L) x = ld_relaxed(desc + idx * DSTRIDE);
+        }
+        const bool agg = lane < L, isL = lane == L;
+        const uint32_t fl = (uint32_t)(x >> 59) & 3u;
+        const bool has = isL || (agg && ((x >> 61) & 1ull));
+        const uint32_t hl = agg ? (uint32_t)(x >> 30) & 0x1FFFFFFFu : 0u;
+        const uint32_t rs = agg ? (uint32_t)x & 0x3FFFFFFFu : 0u;
+        const unsigned has_m = __ballot_sync(0xffffffffu, has);
+        const unsigned kept_m = __ballot_sync(0xffffffffu, has && fl == F_KEPT);
+        // the state carried into my tile = state of the nearest earlier tile with a record start:
+        // the lowest set bit of has_m strictly above my lane
+        const unsigned hm = has_m & (0xFFFFFFFEu << lane);
+        const bool found = hm != 0u;
+        const bool in_kept = found && ((kept_m >> (__ffs(hm) - 1)) & 1u);
+        const uint32_t sumK = __reduce_add_sync(0xffffffffu, rs + (in_kept ? hl : 0u));
+        const uint32_t sumP = __reduce_add_sync(0xffffffffu, found ? 0u : hl);
+        Comp W;
+        W.P = sumP;
+        W.K = sumK;
+        W.has = has_m != 0u;
+        W.out = __shfl_sync(0xffffffffu, fl, has_m ? __ffs(has_m) - 1 : 0);
+        acc_all = compose(W, acc_all);
+        if (L < 32) {
+            inc_total = __shfl_sync(0xffffffffu, x, L) & ((1ull << 59) - 1);
+            break;
+        }
+        base -= 32;
+    }
+    // acc_all starts with the inclusive descriptor (has == 1, P == 0)
+    *kept_before = inc_total + acc_all.K;
+    *carry = acc_all.out;
+}
 __device__ __forceinline__ unsigned long long agg_desc(bool has_start, uint32_t last_flag, uint32_t head_len,
                                                        uint32_t rest) {
     return ST_AGG | (has_start ? (1ull << 61) : 0ull) | ((uint64_t)last_flag << 59) | ((uint64_t)head_len << 30) | rest;
 }
-
-__device__ __noinline__ void sequencer_warp(const FusedParams &P, int lane) {
-    constexpr int K = SGPU_FUSED_SEQ_K;  // windows of 32 aggregates fetched per round trip
-    uint64_t kept = 0;
-    uint32_t carry = F_NONE;  // before the buffer: nothing kept, nothing carried
-    uint64_t base = 0;
-    while (base < P.n_tiles) {
-        unsigned long long x[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const uint64_t idx = base + (uint64_t)(k * 32 + lane);
-            x[k] = idx < P.n_tiles ? ld_relaxed(P.agg + idx) : 0ull;
-        }
-        bool progressed = false;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const unsigned long long d = x[k];
-            const unsigned rm = __ballot_sync(0xffffffffu, (d >> 62) != 0ull);
-            const int cnt = ~rm ? __ffs(~rm) - 1 : 32;  // lanes [0, cnt) hold ready, consecutive tiles
-            if (cnt == 0) break;                         // (warp-uniform)
-            const bool act = lane < cnt;
-            const bool has = act && ((d >> 61) & 1ull);
-            const uint32_t fl = (uint32_t)(d >> 59) & 3u;
-            const uint32_t hl = (uint32_t)(d >> 30) & 0x1FFFFFFFu;
-            const uint32_t rs = (uint32_t)d & 0x3FFFFFFFu;
-            const unsigned has_m = __ballot_sync(0xffffffffu, has);
-            // the state carried into my tile = state of the nearest earlier tile of the window with a record
-            // start, else the state carried into the window
-            const unsigned lower = has_m & ((1u << lane) - 1u);
-            const uint32_t fl_src = __shfl_sync(0xffffffffu, fl, lower ? 31 - __clz(lower) : 0);
-            const uint32_t cin = lower ? fl_src : carry;
-            const uint32_t contrib = act ? rs + (cin == F_KEPT ? hl : 0u) : 0u;
-            uint32_t inc = contrib;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, dd);
-                if (lane >= dd) inc += y;
-            }
-            if (act) st_relaxed(P.pref + base + lane, PREF_READY | ((uint64_t)cin << 59) | (kept + inc - contrib));
-            kept += __shfl_sync(0xffffffffu, inc, cnt - 1);
-            if (has_m) carry = __shfl_sync(0xffffffffu, fl, 31 - __clz(has_m));
-            base += (uint64_t)cnt;
-            progressed = true;
-            if (cnt < 32) break;  // the next window's lanes no longer line up: fetch again
-        }
-        if (!progressed) __nanosleep(SGPU_FUSED_POLL_NS);
-    }
-    if (lane == 0) P.res->kept_total = kept;
+__device__ __forceinline__ unsigned long long inc_desc(bool has_start, uint32_t last_flag, uint32_t head_len,
+                                                       uint32_t rest, uint64_t kept_before, uint32_t carry) {
+    const uint64_t incl = kept_before + (carry == F_KEPT ? head_len : 0u) + rest;
+    return ST_INC | ((uint64_t)(has_start ? last_flag : carry) << 59) | incl;
 }
 
 // ------------------------------------------------------------------ tile load (one thread)
@@ -394,8 +365,7 @@ __device__ __forceinline__ void issue_load(const FusedParams &P, CtaSmem *S, uin
     const uint8_t *src = P.in + src0;
     for (uint32_t o = 0; o < bytes; o += LOAD_PIECE) {
         const uint32_t nb = bytes - o < (uint32_t)LOAD_PIECE ? bytes - o : (uint32_t)LOAD_PIECE;
-        if (HINTS & 1) bulk_g2s_hint(dst + o, src + o, nb, &S->full, policy_evict_last());
-        else bulk_g2s(dst + o, src + o, nb, &S->full);
+        bulk_g2s(dst + o, src + o, nb, &S->full);
     }
 }
 __device__ __forceinline__ void prefetch_tile(const FusedParams &P, uint64_t t) {
@@ -471,15 +441,7 @@ __device__ __forceinline__ Bucket load_bucket(const IdSetView &set, uint64_t lo,
     const Slot *bp = set.table + home_slot(inline_home(lo, hi), set.mask);
     Bucket B;
 #pragma unroll
-    for (int q = 0; q < (int)IDSET_BUCKET; q++) {
-        if (HINTS & 2) {
-            const uint4 v = ld_nc_u4_hint(bp + q, policy_evict_first());
-            B.s[q].lo = (uint64_t)v.x | ((uint64_t)v.y << 32);
-            B.s[q].hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-        } else {
-            B.s[q] = load_slot(bp + q);
-        }
-    }
+    for (int q = 0; q < (int)IDSET_BUCKET; q++) B.s[q] = load_slot(bp + q);
     return B;
 }
 // exact membership given the home bucket; the probe sequence only leaves it when all four slots are taken
@@ -506,8 +468,8 @@ __device__ __forceinline__ bool probe_bucket(const IdSetView &set, const Bucket 
 // maximal group of consecutive lanes with flag == WANT (its bytes are contiguous in the tile AND in the
 // stream); the lane that ends a run cuts it into items of at most PIECE bytes.
 template <uint32_t WANT>
-__device__ __forceinline__ void emit_runs(CtaSmem *S, uint32_t slot_i, uint32_t flag, uint32_t sp, uint32_t e,
-                                          uint32_t Kx, uint32_t head_len, int lane) {
+__device__ __forceinline__ void emit_runs(CtaSmem *S, uint32_t flag, uint32_t sp, uint32_t e, uint32_t Kx,
+                                          uint32_t head_len, int lane) {
     const unsigned km = __ballot_sync(0xffffffffu, flag == WANT);
     if (km == 0) return;  // warp-uniform
     const unsigned below = ~km & ((1u << lane) - 1u);
@@ -520,7 +482,7 @@ __device__ __forceinline__ void emit_runs(CtaSmem *S, uint32_t slot_i, uint32_t 
         const uint32_t run_len = e - s_src;
         const uint32_t rel = WANT == F_KEPT ? s_K : s_src - head_len - s_K;
         const uint32_t np = (run_len + PIECE - 1) / PIECE;
-        const uint32_t slot = atomicAdd(&S->n_items[slot_i], np);
+        const uint32_t slot = atomicAdd(&S->n_items, np);
         for (uint32_t q = 0; q < np; q++) {
             const uint32_t o = q * PIECE;
             const uint32_t l = run_len - o < (uint32_t)PIECE ? run_len - o : (uint32_t)PIECE;
@@ -529,7 +491,7 @@ __device__ __forceinline__ void emit_runs(CtaSmem *S, uint32_t slot_i, uint32_t 
                 it.src = (uint16_t)(s_src + o);
                 it.len = (uint16_t)l;
                 it.rel = (WANT == F_KEPT ? TAG_KEPT : TAG_OTHER) | (rel + o);
-                S->items[slot_i][slot + q] = it;
+                S->items[slot + q] = it;
             }
         }
     }
@@ -572,50 +534,6 @@ __device__ __forceinline__ void copy_piece(uint32_t src_s, uint32_t len, uint8_t
     } else if (lane >= 16 && (uint32_t)(lane - 16) < tn) {
         const uint32_t off = hn + (nfull << 4) + (uint32_t)(lane - 16);
         st_global_u8(dst + off, lds_u8(src_s + off));
-    }
-}
-
-// the same copy with the source in global memory (the tile was read moments ago: L2).  src + len never passes
-// the 16-byte rounded end of the input (the tile loads assume the same)
-template <int WS>
-__device__ __forceinline__ void copy_body_g(const uint8_t *al, uint32_t bsh, uint8_t *d0, uint32_t nfull, int lane) {
-    for (uint32_t i = lane; i < nfull; i += 32) {
-        const uint4 A = ld_tile_u4(al + ((size_t)i << 4)), B = ld_tile_u4(al + ((size_t)i << 4) + 16);
-        const uint32_t x[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
-        uint4 o;
-        o.x = __funnelshift_r(x[WS], x[WS + 1], bsh);
-        o.y = __funnelshift_r(x[WS + 1], x[WS + 2], bsh);
-        o.z = __funnelshift_r(x[WS + 2], x[WS + 3], bsh);
-        o.w = __funnelshift_r(x[WS + 3], x[WS + 4], bsh);
-        st_global_v4(d0 + ((size_t)i << 4), o);
-    }
-}
-__device__ __forceinline__ void copy_piece_g(const uint8_t *src, uint32_t len, uint8_t *dst, int lane) {
-    const uint32_t a = (uint32_t)(uintptr_t)dst & 15u;
-    uint32_t hn = (16u - a) & 15u;  // bytes before the first aligned chunk
-    if (hn > len) hn = len;
-    const uint32_t body = len - hn;
-    const uint32_t nfull = body >> 4, tn = body & 15u;
-    const uint8_t *s0 = src + hn;
-    const uint32_t mis = (uint32_t)(uintptr_t)s0 & 15u;
-    if (mis == 0) {  // (warp-uniform) source and destination agree mod 16: no second load (it could pass the end)
-        for (uint32_t i = lane; i < nfull; i += 32) st_global_v4(dst + hn + ((size_t)i << 4), ld_tile_u4(s0 + ((size_t)i << 4)));
-    } else {
-        // the second load of the last chunk holds bytes of the piece (mis != 0), so it lies inside the input
-        const uint8_t *al = s0 - mis;
-        const uint32_t bsh = (mis & 3u) * 8u;
-        switch (mis >> 2) {
-            case 0: copy_body_g<0>(al, bsh, dst + hn, nfull, lane); break;
-            case 1: copy_body_g<1>(al, bsh, dst + hn, nfull, lane); break;
-            case 2: copy_body_g<2>(al, bsh, dst + hn, nfull, lane); break;
-            default: copy_body_g<3>(al, bsh, dst + hn, nfull, lane); break;
-        }
-    }
-    if ((uint32_t)lane < hn) {
-        st_global_u8(dst + lane, __ldg(src + lane));
-    } else if (lane >= 16 && (uint32_t)(lane - 16) < tn) {
-        const uint32_t off = hn + (nfull << 4) + (uint32_t)(lane - 16);
-        st_global_u8(dst + off, __ldg(src + off));
     }
 }
 
@@ -673,49 +591,6 @@ __device__ __forceinline__ uint32_t check_newline(const uint8_t *tile, uint32_t 
     return fb;
 }
 
-// ---- P4: the kept (and, in split mode, the other) bytes of tile t to their final place.  Every warp reads
-//      the tile's prefix itself (one 64-bit word, written by the sequencer; ready long before in DEFER 2)
-template <bool FROM_GLOBAL>
-__device__ __forceinline__ void retire_tile(const FusedParams &P, CtaSmem *S, uint32_t slot, uint64_t t,
-                                            uint32_t tile_s, int warp, int lane) {
-    unsigned long long pv = 0;
-    if (lane == 0) {
-        while (!((pv = ld_relaxed(P.pref + t)) >> 63)) __nanosleep(SGPU_FUSED_POLL_NS);
-    }
-    pv = __shfl_sync(0xffffffffu, pv, 0);
-    if (warp == 0 && lane == 0) TRACE(t, 3);
-    const uint64_t kept_before = pv & ((1ull << 59) - 1);
-    const uint32_t carry = (uint32_t)(pv >> 59) & 3u;
-    const uint64_t g0 = t * (uint64_t)TILE;
-    const uint32_t head_len = S->head_len[slot];
-    uint32_t n_items = S->n_items[slot];
-    if (n_items > (uint32_t)IMAX) n_items = IMAX;
-    const uint32_t head_kept = carry == F_KEPT ? head_len : 0u;
-    uint8_t *const base_w = P.out_w + kept_before;  // the head goes here when it is kept
-    // bytes of the other stream before this tile = owned bytes before it - kept bytes before it
-    uint8_t *const base_o = P.out_o ? P.out_o + (t == 0 ? 0 : (g0 - P.lead) - kept_before) : nullptr;
-    const uint32_t head_other = carry == F_OTHER ? head_len : 0u;
-    const uint8_t *const gsrc = P.in + g0;
-    for (uint32_t i = warp; i < n_items; i += NW) {
-        const Item itm = S->items[slot][i];
-        const uint32_t tag = itm.rel & (3u << 30), rel = itm.rel & 0x3FFFFFFFu;
-        uint8_t *dst;
-        if (tag == TAG_KEPT) {
-            dst = base_w + head_kept + rel;
-        } else if (tag == TAG_OTHER) {
-            dst = base_o + head_other + rel;
-        } else {
-            if (carry == F_KEPT) dst = base_w + rel;
-            else if (carry == F_OTHER && base_o) dst = base_o + rel;
-            else continue;
-        }
-#ifndef SGPU_ABL_NOCOPY  // ablation (timing only): nothing is written
-        if (FROM_GLOBAL) copy_piece_g(gsrc + itm.src, itm.len, dst, lane);
-        else copy_piece(tile_s + itm.src, itm.len, dst, lane);
-#endif
-    }
-}
-
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(FusedParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     CtaSmem *S = reinterpret_cast<CtaSmem *>(smem_raw);
@@ -723,223 +598,229 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
     uint8_t *buf = S->buf;
     const uint8_t *tile = buf + PRE;  // tile[-16 .. avail)
     const uint32_t tile_s = smem_u32(tile);
-    constexpr uint64_t NO_TILE = ~0ull;
     if (tid == 0) {
-        // the first CTA to arrive is resident before every ticket holder: it runs the sequencer
-        const bool seq = atomicAdd(&P.res->role, 1ull) == 0ull;
-        S->is_seq = seq ? 1u : 0u;
-        if (!seq) {
-            mbar_init(&S->full, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const unsigned long long t0 = atomicAdd(&P.res->ticket, 1ull);
-            S->first_tile = t0;
-            if (t0 < P.n_tiles) {
-                TRACE(t0, 0);
-                issue_load(P, S, t0);
-            }
+        mbar_init(&S->full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned long long t0 = atomicAdd(&P.res->ticket, 1ull);
+        S->first_tile = t0;
+        if (t0 < P.n_tiles) {
+            TRACE(t0, 0);
+            issue_load(P, S, t0);
         }
     }
     __syncthreads();
-    if (S->is_seq) {
-        if (warp == 0) sequencer_warp(P, lane);
-        return;
-    }
     uint64_t t = S->first_tile;
-    uint64_t pend = NO_TILE;  // DEFER 2: the tile whose copy is still owed (its items are in the other slot)
     unsigned long long my_reads_in = 0, my_reads_out = 0;  // thread 0 only
 #ifdef SGPU_FUSED_TIMING
     unsigned long long ph_acc[12] = {0};
     long long ph_last = clock64();
 #endif
-    for (uint32_t it = 0; t < P.n_tiles || pend != NO_TILE; it++) {
-        const bool have = t < P.n_tiles;  // (CTA-uniform)
-        const uint32_t slot = DEFER == 2 ? (it & 1u) : 0u;
-        if (have) {
-            // the tile some CTA will take one generation from now: pull it into L2
-            if (tid == 0 && P.pf_dist) prefetch_tile(P, t + P.pf_dist);
-            if (lane == 0) {
-                while (!mbar_try_wait(&S->full, it & 1)) {
-                }
+    for (uint32_t it = 0; t < P.n_tiles; it++) {
+        // the tile some CTA will take one generation from now: pull it into L2
+        if (tid == 0 && P.pf_dist) prefetch_tile(P, t + P.pf_dist);
+        if (lane == 0) {
+            while (!mbar_try_wait(&S->full, it & 1)) {
             }
-            __syncwarp();
-            PHASE_MARK(0);  // load wait
-            if (tid == 0) {
-                TRACE(t, 1);
+        }
+        __syncwarp();
+        PHASE_MARK(0);  // load wait
+        if (tid == 0) {
+            TRACE(t, 1);
 #ifdef SGPU_FUSED_TIMING
-                if (g_trace) g_trace[t * 8 + 5] = smid();
+            if (g_trace) g_trace[t * 8 + 5] = smid();
 #endif
+        }
+        const uint64_t g0 = t * (uint64_t)TILE;
+        const uint32_t tile_len = (uint32_t)((P.n_in - g0) < (uint64_t)TILE ? (P.n_in - g0) : (uint64_t)TILE);
+        const uint32_t avail =
+            (uint32_t)((P.n_in - g0) < (uint64_t)(TILE + HALO) ? (P.n_in - g0) : (uint64_t)(TILE + HALO));
+        const uint32_t lead_t = t == 0 ? P.lead : 0u;
+        uint32_t fb = 0;  // this thread's fallback reason (0 = none)
+        if (t == 0 || tile_len < (uint32_t)TILE) {  // (CTA-uniform) first / last tile of the buffer
+            // every thread observes the completed load, then the edges are patched
+            while (!mbar_try_wait(&S->full, it & 1)) {
             }
-            const uint64_t g0 = t * (uint64_t)TILE;
-            const uint32_t tile_len = (uint32_t)((P.n_in - g0) < (uint64_t)TILE ? (P.n_in - g0) : (uint64_t)TILE);
-            const uint32_t avail =
-                (uint32_t)((P.n_in - g0) < (uint64_t)(TILE + HALO) ? (P.n_in - g0) : (uint64_t)(TILE + HALO));
-            const uint32_t lead_t = t == 0 ? P.lead : 0u;
-            uint32_t fb = 0;  // this thread's fallback reason (0 = none)
-            if (t == 0 || tile_len < (uint32_t)TILE) {  // (CTA-uniform) first / last tile of the buffer
-                // every thread observes the completed load, then the edges are patched
-                while (!mbar_try_wait(&S->full, it & 1)) {
-                }
-                if (t == 0 && tid < PRE) buf[tid] = '\n';  // no predecessor: the pre-halo reads as a newline
-                // bytes past the end of the buffer are stale: zero them (never a newline, ASCII)
-                for (uint32_t o = tile_len + tid; o < (uint32_t)TILE; o += NT) buf[PRE + o] = 0;
-                __syncthreads();
-            }
+            if (t == 0 && tid < PRE) buf[tid] = '\n';  // no predecessor: the pre-halo reads as a newline
+            // bytes past the end of the buffer are stale: zero them (never a newline, ASCII)
+            for (uint32_t o = tile_len + tid; o < (uint32_t)TILE; o += NT) buf[PRE + o] = 0;
+            __syncthreads();
+        }
 
-            // ---- P1: newline masks and counts.  Warp w owns chunks [w*FC*32, (w+1)*FC*32); lane l takes
-            //      chunk k*32 + l of them in round k (conflict-free 16-byte shared loads)
-            uint32_t m[FC];
-            uint32_t hi_or = 0;
-            const uint32_t cbase = (uint32_t)warp * (FC * 32) + (uint32_t)lane;
+        // ---- P1: newline masks and counts.  Warp w owns chunks [w*FC*32, (w+1)*FC*32); lane l takes
+        //      chunk k*32 + l of them in round k (conflict-free 16-byte shared loads)
+        uint32_t m[FC];
+        uint32_t hi_or = 0;
+        const uint32_t cbase = (uint32_t)warp * (FC * 32) + (uint32_t)lane;
 #pragma unroll
-            for (int k = 0; k < FC; k++) {
-                const uint4 v = lds_v4(tile_s + (cbase + k * 32) * 16);
-                m[k] = nl_mask16_v2(v);
-                hi_or |= (v.x | v.y | v.z | v.w);
-            }
-            if (lead_t && tid == 0) m[0] &= ~((1u << lead_t) - 1u);  // the previous shard's bytes
-            if (hi_or & 0x80808080u) fb = 1;                         // reason 1: non-ASCII byte, Unicode rules needed
-            // inclusive warp scan of the per-round counts: three 10-bit fields per word (a round has <= 512 newlines)
-            constexpr int PW = (FC + 2) / 3;
-            uint32_t pk[PW], inc[PW];
-            uint32_t many = 0;  // a chunk with more than two newlines: lines shorter than the fast path handles
+        for (int k = 0; k < FC; k++) {
+            const uint4 v = lds_v4(tile_s + (cbase + k * 32) * 16);
+            m[k] = nl_mask16_v2(v);
+            hi_or |= (v.x | v.y | v.z | v.w);
+        }
+        if (lead_t && tid == 0) m[0] &= ~((1u << lead_t) - 1u);  // the previous shard's bytes
+        if (hi_or & 0x80808080u) fb = 1;                         // reason 1: non-ASCII byte, Unicode rules needed
+        // inclusive warp scan of the per-round counts: three 10-bit fields per word (a round has <= 512 newlines)
+        constexpr int PW = (FC + 2) / 3;
+        uint32_t pk[PW], inc[PW];
+        uint32_t many = 0;  // a chunk with more than two newlines: lines shorter than the fast path handles
 #pragma unroll
-            for (int q = 0; q < PW; q++) pk[q] = 0;
+        for (int q = 0; q < PW; q++) pk[q] = 0;
 #pragma unroll
-            for (int k = 0; k < FC; k++) {
-                const uint32_t c = (uint32_t)__popc(m[k]);
-                many |= (c + 1u) >> 2;  // != 0 iff c >= 3
-                pk[k / 3] |= c << (10 * (k % 3));
-            }
+        for (int k = 0; k < FC; k++) {
+            const uint32_t c = (uint32_t)__popc(m[k]);
+            many |= (c + 1u) >> 2;  // != 0 iff c >= 3
+            pk[k / 3] |= c << (10 * (k % 3));
+        }
 #pragma unroll
-            for (int q = 0; q < PW; q++) inc[q] = pk[q];
+        for (int q = 0; q < PW; q++) inc[q] = pk[q];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-                for (int q = 0; q < PW; q++) {
-                    const uint32_t x = __shfl_up_sync(0xffffffffu, inc[q], d);
-                    if (lane >= d) inc[q] += x;
-                }
-            }
-            uint32_t row_base[FC];
-            uint32_t wtot = 0;
+        for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
             for (int q = 0; q < PW; q++) {
-                const uint32_t rt = __shfl_sync(0xffffffffu, inc[q], 31);
-                const uint32_t ex = inc[q] - pk[q];  // exclusive within the round
+                const uint32_t x = __shfl_up_sync(0xffffffffu, inc[q], d);
+                if (lane >= d) inc[q] += x;
+            }
+        }
+        uint32_t row_base[FC];
+        uint32_t wtot = 0;
 #pragma unroll
-                for (int k = 3 * q; k < 3 * q + 3 && k < FC; k++) {
-                    row_base[k] = wtot + ((ex >> (10 * (k % 3))) & 1023u);
-                    wtot += (rt >> (10 * (k % 3))) & 1023u;
+        for (int q = 0; q < PW; q++) {
+            const uint32_t rt = __shfl_sync(0xffffffffu, inc[q], 31);
+            const uint32_t ex = inc[q] - pk[q];  // exclusive within the round
+#pragma unroll
+            for (int k = 3 * q; k < 3 * q + 3 && k < FC; k++) {
+                row_base[k] = wtot + ((ex >> (10 * (k % 3))) & 1023u);
+                wtot += (rt >> (10 * (k % 3))) & 1023u;
+            }
+        }
+        const bool many_w = __any_sync(0xffffffffu, many != 0u);
+        if (lane == 0) S->warp_tot[warp] = wtot | (many_w ? 0x80000000u : 0u);
+        if (tid == 0) {
+            S->n_items = 0;
+            S->none_pos = 0xFFFFFFFFu;
+            S->none_cnt = 0;
+        }
+        PHASE_MARK(1);    // P1 own work
+        __syncthreads();  // B1
+        PHASE_MARK(2);    // B1 wait
+        // newlines before the warp's region / in the tile: lane w holds warp w's count
+        uint32_t n_nl, wbase;
+        bool dense;
+        {
+            const uint32_t x = lane < NW ? S->warp_tot[lane] : 0u;
+            const uint32_t cnt = x & 0x7FFFFFFFu;
+            uint32_t ic = cnt;
+#pragma unroll
+            for (int d = 1; d < NW; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ic, d);
+                if (lane >= d) ic += y;
+            }
+            n_nl = __shfl_sync(0xffffffffu, ic, NW - 1);
+            wbase = __shfl_sync(0xffffffffu, ic - cnt, warp);
+            dense = __any_sync(0xffffffffu, (x >> 31) != 0u) || n_nl > (uint32_t)LMAX;
+        }
+        // ---- the newline positions, in order (at most two per 16-byte chunk here: "\n+\n")
+        if (!dense) {
+#pragma unroll
+            for (int k = 0; k < FC; k++) {
+                uint32_t mm = m[k];
+                if (mm) {
+                    const uint32_t r = wbase + row_base[k];
+                    const uint32_t pos = (cbase + k * 32) * 16;
+                    S->nlp[r] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
+                    mm &= mm - 1;
+                    if (mm) S->nlp[r + 1] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
                 }
             }
-            const bool many_w = __any_sync(0xffffffffu, many != 0u);
-            if (lane == 0) S->warp_tot[warp] = wtot | (many_w ? 0x80000000u : 0u);
-            PHASE_MARK(1);    // P1 own work
-            __syncthreads();  // B1 (also: every warp is done with the previous iteration's copy)
-            PHASE_MARK(2);    // B1 wait
-            if (tid == 0) {
-                S->n_items[slot] = 0;
-                S->none_pos = 0xFFFFFFFFu;
-                S->none_cnt = 0;
+        } else {
+            fb = 2;
+        }
+        __syncthreads();  // B2
+        PHASE_MARK(3);    // scatter + B2
+        // ---- line phase: the first newline followed by "+\n" ends a sequence line (role 1).  Every warp
+        //      evaluates the same 32 candidates, so the outcome is CTA-uniform without a barrier.
+        uint32_t c0 = 0;
+        if (t == 0) {
+            if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | (n_nl & 3));
+        } else {
+            bool hit = false;
+            if (!dense && (uint32_t)lane < n_nl) {
+                const uint32_t p = S->nlp[lane];
+                hit = p + 2 < avail && tile[p + 1] == '+' && tile[p + 2] == '\n';
             }
-            // newlines before the warp's region / in the tile: lane w holds warp w's count
-            uint32_t n_nl, wbase;
-            bool dense;
-            {
-                const uint32_t x = lane < NW ? S->warp_tot[lane] : 0u;
-                const uint32_t cnt = x & 0x7FFFFFFFu;
-                uint32_t ic = cnt;
-#pragma unroll
-                for (int d = 1; d < NW; d <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, ic, d);
-                    if (lane >= d) ic += y;
-                }
-                n_nl = __shfl_sync(0xffffffffu, ic, NW - 1);
-                wbase = __shfl_sync(0xffffffffu, ic - cnt, warp);
-                dense = __any_sync(0xffffffffu, (x >> 31) != 0u) || n_nl > (uint32_t)LMAX;
-            }
-            // ---- the newline positions, in order (at most two per 16-byte chunk here: "\n+\n")
-            if (!dense) {
-#pragma unroll
-                for (int k = 0; k < FC; k++) {
-                    uint32_t mm = m[k];
-                    if (mm) {
-                        const uint32_t r = wbase + row_base[k];
-                        const uint32_t pos = (cbase + k * 32) * 16;
-                        S->nlp[r] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
-                        mm &= mm - 1;
-                        if (mm) S->nlp[r + 1] = (uint16_t)(pos + (uint32_t)(__ffs(mm) - 1));
-                    }
-                }
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (b) {
+                c0 = (1u - (uint32_t)(__ffs(b) - 1)) & 3u;  // role(first) = (c0 + first) & 3 == 1
+                if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | ((c0 + n_nl) & 3));
             } else {
-                fb = 2;
-            }
-            __syncthreads();  // B2
-            PHASE_MARK(3);    // scatter + B2
-            // ---- line phase: the first newline followed by "+\n" ends a sequence line (role 1).  Every warp
-            //      evaluates the same 32 candidates, so the outcome is CTA-uniform without a barrier.
-            uint32_t c0 = 0;
-            if (t == 0) {
-                if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | (n_nl & 3));
-            } else {
-                bool hit = false;
-                if (!dense && (uint32_t)lane < n_nl) {
-                    const uint32_t p = S->nlp[lane];
-                    hit = p + 2 < avail && tile[p + 1] == '+' && tile[p + 2] == '\n';
+                if (warp == 0) {
+                    c0 = lookback_phase_warp(P.desc1, t, n_nl, lane);
+                    if (lane == 0) S->c0 = c0;
                 }
-                const unsigned b = __ballot_sync(0xffffffffu, hit);
-                if (b) {
-                    c0 = (1u - (uint32_t)(__ffs(b) - 1)) & 3u;  // role(first) = (c0 + first) & 3 == 1
-                    if (tid == 0) st_relaxed(P.desc1 + t, ST_INC | ((c0 + n_nl) & 3));
-                } else {
-                    if (warp == 0) {
-                        c0 = lookback_phase_warp(P.desc1, t, n_nl, lane);
-                        if (lane == 0) S->c0 = c0;
-                    }
-                    __syncthreads();
-                    c0 = S->c0;
-                }
+                __syncthreads();
+                c0 = S->c0;
             }
-            // the first byte of the tile starts a record iff 4k newlines precede it and the previous byte is one;
-            // tile 0 starts with a record by construction (at `lead`)
-            const bool pos0_start = t == 0 || ((c0 == 0) && tile[-1] == '\n');
-            const uint32_t r3 = (3u - c0) & 3u;  // index of the first newline that ends a record
-            // number of record starts inside the tile
-            const uint32_t n_term = (c0 + n_nl) >> 2;
-            uint32_t n_starts = n_term + (pos0_start ? 1u : 0u);
-            if (n_term > 0 && !dense) {
-                // the last terminating newline may sit on the tile's final byte: its record belongs to the next tile
-                if ((uint32_t)S->nlp[r3 + 4u * (n_term - 1)] + 1u >= tile_len) n_starts--;
-            }
-            if (n_starts > (uint32_t)RMAX) fb = 5;
-            if (dense || n_starts > (uint32_t)RMAX) n_starts = 0;  // (a fallback reason is raised)
-            // the carried-in record's bytes
-            const uint32_t head_len =
-                n_starts ? (pos0_start ? lead_t : (uint32_t)S->nlp[r3] + 1u) : tile_len;
-            if (warp == NW - 1) {
-                // the carried-in head as copy items (its fate comes with the tile's prefix); the `lead` bytes of
-                // tile 0 belong to the previous shard
-                const uint32_t nph = t == 0 ? 0u : (head_len + PIECE - 1) / PIECE;
-                if (nph) {
-                    uint32_t islot = 0;
-                    if (lane == 0) islot = atomicAdd(&S->n_items[slot], nph);
-                    islot = __shfl_sync(0xffffffffu, islot, 0);
-                    if ((uint32_t)lane < nph && islot + lane < (uint32_t)IMAX) {
-                        const uint32_t o = (uint32_t)lane * PIECE;
-                        Item itm;
-                        itm.src = (uint16_t)o;
-                        itm.len = (uint16_t)(head_len - o < (uint32_t)PIECE ? head_len - o : (uint32_t)PIECE);
-                        itm.rel = TAG_HEAD | o;
-                        S->items[slot][islot + lane] = itm;
-                    }
-                }
-                if (lane == 0) S->head_len[slot] = head_len;
-            }
+        }
+        // the first byte of the tile starts a record iff 4k newlines precede it and the previous byte is one;
+        // tile 0 starts with a record by construction (at `lead`)
+        const bool pos0_start = t == 0 || ((c0 == 0) && tile[-1] == '\n');
+        const uint32_t r3 = (3u - c0) & 3u;  // index of the first newline that ends a record
+        // number of record starts inside the tile
+        const uint32_t n_term = (c0 + n_nl) >> 2;
+        uint32_t n_starts = n_term + (pos0_start ? 1u : 0u);
+        if (n_term > 0 && !dense) {
+            // the last terminating newline may sit on the tile's final byte: its record belongs to the next tile
+            if ((uint32_t)S->nlp[r3 + 4u * (n_term - 1)] + 1u >= tile_len) n_starts--;
+        }
+        if (n_starts > (uint32_t)RMAX) fb = 5;
+        if (dense || n_starts > (uint32_t)RMAX) n_starts = 0;  // (a fallback reason is raised)
+        // the carried-in record's bytes
+        const uint32_t head_len =
+            n_starts ? (pos0_start ? lead_t : (uint32_t)S->nlp[r3] + 1u) : tile_len;
+        // the look-back only needs the tiles before this one: when the last warp has no record to look after,
+        // it runs the look-back while the others work on the records (CTA-uniform)
+        const bool early = n_starts <= (uint32_t)(NT - 32);
 
+        uint32_t rest_total = 0, kept_recs = 0;
+        if (early && warp == NW - 1) {
+            if (lane == 0) S->scan_tot[warp] = 0;
+            bar_arrive(1);  // B4: nothing to contribute
+            // the carried-in head as copy items (its fate is known after the look-back); the `lead` bytes of
+            // tile 0 belong to the previous shard
+            const uint32_t nph = t == 0 ? 0u : (head_len + PIECE - 1) / PIECE;
+            if (nph) {
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(&S->n_items, nph);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if ((uint32_t)lane < nph && slot + lane < (uint32_t)IMAX) {
+                    const uint32_t o = (uint32_t)lane * PIECE;
+                    Item itm;
+                    itm.src = (uint16_t)o;
+                    itm.len = (uint16_t)(head_len - o < (uint32_t)PIECE ? head_len - o : (uint32_t)PIECE);
+                    itm.rel = TAG_HEAD | o;
+                    S->items[slot + lane] = itm;
+                }
+            }
+            uint64_t kept_before;
+            uint32_t carry;
+#ifdef SGPU_ABL_NOLB  // ablation (timing only, output is garbage): no in-order commit
+            kept_before = g0 / 2;
+            carry = F_OTHER;
+#else
+            lookback_pred_warp(P.desc2, t, lane, &kept_before, &carry);
+#endif
+            bar_sync(2);  // the workers' totals are in shared memory (and the aggregate is published)
+            if (lane == 0) {
+                TRACE(t, 3);
+                st_relaxed(P.desc2 + t * DSTRIDE,
+                           inc_desc(n_starts > 0, S->last_flag, head_len, S->rest_total, kept_before, carry));
+                S->kept_before = kept_before;
+                S->carry = carry;
+            }
+        } else {
             // ---- P3: one thread per record start: checks of the record's lines, '@', id token -> exact probe,
             //      kept bytes scanned per warp, runs cut into copy items.  NT records per round (almost
             //      always one round)
-            uint32_t rest_total = 0, kept_recs = 0;
             const uint32_t n_rounds = n_starts > (uint32_t)NT ? (n_starts + NT - 1) / NT : 1u;
             for (uint32_t round = 0; round < n_rounds; round++) {
                 const uint32_t jb = round * NT;
@@ -1002,9 +883,9 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                     }
                 }
                 if (lane == 31) S->scan_tot[warp] = inc;
-                PHASE_MARK(5);    // P3 own work (probe included)
-                __syncthreads();  // B4
-                PHASE_MARK(6);    // B4 wait
+                PHASE_MARK(5);  // P3 own work (probe included)
+                bar_sync(1);    // B4
+                PHASE_MARK(6);  // B4 wait
                 uint32_t base = 0, tot = 0;
                 {
                     const uint32_t x = lane < NW ? S->scan_tot[lane] : 0u;
@@ -1021,14 +902,17 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                 rest_total += tot & 0xFFFFu;
                 kept_recs += tot >> 16;
                 if (round + 1 == n_rounds && tid == 0) {
-                    // the aggregate: the sequencer (and through it every later tile) is waiting for it
+                    // the aggregate: every later tile may be waiting for it
                     const uint32_t last_flag = n_starts ? S->last_flag : F_OTHER;
                     TRACE(t, 2);
-                    st_relaxed(P.agg + t, agg_desc(n_starts > 0, last_flag, head_len, rest_total));
+                    st_relaxed(P.desc2 + t * DSTRIDE, agg_desc(n_starts > 0, last_flag, head_len, rest_total));
+                    S->rest_total = rest_total;
+                    if (!n_starts) S->last_flag = F_OTHER;
                 }
+                if (round + 1 == n_rounds && early) bar_arrive(2);  // totals handed to the look-back warp
                 if (warp_active) {
-                    emit_runs<F_KEPT>(S, slot, flag, sp, e, Kx, head_len, lane);
-                    if (P.out_o) emit_runs<F_OTHER>(S, slot, flag, sp, e, Kx, head_len, lane);
+                    emit_runs<F_KEPT>(S, flag, sp, e, Kx, head_len, lane);
+                    if (P.out_o) emit_runs<F_OTHER>(S, flag, sp, e, Kx, head_len, lane);
                 }
                 if (round + 1 < n_rounds) __syncthreads();  // scan_tot is reused
             }
@@ -1077,57 +961,88 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                 // end-of-file condition of canonical input (the line count is checked by the follow-up kernel)
                 if (P.is_last && t + 1 == P.n_tiles && tile[tile_len - 1] != '\n') set_fallback(P.res, 9);
             }
-            if (fb) set_fallback(P.res, (int)fb);
-            PHASE_MARK(7);  // emit
-        }
-        if (DEFER == 0) {
-            // ---- copy from the shared-memory tile, then the next ticket and its load
-            __syncthreads();  // B5: every copy item is there
-            PHASE_MARK(8);
-            retire_tile<false>(P, S, 0, t, tile_s, warp, lane);
-            PHASE_MARK(9);  // look-back wait + copy
-            if (tid == 0) {
-                TRACE(t, 4);
-                const unsigned long long nt = atomicAdd(&P.res->ticket, 1ull);
-                if (nt < P.n_tiles) TRACE(nt, 0);
-                S->next_tile = nt;
-            }
-            __syncthreads();  // B6: every read of the tile buffer and the lists is done
-            PHASE_MARK(10);
-            const uint64_t next_t = S->next_tile;
-            if (tid == 0 && next_t < P.n_tiles) issue_load(P, S, next_t);
-            t = next_t;
-        } else {
-            // ---- the tile buffer is free as soon as the records are decided: next ticket, next load, and the
-            //      copy (from global memory / L2) runs while that load is in flight
-            if (DEFER == 3) {
-                __syncthreads();  // every read of the tile buffer is done, every copy item is there
-                if (tid == 0) {
-                    while (!(ld_relaxed(P.pref + t) >> 63)) __nanosleep(SGPU_FUSED_POLL_NS);
+            if (!early && warp == NW - 1) {
+                // (rare) the last warp had records of its own: head items and look-back only now
+                const uint32_t nph = t == 0 ? 0u : (head_len + PIECE - 1) / PIECE;
+                if (nph) {
+                    uint32_t slot = 0;
+                    if (lane == 0) slot = atomicAdd(&S->n_items, nph);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if ((uint32_t)lane < nph && slot + lane < (uint32_t)IMAX) {
+                        const uint32_t o = (uint32_t)lane * PIECE;
+                        Item itm;
+                        itm.src = (uint16_t)o;
+                        itm.len = (uint16_t)(head_len - o < (uint32_t)PIECE ? head_len - o : (uint32_t)PIECE);
+                        itm.rel = TAG_HEAD | o;
+                        S->items[slot + lane] = itm;
+                    }
+                }
+                uint64_t kept_before;
+                uint32_t carry;
+#ifdef SGPU_ABL_NOLB
+                kept_before = g0 / 2;
+                carry = F_OTHER;
+#else
+                lookback_pred_warp(P.desc2, t, lane, &kept_before, &carry);
+#endif
+                if (lane == 0) {
+                    TRACE(t, 3);
+                    st_relaxed(P.desc2 + t * DSTRIDE, inc_desc(n_starts > 0, n_starts ? S->last_flag : F_OTHER, head_len,
+                                                     rest_total, kept_before, carry));
+                    S->kept_before = kept_before;
+                    S->carry = carry;
                 }
             }
-            if (tid == 0) {
-                unsigned long long nt = NO_TILE;
-                if (have) {
-                    nt = atomicAdd(&P.res->ticket, 1ull);
-                    if (nt < P.n_tiles) TRACE(nt, 0);
-                }
-                S->next_tile = nt;
-            }
-            __syncthreads();  // B5: every read of the tile buffer is done, every copy item is there
-            PHASE_MARK(8);
-            const uint64_t next_t = S->next_tile;
-            if (tid == 0 && next_t < P.n_tiles) issue_load(P, S, next_t);
-            const uint64_t rt = DEFER == 2 ? pend : t;
-            if (rt != NO_TILE && rt < P.n_tiles) {
-                retire_tile<true>(P, S, DEFER == 2 ? (slot ^ 1u) : 0u, rt, tile_s, warp, lane);
-                if (tid == 0) TRACE(rt, 4);
-            }
-            PHASE_MARK(9);  // look-back wait + copy
-            if (DEFER == 2) pend = have ? t : NO_TILE;
-            if (DEFER == 1 || DEFER == 3) __syncthreads();  // the item list is rebuilt by the next tile
-            t = next_t;
         }
+        if (fb) set_fallback(P.res, (int)fb);
+        PHASE_MARK(7);    // emit
+        __syncthreads();  // B5: kept_before / carry / every copy item are there
+        PHASE_MARK(8);    // B5 wait (look-back)
+
+        // ---- P4: a warp per copy item.  The next ticket is taken only now: a ticket held while this tile
+        //      still waits on its look-back would stall every later tile behind this CTA
+        unsigned long long nt = 0;
+        if (tid == 0) nt = atomicAdd(&P.res->ticket, 1ull);
+        {
+            const uint64_t kept_before = S->kept_before;
+            const uint32_t carry = S->carry;
+            uint32_t n_items = S->n_items;
+            if (n_items > (uint32_t)IMAX) n_items = IMAX;
+            const uint32_t head_kept = carry == F_KEPT ? head_len : 0u;
+            uint8_t *const base_w = P.out_w + kept_before;  // the head goes here when it is kept
+            // bytes of the other stream before this tile = owned bytes before it - kept bytes before it
+            uint8_t *const base_o = P.out_o ? P.out_o + (t == 0 ? 0 : (g0 - P.lead) - kept_before) : nullptr;
+            const uint32_t head_other = carry == F_OTHER ? head_len : 0u;
+            for (uint32_t i = warp; i < n_items; i += NW) {
+                const Item itm = S->items[i];
+                const uint32_t tag = itm.rel & (3u << 30), rel = itm.rel & 0x3FFFFFFFu;
+                uint8_t *dst;
+                if (tag == TAG_KEPT) {
+                    dst = base_w + head_kept + rel;
+                } else if (tag == TAG_OTHER) {
+                    dst = base_o + head_other + rel;
+                } else {
+                    if (carry == F_KEPT) dst = base_w + rel;
+                    else if (carry == F_OTHER && base_o) dst = base_o + rel;
+                    else continue;
+                }
+#ifndef SGPU_ABL_NOCOPY  // ablation (timing only): nothing is written
+                copy_piece(tile_s + itm.src, itm.len, dst, lane);
+#endif
+            }
+            if (t + 1 == P.n_tiles && tid == 0) P.res->kept_total = kept_before + head_kept + S->rest_total;
+        }
+        PHASE_MARK(9);  // copy own work
+        if (tid == 0) {
+            TRACE(t, 4);
+            if (nt < P.n_tiles) TRACE(nt, 0);
+        }
+        if (tid == 0) S->next_tile = nt;
+        __syncthreads();  // B6: every read of the tile buffer and the lists is done
+        PHASE_MARK(10);   // ticket + B6 wait
+        const uint64_t next_t = S->next_tile;
+        if (tid == 0 && next_t < P.n_tiles) issue_load(P, S, next_t);
+        t = next_t;
     }
 #ifdef SGPU_FUSED_TIMING
     if (tid == 0)
@@ -1179,13 +1094,13 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     DevBuf<uint32_t> nl_count;
     DevBuf<uint8_t> bytes;
     DevBuf<FusedResult> res;
-    SGPU_TRY(desc.alloc(3 * n_tiles, st));
+    SGPU_TRY(desc.alloc((1 + DSTRIDE) * n_tiles, st));
     SGPU_TRY(sums.alloc(2 * n_tiles, st));
     SGPU_TRY(prefix.alloc(2 * n_tiles, st));
     SGPU_TRY(nl_count.alloc(n_tiles, st));
     SGPU_TRY(bytes.alloc(2 * n_tiles, st));
     SGPU_TRY(res.alloc(1, st));
-    SGPU_CUDA(cudaMemsetAsync(desc.p, 0, 3 * n_tiles * 8, st));
+    SGPU_CUDA(cudaMemsetAsync(desc.p, 0, (1 + DSTRIDE) * n_tiles * 8, st));
     FusedResult init;
     memset(&init, 0, sizeof(init));
     init.owned_end = ~0ull;
@@ -1204,8 +1119,7 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     P.reverse = reverse;
     P.set = view_of(set);
     P.desc1 = desc.p;
-    P.agg = desc.p + n_tiles;
-    P.pref = desc.p + 2 * n_tiles;
+    P.desc2 = desc.p + n_tiles;
     P.sum_total = sums.p;
     P.sum_head = sums.p + n_tiles;
     P.nl_count = nl_count.p;
@@ -1218,9 +1132,8 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
         SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fastq_fused_kernel, NTHREADS, smem));
         occ[c->device & 63] = o > 0 ? o : 1;
     }
-    // persistent: every CTA is resident; one of them (the first to arrive) runs the sequencer
-    uint64_t grid = (uint64_t)c->sm_count * occ[c->device & 63];
-    if (grid > n_tiles + 1) grid = n_tiles + 1;
+    uint64_t grid = (uint64_t)c->sm_count * occ[c->device & 63];  // persistent: every CTA is resident
+    if (grid > n_tiles) grid = n_tiles;
     // tiles are pulled into L2 one generation of CTAs ahead (SGPU_FUSED_PF scales the distance, 0 = off)
     static const double pf_factor = getenv("SGPU_FUSED_PF") ? atof(getenv("SGPU_FUSED_PF")) : 1.0;
     P.pf_dist = (uint64_t)((double)grid * pf_factor);

@@ -383,7 +383,7 @@ def test_fused_long_reads_straddle_many_tiles(ctx):
 
 @pytest.mark.parametrize("n", [1, 2, 49, 50, 51, 3000])
 def test_fused_small_and_tile_edge_sizes(ctx, n):
-    """tiny inputs and inputs whose size lands around a 16 KiB tile edge"""
+    """tiny inputs and inputs whose size lands around a 16 KiB boundary"""
     ids = [f"syn.{i}".encode() for i in range(0, n + 5, 2)]
     gs = api.IdSet.from_ids(ctx, ids)
     os_ = orc.OSet.from_ids(ids)
@@ -393,6 +393,47 @@ def test_fused_small_and_tile_edge_sizes(ctx, n):
         o = orc.clean_fastq(fq, os_)
         assert f.path == 1
         assert f.written == o.written and f.other == o.other
+
+
+def _fastq_with_record_end_at(target: int, n_after: int = 300) -> bytes:
+    """canonical FASTQ whose k-th record ends exactly at byte offset `target` (exclusive)"""
+    out = bytearray()
+    i = 0
+    while True:
+        rec = f"@syn.{i} 1:N:0:ATCACG\n{'ACGT' * 37}AC\n+\n{'I' * 150}\n".encode()
+        if len(out) + len(rec) + 60 > target:
+            break
+        out += rec
+        i += 1
+    rest = target - len(out)  # bytes of the record that must end at `target`
+    hdr = f"@syn.{i} x".encode()
+    body = rest - len(hdr) - 5  # "\n" seq "\n+\n" qual "\n"
+    if body % 2:
+        hdr += b"y"
+        body -= 1
+    L = body // 2
+    assert L >= 1
+    out += hdr + b"\n" + b"G" * L + b"\n+\n" + b"#" * L + b"\n"
+    assert len(out) == target
+    for j in range(i + 1, i + 1 + n_after):
+        out += f"@syn.{j} 1:N:0:ATCACG\n{'ACGT' * 37}AC\n+\n{'I' * 150}\n".encode()
+    return bytes(out)
+
+
+@pytest.mark.parametrize("edge", [16384, 32768, 36864, 2 * 36864])
+@pytest.mark.parametrize("delta", [-2, -1, 0, 1, 2])
+def test_fused_record_boundary_on_tile_edge(ctx, edge, delta):
+    """a record ends exactly on / next to a tile edge (tiles are 36 KiB; 16 / 32 KiB kept for other builds)"""
+    fq = _fastq_with_record_end_at(edge + delta)
+    ids = [f"syn.{i}".encode() for i in range(0, 800, 3)]
+    gs = api.IdSet.from_ids(ctx, ids)
+    os_ = orc.OSet.from_ids(ids)
+    for reverse in (False, True):
+        f = api.clean_fastq(ctx, gs, fq, reverse)
+        o = orc.clean_fastq(fq, os_, reverse)
+        assert f.path == 1
+        assert f.written == o.written and f.other == o.other
+        assert (f.reads_in, f.reads_out) == (o.reads_in, o.reads_out)
 
 
 def test_fused_falls_back_on_noncanonical(ctx):
