@@ -81,7 +81,10 @@ constexpr int IMAX = RMAX + 2 * (TILE / PIECE) + 8;  // copy items per tile
 #define SGPU_FUSED_POLL_NS 500
 #endif
 #ifndef SGPU_FUSED_LOAD_PIECE
-#define SGPU_FUSED_LOAD_PIECE 4096
+#define SGPU_FUSED_LOAD_PIECE 16384
+#endif
+#ifndef SGPU_FUSED_LB_K
+#define SGPU_FUSED_LB_K 1
 #endif
 // 64-bit words between the look-back #2 descriptors of two tiles: one 32-byte sector each, so that the
 // hundreds of polling warps do not all hit the same few L2 lines (measured: 1.18 -> 1.06 ms per 1.65 GB)
@@ -292,9 +295,22 @@ __device__ __forceinline__ void lookback_pred_warp(const unsigned long long *des
     uint64_t inc_total = 0;
     int64_t base = (int64_t)t - 1;  // nearest tile of the window; lane l looks at tile base - l
     const uint64_t virt = ST_INC | ((uint64_t)F_NONE << 59);  // before the buffer: nothing kept, nothing carried
-    while (true) {
-        const int64_t idx = base - lane;
-        unsigned long long x = idx >= 0 ? ld_relaxed(desc + idx * DSTRIDE) : virt;
+    // LBK windows are fetched per round trip: the nearest inclusive descriptor is typically ~200 tiles back
+    // (every resident CTA is between its load and its own look-back), one L2 latency per window adds up
+    constexpr int LBK = SGPU_FUSED_LB_K;
+    bool done = false;
+    while (!done) {
+        unsigned long long xs[LBK];
+#pragma unroll
+        for (int k = 0; k < LBK; k++) {
+            const int64_t idx = base - 32 * k - lane;
+            xs[k] = idx >= 0 ? ld_relaxed(desc + idx * DSTRIDE) : virt;
+        }
+#pragma unroll
+        for (int k = 0; k < LBK; k++) {
+        if (done) break;  // (warp-uniform)
+        const int64_t idx = base - 32 * k - lane;
+        unsigned long long x = xs[k];
         int L;
         // every descriptor up to the nearest inclusive one must be there
         while (true) {
@@ -331,9 +347,10 @@ __device__ __forceinline__ void lookback_pred_warp(const unsigned long long *des
         acc_all = compose(W, acc_all);
         if (L < 32) {
             inc_total = __shfl_sync(0xffffffffu, x, L) & ((1ull << 59) - 1);
-            break;
+            done = true;
         }
-        base -= 32;
+        }
+        base -= 32 * LBK;
     }
     // acc_all starts with the inclusive descriptor (has == 1, P == 0)
     *kept_before = inc_total + acc_all.K;
@@ -1135,7 +1152,7 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     uint64_t grid = (uint64_t)c->sm_count * occ[c->device & 63];  // persistent: every CTA is resident
     if (grid > n_tiles) grid = n_tiles;
     // tiles are pulled into L2 one generation of CTAs ahead (SGPU_FUSED_PF scales the distance, 0 = off)
-    static const double pf_factor = getenv("SGPU_FUSED_PF") ? atof(getenv("SGPU_FUSED_PF")) : 1.0;
+    static const double pf_factor = getenv("SGPU_FUSED_PF") ? atof(getenv("SGPU_FUSED_PF")) : 0.5;
     P.pf_dist = (uint64_t)((double)grid * pf_factor);
     if (c->profiling) {
         if (c->prof_used == c->prof_events.size()) {
