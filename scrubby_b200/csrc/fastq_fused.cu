@@ -11,7 +11,7 @@
 // parse errors, pathological line density) raises the device `fallback` flag and the caller
 // re-runs the always-exact general path (fastq_general.cu); nothing is approximated.
 //
-// Structure (v3): persistent CTAs of 256 threads, several resident per SM, each looping over
+// Structure (v3.3): persistent CTAs of 256 threads, five resident per SM, each looping over
 // dynamically ticketed 36 KiB tiles (tickets are taken in order, so every tile a look-back waits on is
 // owned by a running CTA).  One shared-memory tile buffer per CTA; the latency
 // of a tile's dependent steps (load, set probes, look-back) is hidden by the other resident CTAs.
