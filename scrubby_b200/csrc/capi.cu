@@ -137,6 +137,8 @@ void ctx_release(sgpu_ctx *c) {
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (int i = 0; i < 5; i++)
+        if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
     for (auto &e : c->prof_events) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -361,13 +363,33 @@ static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, cons
     cudaStream_t st = c->stream;
     const size_t K = ceil_div(n_in, CHUNK);
     const size_t obuf = CHUNK + HALO + 64;
-    DevBuf<uint8_t> d_in, d_w[2], d_o[2];
-    SGPU_TRY(d_in.alloc(n_in + 16, st));
+    // context-owned staging (the context is locked): 0 the file, 1-2 kept chunks, 3-4 removed chunks
+    auto staging = [&](int i, size_t bytes, uint8_t **p) -> sgpu_status {
+        if (c->pipe_cap[i] < bytes) {
+            SGPU_CUDA(cudaStreamSynchronize(st));
+            if (c->pipe_buf[i]) SGPU_CUDA(cudaFree(c->pipe_buf[i]));
+            c->pipe_buf[i] = nullptr;
+            c->pipe_cap[i] = 0;
+            const size_t want = bytes + (bytes >> 4);  // a little slack: mate files differ by a few bytes
+            cudaError_t e = cudaMalloc((void **)&c->pipe_buf[i], want);
+            if (e != cudaSuccess) {
+                set_cuda_error(e, __FILE__, __LINE__);
+                return e == cudaErrorMemoryAllocation ? SGPU_ERR_NOMEM : SGPU_ERR_CUDA;
+            }
+            c->pipe_cap[i] = want;
+        }
+        *p = c->pipe_buf[i];
+        return SGPU_OK;
+    };
+    struct Ptr {
+        uint8_t *p = nullptr;
+    } d_in, d_w[2], d_o[2];
+    SGPU_TRY(staging(0, n_in + 16, &d_in.p));
     for (int r = 0; r < 2; r++) {
-        SGPU_TRY(d_w[r].alloc(obuf, st));
-        if (out_o) SGPU_TRY(d_o[r].alloc(obuf, st));
+        SGPU_TRY(staging(1 + r, obuf, &d_w[r].p));
+        if (out_o) SGPU_TRY(staging(3 + r, obuf, &d_o[r].p));
     }
-    SGPU_CUDA(cudaStreamSynchronize(st));  // the allocations are stream-ordered on `st`; the copy streams use them
+    SGPU_CUDA(cudaStreamSynchronize(st));  // earlier work on `st` that used the staging is done
     std::vector<cudaEvent_t> ev_in(K);
     cudaEvent_t ev_k[2], ev_out[2];
     for (size_t k = 0; k < K; k++) SGPU_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));

@@ -90,6 +90,10 @@ struct sgpu_ctx {
     uint64_t *h_pinned = nullptr;  // 64 x u64
     // copy streams of the pipelined host-buffer path (created on first use)
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    // grow-only staging of that path (input file, two kept and two removed chunk buffers): taking GBs from the
+    // stream-ordered pool on every call costs an occasional 0.3-0.6 s remap; released with the context
+    uint8_t *pipe_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t pipe_cap[5] = {0, 0, 0, 0, 0};
     // optional timing of the dominant (fused) kernel with CUDA events on the launching stream
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;

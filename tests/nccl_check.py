@@ -1,0 +1,52 @@
+"""Real NCCL check of the multi-GPU driver (run under torchrun on >= 2 GPUs; not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tests/nccl_check.py
+
+Rank 0 builds the id set from Kraken2 lines, the set is replicated by NCCL broadcast, every rank cleans its
+byte range of both mate files, counters are allreduced, and the rank-order concatenation must be byte-identical
+to the unsharded single-GPU output (which tests/test_gpu_parity.py pins to the oracle).
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from bench import taxids_for_config
+from scrubby_b200 import api, synth
+from scrubby_b200.dist import GpuOps, clean_fastq_sharded
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ctx = api.Context(local)
+ops = GpuOps(ctx)
+n = 300_000
+taxids = taxids_for_config()
+ids = api.IdSet.from_reads(ctx, synth.gen_kraken_reads(n).numpy().tobytes(), 0, taxids) if rank == 0 else None
+ids = ops.replicate_set(ids, dist, 0)
+ok = True
+for mate in (1, 2):
+    fq = synth.gen_fastq(n, mate).numpy().tobytes()
+    for reverse in (False, True):
+        r = clean_fastq_sharded(ops, ids, fq, dist, reverse=reverse, want_other=True)
+        parts = [None] * world
+        dist.all_gather_object(parts, (r.written, r.other))
+        if rank == 0:
+            whole = api.clean_fastq(ctx, ids, fq, reverse)
+            cat_w = b"".join(p[0] for p in parts)
+            cat_o = b"".join(p[1] for p in parts)
+            good = cat_w == whole.written and cat_o == whole.other and \
+                (r.reads_in, r.reads_out) == (whole.reads_in, whole.reads_out) and r.total_written == len(whole.written)
+            print(f"mate {mate} reverse {reverse}: world {world} reads_in {r.reads_in} reads_out {r.reads_out} "
+                  f"bytes {len(cat_w)} -> {'identical' if good else 'MISMATCH'}")
+            ok = ok and good
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.broadcast(flag, 0)
+dist.destroy_process_group()
+if rank == 0:
+    print("nccl_check", "ok" if ok else "FAILED")
+sys.exit(0 if int(flag) else 1)
