@@ -57,7 +57,8 @@ typedef enum {
     SGPU_ERR_INVALID_ARG = 18,
     SGPU_ERR_CAPACITY = 19,             /* an output buffer is too small; required sizes are returned */
     SGPU_ERR_KEY_TOO_LONG = 20,         /* a read id of 16 MiB or more */
-    SGPU_ERR_HALO = 21                  /* shard: the last owned record does not end inside the buffer */
+    SGPU_ERR_HALO = 21,                 /* shard: the last owned record does not end inside the buffer */
+    SGPU_ERR_SAM_RECORD = 22            /* a SAM line htslib's sam_parse1 rejects (rust_htslib error through `result?`, alignment.rs:131) */
 } sgpu_status;
 
 typedef struct sgpu_ctx sgpu_ctx;     /* device, stream, scratch arena */
@@ -101,6 +102,27 @@ sgpu_status sgpu_idset_from_paf(sgpu_ctx *, const uint8_t *buf, size_t n, uint64
                                 double min_cov, uint8_t min_mapq, sgpu_idset **out,
                                 uint64_t *err_line);
 sgpu_status sgpu_idset_from_paf_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, uint64_t min_len,
+                                    double min_cov, uint8_t min_mapq, sgpu_idset **out,
+                                    uint64_t *err_line);
+/* ReadAlignment::from_bam, alignment.rs:117-146 (+ BamRecord::from / qalen_from_cigar / query_coverage
+ * :154-211; `htslib` feature) for TEXT SAM: header lines skipped, unmapped records skipped, aligned length =
+ * sum of CIGAR M and I, query length = SEQ length, the PAF predicate.  BAM / CRAM need BGZF / CRAM decoding
+ * first (a host stage, not built).  The sam_parse1 behaviour restated here (htslib is an un-vendored
+ * dependency of the reference; parity unpinned):
+ *   - lines split on '\n', one trailing '\r' dropped; lines starting with '@' are header lines (skipped);
+ *   - a record has >= 11 tab-separated fields: QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL;
+ *   - FLAG like strtol(.., 0): decimal, 0x hex or 0 octal, 0..65535; POS / PNEXT / TLEN signed decimal;
+ *     MAPQ decimal 0..255; CIGAR "*" or (count op)+ with op in MIDNSHP=XB, count < 2^28;
+ *   - SEQ "*" (length 0) or its byte length; with a CIGAR and a SEQ the CIGAR's query length (M I S = X)
+ *     must equal it; QUAL "*" or as long as SEQ; any violation -> SGPU_ERR_SAM_RECORD at that line;
+ *   - unmapped = FLAG & 4, or RNAME "*", or POS < 1 (htslib sets BAM_FUNMAP for both): skipped;
+ *   - QNAME must be valid UTF-8 (alignment.rs:187) -> SGPU_ERR_RECORD_NAME_UTF8.
+ * Not restated: textual FLAG strings, and RNAME values missing from the @SQ header (htslib warns and treats
+ * the record as unmapped; aligners always declare their references). */
+sgpu_status sgpu_idset_from_sam(sgpu_ctx *, const uint8_t *buf, size_t n, uint64_t min_len,
+                                double min_cov, uint8_t min_mapq, sgpu_idset **out,
+                                uint64_t *err_line);
+sgpu_status sgpu_idset_from_sam_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, uint64_t min_len,
                                     double min_cov, uint8_t min_mapq, sgpu_idset **out,
                                     uint64_t *err_line);
 /* ReadAlignment::from_txt, alignment.rs:60-82: every line verbatim */

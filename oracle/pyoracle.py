@@ -116,6 +116,60 @@ def ids_from_paf(buf: bytes, min_len=0, min_cov=0.0, min_mapq=0) -> set[bytes]:
     return ids
 
 
+E_SAM = 22
+
+
+def ids_from_sam(buf: bytes, min_len=0, min_cov=0.0, min_mapq=0) -> set[bytes]:
+    """alignment.rs:117-146 + :154-211 for text SAM (second, independent restatement of the rules listed in
+    scrubby_oracle.c; regular expressions instead of scanners)"""
+    import re
+
+    ids = set()
+    raw = buf.split(b"\n")
+    if raw and raw[-1] == b"":
+        raw.pop()
+        terminated = [True] * len(raw)
+    else:
+        terminated = [True] * (len(raw) - 1) + [False]
+    for no, (line, term) in enumerate(zip(raw, terminated)):
+        if term and line.endswith(b"\r"):
+            line = line[:-1]
+        if line.startswith(b"@"):
+            continue
+        f = line.split(b"\t")
+        if len(f) < 11:
+            raise RefError(E_SAM, no)
+        q, flag, rname, pos, mapq, cigar, rnext, pnext, tlen, seq, qual = f[:11]
+        m = re.fullmatch(rb"0[xX]([0-9a-fA-F]+)|0([0-7]+)|([1-9][0-9]*|0)", flag)
+        sint = lambda x: re.fullmatch(rb"[+-]?[0-9]{1,18}", x)
+        ops = re.findall(rb"([0-9]+)([MIDNSHP=XB])", cigar)
+        cigar_ok = cigar == b"*" or (ops and b"".join(a + b for a, b in ops) == cigar and
+                                     all(int(a) < (1 << 28) for a, _ in ops))
+        if not (q and m and rname and sint(pos) and re.fullmatch(rb"[0-9]{1,18}", mapq) and int(mapq) <= 255 and
+                cigar_ok and rnext and sint(pnext) and sint(tlen) and seq and qual):
+            raise RefError(E_SAM, no)
+        fl = int(m.group(1), 16) if m.group(1) else int(m.group(2), 8) if m.group(2) else int(m.group(3))
+        if fl > 65535:
+            raise RefError(E_SAM, no)
+        if cigar == b"*":
+            ops = []
+        qlen = 0 if seq == b"*" else len(seq)
+        cq = sum(int(a) for a, o in ops if o in b"MIS=X") & 0xFFFFFFFF
+        qalen = sum(int(a) for a, o in ops if o in b"MI") & 0xFFFFFFFF
+        if (ops and seq != b"*" and cq != qlen) or (qual != b"*" and len(qual) != qlen):
+            raise RefError(E_SAM, no)
+        try:
+            q.decode("utf-8")
+        except UnicodeDecodeError:
+            raise RefError(E_UTF8, no)
+        if (fl & 4) or rname == b"*" or int(pos) < 1:
+            continue
+        cov = 0.0 if qlen == 0 else float(qalen) / float(qlen)
+        if (qalen >= min_len or cov >= min_cov) and int(mapq) >= min_mapq:
+            ids.add(q)
+    return ids
+
+
 def ids_from_txt(buf: bytes) -> set[bytes]:
     """alignment.rs:60-82"""
     return {line.encode("utf-8") for _, line in _lines(buf)}

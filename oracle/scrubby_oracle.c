@@ -419,6 +419,140 @@ int orc_set_from_paf(const uint8_t *buf, size_t n, uint64_t min_len, double min_
     return ORC_OK;
 }
 
+/* alignment.rs:117-146 from_bam + :154-211 (BamRecord::from, qalen_from_cigar, query_coverage), restated for
+ * TEXT SAM.  The reference reads SAM/BAM/CRAM through rust-htslib (optional `htslib` feature, un-vendored C
+ * library): the record fields below are what htslib's sam_parse1 stores for a well-formed line.  Restated
+ * rules (parity unpinned):
+ *   - lines split on '\n', one trailing '\r' dropped; lines starting with '@' are header lines (skipped);
+ *   - a record has >= 11 tab-separated fields: QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL;
+ *   - FLAG like strtol(.., 0): decimal, 0x hex or 0 octal, 0..65535; POS/PNEXT/TLEN signed decimal;
+ *     MAPQ decimal 0..255; CIGAR "*" or (count op)+ with op in MIDNSHP=XB, count < 2^28;
+ *   - SEQ "*" (length 0) or its byte length; with a CIGAR and a SEQ the CIGAR's query length (M I S = X) must
+ *     equal it; QUAL "*" or as long as SEQ;  any violation -> ORC_ERR_SAM_RECORD at that line;
+ *   - unmapped = FLAG & 4, or RNAME "*", or POS < 1 (htslib sets BAM_FUNMAP for both): skipped
+ *     (alignment.rs:132-134);
+ *   - qalen = sum of M and I counts (u32), qlen = SEQ length; pass iff (qalen >= min_len || cov >= min_cov)
+ *     && mapq >= min_mapq with cov = qlen == 0 ? 0 : qalen / qlen (alignment.rs:136-140, :204-209);
+ *   - QNAME must be valid UTF-8 (alignment.rs:187) -> ORC_ERR_RECORD_NAME_UTF8. */
+static int sam_int(const uint8_t *s, size_t n, int allow_sign, int64_t *out) {
+    size_t i = 0;
+    int neg = 0;
+    if (n && allow_sign && (s[0] == '-' || s[0] == '+')) {
+        neg = s[0] == '-';
+        i = 1;
+    }
+    if (i >= n || n - i > 18) return -1;
+    int64_t v = 0;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return -1;
+        v = v * 10 + (s[i] - '0');
+    }
+    *out = neg ? -v : v;
+    return 0;
+}
+static int sam_flag(const uint8_t *s, size_t n, uint32_t *out) {
+    uint32_t base = 10, v = 0;
+    size_t i = 0;
+    if (n >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) {
+        base = 16;
+        i = 2;
+    } else if (n >= 2 && s[0] == '0') {
+        base = 8;
+        i = 1;
+    }
+    if (i >= n) return -1;
+    for (; i < n; i++) {
+        uint32_t d;
+        if (s[i] >= '0' && s[i] <= '9') d = s[i] - '0';
+        else if (s[i] >= 'a' && s[i] <= 'f') d = s[i] - 'a' + 10;
+        else if (s[i] >= 'A' && s[i] <= 'F') d = s[i] - 'A' + 10;
+        else return -1;
+        if (d >= base) return -1;
+        v = v * base + d;
+        if (v > 65535) return -1;
+    }
+    *out = v;
+    return 0;
+}
+/* query length (M I S = X) and aligned length (M I) of a CIGAR string; -1 on a malformed one */
+static int sam_cigar(const uint8_t *s, size_t n, uint32_t *n_ops, uint32_t *qlen, uint32_t *qalen) {
+    *n_ops = *qlen = *qalen = 0;
+    if (n == 1 && s[0] == '*') return 0;
+    size_t i = 0;
+    if (n == 0) return -1;
+    while (i < n) {
+        uint64_t c = 0;
+        size_t d0 = i;
+        while (i < n && s[i] >= '0' && s[i] <= '9') {
+            c = c * 10 + (s[i] - '0');
+            if (c >= (1ull << 28)) return -1;
+            i++;
+        }
+        if (i == d0 || i >= n) return -1;
+        const uint8_t op = s[i++];
+        if (!strchr("MIDNSHP=XB", op)) return -1;
+        (*n_ops)++;
+        if (op == 'M' || op == 'I') *qalen += (uint32_t)c;
+        if (op == 'M' || op == 'I' || op == 'S' || op == '=' || op == 'X') *qlen += (uint32_t)c;
+    }
+    return 0;
+}
+
+int orc_set_from_sam(const uint8_t *buf, size_t n, uint64_t min_len, double min_cov, uint8_t min_mapq,
+                     orc_set **out, uint64_t *err_line) {
+    orc_set *set = orc_set_new();
+    size_t pos = 0;
+    uint64_t line_no = 0;
+    int rc = ORC_OK;
+    while (pos < n && rc == ORC_OK) {
+        const uint8_t *s = buf + pos;
+        const uint8_t *nl = (const uint8_t *)memchr(s, '\n', n - pos);
+        size_t len = nl ? (size_t)(nl - s) : n - pos;
+        pos += len + (nl ? 1 : 0);
+        line_no++;
+        if (nl && len && s[len - 1] == '\r') len--;
+        if (len && s[0] == '@') continue;
+        orc_span f[11];
+        if (split_tabs(s, len, f, 11) < 11) {
+            rc = ORC_ERR_SAM_RECORD;
+            break;
+        }
+        uint32_t flag = 0, n_ops = 0, cq = 0, qalen = 0;
+        int64_t p = 0, mapq = 0, t = 0;
+        if (f[0].len == 0 || sam_flag(f[1].p, f[1].len, &flag) || f[2].len == 0 || sam_int(f[3].p, f[3].len, 1, &p) ||
+            sam_int(f[4].p, f[4].len, 0, &mapq) || mapq > 255 || sam_cigar(f[5].p, f[5].len, &n_ops, &cq, &qalen) ||
+            f[6].len == 0 || sam_int(f[7].p, f[7].len, 1, &t) || sam_int(f[8].p, f[8].len, 1, &t) || f[9].len == 0 ||
+            f[10].len == 0) {
+            rc = ORC_ERR_SAM_RECORD;
+            break;
+        }
+        const int seq_star = f[9].len == 1 && f[9].p[0] == '*';
+        const uint32_t qlen = seq_star ? 0u : (uint32_t)f[9].len;
+        const int qual_star = f[10].len == 1 && f[10].p[0] == '*';
+        if ((n_ops && !seq_star && cq != qlen) || (!qual_star && f[10].len != (seq_star ? 0 : f[9].len))) {
+            rc = ORC_ERR_SAM_RECORD;
+            break;
+        }
+        if (!utf8_valid(f[0].p, f[0].len)) {
+            rc = ORC_ERR_RECORD_NAME_UTF8;
+            break;
+        }
+        const int unmapped = (flag & 4) || (f[2].len == 1 && f[2].p[0] == '*') || p < 1;
+        if (unmapped) continue;
+        const double cov = qlen == 0 ? 0.0 : (double)qalen / (double)qlen;
+        if (((uint64_t)qalen >= min_len || cov >= min_cov) && (uint8_t)mapq >= min_mapq)
+            orc_set_insert(set, f[0].p, f[0].len);
+    }
+    if (rc != ORC_OK) {
+        if (err_line) *err_line = line_no - 1;
+        orc_set_free(set);
+        *out = NULL;
+        return rc;
+    }
+    *out = set;
+    return ORC_OK;
+}
+
 /* alignment.rs:60-82 from_txt: every line verbatim */
 int orc_set_from_txt(const uint8_t *buf, size_t n, orc_set **out, uint64_t *err_line) {
     orc_set *set = orc_set_new();

@@ -39,7 +39,8 @@ enum {
     ORC_ERR_KRAKEN_REPORT_READS = 12,  /* KrakenReportReadFieldConversion */
     ORC_ERR_KRAKEN_REPORT_DIRECT = 13, /* KrakenReportDirectReadFieldConversion */
     ORC_ERR_KRAKEN_REPORT_PARENT = 14, /* KrakenReportTaxonParent */
-    ORC_ERR_FASTA_UNSUPPORTED = 15
+    ORC_ERR_FASTA_UNSUPPORTED = 15,
+    ORC_ERR_SAM_RECORD = 22            /* htslib sam_parse1 would reject the line (rust_htslib::errors::Error) */
 };
 
 typedef struct orc_set orc_set;
@@ -67,6 +68,9 @@ int orc_get_id(const uint8_t *header, size_t len, size_t *off, size_t *id_len);
 int orc_set_from_paf(const uint8_t *buf, size_t n, uint64_t min_len, double min_cov,
                      uint8_t min_mapq, orc_set **out, uint64_t *err_line);
 int orc_set_from_txt(const uint8_t *buf, size_t n, orc_set **out, uint64_t *err_line);
+/* alignment.rs:117-146 from_bam (+ BamRecord :154-211) restated for text SAM */
+int orc_set_from_sam(const uint8_t *buf, size_t n, uint64_t min_len, double min_cov, uint8_t min_mapq,
+                     orc_set **out, uint64_t *err_line);
 int orc_taxids_from_report(const uint8_t *buf, size_t n, const char *const *taxa, size_t n_taxa,
                            const char *const *taxa_direct, size_t n_direct, orc_set **out,
                            uint64_t *err_line);

@@ -40,7 +40,8 @@ SYMBOLS = [
     "sgpu_ctx_create", "sgpu_ctx_destroy", "sgpu_ctx_set_stream", "sgpu_ctx_set_mode", "sgpu_ctx_sync",
     "sgpu_strerror", "sgpu_last_cuda_error", "sgpu_abi_version", "sgpu_ctx_launch_count",
     "sgpu_ctx_set_profiling", "sgpu_ctx_fused_stats",
-    "sgpu_idset_from_paf", "sgpu_idset_from_paf_dev", "sgpu_idset_from_txt", "sgpu_idset_from_txt_dev",
+    "sgpu_idset_from_paf", "sgpu_idset_from_paf_dev", "sgpu_idset_from_sam", "sgpu_idset_from_sam_dev",
+    "sgpu_idset_from_txt", "sgpu_idset_from_txt_dev",
     "sgpu_idset_from_reads", "sgpu_idset_from_reads_dev", "sgpu_idset_from_ids", "sgpu_idset_new",
     "sgpu_idset_len", "sgpu_idset_contains", "sgpu_idset_dump", "sgpu_idset_free", "sgpu_free",
     "sgpu_clean_fastq", "sgpu_clean_fastq_dev", "sgpu_clean_fastq_shard_dev", "sgpu_count_newlines_dev",
@@ -83,7 +84,7 @@ def load():
     L.sgpu_ctx_launch_count.restype = u64
     L.sgpu_ctx_set_profiling.argtypes = [vp, i32]
     L.sgpu_ctx_fused_stats.argtypes = [vp, P(C.c_double), P(u64), P(u64)]
-    for name in ("sgpu_idset_from_paf", "sgpu_idset_from_paf_dev"):
+    for name in ("sgpu_idset_from_paf", "sgpu_idset_from_paf_dev", "sgpu_idset_from_sam", "sgpu_idset_from_sam_dev"):
         getattr(L, name).argtypes = [vp, vp, sz, u64, C.c_double, C.c_uint8, P(vp), P(u64)]
     for name in ("sgpu_idset_from_txt", "sgpu_idset_from_txt_dev"):
         getattr(L, name).argtypes = [vp, vp, sz, P(vp), P(u64)]

@@ -144,6 +144,19 @@ class IdSet:
         return cls(ctx, h)
 
     @classmethod
+    def from_sam(cls, ctx, buf, min_len=0, min_cov=0.0, min_mapq=0):
+        """ReadAlignment::from_bam, alignment.rs:117-146, for text SAM"""
+        h, err = C.c_void_p(), C.c_uint64()
+        if hasattr(buf, "is_cuda") and buf.is_cuda:
+            p, n = _dev_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_sam_dev(ctx.h, p, n, min_len, min_cov, min_mapq, C.byref(h), C.byref(err))
+        else:
+            p, n, keep = _host_ptr(buf)
+            rc = ctx.L.sgpu_idset_from_sam(ctx.h, p, n, min_len, min_cov, min_mapq, C.byref(h), C.byref(err))
+        _check(rc, err.value, "from_sam")
+        return cls(ctx, h)
+
+    @classmethod
     def from_txt(cls, ctx, buf):
         """ReadAlignment::from_txt, alignment.rs:60-82"""
         h, err = C.c_void_p(), C.c_uint64()

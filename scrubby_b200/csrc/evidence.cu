@@ -139,6 +139,141 @@ __global__ void paf_segment_kernel(const uint8_t *pass, const uint8_t *head, uin
     sel[i] = any;
 }
 
+// ------------------------------------------------------------------ SAM (text) records
+// Replaces ReadAlignment::from_bam (alignment.rs:117-146) + BamRecord::from / qalen_from_cigar /
+// query_coverage (:154-211) for text SAM; the restated sam_parse1 rules are listed in include/scrubby_gpu.h.
+__device__ __forceinline__ bool sam_int(const uint8_t *s, uint64_t n, bool allow_sign, long long *out) {
+    uint64_t i = 0;
+    bool neg = false;
+    if (n && allow_sign && (s[0] == '-' || s[0] == '+')) {
+        neg = s[0] == '-';
+        i = 1;
+    }
+    if (i >= n || n - i > 18) return false;
+    long long v = 0;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        v = v * 10 + (s[i] - '0');
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+__device__ __forceinline__ bool sam_flag(const uint8_t *s, uint64_t n, uint32_t *out) {
+    uint32_t base = 10, v = 0;
+    uint64_t i = 0;
+    if (n >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) {
+        base = 16;
+        i = 2;
+    } else if (n >= 2 && s[0] == '0') {
+        base = 8;
+        i = 1;
+    }
+    if (i >= n) return false;
+    for (; i < n; i++) {
+        uint32_t d;
+        const uint8_t ch = s[i];
+        if (ch >= '0' && ch <= '9') d = ch - '0';
+        else if (ch >= 'a' && ch <= 'f') d = ch - 'a' + 10;
+        else if (ch >= 'A' && ch <= 'F') d = ch - 'A' + 10;
+        else return false;
+        if (d >= base) return false;
+        v = v * base + d;
+        if (v > 65535u) return false;
+    }
+    *out = v;
+    return true;
+}
+__device__ __forceinline__ bool sam_cigar(const uint8_t *s, uint64_t n, uint32_t *n_ops, uint32_t *qlen, uint32_t *qalen) {
+    *n_ops = *qlen = *qalen = 0;
+    if (n == 1 && s[0] == '*') return true;
+    if (n == 0) return false;
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t cnt = 0;
+        const uint64_t d0 = i;
+        while (i < n && s[i] >= '0' && s[i] <= '9') {
+            cnt = cnt * 10 + (s[i] - '0');
+            if (cnt >= (1ull << 28)) return false;
+            i++;
+        }
+        if (i == d0 || i >= n) return false;
+        const uint8_t op = s[i++];
+        const bool q = op == 'M' || op == 'I' || op == 'S' || op == '=' || op == 'X';
+        if (!(q || op == 'D' || op == 'N' || op == 'H' || op == 'P' || op == 'B')) return false;
+        (*n_ops)++;
+        if (op == 'M' || op == 'I') *qalen += (uint32_t)cnt;
+        if (q) *qlen += (uint32_t)cnt;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128)
+    sam_parse_kernel(LineParams P, PafParams F, uint64_t n_lines, uint64_t *key_off, uint32_t *key_len, uint8_t *sel,
+                     unsigned long long *err_word) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    uint64_t s, e;
+    uint8_t ok = 0;
+    uint64_t koff = 0;
+    uint32_t klen = 0;
+    if (line_span(P, i, &s, &e)) {
+        const uint8_t *in = P.in;
+        if (i < P.n_nl && e > s && in[e - 1] == '\r') e--;
+        if (!(e > s && in[s] == '@')) {  // header lines are skipped
+            // the first eleven tab-separated fields
+            uint64_t fs[11], fe[11];
+            int f = 0;
+            uint64_t st = s;
+            for (uint64_t pos = s; pos <= e && f < 11; pos++) {
+                if (pos == e || in[pos] == '\t') {
+                    fs[f] = st;
+                    fe[f] = pos;
+                    f++;
+                    st = pos + 1;
+                }
+            }
+            int code = 0;
+            uint32_t flag = 0, n_ops = 0, cq = 0, qalen = 0;
+            long long p = 0, mapq = 0, t = 0;
+            if (f < 11) {
+                code = SGPU_ERR_SAM_RECORD;
+            } else {
+#define FLEN(k) (fe[k] - fs[k])
+                const bool good = FLEN(0) && sam_flag(in + fs[1], FLEN(1), &flag) && FLEN(2) &&
+                                  sam_int(in + fs[3], FLEN(3), true, &p) && sam_int(in + fs[4], FLEN(4), false, &mapq) &&
+                                  mapq <= 255 && sam_cigar(in + fs[5], FLEN(5), &n_ops, &cq, &qalen) && FLEN(6) &&
+                                  sam_int(in + fs[7], FLEN(7), true, &t) && sam_int(in + fs[8], FLEN(8), true, &t) &&
+                                  FLEN(9) && FLEN(10);
+                if (!good) {
+                    code = SGPU_ERR_SAM_RECORD;
+                } else {
+                    const bool seq_star = FLEN(9) == 1 && in[fs[9]] == '*';
+                    const uint32_t qlen = seq_star ? 0u : (uint32_t)FLEN(9);
+                    const bool qual_star = FLEN(10) == 1 && in[fs[10]] == '*';
+                    if ((n_ops && !seq_star && cq != qlen) || (!qual_star && FLEN(10) != (seq_star ? 0 : FLEN(9)))) {
+                        code = SGPU_ERR_SAM_RECORD;
+                    } else if (!utf8_valid(in + fs[0], FLEN(0))) {
+                        code = SGPU_ERR_RECORD_NAME_UTF8;
+                    } else {
+                        const bool unmapped = (flag & 4u) || (FLEN(2) == 1 && in[fs[2]] == '*') || p < 1;
+                        if (!unmapped) {
+                            const double cov = qlen == 0 ? 0.0 : (double)qalen / (double)qlen;
+                            ok = (((uint64_t)qalen >= F.min_len || cov >= F.min_cov) && (uint32_t)mapq >= F.min_mapq) ? 1 : 0;
+                            koff = fs[0];
+                            klen = (uint32_t)FLEN(0);
+                        }
+                    }
+                }
+#undef FLEN
+            }
+            if (code) report_error(err_word, i, code);
+        }
+    }
+    key_off[i] = koff;
+    key_len[i] = klen;
+    sel[i] = ok;
+}
+
 __global__ void __launch_bounds__(128)
     txt_lines_kernel(LineParams P, uint64_t n_lines, uint64_t *key_off, uint32_t *key_len, uint8_t *sel,
                      unsigned long long *err_word) {
@@ -584,7 +719,7 @@ __global__ void __launch_bounds__(LT_NT)
     }
 }
 
-enum EvidenceKind { EV_PAF, EV_TXT, EV_READS };
+enum EvidenceKind { EV_PAF, EV_TXT, EV_READS, EV_SAM };
 
 static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t *d_buf, size_t n, PafParams F,
                                    const TaxSet *T, int need_fields, sgpu_idset **out, uint64_t *err_line) {
@@ -597,7 +732,7 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
     }
     sgpu_status rc = SGPU_OK;
     bool done = false;
-    if (kind != EV_PAF && ((uintptr_t)d_buf & 15) == 0) {
+    if ((kind == EV_TXT || kind == EV_READS) && ((uintptr_t)d_buf & 15) == 0) {
         // ---- order-free evidence: the tile kernel, no newline index
         do {
             DevBuf<uint64_t> cand_off, ctr;
@@ -662,6 +797,10 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
                                                    (unsigned long long *)errw.p);
             SGPU_LAUNCH(c);
             paf_segment_kernel<<<(unsigned)ceil_div(n_lines, 256), 256, 0, st>>>(pass.p, head.p, n_lines, sel.p);
+            SGPU_LAUNCH(c);
+        } else if (kind == EV_SAM) {
+            sam_parse_kernel<<<grid, 128, 0, st>>>(P, F, n_lines, key_off.p, key_len.p, sel.p,
+                                                   (unsigned long long *)errw.p);
             SGPU_LAUNCH(c);
         } else if (kind == EV_TXT) {
             txt_lines_kernel<<<grid, 128, 0, st>>>(P, n_lines, key_off.p, key_len.p, sel.p,
@@ -770,6 +909,29 @@ sgpu_status sgpu_idset_from_paf(sgpu_ctx *c, const uint8_t *buf, size_t n, uint6
         SGPU_TRY(stage_in(c, buf, n, d));
     }
     sgpu_status rc = sgpu_idset_from_paf_dev(c, d.p, n, min_len, min_cov, min_mapq, out, err_line);
+    cudaStreamSynchronize(c->stream);
+    return rc;
+}
+
+sgpu_status sgpu_idset_from_sam_dev(sgpu_ctx *c, const uint8_t *d_buf, size_t n, uint64_t min_len, double min_cov,
+                                    uint8_t min_mapq, sgpu_idset **out, uint64_t *err_line) {
+    if (!c || !out || (n && !d_buf)) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    PafParams F{min_len, min_cov, min_mapq};
+    return evidence_to_set(c, EV_SAM, d_buf, n, F, nullptr, 0, out, err_line);
+}
+
+sgpu_status sgpu_idset_from_sam(sgpu_ctx *c, const uint8_t *buf, size_t n, uint64_t min_len, double min_cov,
+                                uint8_t min_mapq, sgpu_idset **out, uint64_t *err_line) {
+    if (!c || !out || (n && !buf)) return SGPU_ERR_INVALID_ARG;
+    DevBuf<uint8_t> d;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        SGPU_CUDA(cudaSetDevice(c->device));
+        SGPU_TRY(stage_in(c, buf, n, d));
+    }
+    sgpu_status rc = sgpu_idset_from_sam_dev(c, d.p, n, min_len, min_cov, min_mapq, out, err_line);
     cudaStreamSynchronize(c->stream);
     return rc;
 }

@@ -202,14 +202,17 @@ ReadAlignment ReadAlignment::from(const GpuContext &g, const std::string &path, 
         case AlignmentFormat::Paf:
         case AlignmentFormat::Gaf: return from_paf(g, path, min_len, min_cov, min_mapq);
         case AlignmentFormat::Txt: return from_txt(g, path);
-        default: throw ScrubbyError(ScrubbyError::AlignmentInputFormatInvalid,
-                                    "Unable to recognize alignment input format - is this version compiled with 'htslib'?");
+        case AlignmentFormat::Sam: return from_sam(g, path, min_len, min_cov, min_mapq);  // alignment.rs:45 (`htslib`)
+        default:  // BAM / CRAM need a BGZF / CRAM decoder in front of the SAM kernel: not built
+            throw ScrubbyError(ScrubbyError::AlignmentInputFormatInvalid,
+                               "Unable to recognize alignment input format - is this version compiled with 'htslib'?");
         }
     }
     // alignment.rs:48-56: only the LAST extension is seen, so "x.paf.gz" is not recognised
     std::string e = extension(path);
     if (e == "paf" || e == "gaf") return from_paf(g, path, min_len, min_cov, min_mapq);
     if (e == "txt") return from_txt(g, path);
+    if (e == "sam") return from_sam(g, path, min_len, min_cov, min_mapq);  // alignment.rs:54 (`htslib`)
     throw ScrubbyError(ScrubbyError::AlignmentInputFormatNotRecognized,
                        "Unable to recognize alignment input format from extension.");
 }
@@ -222,6 +225,17 @@ ReadAlignment ReadAlignment::from_paf(const GpuContext &g, const std::string &pa
     if (buf.size() < 5) buf.clear();  // is_file_empty => empty set (alignment.rs:93)
     check(sgpu_idset_from_paf(g.get(), buf.data(), buf.size(), min_len, min_cov, min_mapq, r.aligned_reads.out(), &err),
           err, "from_paf");
+    return r;
+}
+
+// alignment.rs:117-146 for text SAM (rust-htslib reads "-" as stdin and has no is_file_empty test here)
+ReadAlignment ReadAlignment::from_sam(const GpuContext &g, const std::string &path, uint64_t min_len, double min_cov,
+                                      uint8_t min_mapq) {
+    std::vector<uint8_t> buf = read_file(path);
+    ReadAlignment r;
+    uint64_t err = 0;
+    check(sgpu_idset_from_sam(g.get(), buf.data(), buf.size(), min_len, min_cov, min_mapq, r.aligned_reads.out(), &err),
+          err, "from_sam");
     return r;
 }
 

@@ -129,6 +129,7 @@ struct ReadAlignment {
     static ReadAlignment from(const GpuContext &, const std::string &path, uint64_t min_qaln_len, double min_qaln_cov,
                               uint8_t min_mapq, std::optional<AlignmentFormat> fmt);
     static ReadAlignment from_paf(const GpuContext &, const std::string &path, uint64_t, double, uint8_t);
+    static ReadAlignment from_sam(const GpuContext &, const std::string &path, uint64_t, double, uint8_t);
     static ReadAlignment from_txt(const GpuContext &, const std::string &path);
 };
 

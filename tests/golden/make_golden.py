@@ -214,12 +214,73 @@ get_id_cases = [
     dict(header=L(b"id\xc2\x85x"), expect="id"),
 ]
 
+# --- 6. SAM evidence: alignment.rs:117-146, 154-211 (htslib feature), text SAM ---------------------
+SAM_HDR = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:chr1\tLN:100000\n@PG\tID:minimap2\n"
+
+
+def sam(q, flag, rname, pos, mapq, cigar, seqlen, qual=None, extra=""):
+    seq = "*" if seqlen is None else "ACGT" * (seqlen // 4) + "ACGT"[: seqlen % 4]
+    if qual is None:
+        qual = "*" if seqlen is None else "I" * seqlen
+    return f"{q}\t{flag}\t{rname}\t{pos}\t{mapq}\t{cigar}\t*\t0\t0\t{seq}\t{qual}{extra}"
+
+
+SAM_BASE = SAM_HDR + "\n".join([
+    sam("s1", 0, "chr1", 100, 60, "150M", 150),
+    sam("s2", 0, "chr1", 100, 60, "40M110S", 150),            # qalen 40, cov 0.267
+    sam("s3", 16, "chr1", 100, 60, "10S35M15S", 60),          # qalen 35, cov 0.583 rescues
+    sam("s4", 0, "chr1", 100, 49, "150M", 150),               # mapq below
+    sam("s5", 4, "*", 0, 0, "*", 150),                        # unmapped flag
+    sam("s6", 0, "chr1", 100, 60, "50M50I50M", 150),          # insertions count: qalen 150
+    sam("s7", 0, "chr1", 100, 60, "100=50M", 150),            # '=' is not Cigar::Match: qalen 50
+    sam("s8", 0, "chr1", 100, 60, "101X49M", 150),            # qalen 49, cov 0.327
+    sam("s9", 0, "chr1", 100, 60, "50M100D50M", 100),         # deletions do not count: qalen 100
+    sam("s10", 16, "chr1", 0, 60, "150M", 150),               # POS 0: htslib treats it as unmapped
+    sam("s11", 0, "chr1", 100, 60, "150M", None),             # SEQ '*': qlen 0, cov 0, qalen 150 >= 50
+    sam("s12", "0x10", "chr1", 100, 60, "150M", 150),         # strtol(.., 0): hex flag
+    sam("s13", "0x4", "chr1", 100, 60, "150M", 150),          # hex unmapped
+    sam("s14", 256, "chr1", 100, 10, "150M", 150),            # same read: secondary fails ...
+    sam("s14", 0, "chr1", 900, 60, "20H130M", 130, extra="\tNM:i:0\tAS:i:130"),  # ... primary passes (qalen 130)
+    sam("s15", 0, "*", 100, 60, "150M", 150),                 # RNAME '*': unmapped
+    sam("s16", 0, "chr1", 100, 50, "25M25N25M50S", 100),      # qalen 50 == min_len, mapq == min_mapq
+]) + "\n"
+sam_cases = [
+    dict(name="predicate_50_0.5_50", buf=L(SAM_BASE.encode()), min_len=50, min_cov=0.5, min_mapq=50,
+         expect=["s1", "s3", "s6", "s7", "s9", "s11", "s12", "s14", "s16"],
+         why="M and I only (alignment.rs:160-168), OR of len/cov, >= comparisons, unmapped skipped"),
+    dict(name="defaults_all_mapped", buf=L(SAM_BASE.encode()), min_len=0, min_cov=0.0, min_mapq=0,
+         expect=["s1", "s2", "s3", "s4", "s6", "s7", "s8", "s9", "s11", "s12", "s14", "s16"],
+         why="every mapped record passes; s5 s10 s13 s15 are unmapped"),
+    dict(name="crlf_and_no_final_newline", buf=L((SAM_HDR.replace("\n", "\r\n") + sam("a", 0, "chr1", 5, 60, "150M", 150)
+                                                + "\r\n" + sam("b", 0, "chr1", 5, 60, "10M", 10)).encode()),
+         min_len=50, min_cov=0.5, min_mapq=0, expect=["a", "b"], why="b: qalen 10 < 50 but cov 1.0"),
+    dict(name="header_only", buf=L(SAM_HDR.encode()), min_len=0, min_cov=0.0, min_mapq=0, expect=[]),
+    dict(name="octal_flag", buf=L((sam("o", "04", "chr1", 5, 60, "150M", 150) + "\n"
+                                  + sam("p", "020", "chr1", 5, 60, "150M", 150) + "\n").encode()),
+         min_len=0, min_cov=0.0, min_mapq=0, expect=["p"], why="04 = unmapped; 020 = 16 reverse strand"),
+]
+sam_errors = [
+    dict(name="ten_fields", buf=L(("\t".join(sam("e", 0, "chr1", 5, 60, "150M", 150).split("\t")[:10]) + "\n").encode()), error=22),
+    dict(name="mapq_256", buf=L((sam("e", 0, "chr1", 5, 256, "150M", 150) + "\n").encode()), error=22),
+    dict(name="bad_cigar_op", buf=L((sam("e", 0, "chr1", 5, 60, "150Q", 150) + "\n").encode()), error=22),
+    dict(name="cigar_without_count", buf=L((sam("e", 0, "chr1", 5, 60, "M", 150) + "\n").encode()), error=22),
+    dict(name="cigar_seq_mismatch", buf=L((sam("e", 0, "chr1", 5, 60, "149M", 150) + "\n").encode()), error=22),
+    dict(name="qual_len_mismatch", buf=L((sam("e", 0, "chr1", 5, 60, "150M", 150, qual="I" * 149) + "\n").encode()), error=22),
+    dict(name="flag_text", buf=L((sam("e", "abc", "chr1", 5, 60, "150M", 150) + "\n").encode()), error=22),
+    dict(name="blank_line", buf=L((sam("a", 0, "chr1", 5, 60, "150M", 150) + "\n\n"
+                                  + sam("b", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()), error=22, error_line=1),
+    dict(name="error_after_header", buf=L((SAM_HDR + sam("a", 0, "chr1", 5, 60, "150M", 150) + "\n"
+                                          + sam("e", 0, "chr1", "x", 60, "150M", 150) + "\n").encode()), error=22, error_line=4),
+    dict(name="qname_not_utf8", buf=L(b"\xff" + (sam("e", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()), error=8),
+]
+
 doc = dict(
     provenance="hand-derived from /root/reference/src (see make_golden.py); reference has no fixtures; parity unpinned",
     report_kraken=L(report(REPORT_ROWS)), report_metabuli=L(report(REPORT_ROWS, True)),
     taxon_cases=taxon_cases, taxon_metabuli=taxon_metabuli, paf_cases=paf_cases, paf_errors=paf_errors,
     fastq_cases=fastq_cases, fastq_errors=fastq_errors, diff_cases=diff_cases, report_case=report_case,
-    reads_cases=reads_cases, reads_errors=reads_errors, txt_cases=txt_cases, get_id_cases=get_id_cases)
+    reads_cases=reads_cases, reads_errors=reads_errors, txt_cases=txt_cases, get_id_cases=get_id_cases,
+    sam_cases=sam_cases, sam_errors=sam_errors)
 
 if __name__ == "__main__":
     with open(os.path.join(HERE, "vectors.json"), "w") as f:

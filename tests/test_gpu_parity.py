@@ -83,6 +83,30 @@ def test_golden_paf(ctx, golden):
             assert e.value.index == c["error_line"]
 
 
+def test_golden_sam(ctx, golden):
+    for c in golden["sam_cases"]:
+        s = api.IdSet.from_sam(ctx, B(c["buf"]), c["min_len"], c["min_cov"], c["min_mapq"])
+        assert s.sorted_ids() == _ids(c["expect"]), c["name"]
+    for c in golden["sam_errors"]:
+        with pytest.raises(api.ScrubbyGpuError) as e:
+            api.IdSet.from_sam(ctx, B(c["buf"]))
+        assert e.value.status == c["error"], c["name"]
+        if "error_line" in c:
+            assert e.value.index == c["error_line"]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_sam_random_matches_oracle(ctx, seed):
+    from test_oracle_golden import _random_sam
+
+    buf = _random_sam(seed, 5000)
+    for args in ((0, 0.0, 0), (50, 0.5, 50), (100, 2.0, 30)):
+        assert api.IdSet.from_sam(ctx, buf, *args).sorted_ids() == orc.set_from_sam(buf, *args).sorted_ids()
+    # device-resident input
+    d = torch.frombuffer(bytearray(buf), dtype=torch.uint8).cuda()
+    assert api.IdSet.from_sam(ctx, d, 50, 0.5, 50).sorted_ids() == orc.set_from_sam(buf, 50, 0.5, 50).sorted_ids()
+
+
 def test_golden_reads_and_txt(ctx, golden):
     for c in golden["reads_cases"]:
         s = api.IdSet.from_reads(ctx, B(c["buf"]), c["style"], [B(t) for t in c["taxids"]])

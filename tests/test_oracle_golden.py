@@ -53,6 +53,62 @@ def test_paf_errors(golden):
         assert e2.value.code == c["error"], c["name"]
 
 
+def _random_sam(seed: int, n: int = 400) -> bytes:
+    """well-formed SAM lines with every CIGAR operator, hex / octal flags, '*' fields and CRLF endings"""
+    import random
+
+    rnd = random.Random(seed)
+    out = ["@HD\tVN:1.6", "@SQ\tSN:chr1\tLN:1000000"]
+    for i in range(n):
+        ops, qlen = [], 0
+        if rnd.random() < 0.9:
+            for _ in range(rnd.randint(1, 6)):
+                op = rnd.choice("MMMIDNSHP=X")
+                c = rnd.randint(1, 90)
+                ops.append(f"{c}{op}")
+                if op in "MIS=X":
+                    qlen += c
+        cigar = "".join(ops) if ops else "*"
+        star = rnd.random() < 0.1 or qlen == 0 and ops
+        if not ops:
+            qlen = rnd.randint(1, 200)
+        seq = "*" if star else "".join(rnd.choice("ACGTN") for _ in range(qlen))
+        qual = "*" if star or rnd.random() < 0.2 else "".join(chr(rnd.randint(33, 73)) for _ in range(qlen))
+        flag = rnd.choice([0, 16, 4, 256, 2048, 83, 163, 77, "0x10", "0x904", "020", "04"])
+        rname = rnd.choice(["chr1", "chr1", "chr1", "*"])
+        pos = rnd.choice([0, 1, 5, 99999])
+        mapq = rnd.choice([0, 1, 30, 49, 50, 60, 255])
+        q = f"read{rnd.randint(0, n // 2)}"
+        out.append(f"{q}\t{flag}\t{rname}\t{pos}\t{mapq}\t{cigar}\t=\t{rnd.randint(0, 500)}\t{rnd.randint(-300, 300)}"
+                   f"\t{seq}\t{qual}" + ("\tNM:i:1" if rnd.random() < 0.5 else ""))
+    eol = "\r\n" if seed % 2 else "\n"
+    return (eol.join(out) + (eol if seed % 3 else "")).encode()
+
+
+def test_sam_cases(golden):
+    for c in golden["sam_cases"]:
+        want = _ids(c["expect"])
+        got = orc.set_from_sam(B(c["buf"]), c["min_len"], c["min_cov"], c["min_mapq"]).sorted_ids()
+        assert got == want, c["name"]
+        assert sorted(pyo.ids_from_sam(B(c["buf"]), c["min_len"], c["min_cov"], c["min_mapq"])) == want, c["name"]
+    for c in golden["sam_errors"]:
+        with pytest.raises(orc.OracleError) as e:
+            orc.set_from_sam(B(c["buf"]), 0, 0.0, 0)
+        assert e.value.code == c["error"], c["name"]
+        if "error_line" in c:
+            assert e.value.index == c["error_line"], c["name"]
+        with pytest.raises(pyo.RefError) as e2:
+            pyo.ids_from_sam(B(c["buf"]))
+        assert (e2.value.code, e2.value.index) == (e.value.code, e.value.index), c["name"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sam_two_restatements_agree(seed):
+    buf = _random_sam(seed)
+    for args in ((0, 0.0, 0), (50, 0.5, 50), (100, 2.0, 30), (10 ** 9, 0.9, 0)):
+        assert orc.set_from_sam(buf, *args).sorted_ids() == sorted(pyo.ids_from_sam(buf, *args))
+
+
 def test_fastq_cases(golden):
     for c in golden["fastq_cases"]:
         ids = [B(i) for i in c["ids"]]
