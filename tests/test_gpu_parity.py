@@ -687,3 +687,41 @@ def test_host_pipeline_crlf_errors_and_long_records(ctx, small_pipeline_chunks):
     long_rec = b"@long\n" + b"A" * 20000 + b"\n+\n" + b"I" * 20000 + b"\n"
     k = fq.index(b"\n@syn.900 ") + 1
     _same_clean(ctx, fq[:k] + long_rec + fq[k:], ids + [b"long"])
+
+
+def test_c2_full_size_properties(ctx):
+    """BASELINE configs[1] at its full size (10 M reads per mate file, 3.3 GB each; the oracle would need minutes):
+    size-independent properties of the fused path -- byte partition, checksum linearity, line counts,
+    removed == |set|, extract mode == the complementary stream, idempotence."""
+    from bench import taxids_for_config
+
+    n = 10_000_000
+    dev = torch.device("cuda", 0)
+    d_k = synth.gen_kraken_reads(n, device=dev)
+    ids = api.IdSet.from_reads(ctx, d_k, 0, taxids_for_config())
+    del d_k
+    assert 0 < len(ids) < n
+    for mate in (1, 2):
+        d_r = synth.gen_fastq(n, mate, device=dev)
+        n_in = d_r.numel()
+        d_w = torch.empty(n_in + 64, dtype=torch.uint8, device=dev)
+        d_o = torch.empty(n_in + 64, dtype=torch.uint8, device=dev)
+        r = api.clean_fastq_dev(ctx, ids, d_r, n_in, d_w, d_o)
+        assert r.path == 1, "the fused kernel must take canonical input"
+        assert r.reads_in == n and r.reads_out == n - len(ids)          # every set id is one read of the file
+        assert r.n_written + r.n_other == n_in                          # byte partition of the input
+        w, o = d_w[: r.n_written], d_o[: r.n_other]
+        assert int(w.sum(dtype=torch.int64)) + int(o.sum(dtype=torch.int64)) == int(d_r.sum(dtype=torch.int64))
+        assert int((w == 10).sum()) == 4 * r.reads_out and int((o == 10).sum()) == 4 * (n - r.reads_out)
+        assert int(w[0]) == ord("@") and int(w[-1]) == 10
+        # extract mode writes exactly the complementary stream
+        d_w2 = torch.empty(n_in + 64, dtype=torch.uint8, device=dev)
+        r2 = api.clean_fastq_dev(ctx, ids, d_r, n_in, d_w2, None, True)
+        assert r2.n_written == r.n_other and torch.equal(d_w2[: r2.n_written], o)
+        # idempotence: the depleted file holds no id of the set
+        r3 = api.clean_fastq_dev(ctx, ids, w.clone(), r.n_written, d_w2, None)
+        assert (r3.reads_in, r3.reads_out, r3.n_written) == (r.reads_out, r.reads_out, r.n_written)
+        assert torch.equal(d_w2[: r3.n_written], w)
+        del d_r, d_w, d_o, d_w2, w, o
+        torch.cuda.empty_cache()
+    ids.free()
