@@ -289,7 +289,11 @@ __device__ __forceinline__ Comp compose(const Comp A /*earlier*/, const Comp B /
 }
 
 // (kept bytes before tile t, state carried into it) from the descriptors of the tiles before t
+#ifdef SGPU_FUSED_LB_NOINLINE
+__device__ __noinline__ void lookback_pred_warp(const unsigned long long *desc, uint64_t t, int lane,
+#else
 __device__ __forceinline__ void lookback_pred_warp(const unsigned long long *desc, uint64_t t, int lane,
+#endif
                                                    uint64_t *kept_before, uint32_t *carry) {
     Comp acc_all = comp_identity();  // composite of every window visited so far (nearer windows are later)
     uint64_t inc_total = 0;

@@ -23,8 +23,14 @@
 namespace sgpu {
 
 constexpr uint32_t IDSET_INLINE_MAX = 15;
-constexpr uint64_t IDSET_BUCKET = 4;      // slots per bucket
-constexpr uint64_t IDSET_INV_LOAD = 5;    // capacity >= IDSET_INV_LOAD * keys
+#ifndef SGPU_IDSET_BUCKET
+#define SGPU_IDSET_BUCKET 4
+#endif
+#ifndef SGPU_IDSET_INV_LOAD
+#define SGPU_IDSET_INV_LOAD 5
+#endif
+constexpr uint64_t IDSET_BUCKET = SGPU_IDSET_BUCKET;      // slots per bucket
+constexpr uint64_t IDSET_INV_LOAD = SGPU_IDSET_INV_LOAD;  // capacity >= IDSET_INV_LOAD * keys
 constexpr uint64_t IDSET_MAX_KEY = (1ull << 24) - 1;
 
 struct IdSetView {

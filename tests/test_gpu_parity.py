@@ -689,19 +689,20 @@ def test_host_pipeline_crlf_errors_and_long_records(ctx, small_pipeline_chunks):
     _same_clean(ctx, fq[:k] + long_rec + fq[k:], ids + [b"long"])
 
 
-def test_c2_full_size_properties(ctx):
-    """BASELINE configs[1] at its full size (10 M reads per mate file, 3.3 GB each; the oracle would need minutes):
+@pytest.mark.parametrize("n,mates", [(10_000_000, (1, 2)), (14_000_000, (2,))])
+def test_c2_full_size_properties(ctx, n, mates):
+    """BASELINE configs[1] at its full size (10 M reads per mate file, 3.3 GB each; the oracle would need minutes)
+    and one file beyond 4 GiB (14 M reads, 4.6 GB: every offset past 2^32, as in configs[3]'s 33 GB files):
     size-independent properties of the fused path -- byte partition, checksum linearity, line counts,
     removed == |set|, extract mode == the complementary stream, idempotence."""
     from bench import taxids_for_config
 
-    n = 10_000_000
     dev = torch.device("cuda", 0)
     d_k = synth.gen_kraken_reads(n, device=dev)
     ids = api.IdSet.from_reads(ctx, d_k, 0, taxids_for_config())
     del d_k
     assert 0 < len(ids) < n
-    for mate in (1, 2):
+    for mate in mates:
         d_r = synth.gen_fastq(n, mate, device=dev)
         n_in = d_r.numel()
         d_w = torch.empty(n_in + 64, dtype=torch.uint8, device=dev)
