@@ -9,6 +9,8 @@ const char *last_cuda_error_text();
 sgpu_status clean_fused(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, int reverse,
                         uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
                         sgpu_counts *counts, int *used);
+sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, uint64_t *span_off,
+                      uint32_t *span_len, uint64_t cap, uint64_t *n_spans, uint64_t *n_records, int *used);
 sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
                               uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
                               size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
@@ -67,6 +69,23 @@ static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, c
     SGPU_TRY(sniff(c, d_buf, n, &empty));
     if (empty) return SGPU_OK;
     cudaStream_t st = c->stream;
+    if (c->mode == 0 && ((uintptr_t)d_buf & 15) == 0) {
+        // canonical input: one pass of the fused kernel in ids mode -> (offset, length) spans of the wanted ids
+        DevBuf<uint64_t> s_off;
+        DevBuf<uint32_t> s_len;
+        const uint64_t cap = n / 100 + 4096;  // the fused kernel handles >= ~102 bytes per record
+        SGPU_TRY(s_off.alloc(cap, st));
+        SGPU_TRY(s_len.alloc(cap, st));
+        uint64_t n_spans = 0, n_rec = 0;
+        int used = 0;
+        SGPU_TRY(ids_fused(c, want_absent ? probe : nullptr, d_buf, n, s_off.p, s_len.p, cap, &n_spans, &n_rec, &used));
+        if (used) {
+            *n_records = n_rec;
+            *n_picked = n_spans;
+            if (into && n_spans) SGPU_TRY(idset_insert_spans(c, into, d_buf, s_off.p, s_len.p, nullptr, (size_t)n_spans));
+            return SGPU_OK;
+        }
+    }
     DevBuf<uint64_t> nlpos, key_off, scratch;
     DevBuf<uint32_t> key_len;
     DevBuf<uint8_t> sel;

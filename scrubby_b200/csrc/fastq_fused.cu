@@ -106,7 +106,7 @@ struct FusedResult {
     unsigned long long ticket;      // dynamic tile counter
     unsigned long long reason;      // first fallback reason (diagnostics)
     unsigned long long owned_end;   // end of the last owned record (shards); ~0 when no foreign record was seen
-    unsigned long long pad;
+    unsigned long long n_spans;     // ids mode: id tokens emitted
 };
 
 struct FusedParams {
@@ -124,6 +124,12 @@ struct FusedParams {
     uint32_t *nl_count;                 // per tile newline count (phase verification)
     uint8_t *has_term, *phase_used;     // per tile: has a record end; line phase (mod 4) the tile assumed
     uint64_t pf_dist;  // L2 prefetch distance in tiles (0 = off)
+    // ids mode (ReadDifference::get_difference, utils.rs:250-285): nothing is copied; the id token of every
+    // record that is NOT in `set` (all records when the set is empty) is appended to a span list, any order
+    int ids_mode;
+    uint64_t *span_off;  // offset of the token in `in`
+    uint32_t *span_len;
+    uint64_t span_cap;
     FusedResult *res;
 };
 
@@ -219,6 +225,7 @@ struct __align__(128) CtaSmem {
     uint64_t next_tile;    // the ticket after the tile in flight
     uint64_t kept_before;  // look-back #2 result
     uint32_t carry;        // state of the record carried into the tile
+    uint64_t span_base;    // ids mode: where this tile's spans go
     uint32_t c0;           // newlines before the tile, mod 4 (only when the speculation found no "\n+\n")
     uint32_t n_items;
     uint32_t last_flag;    // fate of the last record that starts in the tile
@@ -442,8 +449,8 @@ __device__ __forceinline__ uint64_t inline_home(uint64_t lo, uint64_t hi) {
     return mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL));
 }
 // general token scan + probe: skip leading blanks, run to the next blank / newline
-__device__ __noinline__ bool record_probe_slow(const IdSetView &set, const uint8_t *tile, uint32_t sp, uint32_t avail,
-                                               uint32_t *why) {
+__device__ __forceinline__ bool record_probe_scan(const IdSetView &set, const uint8_t *tile, uint32_t sp, uint32_t avail,
+                                                  uint32_t *why, uint32_t *tok_a, uint32_t *tok_len) {
     uint32_t a = sp + 1;
     while (a < avail && is_ws_ascii(tile[a]) && tile[a] != '\n') a++;
     uint32_t q = a;
@@ -452,7 +459,19 @@ __device__ __noinline__ bool record_probe_slow(const IdSetView &set, const uint8
         *why = *why ? *why : 7u;
         return false;
     }
+    *tok_a = a;
+    *tok_len = q - a;
     return idset_contains(set, tile + a, q - a);
+}
+__device__ __noinline__ bool record_probe_slow(const IdSetView &set, const uint8_t *tile, uint32_t sp, uint32_t avail,
+                                               uint32_t *why) {
+    uint32_t ta, tl;
+    return record_probe_scan(set, tile, sp, avail, why, &ta, &tl);
+}
+// ids mode: the token's span as well
+__device__ __noinline__ bool record_probe_slow_span(const IdSetView &set, const uint8_t *tile, uint32_t sp,
+                                                    uint32_t avail, uint32_t *why, uint32_t *tok_a, uint32_t *tok_len) {
+    return record_probe_scan(set, tile, sp, avail, why, tok_a, tok_len);
 }
 // the home bucket of an inline key: four slots, one 64-byte burst, four independent loads
 struct Bucket {
@@ -612,6 +631,7 @@ __device__ __forceinline__ uint32_t check_newline(const uint8_t *tile, uint32_t 
     return fb;
 }
 
+template <bool IDS>
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(FusedParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     CtaSmem *S = reinterpret_cast<CtaSmem *>(smem_raw);
@@ -800,7 +820,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
             n_starts ? (pos0_start ? lead_t : (uint32_t)S->nlp[r3] + 1u) : tile_len;
         // the look-back only needs the tiles before this one: when the last warp has no record to look after,
         // it runs the look-back while the others work on the records (CTA-uniform)
-        const bool early = n_starts <= (uint32_t)(NT - 32);
+        const bool early = !IDS && n_starts <= (uint32_t)(NT - 32);
 
         uint32_t rest_total = 0, kept_recs = 0;
         if (early && warp == NW - 1) {
@@ -848,6 +868,8 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                 const uint32_t j = jb + (uint32_t)tid;
                 const bool warp_active = jb + (uint32_t)warp * 32u < n_starts;
                 uint32_t flag = F_INVALID, sp = 0, e = 0, v = 0, inc = 0;
+                uint32_t tok_a = 0, tok_len = 0;  // ids mode: the id token (tile offset, bytes)
+                bool pick = false;
                 if (warp_active) {
                     if (j < n_starts) {
                         // index of the newline before the record (-1: the record starts the tile)
@@ -885,17 +907,27 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
 #else
                                 if (R.mode == 1) hit = inl && probe_bucket(P.set, first, R.lo, R.hi);
 #endif
+                                else if (IDS) hit = record_probe_slow_span(P.set, tile, sp, avail, &why, &tok_a, &tok_len);
                                 else hit = record_probe_slow(P.set, tile, sp, avail, &why);
+                                if (IDS && R.mode == 1) {
+                                    tok_a = sp + 1;
+                                    tok_len = (uint32_t)(R.lo & 0xFFu);
+                                }
                             }
                             flag = (P.reverse ? hit : !hit) ? F_KEPT : F_OTHER;
                             if (why) {
                                 fb = why;
                                 flag = F_OTHER;
                             }
+                            if (IDS) {
+                                pick = !why && !hit;
+                                flag = F_OTHER;
+                            }
                         }
                         if (j == n_starts - 1) S->last_flag = flag;
                     }
                     v = flag == F_KEPT ? ((e - sp) | (1u << 16)) : 0u;  // kept bytes | kept records << 16
+                    if (IDS) v = pick ? 1u : 0u;                  // ids mode: picked records
                     inc = v;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -920,6 +952,21 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                     base = __shfl_sync(0xffffffffu, ic - x, warp);
                 }
                 const uint32_t Kx = rest_total + ((base + inc - v) & 0xFFFFu);  // kept bytes of the records before
+                if (IDS) {
+                    // one reservation per tile in the span list, then every picked record writes its token
+                    if (tid == 0) S->span_base = atomicAdd(&P.res->n_spans, (unsigned long long)(tot & 0xFFFFu));
+                    __syncthreads();
+                    if (pick) {
+                        const uint64_t idx = S->span_base + ((base + inc - v) & 0xFFFFu);
+                        if (idx < P.span_cap) {
+                            P.span_off[idx] = g0 + tok_a;
+                            P.span_len[idx] = tok_len;
+                        } else {
+                            fb = 13;  // more records than the list was sized for: the general path
+                        }
+                    }
+                    tot = 0;
+                }
                 rest_total += tot & 0xFFFFu;
                 kept_recs += tot >> 16;
                 if (round + 1 == n_rounds && tid == 0) {
@@ -982,7 +1029,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                 // end-of-file condition of canonical input (the line count is checked by the follow-up kernel)
                 if (P.is_last && t + 1 == P.n_tiles && tile[tile_len - 1] != '\n') set_fallback(P.res, 9);
             }
-            if (!early && warp == NW - 1) {
+            if (!early && !IDS && warp == NW - 1) {
                 // (rare) the last warp had records of its own: head items and look-back only now
                 const uint32_t nph = t == 0 ? 0u : (head_len + PIECE - 1) / PIECE;
                 if (nph) {
@@ -1094,18 +1141,30 @@ __global__ void fused_verify_kernel(const uint64_t *sum_prefix, const long long 
 // Runs the fused kernel over d_in[0..n_in).  The first owned record starts at `lead` (< 16); records that
 // start after own_len (when !is_last) are left to the next shard.  *used = 0 when the input turned out
 // not to be canonical (the caller then takes the general path).
+// ids mode (IdsOut != nullptr): nothing is written; the id tokens of the records absent from `set` are listed
+struct IdsOut {
+    uint64_t *off;
+    uint32_t *len;
+    uint64_t cap;
+    uint64_t n_spans;  // out
+};
+
 sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, uint32_t lead,
                               size_t own_len, int is_last, int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w,
-                              uint8_t *d_out_o, size_t cap_o, size_t *n_o, sgpu_counts *counts, int *used) {
+                              uint8_t *d_out_o, size_t cap_o, size_t *n_o, sgpu_counts *counts, int *used,
+                              IdsOut *ids = nullptr) {
     *used = 0;
     // the fused kernel writes a byte partition of the input: both outputs must be able to hold it
-    if (n_in == 0 || lead >= 16 || cap_w < n_in || (d_out_o && cap_o < n_in)) return SGPU_OK;
+    if (n_in == 0 || lead >= 16) return SGPU_OK;
+    if (!ids && (cap_w < n_in || (d_out_o && cap_o < n_in))) return SGPU_OK;
     cudaStream_t st = c->stream;
     static bool attr_done[64] = {false};
     const size_t smem = sizeof(CtaSmem);
     if (!attr_done[c->device & 63]) {
-        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_done[c->device & 63] = true;
     }
     uint64_t n_tiles = ceil_div(n_in, (size_t)TILE);
@@ -1147,10 +1206,14 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     P.has_term = bytes.p;
     P.phase_used = bytes.p + n_tiles;
     P.res = res.p;
+    P.ids_mode = ids ? 1 : 0;
+    P.span_off = ids ? ids->off : nullptr;
+    P.span_len = ids ? ids->len : nullptr;
+    P.span_cap = ids ? ids->cap : 0;
     static int occ[64] = {0};
     if (!occ[c->device & 63]) {
         int o = 0;
-        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fastq_fused_kernel, NTHREADS, smem));
+        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fastq_fused_kernel<false>, NTHREADS, smem));
         occ[c->device & 63] = o > 0 ? o : 1;
     }
     uint64_t grid = (uint64_t)c->sm_count * occ[c->device & 63];  // persistent: every CTA is resident
@@ -1175,7 +1238,8 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     }
     cudaMemcpyToSymbol(g_trace, &d_trace, sizeof(d_trace));
 #endif
-    fastq_fused_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(P);
+    if (ids) fastq_fused_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
+    else fastq_fused_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
     SGPU_LAUNCH(c);
     if (c->profiling) SGPU_CUDA(cudaEventRecord(c->prof_events[c->prof_used++].second, st));
     SGPU_TRY(exclusive_scan_u64(c, (const uint64_t *)P.sum_total, prefix.p, n_tiles, nullptr));
@@ -1221,6 +1285,12 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
         return SGPU_OK;
     }
     *used = 1;
+    if (ids) {
+        ids->n_spans = h.n_spans;
+        counts->reads_in = h.reads_in;
+        counts->path = 1;
+        return SGPU_OK;
+    }
     const uint64_t owned_end = is_last ? n_in : h.owned_end;
     const uint64_t other_total = owned_end - lead - h.kept_total;
     if (c->profiling) c->prof_alg_bytes += n_in + h.kept_total + (d_out_o ? other_total : 0);
@@ -1288,6 +1358,20 @@ sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     const uint64_t skip = s0 - lead;
     return clean_fused_range(c, set, d_in + skip, n_in - skip, lead, own_len - skip, is_last, reverse, d_out_w, cap_w,
                              n_w, d_out_o, cap_o, n_o, counts, used);
+}
+
+// ReadDifference::get_difference's two loops (utils.rs:259-267, 269-283) over canonical FASTQ: the id tokens of
+// the records absent from `probe` (nullptr: every record) as (offset, length) spans; *used = 0: general path
+sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, uint64_t *span_off,
+                      uint32_t *span_len, uint64_t cap, uint64_t *n_spans, uint64_t *n_records, int *used) {
+    IdsOut ids{span_off, span_len, cap, 0};
+    sgpu_counts counts;
+    memset(&counts, 0, sizeof(counts));
+    SGPU_TRY(clean_fused_range(c, probe, d_in, n_in, 0, n_in, 1, 0, nullptr, 0, nullptr, nullptr, 0, nullptr, &counts,
+                               used, &ids));
+    *n_spans = ids.n_spans;
+    *n_records = counts.reads_in;
+    return SGPU_OK;
 }
 
 sgpu_status clean_fused(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, int reverse,

@@ -224,6 +224,33 @@ def test_c3_ont_config_small(ctx_mode):
         assert (g.reads_in, g.reads_out) == (o.reads_in, o.reads_out)
 
 
+def test_diff_fused_ids_pass_matches_general_and_oracle(ctx_mode):
+    """ReadDifference (utils.rs:250-285): the one-pass ids mode of the fused kernel (canonical files) and the
+    indexed general path give the oracle's counts and id set -- short inline ids, 36-byte ONT ids, device and
+    host buffers, an empty output file, and a non-canonical (CRLF) input that must fall back"""
+    n = 150_000
+    fq = synth.gen_fastq(n, 1).numpy().tobytes()
+    keep = orc.OSet.from_ids([f"syn.{i}".encode() for i in range(0, n, 3)])
+    out = orc.clean_fastq(fq, keep, True).written  # extract: the output holds every third read
+    ont, lens, uu = synth.gen_ont_fastq(3000, max_len=60_000)
+    ontb = ont.numpy().tobytes()
+    oset = orc.OSet.from_ids([bytes(uu[i].tolist()) for i in range(0, 3000, 2)])
+    ont_out = orc.clean_fastq(ontb, oset, False).written
+    lines = fq.split(b"\n")
+    crlf = b"\r\n".join(lines[:200]) + b"\r\n"      # 50 records, CRLF line endings
+    crlf_out = b"\r\n".join(lines[:80]) + b"\r\n"   # the first 20 of them
+    cases = [[(fq, out)], [(ontb, ont_out)], [(fq, out), (ontb, ont_out)], [(fq, b"")], [(crlf, crlf_out)]]
+    for pairs in cases:
+        o = orc.diff(pairs)
+        g = api.diff(ctx_mode, pairs)
+        assert g[:3] == o[:3]
+        assert g[3].sorted_ids() == o[3].sorted_ids()
+    d_pairs = [(torch.frombuffer(bytearray(fq), dtype=torch.uint8).cuda(), torch.frombuffer(bytearray(out), dtype=torch.uint8).cuda())]
+    o = orc.diff([(fq, out)])
+    g = api.diff(ctx_mode, d_pairs)
+    assert g[:3] == o[:3] and g[3].sorted_ids() == o[3].sorted_ids()
+
+
 def test_c5_diff_small(ctx):
     n = 40_000
     ids = orc.set_from_txt(synth.gen_txt_ids(n).numpy().tobytes())
