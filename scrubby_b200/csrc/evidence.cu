@@ -478,6 +478,63 @@ __device__ __forceinline__ int evidence_line(const uint8_t *in, uint64_t s, uint
     return 1;
 }
 
+// <uN as FromStr>::from_str for the common case (at most 18 digits cannot overflow a u64); same result as
+// parse_uint
+__device__ __forceinline__ bool parse_uint_short(const uint8_t *p, uint32_t n, uint64_t maxv, uint64_t *out) {
+    if (n == 0 || n > 18 || p[0] == '+' || p[0] == '-') return parse_uint(p, n, maxv, out);
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t d = (uint32_t)p[i] - '0';
+        if (d > 9) return false;
+        v = v * 10 + d;
+    }
+    if (v > maxv) return false;
+    *out = v;
+    return true;
+}
+
+// one PAF line by scanning (non-ASCII tiles, lines that leave the halo, lines with fewer than 12 fields):
+// BufRead::lines semantics (UTF-8 check, "\r\n" stripped), then the fields in column order
+__device__ __noinline__ int paf_line_scan(const uint8_t *in, uint64_t s, uint64_t e_raw, bool has_nl, const PafParams &F,
+                                          uint64_t *koff, uint32_t *klen, unsigned long long *err_word) {
+    uint64_t e = e_raw;
+    if (!utf8_valid(in + s, e - s)) {
+        report_error(err_word, s, SGPU_ERR_IO);
+        return 0;
+    }
+    if (has_nl && e > s && in[e - 1] == '\r') e--;
+    int f = 0, code = 0;
+    uint64_t fs = s, qlen = 0, qstart = 0, qend = 0, mapq = 0, k_end = s;
+    for (uint64_t pos = s; pos <= e && f < 12; pos++) {
+        if (pos == e || in[pos] == '\t') {
+            uint64_t v = 0;
+            const bool is_int = (f >= 1 && f <= 3) || (f >= 6 && f <= 11);
+            if (is_int && !parse_uint(in + fs, pos - fs, f == 11 ? 255ull : ~0ull, &v)) {
+                code = SGPU_ERR_PAF_INTEGER;
+                break;
+            }
+            if (f == 0) k_end = pos;
+            else if (f == 1) qlen = v;
+            else if (f == 2) qstart = v;
+            else if (f == 3) qend = v;
+            else if (f == 11) mapq = v;
+            f++;
+            fs = pos + 1;
+        }
+    }
+    if (!code && f < 12) code = SGPU_ERR_WOULD_PANIC;  // fields[f] out of bounds (alignment.rs:248-259)
+    if (code) {
+        report_error(err_word, s, code);
+        return 0;
+    }
+    const uint64_t alen = qend - qstart;
+    const double cov = qlen == 0 ? 0.0 : __ull2double_rn(alen) / __ull2double_rn(qlen);
+    if (!((alen >= F.min_len || cov >= F.min_cov) && mapq >= F.min_mapq)) return 0;
+    *koff = s;
+    *klen = (uint32_t)(k_end - s);
+    return 1;
+}
+
 // 16-bit masks of the '\n' and '\t' bytes of a 16-byte chunk
 __device__ __forceinline__ void sep_masks16(uint4 v, bool want_tabs, uint32_t *m_nl, uint32_t *m_tab) {
     *m_nl = nl_mask16(v);
@@ -491,7 +548,7 @@ __device__ __forceinline__ void sep_masks16(uint4 v, bool want_tabs, uint32_t *m
 // newline; a line's fields are then consecutive list entries -- no per-line scanning.  Tiles with a
 // non-ASCII byte and lines that run past the halo take the scanning routine (evidence_line) instead.
 __global__ void __launch_bounds__(LT_NT)
-    lines_tile_kernel(const uint8_t *in, uint64_t n, TaxSet T, int need_fields, int mode, TileOut O) {
+    lines_tile_kernel(const uint8_t *in, uint64_t n, TaxSet T, int need_fields, int mode, PafParams F, TileOut O) {
     constexpr int NWARP = LT_NT / 32;
     constexpr int ROWS = LT_FC + 1;  // LT_FC rounds over the tile + one over the halo (warps 0 and 1)
     __shared__ __align__(16) uint8_t tile[LT_TILE + LT_HALO];
@@ -506,7 +563,7 @@ __global__ void __launch_bounds__(LT_NT)
     const uint32_t halo_len =
         tile_len < (uint32_t)LT_TILE ? 0u
                                      : (uint32_t)(((n - g0 - LT_TILE) < (uint64_t)LT_HALO ? (n - g0 - LT_TILE) : (uint64_t)LT_HALO) & ~15ull);
-    const bool want_tabs = mode == 0;
+    const bool want_tabs = mode != 1;  // mode 0: Kraken2 / Metabuli lines, 1: TXT ids, 2: PAF records
     // ---- P1: masks.  Warp w owns tile chunks [w*128, w*128+128): lane l takes chunk k*32 + l in round k;
     //      round LT_FC is the halo (64 chunks: warps 0 and 1)
     uint32_t mn[ROWS], mt[ROWS];
@@ -661,6 +718,55 @@ __global__ void __launch_bounds__(LT_NT)
                         klen = e - s;
                         sel = 1;
                     }
+                } else if (mode == 2) {
+                    // PAF: the twelve fields are the list entries i0+1 .. i0+12 (the twelfth closes at a tab
+                    // or at the line's newline); an earlier newline = fewer than 12 columns: the scanner
+                    // reports what the reference would (bad integer before the missing column, else panic).
+                    // Every passing line offers its qname: the set makes the per-read OR (alignment.rs:102-107)
+                    if (fast && (uint32_t)i0 + 12u < n_all) {
+                        uint32_t any_nl = 0;
+                        for (uint32_t x = 1; x <= 11; x++) any_nl |= seps[i0 + x];
+                        if (any_nl & 0x8000u) fast = false;
+                    } else {
+                        fast = false;
+                    }
+                    if (fast) {
+                        // PafRecord::from_str (alignment.rs:244-263): columns in order, the first bad integer
+                        // is the error; then the predicate (:265-275, :102-104)
+                        uint32_t fs = s, name_end = s;
+                        uint64_t qlen = 0, qstart = 0, qend = 0, mapq = 0;
+                        int code = 0;
+#pragma unroll
+                        for (int x = 0; x < 12; x++) {
+                            const uint32_t pe = (uint32_t)seps[i0 + 1 + x] & 0x7FFFu;
+                            uint32_t fe = pe;
+                            // lines() strips the '\r' of "\r\n": it can only sit at the end of the twelfth field
+                            if (x == 11 && (seps[i0 + 12] & 0x8000u) && fe > fs && tile[fe - 1] == '\r') fe--;
+                            if (x == 0) {
+                                name_end = pe;
+                            } else if (x <= 3 || x >= 6) {
+                                uint64_t v = 0;
+                                if (!code && !parse_uint_short(tile + fs, fe - fs, x == 11 ? 255ull : ~0ull, &v))
+                                    code = SGPU_ERR_PAF_INTEGER;
+                                if (x == 1) qlen = v;
+                                else if (x == 2) qstart = v;
+                                else if (x == 3) qend = v;
+                                else if (x == 11) mapq = v;
+                            }
+                            fs = pe + 1u;
+                        }
+                        if (code) {
+                            report_error(O.err_word, g0 + s, code);
+                        } else {
+                            const uint64_t alen = qend - qstart;  // usize subtraction wraps in release builds
+                            const double cov = qlen == 0 ? 0.0 : __ull2double_rn(alen) / __ull2double_rn(qlen);
+                            if ((alen >= F.min_len || cov >= F.min_cov) && mapq >= F.min_mapq) {
+                                sel = 1;
+                                koff = g0 + s;
+                                klen = name_end - s;
+                            }
+                        }
+                    }
                 } else if (fast) {
                     // fields 1 and 2 end at tabs 2 and 3; the line must have need_fields - 1 tabs
                     const uint32_t need_tabs = (uint32_t)need_fields - 1u;
@@ -691,7 +797,8 @@ __global__ void __launch_bounds__(LT_NT)
                     // scanning routine over the buffer: non-ASCII tile, or a line that leaves the halo
                     uint64_t e = g0 + s;
                     while (e < n && in[e] != '\n') e++;
-                    sel = evidence_line(in, g0 + s, e, e < n, mode, T, need_fields, &koff, &klen, O.err_word, 0);
+                    if (mode == 2) sel = paf_line_scan(in, g0 + s, e, e < n, F, &koff, &klen, O.err_word);
+                    else sel = evidence_line(in, g0 + s, e, e < n, mode, T, need_fields, &koff, &klen, O.err_word, 0);
                 }
             }
         }
@@ -732,7 +839,7 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
     }
     sgpu_status rc = SGPU_OK;
     bool done = false;
-    if ((kind == EV_TXT || kind == EV_READS) && ((uintptr_t)d_buf & 15) == 0) {
+    if (c->mode == 0 && (kind == EV_TXT || kind == EV_READS || kind == EV_PAF) && ((uintptr_t)d_buf & 15) == 0) {
         // ---- order-free evidence: the tile kernel, no newline index
         do {
             DevBuf<uint64_t> cand_off, ctr;
@@ -749,7 +856,7 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
                 TileOut O{cand_off.p, cand_len.p, cap, (unsigned long long *)ctr.p, (unsigned long long *)ctr.p + 1,
                           (unsigned long long *)ctr.p + 2};
                 lines_tile_kernel<<<(unsigned)ceil_div(n, (size_t)LT_TILE), LT_NT, 0, st>>>(
-                    d_buf, (uint64_t)n, T ? *T : none, need_fields, kind == EV_TXT ? 1 : 0, O);
+                    d_buf, (uint64_t)n, T ? *T : none, need_fields, kind == EV_TXT ? 1 : kind == EV_PAF ? 2 : 0, F, O);
                 SGPU_LAUNCH(c);
                 uint64_t h[3];
                 if ((rc = read_u64s(c, ctr.p, h, 3)) != SGPU_OK) break;

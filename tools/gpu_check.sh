@@ -12,4 +12,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:fastq_fused -s 1 -c 1 -f -o gpurun_out/fused python tools/prof_step.py --pairs 10000000 --steps 1 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log
-timeout 200 python tools/prof_step.py --ont 200000 --steps 2 > gpurun_out/quick_time_ont.log 2>&1; tail -2 gpurun_out/quick_time_ont.log
+
+timeout 300 python tools/config_times.py > gpurun_out/config_times.log 2>&1; grep -E "^C[1-5]" gpurun_out/config_times.log
