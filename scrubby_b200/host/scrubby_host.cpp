@@ -4,6 +4,9 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <atomic>
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -166,18 +169,52 @@ void write_file(const std::string &path, const uint8_t *data, size_t n, int gz_l
     if (c == Compression::Bzip || c == Compression::Lzma)
         throw ScrubbyError(ScrubbyError::NifflerError, "bzip2/xz output: feature disabled in this build: " + path);
     if (c == Compression::Gzip) {
-        gzFile g = gzopen(path.c_str(), ("wb" + std::to_string(gz_level)).c_str());
-        if (!g) throw ScrubbyError(ScrubbyError::IoError, "cannot create " + path);
-        size_t pos = 0;
-        while (pos < n) {
-            unsigned w = (unsigned)std::min<size_t>(n - pos, 1u << 30);
-            if (gzwrite(g, data + pos, w) <= 0) {
-                gzclose(g);
+        // Host stage: the output is deflated in independent 4 MiB blocks on all host threads,
+        // each block a complete gzip member (as pigz -i / bgzip do).  The concatenation is a valid gzip file
+        // whose DEcompressed bytes equal the reference's output; the compressed bytes differ (they depend on
+        // flate2's backend in the reference and are not part of the parity contract).
+        const size_t BLOCK = (size_t)4 << 20;
+        const size_t nb = n ? (n + BLOCK - 1) / BLOCK : 1;
+        std::vector<std::vector<uint8_t>> parts(nb);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> failed{false};
+        auto work = [&]() {
+            for (size_t b = next.fetch_add(1); b < nb && !failed; b = next.fetch_add(1)) {
+                const size_t a = b * BLOCK, len = std::min(BLOCK, n - a);
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (deflateInit2(&zs, gz_level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+                    failed = true;
+                    return;
+                }
+                std::vector<uint8_t> &o = parts[b];
+                o.resize(deflateBound(&zs, (uLong)len) + 64);
+                zs.next_in = const_cast<Bytef *>(data + a);
+                zs.avail_in = (uInt)len;
+                zs.next_out = o.data();
+                zs.avail_out = (uInt)o.size();
+                const int rc = deflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END) failed = true;
+                o.resize(o.size() - zs.avail_out);
+                deflateEnd(&zs);
+            }
+        };
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), nb);
+        std::vector<std::thread> th;
+        for (size_t i = 1; i < nt; i++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        if (failed) throw ScrubbyError(ScrubbyError::NifflerError, "deflate failed: " + path);
+        FILE *f = fopen(path.c_str(), "wb");
+        if (!f) throw ScrubbyError(ScrubbyError::IoError, "cannot create " + path);
+        for (auto &o : parts) {
+            if (!o.empty() && fwrite(o.data(), 1, o.size(), f) != o.size()) {
+                fclose(f);
                 throw ScrubbyError(ScrubbyError::IoError, "write failed: " + path);
             }
-            pos += w;
         }
-        gzclose(g);
+        fclose(f);
         return;
     }
     FILE *f = fopen(path.c_str(), "wb");
