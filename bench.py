@@ -279,7 +279,7 @@ def run_ours(args):
         return r
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):  # first touches of the pinned buffers, the chunk buffers of the pipeline, the mem pool
+    for _ in range(3):  # first touches of the pinned buffers, the chunk buffers of the pipeline, the mem pool
         rh = step_host()
     barrier()
     e2e_each = []
