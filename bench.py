@@ -100,6 +100,33 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
+def bind_to_gpu_numa_node(device: int):
+    """Best effort: run this rank on the CPUs next to its GPU (sysfs local_cpulist of the PCI device) so that
+    the pinned host buffers of the end-to-end arm are allocated on the GPU's NUMA node.  Returns the cpulist."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = device
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            idx = int(vis.split(",")[device])
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/local_cpulist"
+        cpulist = open(path).read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpulist
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
 def taxids_for_config():
     """host stage: report -> taxid strings (-T Chordata -D 9606), the C++ state machine"""
     from scrubby_b200 import hostlib, synth
@@ -209,6 +236,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpulist = bind_to_gpu_numa_node(local) if not args.no_bind else "unbound (--no-bind)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -325,6 +353,7 @@ def run_ours(args):
                 "pairs_per_gpu": pairs, "fastq_bytes_per_gpu": sum(n_r), "kraken_bytes_per_gpu": n_k,
                 "outputs": "kept+removed" if args.split else "kept (reference-equivalent single output)",
                 "fraction_kept": kept_all / reads_all, "parallelism": f"chunk-sharded x{world}",
+                "host_cpus_rank0": cpulist,
                 "l2": "inputs (6.6 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
                 "fastq_gb_per_s": bytes_all / (ms * 1e-3) / 1e9,
             },
@@ -359,6 +388,7 @@ def main():
     ap.add_argument("--cpu-step-seconds", type=float, default=3.0, help="--impl reference: CPU work per step")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--split", action="store_true", help="also write the removed records (kept + removed)")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's NUMA-local CPUs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
