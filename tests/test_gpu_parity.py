@@ -487,6 +487,25 @@ def test_fused_record_boundary_on_tile_edge(ctx, edge, delta):
         assert (f.reads_in, f.reads_out) == (o.reads_in, o.reads_out)
 
 
+@pytest.mark.parametrize("read_len", [1, 5, 20, 30, 36, 41, 45, 50, 75, 100, 251, 1000])
+def test_record_density_sweep(ctx, read_len):
+    """short reads put hundreds of records into one 36 KiB tile (the fused kernel handles <= 360 per tile and
+    two newlines per 16-byte chunk, denser input must fall back to the general path): same bytes either way"""
+    n = 6000
+    fq = synth.gen_fastq(n, 1, read_len=read_len).numpy().tobytes()
+    ids = [f"syn.{i}".encode() for i in range(0, n, 2)] + [f"syn.{i}".encode() for i in range(1, n, 7)]
+    gs = api.IdSet.from_ids(ctx, ids)
+    os_ = orc.OSet.from_ids(ids)
+    for reverse in (False, True):
+        f = api.clean_fastq(ctx, gs, fq, reverse)
+        o = orc.clean_fastq(fq, os_, reverse)
+        assert f.written == o.written and f.other == o.other, (read_len, f.path)
+        assert (f.reads_in, f.reads_out) == (o.reads_in, o.reads_out)
+    d = api.diff(ctx, [(fq, orc.clean_fastq(fq, os_, False).written)])
+    od = orc.diff([(fq, orc.clean_fastq(fq, os_, False).written)])
+    assert d[:3] == od[:3] and d[3].sorted_ids() == od[3].sorted_ids()
+
+
 def test_fused_falls_back_on_noncanonical(ctx):
     fq = synth.gen_fastq(3000, 1).numpy().tobytes()
     gs = api.IdSet.from_ids(ctx, [b"syn.5", b"syn.77"])
