@@ -139,11 +139,20 @@ __device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t c4) {
     return ((t >> 7) & 1u) | ((t >> 14) & 2u) | ((t >> 21) & 4u) | ((t >> 28) & 8u);
 }
 
-// 16-bit mask of bytes equal to '\n' in a 16-byte chunk (bit i <-> byte i)
-__device__ __forceinline__ uint32_t nl_mask16(uint4 v) {
-    const uint32_t c = 0x0a0a0a0au;
-    return eq_mask4(v.x, c) | (eq_mask4(v.y, c) << 4) | (eq_mask4(v.z, c) << 8) | (eq_mask4(v.w, c) << 12);
+// 0x80 in every byte of w that equals the byte of c4 (exact for every byte value)
+__device__ __forceinline__ uint32_t eq_flags4(uint32_t w, uint32_t c4) {
+    const uint32_t x = w ^ c4;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
 }
+// 16-bit mask (bit i <-> byte i) of the bytes of a 16-byte chunk that equal the byte of c4: four words of
+// 0x80 flags gathered with dp4a (the flag byte times its bit weight, summed per word pair)
+__device__ __forceinline__ uint32_t eq_mask16(uint4 v, uint32_t c4) {
+    const uint32_t lo = __dp4a(eq_flags4(v.x, c4), 0x08040201u, __dp4a(eq_flags4(v.y, c4), 0x80402010u, 0u));
+    const uint32_t hi = __dp4a(eq_flags4(v.z, c4), 0x08040201u, __dp4a(eq_flags4(v.w, c4), 0x80402010u, 0u));
+    return (lo >> 7) | (hi << 1);
+}
+// 16-bit mask of bytes equal to '\n' in a 16-byte chunk (bit i <-> byte i)
+__device__ __forceinline__ uint32_t nl_mask16(uint4 v) { return eq_mask16(v, 0x0a0a0a0au); }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x ^= x >> 32;

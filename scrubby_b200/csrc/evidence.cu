@@ -539,8 +539,7 @@ __device__ __noinline__ int paf_line_scan(const uint8_t *in, uint64_t s, uint64_
 __device__ __forceinline__ void sep_masks16(uint4 v, bool want_tabs, uint32_t *m_nl, uint32_t *m_tab) {
     *m_nl = nl_mask16(v);
     const uint32_t c = 0x09090909u;
-    *m_tab = want_tabs ? (eq_mask4(v.x, c) | (eq_mask4(v.y, c) << 4) | (eq_mask4(v.z, c) << 8) | (eq_mask4(v.w, c) << 12))
-                       : 0u;
+    *m_tab = want_tabs ? eq_mask16(v, c) : 0u;
 }
 
 // The tile kernel proper.  P1 turns every 16-byte chunk of the tile (+ halo) into '\n' / '\t' masks and
