@@ -186,6 +186,14 @@ sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *, const sgpu_idset *, const uin
 sgpu_status sgpu_count_newlines_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, uint64_t *count);
 
 /* ---- diff / report counts -------------------------------------------------------- */
+/* One shard of either loop of ReadDifference::get_difference (utils.rs:259-267 collects the output file's ids,
+ * :269-283 tests the input file's ids) for multi-GPU runs: the ids of the records that START in the
+ * owned range of the buffer (same shard convention as sgpu_clean_fastq_shard_dev) and are absent from `probe`
+ * (NULL: every record) are inserted into `into` (NULL: count only).  counts->reads_in += records,
+ * counts->difference += picked records; both accumulate so that shards and file pairs can share one struct. */
+sgpu_status sgpu_fastq_ids_shard_dev(sgpu_ctx *, const sgpu_idset *probe, const uint8_t *d_buf, size_t n_buf,
+                                     size_t own_len, uint64_t newlines_before, int is_first, int is_last,
+                                     sgpu_idset *into, sgpu_counts *counts);
 /* ReadDifference::get_difference, utils.rs:250-285, for ONE (input, output) file pair:
  * counts->{reads_in, reads_out, difference} are incremented (+=) and the ids absent from the
  * output are inserted into *diff_ids (created when *diff_ids == NULL), so calling it once

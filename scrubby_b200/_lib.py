@@ -45,7 +45,7 @@ SYMBOLS = [
     "sgpu_idset_from_reads", "sgpu_idset_from_reads_dev", "sgpu_idset_from_ids", "sgpu_idset_new",
     "sgpu_idset_len", "sgpu_idset_contains", "sgpu_idset_dump", "sgpu_idset_free", "sgpu_free",
     "sgpu_clean_fastq", "sgpu_clean_fastq_dev", "sgpu_clean_fastq_shard_dev", "sgpu_count_newlines_dev",
-    "sgpu_diff", "sgpu_diff_dev", "sgpu_idset_export", "sgpu_idset_import",
+    "sgpu_diff", "sgpu_diff_dev", "sgpu_fastq_ids_shard_dev", "sgpu_idset_export", "sgpu_idset_import",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def load():
     L.sgpu_clean_fastq_shard_dev.argtypes = [vp, vp, vp, sz, sz, u64, i32, i32, i32, i32, vp, sz, P(sz), vp, sz,
                                              P(sz), P(Counts)]
     L.sgpu_count_newlines_dev.argtypes = [vp, vp, sz, P(u64)]
+    L.sgpu_fastq_ids_shard_dev.argtypes = [vp, vp, vp, sz, sz, u64, i32, i32, vp, P(Counts)]
     for name in ("sgpu_diff", "sgpu_diff_dev"):
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, P(Counts), P(vp)]
     L.sgpu_idset_export.argtypes = [vp, P(IdSetImage)]

@@ -299,6 +299,18 @@ def count_newlines_dev(ctx: Context, d_buf, n: int) -> int:
     return int(out.value)
 
 
+def fastq_ids_shard_dev(ctx: Context, probe, d_buf, n_buf: int, own_len: int, newlines_before: int, is_first: bool,
+                        is_last: bool, into: IdSet):
+    """one shard of ReadDifference::get_difference's loops (utils.rs:259-283): ids of the records that start in the
+    owned range and are absent from `probe` (None: all) go into `into`; returns (records, picked records)"""
+    c = _lib.Counts()
+    rc = ctx.L.sgpu_fastq_ids_shard_dev(ctx.h, probe.h if probe is not None else None, C.c_void_p(d_buf.data_ptr()),
+                                        n_buf, own_len, newlines_before, int(is_first), int(is_last),
+                                        into.h if into is not None else None, C.byref(c))
+    _check(rc, c.error_record, "fastq_ids_shard_dev")
+    return c.reads_in, c.difference
+
+
 def diff(ctx: Context, pairs, raise_on_error: bool = True):
     """ReadDifference::get_difference (utils.rs:250-285) over [(input, output), ...] host or device buffers
     -> (reads_in, reads_out, difference, IdSet of absent ids)"""

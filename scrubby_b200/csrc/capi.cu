@@ -9,8 +9,9 @@ const char *last_cuda_error_text();
 sgpu_status clean_fused(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, int reverse,
                         uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
                         sgpu_counts *counts, int *used);
-sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, uint64_t *span_off,
-                      uint32_t *span_len, uint64_t cap, uint64_t *n_spans, uint64_t *n_records, int *used);
+sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, size_t own_len,
+                      uint64_t newlines_before, int is_first, int is_last, uint64_t *span_off, uint32_t *span_len,
+                      uint64_t cap, uint64_t *n_spans, uint64_t *span_base, uint64_t *n_records, int *used);
 sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
                               uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
                               size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
@@ -60,14 +61,19 @@ static sgpu_status sniff(sgpu_ctx *c, const uint8_t *d_in, size_t n_in, bool *em
     return SGPU_OK;
 }
 
-// one FASTQ buffer -> ids (all, or only those absent from `probe`) inserted into `into`
-static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, const sgpu_idset *probe,
-                                  int want_absent, sgpu_idset *into, uint64_t *n_records, uint64_t *n_picked,
-                                  uint64_t *err_record) {
+// one FASTQ buffer (or one shard of it: the records that start in [0, own_len], see sgpu_clean_fastq_shard_dev)
+// -> ids (all, or only those absent from `probe`) inserted into `into`
+static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, size_t own_len, uint64_t newlines_before,
+                                  int is_first, int is_last, const sgpu_idset *probe, int want_absent, sgpu_idset *into,
+                                  uint64_t *n_records, uint64_t *n_picked, uint64_t *err_record) {
     *n_records = *n_picked = 0;
-    bool empty;
-    SGPU_TRY(sniff(c, d_buf, n, &empty));
-    if (empty) return SGPU_OK;
+    if (is_first) {
+        bool empty;
+        SGPU_TRY(sniff(c, d_buf, n, &empty));
+        if (empty) return SGPU_OK;
+    } else if (n == 0 || own_len == 0) {
+        return SGPU_OK;
+    }
     cudaStream_t st = c->stream;
     if (c->mode == 0 && ((uintptr_t)d_buf & 15) == 0) {
         // canonical input: one pass of the fused kernel in ids mode -> (offset, length) spans of the wanted ids
@@ -76,13 +82,15 @@ static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, c
         const uint64_t cap = n / 100 + 4096;  // the fused kernel handles >= ~102 bytes per record
         SGPU_TRY(s_off.alloc(cap, st));
         SGPU_TRY(s_len.alloc(cap, st));
-        uint64_t n_spans = 0, n_rec = 0;
+        uint64_t n_spans = 0, n_rec = 0, base = 0;
         int used = 0;
-        SGPU_TRY(ids_fused(c, want_absent ? probe : nullptr, d_buf, n, s_off.p, s_len.p, cap, &n_spans, &n_rec, &used));
+        SGPU_TRY(ids_fused(c, want_absent ? probe : nullptr, d_buf, n, own_len, newlines_before, is_first, is_last,
+                           s_off.p, s_len.p, cap, &n_spans, &base, &n_rec, &used));
         if (used) {
             *n_records = n_rec;
             *n_picked = n_spans;
-            if (into && n_spans) SGPU_TRY(idset_insert_spans(c, into, d_buf, s_off.p, s_len.p, nullptr, (size_t)n_spans));
+            if (into && n_spans)
+                SGPU_TRY(idset_insert_spans(c, into, d_buf + base, s_off.p, s_len.p, nullptr, (size_t)n_spans));
             return SGPU_OK;
         }
     }
@@ -94,13 +102,16 @@ static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, c
     RecParams P;
     P.in = d_buf;
     P.n_in = n;
-    P.own_len = n;
+    P.own_len = own_len;
     P.nlpos = nlpos.p;
-    P.is_last = 1;
+    P.is_last = is_last;
     P.reverse = 0;
     P.crlf = 0;
     P.set = view_of(nullptr);
-    setup_records(P, n_nl, 0, 1);
+    if (!setup_records(P, n_nl, newlines_before, is_first)) {
+        // no record boundary in the whole buffer: a record longer than the halo (or a truncated file)
+        return is_last ? SGPU_ERR_FASTQ_UNEXPECTED_END : SGPU_ERR_HALO;
+    }
     uint64_t n_thr = P.k_full + 1;
     SGPU_TRY(key_off.alloc(n_thr, st));
     SGPU_TRY(key_len.alloc(n_thr, st));
@@ -540,10 +551,10 @@ sgpu_status sgpu_diff_dev(sgpu_ctx *c, const uint8_t *d_in, size_t n_in, const u
     sgpu_idset *o_ids = nullptr;  // utils.rs:257 reads2_ids
     SGPU_TRY(idset_create(c, &o_ids));
     uint64_t n_rec = 0, n_pick = 0, err = 0;
-    sgpu_status rc = fastq_ids_into(c, d_out, n_out, nullptr, 0, o_ids, &n_rec, &n_pick, &err);  // :259-267
+    sgpu_status rc = fastq_ids_into(c, d_out, n_out, n_out, 0, 1, 1, nullptr, 0, o_ids, &n_rec, &n_pick, &err);  // :259-267
     if (rc == SGPU_OK) {
         counts->reads_out += n_rec;
-        rc = fastq_ids_into(c, d_in, n_in, o_ids, 1, *diff_ids, &n_rec, &n_pick, &err);  // :269-283
+        rc = fastq_ids_into(c, d_in, n_in, n_in, 0, 1, 1, o_ids, 1, *diff_ids, &n_rec, &n_pick, &err);  // :269-283
         if (rc == SGPU_OK) {
             counts->reads_in += n_rec;
             counts->difference += n_pick;
@@ -552,6 +563,28 @@ sgpu_status sgpu_diff_dev(sgpu_ctx *c, const uint8_t *d_in, size_t n_in, const u
     if (rc != SGPU_OK) counts->error_record = err;
     cudaStreamSynchronize(c->stream);
     sgpu_idset_free(o_ids);
+    return rc;
+}
+
+sgpu_status sgpu_fastq_ids_shard_dev(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_buf, size_t n_buf,
+                                     size_t own_len, uint64_t newlines_before, int is_first, int is_last,
+                                     sgpu_idset *into, sgpu_counts *counts) {
+    if (!c || !counts || (n_buf && !d_buf) || own_len > n_buf || (is_last && own_len != n_buf) ||
+        (is_first && newlines_before != 0))
+        return SGPU_ERR_INVALID_ARG;
+    if (n_buf && ((uintptr_t)d_buf & 15)) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    uint64_t n_rec = 0, n_pick = 0, err = 0;
+    sgpu_status rc = fastq_ids_into(c, d_buf, n_buf, own_len, newlines_before, is_first, is_last, probe, probe != nullptr,
+                                    into, &n_rec, &n_pick, &err);
+    if (rc == SGPU_OK) {
+        counts->reads_in += n_rec;
+        counts->difference += n_pick;
+    } else {
+        counts->error_record = err;
+    }
+    cudaStreamSynchronize(c->stream);
     return rc;
 }
 

@@ -1147,6 +1147,7 @@ struct IdsOut {
     uint32_t *len;
     uint64_t cap;
     uint64_t n_spans;  // out
+    uint64_t base;     // out: the spans' offsets are relative to d_in + base
 };
 
 sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, uint32_t lead,
@@ -1334,10 +1335,10 @@ __global__ void kth_newline_kernel(const uint8_t *buf, uint64_t n, uint32_t k, u
 
 // one shard (see sgpu_clean_fastq_shard_dev): locate the first owned record start, then run the fused kernel
 // from the 16-byte aligned address below it.  *used = 0: take the general path.
-sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
-                              uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
-                              size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
-                              sgpu_counts *counts, int *used) {
+static sgpu_status fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
+                               uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
+                               size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
+                               sgpu_counts *counts, int *used, IdsOut *ids) {
     *used = 0;
     uint64_t s0 = 0;
     if (!is_first) {
@@ -1356,20 +1357,37 @@ sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     }
     const uint32_t lead = (uint32_t)(s0 & 15);
     const uint64_t skip = s0 - lead;
+    if (ids) {  // span offsets are relative to the range the kernel sees: rebase them to d_in afterwards
+        sgpu_status rc = clean_fused_range(c, set, d_in + skip, n_in - skip, lead, own_len - skip, is_last, reverse,
+                                           nullptr, 0, nullptr, nullptr, 0, nullptr, counts, used, ids);
+        ids->base = skip;
+        return rc;
+    }
     return clean_fused_range(c, set, d_in + skip, n_in - skip, lead, own_len - skip, is_last, reverse, d_out_w, cap_w,
                              n_w, d_out_o, cap_o, n_o, counts, used);
 }
 
+sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
+                              uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
+                              size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
+                              sgpu_counts *counts, int *used) {
+    return fused_shard(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, reverse, d_out_w, cap_w, n_w,
+                       d_out_o, cap_o, n_o, counts, used, nullptr);
+}
+
 // ReadDifference::get_difference's two loops (utils.rs:259-267, 269-283) over canonical FASTQ: the id tokens of
 // the records absent from `probe` (nullptr: every record) as (offset, length) spans; *used = 0: general path
-sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, uint64_t *span_off,
-                      uint32_t *span_len, uint64_t cap, uint64_t *n_spans, uint64_t *n_records, int *used) {
-    IdsOut ids{span_off, span_len, cap, 0};
+// (shards as in clean_fused_shard; *span_base: the offsets are relative to d_in + *span_base)
+sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, size_t own_len,
+                      uint64_t newlines_before, int is_first, int is_last, uint64_t *span_off, uint32_t *span_len,
+                      uint64_t cap, uint64_t *n_spans, uint64_t *span_base, uint64_t *n_records, int *used) {
+    IdsOut ids{span_off, span_len, cap, 0, 0};
     sgpu_counts counts;
     memset(&counts, 0, sizeof(counts));
-    SGPU_TRY(clean_fused_range(c, probe, d_in, n_in, 0, n_in, 1, 0, nullptr, 0, nullptr, nullptr, 0, nullptr, &counts,
-                               used, &ids));
+    SGPU_TRY(fused_shard(c, probe, d_in, n_in, own_len, newlines_before, is_first, is_last, 0, nullptr, 0, nullptr,
+                         nullptr, 0, nullptr, &counts, used, &ids));
     *n_spans = ids.n_spans;
+    *span_base = ids.base;
     *n_records = counts.reads_in;
     return SGPU_OK;
 }

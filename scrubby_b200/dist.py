@@ -89,6 +89,20 @@ class GpuOps:
         other = bytes(d_oth[: r.n_other].cpu().numpy()) if want_other else b""
         return written, other, r.reads_in, r.reads_out
 
+    def new_set(self):
+        return self.api.IdSet.empty(self.ctx)
+
+    def ids_shard(self, probe, d_buf, sh: Shard, newlines_before, into):
+        """ids of the shard's own records that are absent from `probe` (None: all) -> `into`; (records, picked)"""
+        return self.api.fastq_ids_shard_dev(self.ctx, probe, d_buf, sh.buf_len, sh.own_len, newlines_before,
+                                            sh.is_first, sh.is_last, into)
+
+    def set_ids(self, ids):
+        return ids.sorted_ids()
+
+    def set_from_ids(self, id_list):
+        return self.api.IdSet.from_ids(self.ctx, id_list)
+
     def replicate_set(self, ids, dist, src: int = 0):
         """broadcast the table and the key arena of rank `src`'s set (NCCL over NVLink) and import them"""
         torch, api = self.torch, self.api
@@ -181,6 +195,74 @@ def clean_fastq_sharded(ops, ids, file_bytes, dist=None, reverse: bool = False, 
         return ShardedResult(w, o, sum(r[1] for r in res[:rank]), sum(r[2] for r in res[:rank]),
                              sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res),
                              sum(r[4] for r in res), crlf)
+
+
+@dataclass
+class ShardedDiff:
+    reads_in: int       # allreduced over ranks and file pairs (utils.rs:250-285)
+    reads_out: int
+    difference: int
+    diff_ids: list      # sorted unique ids of the input records missing from their output file (every rank)
+
+
+def _ids_of_file_sharded(ops, file_bytes, dist, probe, into, halo, max_halo):
+    """one loop of ReadDifference::get_difference over one file, every rank on its own byte range; returns the
+    (records, picked) totals of this rank.  A record longer than the halo makes all ranks retry with a larger one."""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    n = len(file_bytes)
+    while True:
+        sh = plan_shards(n, world, halo)[rank]
+        d_buf = ops.upload(file_bytes[sh.start : sh.start + sh.buf_len])
+        own_nl = ops.count_newlines(d_buf, sh.own_len)
+        counts = _all_gather_ints(dist, [own_nl], world)
+        newlines_before = sum(c[0] for c in counts[:rank])
+        halo_short, rec, picked = 0, 0, 0
+        scratch = ops.new_set()  # a retry must not leave ids of the failed attempt behind
+        try:
+            if sh.own_len:
+                rec, picked = ops.ids_shard(probe, d_buf, sh, newlines_before, scratch)
+        except Exception as e:  # SGPU_ERR_HALO == 21
+            if getattr(e, "status", None) != 21:
+                raise
+            halo_short = 1
+        if any(r[0] for r in _all_gather_ints(dist, [halo_short], world)):
+            if halo >= max_halo:
+                raise RuntimeError("a record is longer than the maximum shard halo")
+            halo = min(max_halo, halo * 8)
+            continue
+        into.extend(ops.set_ids(scratch))
+        return rec, picked
+
+
+def diff_sharded(ops, pairs, dist=None, halo: int = 1 << 20, max_halo: int = 1 << 30) -> ShardedDiff:
+    """ReadDifference::get_difference (utils.rs:250-285) across all ranks (SURVEY 8e, config 5).  For every
+    (input, output) file pair: each rank lists the ids of its byte range of the OUTPUT file, the lists are
+    all-gathered into the replicated set O_i, each rank probes its byte range of the INPUT file against it;
+    counters are summed over ranks, the absent ids are united (the reference keeps one global diff set, so mates
+    with the same id appear once but count twice)."""
+    world = dist.get_world_size() if dist is not None else 1
+    reads_in = reads_out = difference = 0
+    diff_local: list = []
+    for fin, fout in pairs:
+        out_local: list = []
+        rec_out, _ = _ids_of_file_sharded(ops, fout, dist, None, out_local, halo, max_halo)
+        gathered = [out_local]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, out_local)
+        o_set = ops.set_from_ids(sorted(set(x for part in gathered for x in part)))
+        rec_in, picked = _ids_of_file_sharded(ops, fin, dist, o_set, diff_local, halo, max_halo)
+        reads_out += rec_out
+        reads_in += rec_in
+        difference += picked
+    tot = _all_gather_ints(dist, [reads_in, reads_out, difference], world)
+    gathered = [diff_local]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, diff_local)
+    ids = sorted(set(x for part in gathered for x in part))
+    return ShardedDiff(sum(t[0] for t in tot), sum(t[1] for t in tot), sum(t[2] for t in tot), ids)
 
 
 def _all_gather_ints(dist, vals, world):

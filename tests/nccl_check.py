@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 from bench import taxids_for_config
 from scrubby_b200 import api, synth
-from scrubby_b200.dist import GpuOps, clean_fastq_sharded
+from scrubby_b200.dist import GpuOps, clean_fastq_sharded, diff_sharded
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -44,6 +44,18 @@ for mate in (1, 2):
             print(f"mate {mate} reverse {reverse}: world {world} reads_in {r.reads_in} reads_out {r.reads_out} "
                   f"bytes {len(cat_w)} -> {'identical' if good else 'MISMATCH'}")
             ok = ok and good
+# ---- config 5: sharded diff (output-id set all-gathered, counters summed, absent ids united) vs one GPU
+pairs = []
+for mate in (1, 2):
+    fq = synth.gen_fastq(n, mate).numpy().tobytes()
+    pairs.append((fq, api.clean_fastq(ctx, ids, fq, False).written))
+sd = diff_sharded(ops, pairs, dist)
+if rank == 0:
+    whole = api.diff(ctx, pairs)
+    good = (sd.reads_in, sd.reads_out, sd.difference) == whole[:3] and sd.diff_ids == whole[3].sorted_ids()
+    print(f"diff: world {world} reads_in {sd.reads_in} reads_out {sd.reads_out} difference {sd.difference} "
+          f"unique ids {len(sd.diff_ids)} -> {'identical' if good else 'MISMATCH'}")
+    ok = ok and good
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()

@@ -66,6 +66,60 @@ class OracleOps:
         r = orc.clean_fastq(buf[start:end], ids, reverse)
         return r.written, (r.other if want_other else b""), r.reads_in, r.reads_out
 
+    # ---- sharded diff (dist.diff_sharded): python sets stand in for device id sets
+    def new_set(self):
+        return set()
+
+    def set_ids(self, s):
+        return sorted(s)
+
+    def set_from_ids(self, id_list):
+        return set(id_list)
+
+    def ids_shard(self, probe, buf, sh: Shard, newlines_before, into):
+        from oracle import oracle as orc
+
+        pos, line = 0, newlines_before
+        if not sh.is_first:
+            while line % 4 != 0:
+                p = buf.find(b"\n", pos)
+                if p < 0:
+                    return 0, 0
+                pos, line = p + 1, line + 1
+        rec = picked = 0
+        while pos < len(buf) and (pos < sh.own_len or (pos == sh.own_len and not sh.is_last)):
+            lines = []
+            e = pos
+            for _ in range(4):
+                p = buf.find(b"\n", e)
+                if p < 0:
+                    if sh.is_last:
+                        p = len(buf)
+                    else:
+                        raise HaloError()
+                lines.append(buf[e:p])
+                e = p + 1
+            if not lines[0]:
+                break  # trailing blank line at EOF
+            rid = orc.get_id(lines[0][1:].rstrip(b"\r"))
+            rec += 1
+            if probe is None or rid not in probe:
+                picked += 1
+                into.add(rid)
+            pos = e
+        return rec, picked
+
+
+def _diff_worker(rank, world, port, pairs, halo, q):
+    from scrubby_b200.dist import diff_sharded
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        r = diff_sharded(OracleOps(), pairs, dist, halo=halo)
+        q.put((rank, r.reads_in, r.reads_out, r.difference, r.diff_ids))
+    finally:
+        dist.destroy_process_group()
+
 
 def _free_port():
     s = socket.socket()
@@ -149,3 +203,31 @@ def test_halo_retry_is_collective():
     res = _run(2, fq, ids_txt, halo=64)
     assert b"".join(r[1] for r in res) == whole.written
     assert res[0][7] == whole.reads_in and res[0][8] == whole.reads_out
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_diff_matches_unsharded(world):
+    """dist.diff_sharded: per-rank byte ranges of the output and input files, replicated output-id set, summed
+    counters and united id lists equal ReadDifference::get_difference on the whole files (utils.rs:250-285)"""
+    from oracle import oracle as orc
+
+    n = 3000
+    ids = orc.set_from_txt(synth.gen_txt_ids(n).numpy().tobytes())
+    pairs = []
+    for mate in (1, 2):
+        fq = synth.gen_fastq(n, mate).numpy().tobytes()
+        pairs.append((fq, orc.clean_fastq(fq, ids).written))
+    want = orc.diff(pairs)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_diff_worker, args=(r, world, port, pairs, 4096, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rin, rout, d, dids in res:
+        assert (rin, rout, d) == want[:3]
+        assert dids == want[3].sorted_ids()

@@ -251,6 +251,37 @@ def test_diff_fused_ids_pass_matches_general_and_oracle(ctx_mode):
     assert g[:3] == o[:3] and g[3].sorted_ids() == o[3].sorted_ids()
 
 
+@pytest.mark.parametrize("k", [1, 2, 5])
+def test_fastq_ids_shards_unite_to_the_whole_file(ctx_mode, k):
+    """sgpu_fastq_ids_shard_dev: the shards' records and picked ids add up to ReadDifference's loops over the
+    whole file (utils.rs:259-283), for 2x150 reads and long ONT reads, with and without a probe set"""
+    from scrubby_b200.dist import GpuOps, plan_shards
+
+    ops = GpuOps(ctx_mode)
+    fq = synth.gen_fastq(30_000, 1).numpy().tobytes()
+    ont, lens, uu = synth.gen_ont_fastq(1500, max_len=80_000)
+    for buf, probe_ids, halo in ((fq, [f"syn.{i}".encode() for i in range(0, 30_000, 3)], 4096),
+                                 (ont.numpy().tobytes(), [bytes(uu[i].tolist()) for i in range(0, 1500, 2)], 1 << 20)):
+        oprobe = orc.OSet.from_ids(probe_ids)
+        kept = orc.clean_fastq(buf, oprobe, True).written          # a file holding exactly the probe's records
+        want_all = orc.diff([(buf, b"")])                           # every id of the file
+        want_abs = orc.diff([(buf, kept)])                          # ids absent from the probe
+        gprobe = api.IdSet.from_ids(ctx_mode, probe_ids)
+        for probe, want in ((None, want_all), (gprobe, want_abs)):
+            into = api.IdSet.empty(ctx_mode)
+            rec = picked = 0
+            nlb = 0
+            for sh in plan_shards(len(buf), k, halo):
+                if sh.own_len == 0:
+                    continue
+                d = ops.upload(buf[sh.start : sh.start + sh.buf_len])
+                r, p_ = ops.ids_shard(probe, d, sh, nlb, into)
+                rec, picked = rec + r, picked + p_
+                nlb += buf[sh.start : sh.start + sh.own_len].count(b"\n")
+            assert (rec, picked) == (want[0], want[2])
+            assert into.sorted_ids() == want[3].sorted_ids()
+
+
 def test_c5_diff_small(ctx):
     n = 40_000
     ids = orc.set_from_txt(synth.gen_txt_ids(n).numpy().tobytes())
