@@ -70,7 +70,10 @@ constexpr int TILE = NT * FC * 16;      // 36 KiB
 constexpr int PRE = 16;                 // pre-halo (previous 16 bytes)
 constexpr int HALO = SGPU_FUSED_HALO;   // post-halo: id token of the last record start, "+\n" after the last newline
 constexpr int BUF = PRE + TILE + HALO;  // bytes of the tile buffer
-constexpr int RMAX = TILE / 1024 * 10;  // record starts per tile (>= 102 bytes per record on average)
+#ifndef SGPU_FUSED_RMAX_PER_KIB
+#define SGPU_FUSED_RMAX_PER_KIB 10
+#endif
+constexpr int RMAX = TILE / 1024 * SGPU_FUSED_RMAX_PER_KIB;  // record starts per tile (>= 102 bytes per record on average)
 constexpr int LMAX = 4 * RMAX + 8;      // newline list capacity per tile
 constexpr int PIECE = SGPU_FUSED_PIECE; // copy items are at most this long
 constexpr int IMAX = RMAX + 2 * (TILE / PIECE) + 8;  // copy items per tile
@@ -296,6 +299,7 @@ __device__ __forceinline__ Comp compose(const Comp A /*earlier*/, const Comp B /
 }
 
 // (kept bytes before tile t, state carried into it) from the descriptors of the tiles before t
+#ifndef SGPU_FUSED_LB_HIER
 #ifdef SGPU_FUSED_LB_NOINLINE
 __device__ __noinline__ void lookback_pred_warp(const unsigned long long *desc, uint64_t t, int lane,
 #else
@@ -367,6 +371,80 @@ __device__ __forceinline__ void lookback_pred_warp(const unsigned long long *des
     *kept_before = inc_total + acc_all.K;
     *carry = acc_all.out;
 }
+#endif
+#ifdef SGPU_FUSED_LB_HIER
+// Two-level look-back.  Each tile's sector holds three words: [0] its aggregate (never overwritten), [1] B(t) = the
+// composite of the 32 tiles before t (published by t's look-back warp as soon as their aggregates are there),
+// [2] its inclusive descriptor.  A look-back reads the 32 aggregates before t AND, in the same round trip, the
+// block composites B(t-32), B(t-64), ... together with the inclusive words of t-33, t-65, ...: 1024 tiles per
+// memory round trip instead of 32 (the nearest inclusive descriptor is typically ~200 tiles back).
+__device__ __forceinline__ Comp window_comp(unsigned long long x, int L, int lane) {
+    const bool agg = lane < L, isL = lane == L;
+    const uint32_t fl = (uint32_t)(x >> 59) & 3u;
+    const bool has = isL || (agg && ((x >> 61) & 1ull));
+    const uint32_t hl = agg ? (uint32_t)(x >> 30) & 0x1FFFFFFFu : 0u;
+    const uint32_t rs = agg ? (uint32_t)x & 0x3FFFFFFFu : 0u;
+    const unsigned has_m = __ballot_sync(0xffffffffu, has);
+    const unsigned kept_m = __ballot_sync(0xffffffffu, has && fl == F_KEPT);
+    const unsigned hm = has_m & (0xFFFFFFFEu << lane);
+    const bool found = hm != 0u;
+    const bool in_kept = found && ((kept_m >> (__ffs(hm) - 1)) & 1u);
+    Comp W;
+    W.K = __reduce_add_sync(0xffffffffu, rs + (in_kept ? hl : 0u));
+    W.P = __reduce_add_sync(0xffffffffu, found ? 0u : hl);
+    W.has = has_m != 0u;
+    W.out = __shfl_sync(0xffffffffu, fl, has_m ? __ffs(has_m) - 1 : 0);
+    return W;
+}
+__device__ __forceinline__ void lookback_pred_warp(unsigned long long *desc, uint64_t t, int lane,
+                                                   uint64_t *kept_before, uint32_t *carry) {
+    static_assert(DSTRIDE >= 3, "three words per tile");
+    const unsigned long long virt = ST_INC | ((uint64_t)F_NONE << 59);  // before the buffer: nothing kept / carried
+    const int64_t i0 = (int64_t)t - 1 - lane;
+    int64_t y = (int64_t)t - 32 - 32 * (int64_t)lane;
+    unsigned long long x = i0 >= 0 ? ld_relaxed(desc + i0 * DSTRIDE) : ST_AGG;  // tiles before the buffer: identity
+    unsigned long long d = y >= 1 ? ld_relaxed(desc + (y - 1) * DSTRIDE + 2) : virt;
+    unsigned long long b = y >= 1 ? ld_relaxed(desc + y * DSTRIDE + 1) : ST_AGG;
+    while (__any_sync(0xffffffffu, (x >> 62) == 0ull)) {
+        __nanosleep(SGPU_FUSED_POLL_NS);
+        if ((x >> 62) == 0ull) x = ld_relaxed(desc + i0 * DSTRIDE);
+    }
+    Comp acc_all = window_comp(x, 32, lane);
+    if (lane == 0)
+        st_relaxed(desc + t * DSTRIDE + 1, ST_AGG | (acc_all.has ? (1ull << 61) : 0ull) | ((uint64_t)acc_all.out << 59) |
+                                               ((uint64_t)acc_all.P << 30) | acc_all.K);
+    uint64_t inc_total = 0;
+    while (true) {
+        int L;
+        while (true) {
+            const unsigned binc = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+            L = binc ? __ffs(binc) - 1 : 32;
+            const unsigned below = L < 32 ? (1u << L) - 1u : 0xffffffffu;
+            const unsigned bmiss = __ballot_sync(0xffffffffu, (b >> 62) == 0ull) & below;
+            if (!bmiss) break;
+            __nanosleep(SGPU_FUSED_POLL_NS);
+            if (lane < L) {
+                if ((d >> 62) != 2ull) d = ld_relaxed(desc + (y - 1) * DSTRIDE + 2);
+                if ((b >> 62) == 0ull) b = ld_relaxed(desc + y * DSTRIDE + 1);
+            }
+        }
+        const Comp W = window_comp(lane < L ? b : d, L, lane);
+        acc_all = compose(W, acc_all);
+        if (L < 32) {
+            inc_total = __shfl_sync(0xffffffffu, d, L) & ((1ull << 59) - 1);
+            break;
+        }
+        y -= 1024;  // (only when more than 1024 tiles are between their aggregate and their inclusive prefix)
+        d = y >= 1 ? ld_relaxed(desc + (y - 1) * DSTRIDE + 2) : virt;
+        b = y >= 1 ? ld_relaxed(desc + y * DSTRIDE + 1) : ST_AGG;
+    }
+    *kept_before = inc_total + acc_all.K;
+    *carry = acc_all.out;
+}
+constexpr int INC_WORD = 2;
+#else
+constexpr int INC_WORD = 0;
+#endif
 __device__ __forceinline__ unsigned long long agg_desc(bool has_start, uint32_t last_flag, uint32_t head_len,
                                                        uint32_t rest) {
     return ST_AGG | (has_start ? (1ull << 61) : 0ull) | ((uint64_t)last_flag << 59) | ((uint64_t)head_len << 30) | rest;
@@ -853,7 +931,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
             bar_sync(2);  // the workers' totals are in shared memory (and the aggregate is published)
             if (lane == 0) {
                 TRACE(t, 3);
-                st_relaxed(P.desc2 + t * DSTRIDE,
+                st_relaxed(P.desc2 + t * DSTRIDE + INC_WORD,
                            inc_desc(n_starts > 0, S->last_flag, head_len, S->rest_total, kept_before, carry));
                 S->kept_before = kept_before;
                 S->carry = carry;
@@ -1055,7 +1133,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
 #endif
                 if (lane == 0) {
                     TRACE(t, 3);
-                    st_relaxed(P.desc2 + t * DSTRIDE, inc_desc(n_starts > 0, n_starts ? S->last_flag : F_OTHER, head_len,
+                    st_relaxed(P.desc2 + t * DSTRIDE + INC_WORD, inc_desc(n_starts > 0, n_starts ? S->last_flag : F_OTHER, head_len,
                                                      rest_total, kept_before, carry));
                     S->kept_before = kept_before;
                     S->carry = carry;
@@ -1216,6 +1294,8 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
         int o = 0;
         SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fastq_fused_kernel<false>, NTHREADS, smem));
         occ[c->device & 63] = o > 0 ? o : 1;
+        if (getenv("SGPU_DEBUG"))
+            fprintf(stderr, "[sgpu] fused kernel: tile %d B, %zu B shared memory per CTA, %d CTAs per SM\n", TILE, smem, o);
     }
     uint64_t grid = (uint64_t)c->sm_count * occ[c->device & 63];  // persistent: every CTA is resident
     if (grid > n_tiles) grid = n_tiles;
