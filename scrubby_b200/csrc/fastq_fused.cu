@@ -238,11 +238,6 @@ struct __align__(128) CtaSmem {
     uint32_t none_cnt;
     uint32_t warp_tot[NW];  // newlines of the warp's region (bit 31: a 16-byte chunk with more than two)
     uint32_t scan_tot[NW];
-#ifdef SGPU_FUSED_LB_WIDE
-    uint32_t lb_found;       // nearest window (warp) that holds an inclusive descriptor; NW: none yet
-    uint32_t lb_comp[NW][4];  // composite of every warp's window
-    uint64_t lb_inc[NW];     // payload of the window's inclusive descriptor
-#endif
     __align__(16) uint16_t nlp[LMAX];  // newline positions of the tile, in order
     Item items[IMAX];
     __align__(16) uint8_t buf[BUF];
@@ -303,100 +298,7 @@ __device__ __forceinline__ Comp compose(const Comp A /*earlier*/, const Comp B /
     return R;
 }
 
-// composite of one window of 32 descriptors (lane l <-> tile base - l): lanes < L are aggregates, lane L (if < 32)
-// is the nearest inclusive descriptor, lanes beyond it do not count
-__device__ __forceinline__ Comp window_comp(unsigned long long x, int L, int lane) {
-    const bool agg = lane < L, isL = lane == L;
-    const uint32_t fl = (uint32_t)(x >> 59) & 3u;
-    const bool has = isL || (agg && ((x >> 61) & 1ull));
-    const uint32_t hl = agg ? (uint32_t)(x >> 30) & 0x1FFFFFFFu : 0u;
-    const uint32_t rs = agg ? (uint32_t)x & 0x3FFFFFFFu : 0u;
-    const unsigned has_m = __ballot_sync(0xffffffffu, has);
-    const unsigned kept_m = __ballot_sync(0xffffffffu, has && fl == F_KEPT);
-    // the state carried into my tile = state of the nearest earlier tile with a record start:
-    // the lowest set bit of has_m strictly above my lane
-    const unsigned hm = has_m & (0xFFFFFFFEu << lane);
-    const bool found = hm != 0u;
-    const bool in_kept = found && ((kept_m >> (__ffs(hm) - 1)) & 1u);
-    Comp W;
-    W.K = __reduce_add_sync(0xffffffffu, rs + (in_kept ? hl : 0u));
-    W.P = __reduce_add_sync(0xffffffffu, found ? 0u : hl);
-    W.has = has_m != 0u;
-    W.out = __shfl_sync(0xffffffffu, fl, has_m ? __ffs(has_m) - 1 : 0);
-    return W;
-}
-#ifdef SGPU_FUSED_LB_PAR
-// Look-back over K windows AT ONCE: the 32 K descriptors before the tile are fetched in one memory round trip
-// and the entries that are still empty are re-polled together, so that once the last aggregate in front of the
-// tile is published the look-back ends one round trip later -- the window-by-window walk needs one round trip
-// per window (the nearest inclusive descriptor is ~200 tiles back: ~2 us of the ~4 us a tile waits in order).
-__device__ __forceinline__ void lookback_pred_warp(const unsigned long long *desc, uint64_t t, int lane,
-                                                   uint64_t *kept_before, uint32_t *carry) {
-    constexpr int K = SGPU_FUSED_LB_K;
-    Comp acc_all = comp_identity();
-    uint64_t inc_total = 0;
-    int64_t base = (int64_t)t - 1;
-    const uint64_t virt = ST_INC | ((uint64_t)F_NONE << 59);  // before the buffer: nothing kept, nothing carried
-#ifdef SGPU_FUSED_LB_PREPOLL
-    // the tile just before this one is the last to publish (tickets are taken in order): ONE lane polls its
-    // descriptor; only when it is there are the K windows fetched (32 K polling loads per round are a storm)
-    if (t > 0) {
-        if (lane == 0) {
-            while ((ld_relaxed(desc + (t - 1) * DSTRIDE) >> 62) == 0ull) __nanosleep(SGPU_FUSED_POLL_NS);
-        }
-        __syncwarp();
-    }
-#endif
-    while (true) {
-        unsigned long long xs[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const int64_t idx = base - 32 * k - lane;
-            xs[k] = idx >= 0 ? ld_relaxed(desc + idx * DSTRIDE) : virt;
-        }
-        int kstar, L;  // window / lane of the nearest inclusive descriptor (kstar == K: none in these windows)
-        while (true) {
-            bool missing = false;
-            kstar = K;
-            L = 32;
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (kstar == K) {  // (warp-uniform)
-                    const uint32_t st = (uint32_t)(xs[k] >> 62);
-                    const unsigned binc = __ballot_sync(0xffffffffu, st == 2u);
-                    const unsigned bzero = __ballot_sync(0xffffffffu, st == 0u);
-                    const int Lk = binc ? __ffs(binc) - 1 : 32;
-                    const unsigned upto = Lk < 31 ? (2u << Lk) - 1u : 0xffffffffu;
-                    missing |= (bzero & upto) != 0u;
-                    if (binc) {
-                        kstar = k;
-                        L = Lk;
-                    }
-                }
-            }
-            if (!missing) break;
-            __nanosleep(SGPU_FUSED_POLL_NS);
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (k <= kstar && (xs[k] >> 62) == 0ull && (k < kstar || lane <= L))
-                    xs[k] = ld_relaxed(desc + (base - 32 * k - lane) * DSTRIDE);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            if (k <= kstar) {  // (warp-uniform)
-                const Comp W = window_comp(xs[k], k == kstar ? L : 32, lane);
-                acc_all = compose(W, acc_all);
-                if (k == kstar) inc_total = __shfl_sync(0xffffffffu, xs[k], L) & ((1ull << 59) - 1);
-            }
-        }
-        if (kstar < K) break;
-        base -= 32 * K;
-    }
-    *kept_before = inc_total + acc_all.K;
-    *carry = acc_all.out;
-}
-#else
+// (kept bytes before tile t, state carried into it) from the descriptors of the tiles before t
 #ifdef SGPU_FUSED_LB_NOINLINE
 __device__ __noinline__ void lookback_pred_warp(const unsigned long long *desc, uint64_t t, int lane,
 #else
@@ -468,72 +370,6 @@ __device__ __forceinline__ void lookback_pred_warp(const unsigned long long *des
     *kept_before = inc_total + acc_all.K;
     *carry = acc_all.out;
 }
-#endif
-#ifdef SGPU_FUSED_LB_WIDE
-// Look-back by the WHOLE CTA: warp w takes the window of tiles t-1-32w .. t-32-32w, so 32 NW tiles are covered
-// in the time one warp needs for one window (memory round trip + ~60 dependent instructions); the window-by-window
-// walk of one warp costs that once per window, ~2 us of the ~4 us a tile waits in order.  Every warp polls its
-// window until it is complete up to its nearest inclusive descriptor -- or until a nearer window has found one.
-__device__ __forceinline__ void lookback_wide(CtaSmem *S, const unsigned long long *desc, uint64_t t, int warp,
-                                              int lane, uint64_t *kept_before, uint32_t *carry) {
-    Comp acc_all = comp_identity();
-    uint64_t inc_total = 0;
-    const uint64_t virt = ST_INC | ((uint64_t)F_NONE << 59);  // before the buffer: nothing kept, nothing carried
-    int64_t base = (int64_t)t - 1;
-    volatile uint32_t *found = &S->lb_found;  // == NW on entry
-    while (true) {
-        const int64_t idx = base - 32 * warp - lane;
-        unsigned long long x = idx >= 0 ? ld_relaxed(desc + idx * DSTRIDE) : virt;
-        int L;
-        bool complete;
-        while (true) {
-            const uint32_t st = (uint32_t)(x >> 62);
-            const unsigned binc = __ballot_sync(0xffffffffu, st == 2u);
-            const unsigned bzero = __ballot_sync(0xffffffffu, st == 0u);
-            L = binc ? __ffs(binc) - 1 : 32;
-            const unsigned upto = L < 31 ? (2u << L) - 1u : 0xffffffffu;  // lanes <= L
-            complete = (bzero & upto) == 0u;
-            if (complete) break;
-            uint32_t f = 0;
-            if (lane == 0) f = *found;
-            f = __shfl_sync(0xffffffffu, f, 0);
-            if (f < (uint32_t)warp) break;  // a nearer window ends the look-back: this one does not count
-            __nanosleep(SGPU_FUSED_POLL_NS);
-            if (st == 0u && lane <= L) x = ld_relaxed(desc + idx * DSTRIDE);
-        }
-        if (complete) {
-            if (L < 32 && lane == 0) atomicMin(&S->lb_found, (uint32_t)warp);
-            const Comp W = window_comp(x, L, lane);
-            const unsigned long long incv = __shfl_sync(0xffffffffu, x, L < 32 ? L : 0) & ((1ull << 59) - 1);
-            if (lane == 0) {
-                S->lb_comp[warp][0] = W.P;
-                S->lb_comp[warp][1] = W.K;
-                S->lb_comp[warp][2] = W.has;
-                S->lb_comp[warp][3] = W.out;
-                S->lb_inc[warp] = incv;
-            }
-        }
-        __syncthreads();  // (also: every copy item of the tile is in shared memory)
-        const uint32_t kf = S->lb_found;
-        for (uint32_t k = 0; k < (uint32_t)NW && k <= kf; k++) {
-            Comp W;
-            W.P = S->lb_comp[k][0];
-            W.K = S->lb_comp[k][1];
-            W.has = S->lb_comp[k][2];
-            W.out = S->lb_comp[k][3];
-            acc_all = compose(W, acc_all);
-        }
-        if (kf < (uint32_t)NW) {
-            inc_total = S->lb_inc[kf];
-            break;
-        }
-        base -= 32 * NW;
-        __syncthreads();  // the windows' results are re-used by the next round
-    }
-    *kept_before = inc_total + acc_all.K;
-    *carry = acc_all.out;
-}
-#endif
 __device__ __forceinline__ unsigned long long agg_desc(bool has_start, uint32_t last_flag, uint32_t head_len,
                                                        uint32_t rest) {
     return ST_AGG | (has_start ? (1ull << 61) : 0ull) | ((uint64_t)last_flag << 59) | ((uint64_t)head_len << 30) | rest;
@@ -907,9 +743,6 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
             S->n_items = 0;
             S->none_pos = 0xFFFFFFFFu;
             S->none_cnt = 0;
-#ifdef SGPU_FUSED_LB_WIDE
-            S->lb_found = NW;
-#endif
         }
         PHASE_MARK(1);    // P1 own work
         __syncthreads();  // B1
@@ -1012,7 +845,6 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                     S->items[slot + lane] = itm;
                 }
             }
-#ifndef SGPU_FUSED_LB_WIDE
             uint64_t kept_before;
             uint32_t carry;
 #ifdef SGPU_ABL_NOLB  // ablation (timing only, output is garbage): no in-order commit
@@ -1029,7 +861,6 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                 S->kept_before = kept_before;
                 S->carry = carry;
             }
-#endif
         } else {
             // ---- P3: one thread per record start: checks of the record's lines, '@', id token -> exact probe,
             //      kept bytes scanned per warp, runs cut into copy items.  NT records per round (almost
@@ -1149,9 +980,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                     S->rest_total = rest_total;
                     if (!n_starts) S->last_flag = F_OTHER;
                 }
-#ifndef SGPU_FUSED_LB_WIDE
                 if (round + 1 == n_rounds && early) bar_arrive(2);  // totals handed to the look-back warp
-#endif
                 if (warp_active) {
                     emit_runs<F_KEPT>(S, flag, sp, e, Kx, head_len, lane);
                     if (P.out_o) emit_runs<F_OTHER>(S, flag, sp, e, Kx, head_len, lane);
@@ -1219,7 +1048,6 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                         S->items[slot + lane] = itm;
                     }
                 }
-#ifndef SGPU_FUSED_LB_WIDE
                 uint64_t kept_before;
                 uint32_t carry;
 #ifdef SGPU_ABL_NOLB
@@ -1235,27 +1063,11 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                     S->kept_before = kept_before;
                     S->carry = carry;
                 }
-#endif
             }
         }
         if (fb) set_fallback(P.res, (int)fb);
         PHASE_MARK(7);    // emit
-#ifdef SGPU_FUSED_LB_WIDE
-        uint64_t kb = 0;
-        uint32_t cr = F_OTHER;
-        if (!IDS) {
-            lookback_wide(S, P.desc2, t, warp, lane, &kb, &cr);  // (B5 is inside)
-            if (tid == 0) {
-                TRACE(t, 3);
-                st_relaxed(P.desc2 + t * DSTRIDE,
-                           inc_desc(n_starts > 0, n_starts ? S->last_flag : F_OTHER, head_len, rest_total, kb, cr));
-            }
-        } else {
-            __syncthreads();
-        }
-#else
         __syncthreads();  // B5: kept_before / carry / every copy item are there
-#endif
         PHASE_MARK(8);    // B5 wait (look-back)
 
         // ---- P4: a warp per copy item.  The next ticket is taken only now: a ticket held while this tile
@@ -1263,13 +1075,8 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
         unsigned long long nt = 0;
         if (tid == 0) nt = atomicAdd(&P.res->ticket, 1ull);
         {
-#ifdef SGPU_FUSED_LB_WIDE
-            const uint64_t kept_before = kb;
-            const uint32_t carry = cr;
-#else
             const uint64_t kept_before = S->kept_before;
             const uint32_t carry = S->carry;
-#endif
             uint32_t n_items = S->n_items;
             if (n_items > (uint32_t)IMAX) n_items = IMAX;
             const uint32_t head_kept = carry == F_KEPT ? head_len : 0u;
