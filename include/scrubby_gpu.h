@@ -213,6 +213,13 @@ typedef struct {
     uint64_t count;       /* distinct ids                                     */
     uint64_t has_empty;   /* the empty string is a member (txt blank line)    */
 } sgpu_idset_image;
+/* the set's keys as an unsorted one-column list ("id\n" per key; a blank line for the empty id) written to a
+ * caller-owned DEVICE buffer.  *n = bytes needed / written; SGPU_ERR_CAPACITY (with *n set) when d_out is NULL
+ * or cap < *n.  Exchange format of the multi-GPU diff: ReadDifference::get_difference (utils.rs:250-285) keeps
+ * one HashSet per output file and one global diff set; across ranks they are united by an all-gather of these
+ * lists followed by sgpu_idset_from_txt_dev on the concatenation (exact for FASTQ ids: tokens hold no
+ * whitespace and are valid UTF-8, so BufRead::lines returns them verbatim). */
+sgpu_status sgpu_idset_keys_dev(sgpu_ctx *, const sgpu_idset *, uint8_t *d_out, size_t cap, size_t *n);
 /* the set's device buffers (still owned by the set): broadcast them, then import */
 sgpu_status sgpu_idset_export(const sgpu_idset *, sgpu_idset_image *img);
 /* builds a set on this context's device by COPYING the image's device buffers */

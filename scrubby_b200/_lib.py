@@ -46,6 +46,7 @@ SYMBOLS = [
     "sgpu_idset_len", "sgpu_idset_contains", "sgpu_idset_dump", "sgpu_idset_free", "sgpu_free",
     "sgpu_clean_fastq", "sgpu_clean_fastq_dev", "sgpu_clean_fastq_shard_dev", "sgpu_count_newlines_dev",
     "sgpu_diff", "sgpu_diff_dev", "sgpu_fastq_ids_shard_dev", "sgpu_idset_export", "sgpu_idset_import",
+    "sgpu_idset_keys_dev",
 ]
 
 _lib = None
@@ -110,5 +111,6 @@ def load():
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, P(Counts), P(vp)]
     L.sgpu_idset_export.argtypes = [vp, P(IdSetImage)]
     L.sgpu_idset_import.argtypes = [vp, P(IdSetImage), P(vp)]
+    L.sgpu_idset_keys_dev.argtypes = [vp, vp, vp, sz, P(sz)]
     _lib = L
     return L

@@ -202,6 +202,20 @@ class IdSet:
         self.ctx.L.sgpu_free(out)
         return raw.split(b"\n")[:-1] if raw else []
 
+    def keys_dev(self):
+        """the keys as an unsorted "id\\n" list in a device uint8 tensor (sgpu_idset_keys_dev)"""
+        import torch
+
+        n = C.c_size_t()
+        rc = self.ctx.L.sgpu_idset_keys_dev(self.ctx.h, self.h, None, 0, C.byref(n))
+        if rc not in (0, _lib.SGPU_ERR_CAPACITY):
+            _check(rc, 0, "idset_keys_dev")
+        out = torch.empty(n.value, dtype=torch.uint8, device=torch.device("cuda", self.ctx.device))
+        if n.value:
+            _check(self.ctx.L.sgpu_idset_keys_dev(self.ctx.h, self.h, C.c_void_p(out.data_ptr()), n.value, C.byref(n)),
+                   0, "idset_keys_dev")
+        return out
+
     def image(self) -> _lib.IdSetImage:
         img = _lib.IdSetImage()
         _check(self.ctx.L.sgpu_idset_export(self.h, C.byref(img)))

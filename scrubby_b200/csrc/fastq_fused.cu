@@ -244,7 +244,12 @@ struct __align__(128) CtaSmem {
 };
 
 __device__ __forceinline__ void set_fallback(FusedResult *res, int reason) {
-    if (atomicExch(&res->fallback, 1ull) == 0ull) res->reason = (unsigned long long)reason;
+    if (atomicExch(&res->fallback, 1ull) == 0ull) {
+        res->reason = (unsigned long long)reason;
+        // the result will be discarded: no CTA takes another tile (the tiles in flight finish: everything they
+        // wait for was ticketed before them)
+        atomicAdd(&res->ticket, 1ull << 40);
+    }
 }
 
 // ------------------------------------------------------------------ look-back #1 (rare): line phase

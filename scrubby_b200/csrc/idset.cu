@@ -405,6 +405,39 @@ sgpu_status sgpu_idset_dump(sgpu_ctx *c, const sgpu_idset *s, uint8_t **out, siz
     return SGPU_OK;
 }
 
+// the set's keys as an unsorted one-column list ("id\n" per key) in a caller-owned DEVICE buffer: the exchange
+// format of the multi-GPU diff (ReadDifference::get_difference's HashSets, utils.rs:251-283, united across ranks by
+// an all-gather of these lists and sgpu_idset_from_txt_dev on the concatenation)
+sgpu_status sgpu_idset_keys_dev(sgpu_ctx *c, const sgpu_idset *s, uint8_t *d_out, size_t cap, size_t *n) {
+    if (!c || !s || !n) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    uint64_t bytes = 0;
+    DevBuf<uint32_t> len;
+    DevBuf<uint64_t> off, total;
+    const unsigned grid = (unsigned)ceil_div(s->capacity, 256);
+    if (s->capacity && s->count) {
+        SGPU_TRY(len.alloc(s->capacity, st));
+        SGPU_TRY(off.alloc(s->capacity, st));
+        SGPU_TRY(total.alloc(1, st));
+        idset_dump_len_kernel<<<grid, 256, 0, st>>>(s->d_table, s->capacity, len.p);
+        SGPU_LAUNCH(c);
+        SGPU_TRY(exclusive_scan_u32_to_u64(c, len.p, off.p, s->capacity, total.p));
+        SGPU_TRY(read_u64s(c, total.p, &bytes, 1));
+    }
+    *n = (size_t)bytes + (s->has_empty ? 1 : 0);
+    if (*n == 0) return SGPU_OK;
+    if (!d_out || cap < *n) return SGPU_ERR_CAPACITY;  // *n tells the size to come back with
+    if (bytes) {
+        idset_dump_copy_kernel<<<grid, 256, 0, st>>>(s->d_table, s->capacity, s->d_arena, off.p, d_out);
+        SGPU_LAUNCH(c);
+    }
+    if (s->has_empty) SGPU_CUDA(cudaMemsetAsync(d_out + bytes, '\n', 1, st));  // the empty id: a blank line
+    SGPU_CUDA(cudaStreamSynchronize(st));
+    return SGPU_OK;
+}
+
 sgpu_status sgpu_idset_export(const sgpu_idset *s, sgpu_idset_image *img) {
     if (!s || !img) return SGPU_ERR_INVALID_ARG;
     img->d_table = s->d_table;

@@ -103,6 +103,23 @@ class GpuOps:
     def set_from_ids(self, id_list):
         return self.api.IdSet.from_ids(self.ctx, id_list)
 
+    def unite_sets(self, sets, dist):
+        """the union of `sets` over ALL ranks, replicated on every rank, without leaving the device: every set's
+        keys as an "id\\n" list (sgpu_idset_keys_dev), all-gathered (NCCL over NVLink), one set build from the
+        concatenation (sgpu_idset_from_txt_dev).  Exact for FASTQ ids (no whitespace, valid UTF-8)."""
+        torch = self.torch
+        parts = [s.keys_dev() for s in sets]
+        txt = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=self.device)
+        world = dist.get_world_size() if dist is not None else 1
+        if world > 1:
+            sizes = [r[0] for r in _all_gather_ints(dist, [txt.numel()], world)]
+            pad = torch.zeros(max(max(sizes), 16), dtype=torch.uint8, device=self.device)
+            pad[: txt.numel()] = txt
+            gathered = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(gathered, pad)
+            txt = torch.cat([g[:n] for g, n in zip(gathered, sizes)])
+        return self.api.IdSet.from_txt(self.ctx, txt) if txt.numel() else self.api.IdSet.empty(self.ctx)
+
     def replicate_set(self, ids, dist, src: int = 0):
         """broadcast the table and the key arena of rank `src`'s set (NCCL over NVLink) and import them"""
         torch, api = self.torch, self.api
@@ -205,9 +222,10 @@ class ShardedDiff:
     diff_ids: list      # sorted unique ids of the input records missing from their output file (every rank)
 
 
-def _ids_of_file_sharded(ops, file_bytes, dist, probe, into, halo, max_halo):
-    """one loop of ReadDifference::get_difference over one file, every rank on its own byte range; returns the
-    (records, picked) totals of this rank.  A record longer than the halo makes all ranks retry with a larger one."""
+def _ids_of_file_sharded(ops, file_bytes, dist, probe, collect, halo, max_halo):
+    """one loop of ReadDifference::get_difference over one file, every rank on its own byte range; the set of the
+    rank's ids goes to `collect`; returns the (records, picked) totals of this rank.  A record longer than the halo
+    makes all ranks retry with a larger one."""
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
     n = len(file_bytes)
@@ -231,7 +249,7 @@ def _ids_of_file_sharded(ops, file_bytes, dist, probe, into, halo, max_halo):
                 raise RuntimeError("a record is longer than the maximum shard halo")
             halo = min(max_halo, halo * 8)
             continue
-        into.extend(ops.set_ids(scratch))
+        collect(scratch)
         return rec, picked
 
 
@@ -243,25 +261,34 @@ def diff_sharded(ops, pairs, dist=None, halo: int = 1 << 20, max_halo: int = 1 <
     with the same id appear once but count twice)."""
     world = dist.get_world_size() if dist is not None else 1
     reads_in = reads_out = difference = 0
-    diff_local: list = []
+    on_device = hasattr(ops, "unite_sets")  # the product: id lists never leave the GPUs until the final TSV
+    diff_local: list = []                   # ids (host stand-in) or per-file sets (device) of this rank
     for fin, fout in pairs:
         out_local: list = []
-        rec_out, _ = _ids_of_file_sharded(ops, fout, dist, None, out_local, halo, max_halo)
-        gathered = [out_local]
-        if world > 1:
-            gathered = [None] * world
-            dist.all_gather_object(gathered, out_local)
-        o_set = ops.set_from_ids(sorted(set(x for part in gathered for x in part)))
-        rec_in, picked = _ids_of_file_sharded(ops, fin, dist, o_set, diff_local, halo, max_halo)
+        keep = out_local.append if on_device else (lambda s: out_local.extend(ops.set_ids(s)))
+        rec_out, _ = _ids_of_file_sharded(ops, fout, dist, None, keep, halo, max_halo)
+        if on_device:
+            o_set = ops.unite_sets(out_local, dist)
+        else:
+            gathered = [out_local]
+            if world > 1:
+                gathered = [None] * world
+                dist.all_gather_object(gathered, out_local)
+            o_set = ops.set_from_ids(sorted(set(x for part in gathered for x in part)))
+        keep = diff_local.append if on_device else (lambda s: diff_local.extend(ops.set_ids(s)))
+        rec_in, picked = _ids_of_file_sharded(ops, fin, dist, o_set, keep, halo, max_halo)
         reads_out += rec_out
         reads_in += rec_in
         difference += picked
     tot = _all_gather_ints(dist, [reads_in, reads_out, difference], world)
-    gathered = [diff_local]
-    if world > 1:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, diff_local)
-    ids = sorted(set(x for part in gathered for x in part))
+    if on_device:
+        ids = ops.set_ids(ops.unite_sets(diff_local, dist))
+    else:
+        gathered = [diff_local]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, diff_local)
+        ids = sorted(set(x for part in gathered for x in part))
     return ShardedDiff(sum(t[0] for t in tot), sum(t[1] for t in tot), sum(t[2] for t in tot), ids)
 
 

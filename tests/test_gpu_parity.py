@@ -595,6 +595,38 @@ def test_dist_driver_world1_and_set_image(ctx):
     assert t.is_cuda and t.numel() == 64
 
 
+def test_idset_keys_dev_and_device_union(ctx):
+    """sgpu_idset_keys_dev (the exchange format of the multi-GPU diff): the keys as "id\\n" lines on the device, and
+    GpuOps.unite_sets (all-gather of those lists + one set build) at world 1; diff_sharded through the device path
+    equals sgpu_diff and the oracle"""
+    from scrubby_b200 import dist as sdist
+
+    rng = random.Random(11)
+    keys = {bytes(rng.randrange(33, 127) for _ in range(n)) for n in list(range(1, 40)) * 8 + [100, 700]}
+    keys |= {b"x" * 15, b"x" * 16, "éè".encode(), "rあd".encode() * 6}
+    a, b = sorted(keys)[::2], sorted(keys)[1::2] + sorted(keys)[:7]
+    sa, sb = api.IdSet.from_ids(ctx, a), api.IdSet.from_ids(ctx, b)
+    flat = bytes(sa.keys_dev().cpu().numpy())
+    assert flat.endswith(b"\n") and sorted(flat.split(b"\n")[:-1]) == sorted(a)
+    ops = sdist.GpuOps(ctx)
+    assert ops.unite_sets([sa, sb], None).sorted_ids() == sorted(keys)
+    assert ops.unite_sets([], None).sorted_ids() == [] and len(api.IdSet.empty(ctx).keys_dev()) == 0
+    # a set with the empty id (a blank TXT line, alignment.rs:72-75) keeps it through the exchange
+    se = api.IdSet.from_txt(ctx, b"r1\n\nr2\n")
+    assert ops.unite_sets([se], None).sorted_ids() == [b"", b"r1", b"r2"]
+    # config 5 through the sharded driver's device path
+    n = 3000
+    pairs = []
+    ids = api.IdSet.from_txt(ctx, synth.gen_txt_ids(n).numpy().tobytes())
+    for mate in (1, 2):
+        fq = synth.gen_fastq(n, mate).numpy().tobytes()
+        pairs.append((fq, api.clean_fastq(ctx, ids, fq).written))
+    sd = sdist.diff_sharded(ops, pairs, None)
+    whole, o = api.diff(ctx, pairs), orc.diff(pairs)
+    assert (sd.reads_in, sd.reads_out, sd.difference) == whole[:3] == o[:3]
+    assert sd.diff_ids == whole[3].sorted_ids() == o[3].sorted_ids()
+
+
 def test_sharded_long_reads_fused(ctx):
     """ONT-like records that straddle many tiles, cut into shards at arbitrary offsets"""
     n = 300

@@ -20,7 +20,7 @@ dev = torch.device("cuda", 0)
 ctx = api.Context(0)
 fq = synth.gen_fastq(a.pairs, 1, device=dev)
 ids = api.IdSet.from_reads(ctx, synth.gen_kraken_reads(a.pairs, device=dev), 0, taxids_for_config())
-out = torch.empty(fq.numel() + 64, dtype=torch.uint8, device=dev)
+out = torch.empty(fq.numel() + (fq.numel() >> 3) + 64, dtype=torch.uint8, device=dev)  # room for the "+id" variant
 
 
 def timed(label, buf, mode):
