@@ -110,12 +110,32 @@ class OracleOps:
         return rec, picked
 
 
-def _diff_worker(rank, world, port, pairs, halo, q):
+class OracleOpsUnite(OracleOps):
+    """the same stand-in with GpuOps.unite_sets' exchange (key lists as "id\\n" bytes, all-gathered as padded uint8
+    tensors, one set build from the concatenation): drives diff_sharded's device-path control flow on gloo"""
+
+    def unite_sets(self, sets, dist):
+        from scrubby_b200.dist import _all_gather_ints
+
+        flat = b"".join(k + b"\n" for s in sets for k in sorted(s))
+        world = dist.get_world_size() if dist is not None else 1
+        if world > 1:
+            sizes = [r[0] for r in _all_gather_ints(dist, [len(flat)], world)]
+            pad = torch.zeros(max(max(sizes), 16), dtype=torch.uint8)
+            if flat:
+                pad[: len(flat)] = torch.frombuffer(bytearray(flat), dtype=torch.uint8)
+            gathered = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(gathered, pad)
+            flat = b"".join(bytes(g[:n].numpy()) for g, n in zip(gathered, sizes))
+        return set(flat.split(b"\n")[:-1]) if flat else set()
+
+
+def _diff_worker(rank, world, port, pairs, halo, q, unite=False):
     from scrubby_b200.dist import diff_sharded
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        r = diff_sharded(OracleOps(), pairs, dist, halo=halo)
+        r = diff_sharded(OracleOpsUnite() if unite else OracleOps(), pairs, dist, halo=halo)
         q.put((rank, r.reads_in, r.reads_out, r.difference, r.diff_ids))
     finally:
         dist.destroy_process_group()
@@ -205,8 +225,8 @@ def test_halo_retry_is_collective():
     assert res[0][7] == whole.reads_in and res[0][8] == whole.reads_out
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_diff_matches_unsharded(world):
+@pytest.mark.parametrize("world,unite", [(2, False), (3, False), (2, True), (3, True)])
+def test_sharded_diff_matches_unsharded(world, unite):
     """dist.diff_sharded: per-rank byte ranges of the output and input files, replicated output-id set, summed
     counters and united id lists equal ReadDifference::get_difference on the whole files (utils.rs:250-285)"""
     from oracle import oracle as orc
@@ -221,7 +241,7 @@ def test_sharded_diff_matches_unsharded(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_diff_worker, args=(r, world, port, pairs, 4096, q)) for r in range(world)]
+    ps = [ctx.Process(target=_diff_worker, args=(r, world, port, pairs, 4096, q, unite)) for r in range(world)]
     for p in ps:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
