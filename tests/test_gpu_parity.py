@@ -737,6 +737,41 @@ def test_reads_tile_kernel_errors(ctx):
     _reads_vs_oracle(ctx, "".join(two).encode(), 0, ["9606"])  # the first error wins
 
 
+def _paf_vs_oracle(ctx, buf: bytes, ml=0, mc=0.0, mq=0):
+    try:
+        o, oerr = orc.set_from_paf(buf, ml, mc, mq), None
+    except orc.OracleError as e:
+        o, oerr = None, (e.code, e.index)
+    try:
+        g, gerr = api.IdSet.from_paf(ctx, buf, ml, mc, mq), None
+    except api.ScrubbyGpuError as e:
+        g, gerr = None, (e.status, e.index)
+    assert gerr == oerr, (gerr, oerr)
+    if o is not None:
+        assert g.sorted_ids() == o.sorted_ids()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_paf_adversarial_fields(ctx_mode, seed):
+    """random PAF with Rust-parse edge cases ('+150', '', ' 15', '-1', 2^64, mapq 256, short rows, CRLF, missing final
+    newline, invalid UTF-8), alone and buried in thousands of valid lines (tile edges): same set, or the same error
+    class at the same line, on the tile path and on the indexed path"""
+    from test_oracle_differential import _rand_paf
+
+    rng = random.Random(7000 + seed)
+    small = _rand_paf(rng, rng.choice([3, 10, 40]))
+    good = "".join(f"r{i % 997}\t150\t{i % 50}\t{100 + i % 50}\t+\tt\t1000\t0\t100\t90\t100\t{(i * 7) % 61}\ttp:A:P\n"
+                   for i in range(4000)).encode()
+    cut = good.rfind(b"\n", 0, rng.randrange(1, len(good))) + 1
+    big = good[:cut] + small + (b"" if small.endswith(b"\n") else b"\n") + good[cut:]
+    for buf in (small, big):
+        for ml, mc, mq in [(0, 0.0, 0), (50, 0.5, 50), (1 << 63, 2.0, 0)]:
+            _paf_vs_oracle(ctx_mode, buf, ml, mc, mq)
+    bad = bytearray(big)
+    bad[rng.randrange(len(bad))] = 0xFF
+    _paf_vs_oracle(ctx_mode, bytes(bad), 50, 0.5, 50)
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_txt_tile_kernel_edge_cases(ctx, seed):
     rng = random.Random(2000 + seed)

@@ -206,3 +206,45 @@ def test_report_state_machine_two_restatements_agree(seed):
                          (["root"], []), (["n%d" % seed], ["t3"])]:
         _both(orc.taxids_from_report, po.taxids_from_report, (buf, taxa, direct), (buf, taxa, direct),
               lambda s: s.sorted_ids(), sorted)
+
+
+# ---------------------------------------------------------------------------------------------- product host code
+def _rand_report(rng, seed):
+    ranks = RANKS_K if seed % 3 else RANKS_M
+    names = ["root", "Bacteria", "Eukaryota", "Chordata", "Homo", "Homo sapiens", "Mammalia", "Aves", "n%d" % seed]
+    lines = []
+    for i in range(rng.choice([5, 30, 120])):
+        name = rng.choice(names + ["t%d" % i] * 6)
+        tid = rng.choice(["9606", "7711", "2", "1", str(100 + i)])
+        direct = rng.choice(["0", "0", "1", "17", "+3"])
+        if rng.random() < 0.01:
+            direct = rng.choice(["", "x", "-1"])
+        f = ["%.2f" % rng.random(), str(rng.randrange(1000)), direct, rng.choice(ranks), tid,
+             " " * rng.randrange(0, 6) + name + rng.choice(["", " ", " ", " "])]
+        if rng.random() < 0.01:
+            f = f[: rng.randrange(0, 6)]
+        lines.append("\t".join(f) + rng.choice(["\n", "\n", "\r\n"]))
+    return "".join(lines).encode()
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_host_report_state_machine_matches_oracle(seed):
+    """the C++ host's get_taxids_from_report (classifier.rs:124-252; it stays on the host by design) against
+    the oracle on random reports: same taxid sets, same error class and line"""
+    from scrubby_b200 import hostlib
+
+    kinds = {hostlib.KIND_IO: po.E_IO, hostlib.KIND_KR_PARENT: po.E_KR_PARENT, hostlib.KIND_KR_READS: po.E_KR_READS,
+             hostlib.KIND_KR_DIRECT: po.E_KR_DIRECT, hostlib.KIND_WOULD_PANIC: po.E_PANIC}
+    rng = random.Random(5000 + seed)
+    buf = _rand_report(rng, seed)
+    for taxa, direct in [(["Chordata"], ["9606"]), (["7711"], []), ([], ["root", "2"]), (["Eukaryota", " Homo "], ["Aves"]),
+                         (["root"], []), (["n%d" % seed], ["t3"])]:
+        try:
+            want = ("ok", orc.taxids_from_report(buf, taxa, direct).sorted_ids())
+        except orc.OracleError as e:
+            want = ("err", _err_of(e))
+        try:
+            got = ("ok", hostlib.get_taxids_from_report(buf, taxa, direct))
+        except hostlib.HostError as e:
+            got = ("err", (kinds.get(e.kind, -e.kind), e.line))
+        assert got == want, (taxa, direct)
