@@ -58,7 +58,8 @@ typedef enum {
     SGPU_ERR_CAPACITY = 19,             /* an output buffer is too small; required sizes are returned */
     SGPU_ERR_KEY_TOO_LONG = 20,         /* a read id of 16 MiB or more */
     SGPU_ERR_HALO = 21,                 /* shard: the last owned record does not end inside the buffer */
-    SGPU_ERR_SAM_RECORD = 22            /* a SAM line htslib's sam_parse1 rejects (rust_htslib error through `result?`, alignment.rs:131) */
+    SGPU_ERR_SAM_RECORD = 22,           /* a SAM line htslib's sam_parse1 rejects (rust_htslib error through `result?`, alignment.rs:131) */
+    SGPU_ERR_BAM_RECORD = 23            /* a BAM header / record htslib's bam_hdr_read / bam_read1 rejects (bad magic, truncated or inconsistent) */
 } sgpu_status;
 
 typedef struct sgpu_ctx sgpu_ctx;     /* device, stream, scratch arena */
@@ -106,8 +107,7 @@ sgpu_status sgpu_idset_from_paf_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, 
                                     uint64_t *err_line);
 /* ReadAlignment::from_bam, alignment.rs:117-146 (+ BamRecord::from / qalen_from_cigar / query_coverage
  * :154-211; `htslib` feature) for TEXT SAM: header lines skipped, unmapped records skipped, aligned length =
- * sum of CIGAR M and I, query length = SEQ length, the PAF predicate.  BAM / CRAM need BGZF / CRAM decoding
- * first (a host stage, not built).  The sam_parse1 behaviour restated here (htslib is an un-vendored
+ * sum of CIGAR M and I, query length = SEQ length, the PAF predicate.  (Binary BAM: sgpu_idset_from_bam below.)  The sam_parse1 behaviour restated here (htslib is an un-vendored
  * dependency of the reference; parity unpinned):
  *   - lines split on '\n', one trailing '\r' dropped; lines starting with '@' are header lines (skipped);
  *   - a record has >= 11 tab-separated fields: QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL;
@@ -125,6 +125,25 @@ sgpu_status sgpu_idset_from_sam(sgpu_ctx *, const uint8_t *buf, size_t n, uint64
 sgpu_status sgpu_idset_from_sam_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, uint64_t min_len,
                                     double min_cov, uint8_t min_mapq, sgpu_idset **out,
                                     uint64_t *err_line);
+/* ReadAlignment::from_bam, alignment.rs:117-146 (+ BamRecord::from :180-197) for BINARY BAM records.  `buf` is the
+ * BGZF-DECOMPRESSED BAM stream in host memory (BGZF blocks are concatenated gzip members: inflating them is a host
+ * stage like gz for FASTQ; the C++ host's reader does it).  Restated from the BAM specification (SAMv1 4.2) and
+ * htslib's bam_hdr_read / bam_read1 / bam_tag2cigar (un-vendored dependency; parity unpinned):
+ *   - header: magic "BAM\1", l_text, text, n_ref, (l_name, name, l_ref) per reference; anything else ->
+ *     SGPU_ERR_BAM_RECORD with *err_record = 0;
+ *   - records: block_size (u32 LE) + block_size bytes; the data may end only at a record boundary; block_size >= 32,
+ *     l_read_name >= 1, l_seq >= 0 and 32 + l_read_name + 4 n_cigar_op + (l_seq+1)/2 + l_seq <= block_size, else
+ *     SGPU_ERR_BAM_RECORD at that record's index (the first failing record wins);
+ *   - FLAG & 4 (unmapped): skipped before anything else is looked at (alignment.rs:132-134);
+ *   - qname = the l_read_name - 1 bytes before the terminating NUL (rust_htslib Record::qname; a read_name without
+ *     the NUL is taken whole: htslib appends it); must be UTF-8 -> SGPU_ERR_RECORD_NAME_UTF8;
+ *   - aligned length = sum of M and I operation lengths (u32, wrapping), query length = l_seq; a record with the
+ *     long-CIGAR placeholder (first op soft clip of l_seq, refID >= 0, pos >= 0) and a CG:B,I tag of >= n_cigar_op
+ *     and < 2^29 entries takes its CIGAR from the tag (bam_tag2cigar); then the PAF predicate.
+ * CRAM needs a reference-based decoder and is not built. */
+sgpu_status sgpu_idset_from_bam(sgpu_ctx *, const uint8_t *buf, size_t n, uint64_t min_len,
+                                double min_cov, uint8_t min_mapq, sgpu_idset **out,
+                                uint64_t *err_record);
 /* ReadAlignment::from_txt, alignment.rs:60-82: every line verbatim */
 sgpu_status sgpu_idset_from_txt(sgpu_ctx *, const uint8_t *buf, size_t n, sgpu_idset **out,
                                 uint64_t *err_line);

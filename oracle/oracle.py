@@ -54,6 +54,7 @@ def lib():
         L.orc_get_id.argtypes = [u8p, sz, C.POINTER(sz), C.POINTER(sz)]
         L.orc_set_from_paf.argtypes = [vp, sz, u64, C.c_double, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]
         L.orc_set_from_sam.argtypes = [vp, sz, u64, C.c_double, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]
+        L.orc_set_from_bam.argtypes = [vp, sz, u64, C.c_double, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]
         L.orc_set_from_txt.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(u64)]
         L.orc_taxids_from_report.argtypes = [
             vp, sz, C.POINTER(C.c_char_p), sz, C.POINTER(C.c_char_p), sz, C.POINTER(vp), C.POINTER(u64)]
@@ -141,6 +142,16 @@ def set_from_sam(buf, min_len=0, min_cov=0.0, min_mapq=0) -> OSet:
     p, n, keep = _ptr(buf)
     out, err = C.c_void_p(), C.c_uint64()
     rc = lib().orc_set_from_sam(p, n, min_len, min_cov, min_mapq, C.byref(out), C.byref(err))
+    if rc:
+        raise OracleError(rc, err.value)
+    return OSet(out.value)
+
+
+def set_from_bam(buf, min_len=0, min_cov=0.0, min_mapq=0) -> OSet:
+    """alignment.rs:117-146 for binary BAM records; `buf` is the BGZF-decompressed stream"""
+    p, n, keep = _ptr(buf)
+    out, err = C.c_void_p(), C.c_uint64()
+    rc = lib().orc_set_from_bam(p, n, min_len, min_cov, min_mapq, C.byref(out), C.byref(err))
     if rc:
         raise OracleError(rc, err.value)
     return OSet(out.value)

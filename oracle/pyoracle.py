@@ -170,6 +170,94 @@ def ids_from_sam(buf: bytes, min_len=0, min_cov=0.0, min_mapq=0) -> set[bytes]:
     return ids
 
 
+E_BAM = 23
+
+
+def ids_from_bam(buf: bytes, min_len=0, min_cov=0.0, min_mapq=0) -> set[bytes]:
+    """alignment.rs:117-146 + BamRecord::from :180-197 over the BGZF-decompressed BAM stream (second, independent
+    restatement of the rules listed in scrubby_oracle.c: struct.unpack and slices instead of pointer walks)"""
+    import struct
+
+    def need(cond, rec=0):
+        if not cond:
+            raise RefError(E_BAM, rec)
+
+    need(len(buf) >= 12 and buf[:4] == b"BAM\x01")
+    (l_text,) = struct.unpack_from("<I", buf, 4)
+    pos = 8 + l_text
+    need(pos + 4 <= len(buf))
+    (n_ref,) = struct.unpack_from("<I", buf, pos)
+    pos += 4
+    for _ in range(n_ref):
+        need(pos + 4 <= len(buf))
+        (l_name,) = struct.unpack_from("<I", buf, pos)
+        pos += 4 + l_name + 4
+        need(pos <= len(buf))
+    ids, rec = set(), 0
+    while pos < len(buf):
+        need(pos + 4 <= len(buf), rec)
+        (bs,) = struct.unpack_from("<I", buf, pos)
+        need(bs >= 32 and pos + 4 + bs <= len(buf), rec)
+        blk = buf[pos + 4: pos + 4 + bs]
+        ref_id, rpos, l_name, mapq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiBBHHHi", blk, 0)
+        need(l_name >= 1 and l_seq >= 0 and 32 + l_name + 4 * n_cig + (l_seq + 1) // 2 + l_seq <= bs, rec)
+        pos += 4 + bs
+        rec += 1
+        if flag & 4:
+            continue
+        name = blk[32: 32 + l_name]
+        qname = name[:-1] if name.endswith(b"\x00") else name
+        try:
+            qname.decode("utf-8")
+        except UnicodeDecodeError:
+            raise RefError(E_UTF8, rec - 1)
+        c0 = 32 + l_name
+        ops = list(struct.unpack_from("<%dI" % n_cig, blk, c0))
+        if ops and ref_id >= 0 and rpos >= 0 and ops[0] & 15 == 4 and ops[0] >> 4 == l_seq:
+            cg = _bam_cg(blk[c0 + 4 * n_cig + (l_seq + 1) // 2 + l_seq:])
+            if cg is not None and n_cig <= len(cg) < (1 << 29):
+                ops = cg
+        qalen = sum(v >> 4 for v in ops if v & 15 in (0, 1)) & 0xFFFFFFFF
+        cov = 0.0 if l_seq == 0 else float(qalen) / float(l_seq)
+        if (qalen >= min_len or cov >= min_cov) and mapq >= min_mapq:
+            ids.add(bytes(qname))
+    return ids
+
+
+def _bam_cg(aux: bytes):
+    """the CG:B,I (or B,i) array of a record's auxiliary fields, or None (htslib bam_aux_get + bam_tag2cigar)"""
+    import struct
+
+    fixed = {"A": 1, "c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4, "d": 8}
+    p = 0
+    while len(aux) - p >= 3:
+        tag, ty = aux[p: p + 2], chr(aux[p + 2])
+        p += 3
+        if ty in fixed:
+            size = fixed[ty]
+        elif ty in "ZH":
+            z = aux.find(b"\x00", p)
+            if z < 0:
+                return None
+            size = z - p + 1
+        elif ty == "B":
+            if len(aux) - p < 5:
+                return None
+            sub, cnt = chr(aux[p]), struct.unpack_from("<I", aux, p + 1)[0]
+            es = {"c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}.get(sub)
+            if es is None or cnt * es > len(aux) - p - 5:
+                return None
+            if tag == b"CG":
+                return list(struct.unpack_from("<%dI" % cnt, aux, p + 5)) if sub in "Ii" else None
+            size = 5 + cnt * es
+        else:
+            return None
+        if tag == b"CG" or len(aux) - p < size:
+            return None
+        p += size
+    return None
+
+
 def ids_from_txt(buf: bytes) -> set[bytes]:
     """alignment.rs:60-82"""
     return {line.encode("utf-8") for _, line in _lines(buf)}

@@ -553,6 +553,135 @@ int orc_set_from_sam(const uint8_t *buf, size_t n, uint64_t min_len, double min_
     return ORC_OK;
 }
 
+/* alignment.rs:117-146 from_bam + BamRecord::from :180-197 for BINARY BAM records.  `buf` is the BGZF-DECOMPRESSED
+ * stream (inflating the BGZF blocks -- concatenated gzip members -- is a host stage, like gz for FASTQ).  Restated from
+ * the SAM/BAM specification (SAMv1 section 4.2) and htslib's bam_hdr_read / bam_read1 / bam_tag2cigar, which
+ * rust_htslib::bam::Reader::records drives (htslib is an un-vendored dependency: parity unpinned):
+ *   header : magic "BAM\1", l_text, text, n_ref, per reference l_name, name, l_ref; anything else -> ORC_ERR_BAM_RECORD
+ *            at record 0 (bam::Reader::from_path fails);
+ *   record : block_size (u32 LE) then block_size bytes; end of data exactly at a record boundary ends the file, a
+ *            partial block_size or a block that runs past the end is an error (truncated file), block_size < 32 too;
+ *            l_read_name >= 1, l_seq >= 0 and 32 + l_read_name + 4 n_cigar_op + (l_seq+1)/2 + l_seq <= block_size,
+ *            else error -- all ORC_ERR_BAM_RECORD at that record's index, and the records before it have been seen
+ *            (an error is returned through `result?`, alignment.rs:131: the run fails);
+ *   unmapped (FLAG & 4) records are skipped BEFORE anything else is looked at (alignment.rs:132-134);
+ *   qname  : the l_read_name - 1 bytes before the terminating NUL (rust_htslib Record::qname); a read_name whose last
+ *            byte is not NUL is taken whole (htslib appends the missing NUL); must be UTF-8 (alignment.rs:187);
+ *   CIGAR  : n_cigar_op u32 values (len << 4 | op); when the record carries the long-CIGAR placeholder (first op
+ *            soft clip of l_seq, refID >= 0, pos >= 0) and a CG:B,I tag with at least n_cigar_op and fewer than 2^29
+ *            entries, the tag's array IS the CIGAR (bam_tag2cigar);
+ *   qalen  = sum of the lengths of M (op 0) and I (op 1) operations, u32 wrapping (release build); qlen = l_seq. */
+static uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint32_t le16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+/* finds the CG:B,I/i array among the auxiliary fields [a, e): returns its element count and sets *arr, or -1 */
+static int64_t bam_find_cg(const uint8_t *a, const uint8_t *e, const uint8_t **arr) {
+    while (e - a >= 3) {
+        const uint8_t t0 = a[0], t1 = a[1], ty = a[2];
+        a += 3;
+        size_t sz = 0;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'd': sz = 8; break;
+            case 'Z': case 'H': {
+                const uint8_t *z = (const uint8_t *)memchr(a, 0, (size_t)(e - a));
+                if (!z) return -1;
+                sz = (size_t)(z - a) + 1;
+                break;
+            }
+            case 'B': {
+                if (e - a < 5) return -1;
+                const uint8_t sub = a[0];
+                const uint32_t cnt = le32(a + 1);
+                size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+                if (!es) return -1;
+                if ((uint64_t)cnt * es > (uint64_t)(e - a - 5)) return -1;
+                if (t0 == 'C' && t1 == 'G') {
+                    if (sub != 'I' && sub != 'i') return -1;
+                    *arr = a + 5;
+                    return (int64_t)cnt;
+                }
+                sz = 5 + (size_t)cnt * es;
+                break;
+            }
+            default: return -1;
+        }
+        if (t0 == 'C' && t1 == 'G') return -1; /* a CG tag of another type is not a CIGAR */
+        if ((size_t)(e - a) < sz) return -1;
+        a += sz;
+    }
+    return -1;
+}
+
+int orc_set_from_bam(const uint8_t *buf, size_t n, uint64_t min_len, double min_cov, uint8_t min_mapq,
+                     orc_set **out, uint64_t *err_record) {
+    *out = NULL;
+    if (err_record) *err_record = 0;
+    /* header */
+    if (n < 12 || memcmp(buf, "BAM\1", 4) != 0) return ORC_ERR_BAM_RECORD;
+    size_t pos = 4;
+    const uint32_t l_text = le32(buf + pos);
+    pos += 4;
+    if (l_text > n - pos || n - pos - l_text < 4) return ORC_ERR_BAM_RECORD;
+    pos += l_text;
+    const uint32_t n_ref = le32(buf + pos);
+    pos += 4;
+    for (uint32_t r = 0; r < n_ref; r++) {
+        if (n - pos < 4) return ORC_ERR_BAM_RECORD;
+        const uint32_t l_name = le32(buf + pos);
+        pos += 4;
+        if (l_name > n - pos || n - pos - l_name < 4) return ORC_ERR_BAM_RECORD;
+        pos += (size_t)l_name + 4;
+    }
+    orc_set *set = orc_set_new();
+    uint64_t rec = 0;
+    int rc = ORC_OK;
+    while (pos < n) {
+        if (n - pos < 4) { rc = ORC_ERR_BAM_RECORD; break; }
+        const uint32_t bs = le32(buf + pos);
+        if (bs < 32 || bs > n - pos - 4) { rc = ORC_ERR_BAM_RECORD; break; }
+        const uint8_t *b = buf + pos + 4;
+        const int32_t ref_id = (int32_t)le32(b), rpos = (int32_t)le32(b + 4);
+        const uint32_t l_name = b[8], mapq = b[9], n_cig = le16(b + 12), flag = le16(b + 14);
+        const int32_t l_seq = (int32_t)le32(b + 16);
+        if (l_name < 1 || l_seq < 0 ||
+            32ull + l_name + 4ull * n_cig + (((uint64_t)l_seq + 1) >> 1) + (uint64_t)l_seq > bs) {
+            rc = ORC_ERR_BAM_RECORD;
+            break;
+        }
+        pos += 4 + (size_t)bs;
+        if (flag & 4) { rec++; continue; }
+        const uint8_t *name = b + 32;
+        const uint32_t qn = name[l_name - 1] == 0 ? l_name - 1 : l_name;
+        if (!utf8_valid(name, qn)) { rc = ORC_ERR_RECORD_NAME_UTF8; break; }
+        const uint8_t *cig = name + l_name;
+        uint64_t n_ops = n_cig;
+        if (n_cig && ref_id >= 0 && rpos >= 0 && (le32(cig) & 15) == 4 && (le32(cig) >> 4) == (uint32_t)l_seq) {
+            const uint8_t *aux = cig + 4ull * n_cig + (((uint64_t)l_seq + 1) >> 1) + (uint64_t)l_seq, *arr = NULL;
+            const int64_t k = bam_find_cg(aux, b + bs, &arr);
+            if (k >= (int64_t)n_cig && k < (1ll << 29)) { cig = arr; n_ops = (uint64_t)k; }
+        }
+        uint32_t qalen = 0;
+        for (uint64_t i = 0; i < n_ops; i++) {
+            const uint32_t v = le32(cig + 4 * i);
+            if ((v & 15) <= 1) qalen += v >> 4;
+        }
+        const uint32_t qlen = (uint32_t)l_seq;
+        const double cov = qlen == 0 ? 0.0 : (double)qalen / (double)qlen;
+        if (((uint64_t)qalen >= min_len || cov >= min_cov) && mapq >= min_mapq) orc_set_insert(set, name, qn);
+        rec++;
+    }
+    if (rc != ORC_OK) {
+        if (err_record) *err_record = rec;
+        orc_set_free(set);
+        return rc;
+    }
+    *out = set;
+    return ORC_OK;
+}
+
 /* alignment.rs:60-82 from_txt: every line verbatim */
 int orc_set_from_txt(const uint8_t *buf, size_t n, orc_set **out, uint64_t *err_line) {
     orc_set *set = orc_set_new();

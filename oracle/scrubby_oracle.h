@@ -40,7 +40,8 @@ enum {
     ORC_ERR_KRAKEN_REPORT_DIRECT = 13, /* KrakenReportDirectReadFieldConversion */
     ORC_ERR_KRAKEN_REPORT_PARENT = 14, /* KrakenReportTaxonParent */
     ORC_ERR_FASTA_UNSUPPORTED = 15,
-    ORC_ERR_SAM_RECORD = 22            /* htslib sam_parse1 would reject the line (rust_htslib::errors::Error) */
+    ORC_ERR_SAM_RECORD = 22,           /* htslib sam_parse1 would reject the line (rust_htslib::errors::Error) */
+    ORC_ERR_BAM_RECORD = 23            /* htslib bam_hdr_read / bam_read1 would fail (bad magic, truncated or inconsistent record) */
 };
 
 typedef struct orc_set orc_set;
@@ -71,6 +72,9 @@ int orc_set_from_txt(const uint8_t *buf, size_t n, orc_set **out, uint64_t *err_
 /* alignment.rs:117-146 from_bam (+ BamRecord :154-211) restated for text SAM */
 int orc_set_from_sam(const uint8_t *buf, size_t n, uint64_t min_len, double min_cov, uint8_t min_mapq,
                      orc_set **out, uint64_t *err_line);
+/* alignment.rs:117-146 from_bam for binary BAM records (the BGZF-decompressed stream) */
+int orc_set_from_bam(const uint8_t *buf, size_t n, uint64_t min_len, double min_cov, uint8_t min_mapq,
+                     orc_set **out, uint64_t *err_record);
 int orc_taxids_from_report(const uint8_t *buf, size_t n, const char *const *taxa, size_t n_taxa,
                            const char *const *taxa_direct, size_t n_direct, orc_set **out,
                            uint64_t *err_line);

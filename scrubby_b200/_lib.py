@@ -14,7 +14,8 @@ STATUS = {
     9: "SGPU_ERR_FASTQ_HEADER", 10: "SGPU_ERR_PAF_INTEGER", 11: "SGPU_ERR_WOULD_PANIC",
     12: "SGPU_ERR_KRAKEN_REPORT_READS", 13: "SGPU_ERR_KRAKEN_REPORT_DIRECT", 14: "SGPU_ERR_KRAKEN_REPORT_PARENT",
     15: "SGPU_ERR_FASTA_UNSUPPORTED", 16: "SGPU_ERR_CUDA", 17: "SGPU_ERR_NOMEM", 18: "SGPU_ERR_INVALID_ARG",
-    19: "SGPU_ERR_CAPACITY", 20: "SGPU_ERR_KEY_TOO_LONG", 21: "SGPU_ERR_HALO",
+    19: "SGPU_ERR_CAPACITY", 20: "SGPU_ERR_KEY_TOO_LONG", 21: "SGPU_ERR_HALO", 22: "SGPU_ERR_SAM_RECORD",
+    23: "SGPU_ERR_BAM_RECORD",
 }
 SGPU_ERR_CAPACITY = 19
 SGPU_ERR_HALO = 21
@@ -46,7 +47,7 @@ SYMBOLS = [
     "sgpu_idset_len", "sgpu_idset_contains", "sgpu_idset_dump", "sgpu_idset_free", "sgpu_free",
     "sgpu_clean_fastq", "sgpu_clean_fastq_dev", "sgpu_clean_fastq_shard_dev", "sgpu_count_newlines_dev",
     "sgpu_diff", "sgpu_diff_dev", "sgpu_fastq_ids_shard_dev", "sgpu_idset_export", "sgpu_idset_import",
-    "sgpu_idset_keys_dev",
+    "sgpu_idset_keys_dev", "sgpu_idset_from_bam",
 ]
 
 _lib = None
@@ -85,7 +86,8 @@ def load():
     L.sgpu_ctx_launch_count.restype = u64
     L.sgpu_ctx_set_profiling.argtypes = [vp, i32]
     L.sgpu_ctx_fused_stats.argtypes = [vp, P(C.c_double), P(u64), P(u64)]
-    for name in ("sgpu_idset_from_paf", "sgpu_idset_from_paf_dev", "sgpu_idset_from_sam", "sgpu_idset_from_sam_dev"):
+    for name in ("sgpu_idset_from_paf", "sgpu_idset_from_paf_dev", "sgpu_idset_from_sam", "sgpu_idset_from_sam_dev",
+                 "sgpu_idset_from_bam"):
         getattr(L, name).argtypes = [vp, vp, sz, u64, C.c_double, C.c_uint8, P(vp), P(u64)]
     for name in ("sgpu_idset_from_txt", "sgpu_idset_from_txt_dev"):
         getattr(L, name).argtypes = [vp, vp, sz, P(vp), P(u64)]

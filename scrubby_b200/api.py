@@ -157,6 +157,15 @@ class IdSet:
         return cls(ctx, h)
 
     @classmethod
+    def from_bam(cls, ctx, buf, min_len=0, min_cov=0.0, min_mapq=0):
+        """ReadAlignment::from_bam, alignment.rs:117-146, for binary BAM: `buf` = the BGZF-decompressed stream (host)"""
+        h, err = C.c_void_p(), C.c_uint64()
+        p, n, keep = _host_ptr(buf)
+        rc = ctx.L.sgpu_idset_from_bam(ctx.h, p, n, min_len, min_cov, min_mapq, C.byref(h), C.byref(err))
+        _check(rc, err.value, "from_bam")
+        return cls(ctx, h)
+
+    @classmethod
     def from_txt(cls, ctx, buf):
         """ReadAlignment::from_txt, alignment.rs:60-82"""
         h, err = C.c_void_p(), C.c_uint64()

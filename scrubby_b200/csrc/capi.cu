@@ -211,6 +211,7 @@ const char *sgpu_strerror(int s) {
     case SGPU_ERR_KEY_TOO_LONG: return "read id of 16 MiB or more";
     case SGPU_ERR_HALO: return "shard halo too small: last owned record does not end inside the buffer";
     case SGPU_ERR_SAM_RECORD: return "failed to parse a SAM record";
+    case SGPU_ERR_BAM_RECORD: return "failed to read a BAM header or record";
     default: return "unknown status";
     }
 }

@@ -274,6 +274,104 @@ __global__ void __launch_bounds__(128)
     sel[i] = ok;
 }
 
+// ---------------------------------------------------------------- binary BAM records
+// ReadAlignment::from_bam (alignment.rs:117-146) + BamRecord::from (:180-197) over the BGZF-decompressed BAM stream:
+// one thread per record (the host has walked the block_size chain: rec_off[i] is where record i's block_size sits
+// and every block lies inside the buffer with block_size >= 32).  The rules restated from the BAM specification and
+// htslib's bam_read1 / bam_tag2cigar are listed in include/scrubby_gpu.h.
+__device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+// the CG:B,I / B,i array among the auxiliary fields [a, e): element count (and *arr), or -1
+__device__ inline long long bam_find_cg(const uint8_t *a, const uint8_t *e, const uint8_t **arr) {
+    while (e - a >= 3) {
+        const uint8_t t0 = a[0], t1 = a[1], ty = a[2];
+        a += 3;
+        size_t sz = 0;
+        if (ty == 'A' || ty == 'c' || ty == 'C') sz = 1;
+        else if (ty == 's' || ty == 'S') sz = 2;
+        else if (ty == 'i' || ty == 'I' || ty == 'f') sz = 4;
+        else if (ty == 'd') sz = 8;
+        else if (ty == 'Z' || ty == 'H') {
+            const uint8_t *z = a;
+            while (z < e && *z) z++;
+            if (z == e) return -1;
+            sz = (size_t)(z - a) + 1;
+        } else if (ty == 'B') {
+            if (e - a < 5) return -1;
+            const uint8_t sub = a[0];
+            const uint32_t cnt = ld_le32(a + 1);
+            const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2
+                              : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+            if (!es || (unsigned long long)cnt * es > (unsigned long long)(e - a - 5)) return -1;
+            if (t0 == 'C' && t1 == 'G') {
+                if (sub != 'I' && sub != 'i') return -1;
+                *arr = a + 5;
+                return (long long)cnt;
+            }
+            sz = 5 + (size_t)cnt * es;
+        } else {
+            return -1;
+        }
+        if (t0 == 'C' && t1 == 'G') return -1;  // a CG tag of another type is not a CIGAR
+        if ((size_t)(e - a) < sz) return -1;
+        a += sz;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(128)
+    bam_parse_kernel(const uint8_t *in, const uint64_t *rec_off, uint64_t n_rec, PafParams F, uint64_t *key_off,
+                     uint32_t *key_len, uint8_t *sel, unsigned long long *err_word) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const uint8_t *b = in + rec_off[i] + 4;
+    const uint32_t bs = ld_le32(b - 4);
+    const int32_t ref_id = (int32_t)ld_le32(b), rpos = (int32_t)ld_le32(b + 4);
+    const uint32_t l_name = b[8], mapq = b[9];
+    const uint32_t n_cig = (uint32_t)b[12] | ((uint32_t)b[13] << 8), flag = (uint32_t)b[14] | ((uint32_t)b[15] << 8);
+    const int32_t l_seq = (int32_t)ld_le32(b + 16);
+    uint8_t ok = 0;
+    uint64_t koff = 0;
+    uint32_t klen = 0;
+    if (l_name < 1 || l_seq < 0 ||
+        32ull + l_name + 4ull * n_cig + (((unsigned long long)l_seq + 1) >> 1) + (unsigned long long)l_seq > bs) {
+        report_error(err_word, i, SGPU_ERR_BAM_RECORD);
+    } else if (!(flag & 4u)) {  // unmapped records are skipped before anything else is looked at
+        const uint8_t *name = b + 32;
+        const uint32_t qn = name[l_name - 1] == 0 ? l_name - 1 : l_name;
+        if (!utf8_valid(name, qn)) {
+            report_error(err_word, i, SGPU_ERR_RECORD_NAME_UTF8);
+        } else {
+            const uint8_t *cig = name + l_name;
+            unsigned long long n_ops = n_cig;
+            if (n_cig && ref_id >= 0 && rpos >= 0 && (ld_le32(cig) & 15u) == 4u && (ld_le32(cig) >> 4) == (uint32_t)l_seq) {
+                // the long-CIGAR placeholder: the real CIGAR is the CG:B,I tag (htslib bam_tag2cigar)
+                const uint8_t *aux = cig + 4ull * n_cig + (((unsigned long long)l_seq + 1) >> 1) + (unsigned long long)l_seq;
+                const uint8_t *arr = nullptr;
+                const long long k = bam_find_cg(aux, b + bs, &arr);
+                if (k >= (long long)n_cig && k < (1ll << 29)) {
+                    cig = arr;
+                    n_ops = (unsigned long long)k;
+                }
+            }
+            uint32_t qalen = 0;  // u32: wraps like the reference's release build (alignment.rs:161-169)
+            for (unsigned long long q = 0; q < n_ops; q++) {
+                const uint32_t v = ld_le32(cig + 4 * q);
+                if ((v & 15u) <= 1u) qalen += v >> 4;  // M and I
+            }
+            const uint32_t qlen = (uint32_t)l_seq;
+            const double cov = qlen == 0 ? 0.0 : (double)qalen / (double)qlen;
+            ok = (((uint64_t)qalen >= F.min_len || cov >= F.min_cov) && mapq >= F.min_mapq) ? 1 : 0;
+            koff = (uint64_t)(name - in);
+            klen = qn;
+        }
+    }
+    key_off[i] = koff;
+    key_len[i] = klen;
+    sel[i] = ok;
+}
+
 __global__ void __launch_bounds__(128)
     txt_lines_kernel(LineParams P, uint64_t n_lines, uint64_t *key_off, uint32_t *key_len, uint8_t *sel,
                      unsigned long long *err_word) {
@@ -1040,6 +1138,97 @@ sgpu_status sgpu_idset_from_sam(sgpu_ctx *c, const uint8_t *buf, size_t n, uint6
     sgpu_status rc = sgpu_idset_from_sam_dev(c, d.p, n, min_len, min_cov, min_mapq, out, err_line);
     cudaStreamSynchronize(c->stream);
     return rc;
+}
+
+// binary BAM: `buf` is the BGZF-decompressed stream in HOST memory.  The block_size chain is sequential, so the host
+// walks it (one 4-byte read per record) while the bytes are on their way to the device; the records are then parsed by
+// one thread each.  An error found by the walk (truncated / undersized record k) only counts when no record before k
+// fails on the device: the reference stops at the FIRST failing record.
+sgpu_status sgpu_idset_from_bam(sgpu_ctx *c, const uint8_t *buf, size_t n, uint64_t min_len, double min_cov,
+                                uint8_t min_mapq, sgpu_idset **out, uint64_t *err_record) {
+    if (!c || !out || (n && !buf)) return SGPU_ERR_INVALID_ARG;
+    if (err_record) *err_record = 0;
+    auto le32 = [&](size_t p) {
+        return (uint32_t)buf[p] | ((uint32_t)buf[p + 1] << 8) | ((uint32_t)buf[p + 2] << 16) | ((uint32_t)buf[p + 3] << 24);
+    };
+    // header: magic, l_text, text, n_ref, (l_name, name, l_ref) per reference
+    if (n < 12 || memcmp(buf, "BAM\1", 4) != 0) return SGPU_ERR_BAM_RECORD;
+    size_t pos = 8;
+    const uint32_t l_text = le32(4);
+    if (l_text > n - pos || n - pos - l_text < 4) return SGPU_ERR_BAM_RECORD;
+    pos += l_text;
+    const uint32_t n_ref = le32(pos);
+    pos += 4;
+    for (uint32_t r = 0; r < n_ref; r++) {
+        if (n - pos < 4) return SGPU_ERR_BAM_RECORD;
+        const uint32_t l_name = le32(pos);
+        pos += 4;
+        if (l_name > n - pos || n - pos - l_name < 4) return SGPU_ERR_BAM_RECORD;
+        pos += (size_t)l_name + 4;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    DevBuf<uint8_t> d;
+    SGPU_TRY(stage_in(c, buf, n, d));  // (asynchronous for pinned buffers: overlaps the walk below)
+    std::vector<uint64_t> offs;
+    offs.reserve((n - pos) / 256 + 16);
+    bool walk_error = false;
+    while (pos < n) {
+        if (n - pos < 4) {
+            walk_error = true;
+            break;
+        }
+        const uint32_t bs = le32(pos);
+        if (bs < 32 || bs > n - pos - 4) {
+            walk_error = true;
+            break;
+        }
+        offs.push_back((uint64_t)pos);
+        pos += 4 + (size_t)bs;
+    }
+    sgpu_idset *set = nullptr;
+    SGPU_TRY(idset_create(c, &set));
+    sgpu_status rc = SGPU_OK;
+    const uint64_t n_rec = offs.size();
+    if (n_rec) do {
+        DevBuf<uint64_t> d_off, key_off, errw;
+        DevBuf<uint32_t> key_len;
+        DevBuf<uint8_t> sel;
+        if ((rc = d_off.alloc(n_rec, st)) != SGPU_OK) break;
+        if ((rc = key_off.alloc(n_rec, st)) != SGPU_OK) break;
+        if ((rc = key_len.alloc(n_rec, st)) != SGPU_OK) break;
+        if ((rc = sel.alloc(n_rec, st)) != SGPU_OK) break;
+        if ((rc = errw.alloc(1, st)) != SGPU_OK) break;
+        if (cudaMemcpyAsync(d_off.p, offs.data(), n_rec * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            rc = SGPU_ERR_CUDA;
+            break;
+        }
+        cudaMemsetAsync(errw.p, 0xFF, 8, st);
+        bam_parse_kernel<<<(unsigned)ceil_div(n_rec, (uint64_t)128), 128, 0, st>>>(
+            d.p, d_off.p, n_rec, PafParams{min_len, min_cov, min_mapq}, key_off.p, key_len.p, sel.p,
+            (unsigned long long *)errw.p);
+        SGPU_LAUNCH(c);
+        uint64_t ew;
+        if ((rc = read_u64s(c, errw.p, &ew, 1)) != SGPU_OK) break;  // (synchronises: `offs` may go out of scope)
+        if (ew != ~0ull) {
+            rc = (sgpu_status)(ew & 0xFF);
+            if (err_record) *err_record = ew >> 8;
+            break;
+        }
+        if (!walk_error) rc = idset_insert_spans(c, set, d.p, key_off.p, key_len.p, sel.p, (size_t)n_rec);
+    } while (0);
+    if (rc == SGPU_OK && walk_error) {
+        rc = SGPU_ERR_BAM_RECORD;
+        if (err_record) *err_record = n_rec;
+    }
+    cudaStreamSynchronize(st);
+    if (rc != SGPU_OK) {
+        sgpu_idset_free(set);
+        return rc;
+    }
+    *out = set;
+    return SGPU_OK;
 }
 
 sgpu_status sgpu_idset_from_txt_dev(sgpu_ctx *c, const uint8_t *d_buf, size_t n, sgpu_idset **out,

@@ -121,11 +121,74 @@ static std::vector<uint8_t> slurp(const std::string &path) {
 
 // niffler::get_reader: sniff the magic bytes (needs 5 bytes), then decode.  gz via zlib (multi-member);
 // bz2 / xz need libraries this image does not have and are reported as NifflerError.
+// BGZF (bgzip, BAM): every gzip member carries its compressed size in a "BC" extra field and its inflated size in the
+// trailer, so the members are located without inflating and inflated on all host threads, each into its own slice
+// of the output.  Returns false (nothing done) when some member is not a BGZF block: the serial path takes over.
+static bool inflate_bgzf_parallel(const std::vector<uint8_t> &raw, std::vector<uint8_t> &out) {
+    struct Blk {
+        size_t src, clen, dst;
+        uint32_t isize, crc;
+    };
+    std::vector<Blk> blks;
+    size_t p = 0, total = 0;
+    while (p < raw.size()) {
+        if (raw.size() - p < 18 || raw[p] != 0x1f || raw[p + 1] != 0x8b || raw[p + 2] != 8 || !(raw[p + 3] & 4)) return false;
+        const size_t xlen = raw[p + 10] | (raw[p + 11] << 8);
+        if (raw.size() - p < 12 + xlen + 8) return false;
+        size_t bsize = 0;
+        for (size_t q = p + 12; q + 4 <= p + 12 + xlen;) {
+            const size_t sl = raw[q + 2] | (raw[q + 3] << 8);
+            if (raw[q] == 'B' && raw[q + 1] == 'C' && sl == 2 && q + 6 <= p + 12 + xlen) bsize = (raw[q + 4] | (raw[q + 5] << 8)) + 1;
+            q += 4 + sl;
+        }
+        if (bsize < 12 + xlen + 8 || bsize > raw.size() - p) return false;
+        const uint8_t *t = raw.data() + p + bsize - 4;
+        const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        const uint32_t crc = (uint32_t)t[-4] | ((uint32_t)t[-3] << 8) | ((uint32_t)t[-2] << 16) | ((uint32_t)t[-1] << 24);
+        blks.push_back(Blk{p + 12 + xlen, bsize - 12 - xlen - 8, total, isize, crc});
+        total += isize;
+        p += bsize;
+    }
+    out.resize(total);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, blks.size() / 16));
+    std::atomic<size_t> next{0};
+    std::atomic<bool> bad{false};
+    auto work = [&] {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            bad = true;
+            return;
+        }
+        for (size_t i; (i = next.fetch_add(1)) < blks.size() && !bad;) {
+            const Blk &b = blks[i];
+            inflateReset(&zs);
+            zs.next_in = const_cast<uint8_t *>(raw.data() + b.src);
+            zs.avail_in = (uInt)b.clen;
+            zs.next_out = out.data() + b.dst;
+            zs.avail_out = b.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || zs.avail_in != 0 ||
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + b.dst, b.isize) != b.crc)
+                bad = true;  // (the serial path then reports the corrupt member)
+        }
+        inflateEnd(&zs);
+    };
+    std::vector<std::thread> th;
+    for (unsigned k = 1; k < nt; k++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    return !bad;
+}
+
 std::vector<uint8_t> read_file(const std::string &path) {
     std::vector<uint8_t> raw = slurp(path);
     if (raw.size() < 5) return raw;  // FileTooShort => callers treat it as empty (utils.rs:365)
     if (raw[0] == 0x1f && raw[1] == 0x8b) {
         std::vector<uint8_t> out;
+        if ((raw[3] & 4) && inflate_bgzf_parallel(raw, out)) return out;
+        out.clear();
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, 15 + 32) != Z_OK) throw ScrubbyError(ScrubbyError::NifflerError, "zlib init failed");
@@ -239,17 +302,17 @@ ReadAlignment ReadAlignment::from(const GpuContext &g, const std::string &path, 
         case AlignmentFormat::Paf:
         case AlignmentFormat::Gaf: return from_paf(g, path, min_len, min_cov, min_mapq);
         case AlignmentFormat::Txt: return from_txt(g, path);
-        case AlignmentFormat::Sam: return from_sam(g, path, min_len, min_cov, min_mapq);  // alignment.rs:45 (`htslib`)
-        default:  // BAM / CRAM need a BGZF / CRAM decoder in front of the SAM kernel: not built
-            throw ScrubbyError(ScrubbyError::AlignmentInputFormatInvalid,
-                               "Unable to recognize alignment input format - is this version compiled with 'htslib'?");
+        case AlignmentFormat::Sam:
+        case AlignmentFormat::Bam:
+        case AlignmentFormat::Cram:  // alignment.rs:45 (`htslib`): one reader, it sniffs the CONTENT
+            return from_sam(g, path, min_len, min_cov, min_mapq);
         }
     }
     // alignment.rs:48-56: only the LAST extension is seen, so "x.paf.gz" is not recognised
     std::string e = extension(path);
     if (e == "paf" || e == "gaf") return from_paf(g, path, min_len, min_cov, min_mapq);
     if (e == "txt") return from_txt(g, path);
-    if (e == "sam") return from_sam(g, path, min_len, min_cov, min_mapq);  // alignment.rs:54 (`htslib`)
+    if (e == "sam" || e == "bam" || e == "cram") return from_sam(g, path, min_len, min_cov, min_mapq);  // alignment.rs:54 (`htslib`)
     throw ScrubbyError(ScrubbyError::AlignmentInputFormatNotRecognized,
                        "Unable to recognize alignment input format from extension.");
 }
@@ -265,12 +328,23 @@ ReadAlignment ReadAlignment::from_paf(const GpuContext &g, const std::string &pa
     return r;
 }
 
-// alignment.rs:117-146 for text SAM (rust-htslib reads "-" as stdin and has no is_file_empty test here)
+// alignment.rs:117-146 (rust-htslib reads "-" as stdin and has no is_file_empty test here).  Like htslib's reader this
+// looks at the content, not at --format or the extension: BGZF / gzip is inflated by read_file (BGZF blocks are gzip
+// members), a stream that starts with "BAM\1" is binary BAM, "CRAM" is refused (reference-based decoder: not built),
+// anything else is SAM text
 ReadAlignment ReadAlignment::from_sam(const GpuContext &g, const std::string &path, uint64_t min_len, double min_cov,
                                       uint8_t min_mapq) {
     std::vector<uint8_t> buf = read_file(path);
     ReadAlignment r;
     uint64_t err = 0;
+    if (buf.size() >= 4 && memcmp(buf.data(), "BAM\1", 4) == 0) {
+        check(sgpu_idset_from_bam(g.get(), buf.data(), buf.size(), min_len, min_cov, min_mapq, r.aligned_reads.out(), &err),
+              err, "from_bam");
+        return r;
+    }
+    if (buf.size() >= 4 && memcmp(buf.data(), "CRAM", 4) == 0)
+        throw ScrubbyError(ScrubbyError::AlignmentInputFormatInvalid,
+                           "CRAM input needs a reference-based decoder, which this build does not have: " + path);
     check(sgpu_idset_from_sam(g.get(), buf.data(), buf.size(), min_len, min_cov, min_mapq, r.aligned_reads.out(), &err),
           err, "from_sam");
     return r;
@@ -818,6 +892,20 @@ int scrubby_host_taxids_from_report(const uint8_t *buf, size_t n, const char *co
 }
 
 void scrubby_host_free(void *p) { free(p); }
+
+// niffler::get_reader's role (magic-byte sniffing + inflate; BGZF members on all host threads): the decoded bytes of
+// a file in a malloc'ed buffer; returns 0 or 100 + ScrubbyError::Kind
+int scrubby_host_read_file(const char *path, uint8_t **out, size_t *out_n) {
+    try {
+        std::vector<uint8_t> v = scrubby::read_file(path);
+        *out = (uint8_t *)malloc(v.size() + 1);
+        if (!v.empty()) memcpy(*out, v.data(), v.size());
+        *out_n = v.size();
+        return 0;
+    } catch (const scrubby::ScrubbyError &e) {
+        return 100 + (int)e.kind;
+    }
+}
 
 // report JSON of a classifier / alignment run with the given counts (date passed in): layout test
 int scrubby_host_format_f64(double v, char *out, size_t cap) {

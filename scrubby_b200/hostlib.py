@@ -41,6 +41,7 @@ def load():
         H.scrubby_host_free.argtypes = [C.c_void_p]
         H.scrubby_host_free.restype = None
         H.scrubby_host_format_f64.argtypes = [C.c_double, C.c_char_p, C.c_size_t]
+        H.scrubby_host_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         _h = H
     return _h
 
@@ -75,3 +76,14 @@ def format_f64(v: float) -> str:
     buf = C.create_string_buffer(64)
     n = load().scrubby_host_format_f64(v, buf, 64)
     return buf.raw[:n].decode()
+
+
+def read_file(path: str) -> bytes:
+    """the host stage in front of every parser: gz / BGZF sniffing and inflate (niffler::get_reader's role)"""
+    out, n = C.c_void_p(), C.c_size_t()
+    rc = load().scrubby_host_read_file(path.encode(), C.byref(out), C.byref(n))
+    if rc:
+        raise HostError(rc - 100, 0)
+    raw = C.string_at(out, n.value)
+    load().scrubby_host_free(out)
+    return raw

@@ -118,8 +118,37 @@ def test_cli_sam_format_and_errors(cli, data):
     o2 = d / "s2.fq"
     _run(cli, "alignment", "-i", data["r1"], "-o", o2, "-a", sp2, "-f", "sam", "--min-len", 100)
     assert open(o2, "rb").read() == want.written
-    # unknown extension without --format: AlignmentInputFormatNotRecognized; bam: not built
+    # unknown extension without --format: AlignmentInputFormatNotRecognized
     assert _run(cli, "alignment", "-i", data["r1"], "-o", d / "x.fq", "-a", sp2, ok=False).returncode != 0
-    assert _run(cli, "alignment", "-i", data["r1"], "-o", d / "x.fq", "-a", sp2, "-f", "bam", ok=False).returncode != 0
+    # sam / bam / cram share one htslib reader that looks at the CONTENT (alignment.rs:45): SAM text under -f bam works
+    o3 = d / "s3.fq"
+    _run(cli, "alignment", "-i", data["r1"], "-o", o3, "-a", sp2, "-f", "bam", "--min-len", 100)
+    assert open(o3, "rb").read() == want.written
     # mismatched input / output counts (scrubby.rs:760-779)
     assert _run(cli, "alignment", "-i", data["r1"], data["r2"], "-o", d / "x.fq", "-a", data["paf_p"], ok=False).returncode != 0
+
+
+def test_cli_bam_alignment(cli, data):
+    """binary BAM evidence, BGZF-compressed as samtools writes it (host stage: parallel BGZF inflate; GPU: one thread
+    per record), by extension and by --format; truncated BAM fails like htslib's reader"""
+    import bam_build as bb
+
+    d = data["d"]
+    recs = []
+    for i in range(0, data["n"], 2):
+        cig = "150M" if i % 6 == 0 else "40M110S" if i % 6 == 2 else "20S100M5I25S"
+        recs.append(bb.record(b"syn.%d" % i, flag=4 if i % 10 == 0 else 16 * (i % 4 == 0), mapq=60 if i % 14 else 3, cigar=cig))
+    raw = bb.stream(recs)
+    bp = _write(d / "aln.bam", bb.bgzf(raw))
+    want = orc.clean_fastq(data["fq"][0], orc.set_from_bam(raw, 50, 0.5, 50), False)
+    assert 0 < want.reads_out < want.reads_in
+    o1, o2 = d / "b1.fq", d / "b2.fq"
+    _run(cli, "alignment", "-i", data["r1"], "-o", o1, "-a", bp, "--min-len", 50, "--min-cov", 0.5, "--min-mapq", 50)
+    assert open(o1, "rb").read() == want.written
+    up = _write(d / "aln_uncompressed.dat", raw)  # `samtools view -u` style stream, explicit format
+    _run(cli, "alignment", "-i", data["r1"], "-o", o2, "-a", up, "-f", "bam", "--min-len", 50, "--min-cov", 0.5, "--min-mapq", 50)
+    assert open(o2, "rb").read() == want.written
+    tp = _write(d / "trunc.bam", bb.bgzf(raw[:-7]))
+    assert _run(cli, "alignment", "-i", data["r1"], "-o", d / "x.fq", "-a", tp, ok=False).returncode != 0
+    cp = _write(d / "x.cram", b"CRAM\x03\x00" + b"\x00" * 40)
+    assert _run(cli, "alignment", "-i", data["r1"], "-o", d / "x.fq", "-a", cp, ok=False).returncode != 0

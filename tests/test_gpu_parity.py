@@ -737,6 +737,84 @@ def test_reads_tile_kernel_errors(ctx):
     _reads_vs_oracle(ctx, "".join(two).encode(), 0, ["9606"])  # the first error wins
 
 
+def _bam_vs_oracle(ctx, buf: bytes, ml=0, mc=0.0, mq=0):
+    try:
+        o, oerr = orc.set_from_bam(buf, ml, mc, mq), None
+    except orc.OracleError as e:
+        o, oerr = None, (e.code, e.index)
+    try:
+        g, gerr = api.IdSet.from_bam(ctx, buf, ml, mc, mq), None
+    except api.ScrubbyGpuError as e:
+        g, gerr = None, (e.status, e.index)
+    assert gerr == oerr, (gerr, oerr)
+    if o is not None:
+        assert g.sorted_ids() == o.sorted_ids()
+    return g
+
+
+def test_bam_hand_derived_and_edge_cases(ctx):
+    """sgpu_idset_from_bam (alignment.rs:117-146 for binary BAM) on the vectors of tests/test_oracle_bam.py"""
+    import struct
+
+    import bam_build as bb
+
+    recs = [bb.record(b"r1", cigar="150M"), bb.record(b"r2", cigar="40M110S"), bb.record(b"r3", cigar="10S35M15S"),
+            bb.record(b"r4", cigar="150M", mapq=49), bb.record(b"r5", flag=4), bb.record(b"r6", cigar="30M10I10D40M70S"),
+            bb.record(b"r7", cigar="40=40X70S"), bb.record(b"r8", cigar="40M40S", mapq=50), bb.record(b"r9", cigar="", l_seq=0),
+            bb.record(b"r5", flag=0x904, cigar="150M"), bb.record(b"ra", flag=0x110, cigar="100M50H")]
+    s = bb.stream(recs)
+    g = _bam_vs_oracle(ctx, s, 50, 0.5, 50)
+    assert g.sorted_ids() == [b"r1", b"r3", b"r6", b"r8", b"ra"]
+    for thr in [(0, 0.0, 0), (0, 2.0, 0), (1, 2.0, 0)]:
+        _bam_vs_oracle(ctx, s, *thr)
+    _bam_vs_oracle(ctx, bb.stream([]))
+    # qname rules
+    for rs in ([bb.record(b"ok", cigar="10M"), bb.record(b"r\xff", cigar="10M")], [bb.record(b"r\xff", flag=4), bb.record(b"ok", cigar="10M")],
+               [bb.record(b"nonul", cigar="10M", nul=False)], [bb.record(b"a\x00b", cigar="10M")], [bb.record(b"", cigar="10M")],
+               [bb.record(b"", cigar="10M", nul=False)], [bb.record(b"x" * 15, cigar="9M"), bb.record(b"x" * 16, cigar="9M"), bb.record(b"y" * 200, cigar="9M")]):
+        _bam_vs_oracle(ctx, bb.stream(rs))
+    # long CIGAR in the CG tag
+    real = bb.cigar_ops("100M20I30M50S")
+    cg = b"CGBI" + struct.pack("<I", len(real)) + b"".join(struct.pack("<I", v) for v in real)
+    other = b"NMi" + struct.pack("<i", 3) + b"MDZ" + b"10A5\x00" + b"XSBc" + struct.pack("<I", 3) + b"\x01\x02\x03"
+    fake = [(200 << 4) | 4, (1000 << 4) | 3]
+    for aux, kw in ((other + cg, {}), (other, {}), (other + cg, dict(ref_id=-1)), (other + cg, dict(pos=-1)),
+                    (b"CGZ100M\x00" + cg, {}), (b"XXq\x00" + cg, {}),
+                    (b"CGBI" + struct.pack("<I", 1) + struct.pack("<I", 200 << 4), {})):
+        for thr in [(150, 2.0, 0), (1, 2.0, 0)]:
+            _bam_vs_oracle(ctx, bb.stream([bb.record(b"long", ops=fake, l_seq=200, aux=aux, **kw)]), *thr)
+    wrap = [(0xFFFFFFF << 4) | 0] * 17
+    for ml in ((17 * 0xFFFFFFF) & 0xFFFFFFFF, ((17 * 0xFFFFFFF) & 0xFFFFFFFF) + 1):
+        _bam_vs_oracle(ctx, bb.stream([bb.record(b"w", ops=wrap, l_seq=10)]), ml, 1e30, 0)
+    # structural errors: the first failing record wins
+    r = [bb.record(b"r%d" % i, cigar="100M") for i in range(5)]
+    s = bb.stream(r)
+    neg = bytearray(bb.record(b"x", cigar="10M"))
+    neg[20:24] = struct.pack("<i", -1)
+    for buf in (s[:-1], s[: len(s) - len(r[4]) + 2], s[: len(s) - len(r[4])], b"BAM\x02" + s[4:], b"", s[:10],
+                bb.stream(r[:2] + [struct.pack("<I", 8) + b"\x00" * 8] + r[2:]),
+                bb.stream(r[:3] + [bb.record(b"x", cigar="100M", block_size_delta=-60)]), bb.stream(r[:1] + [bytes(neg)]),
+                bb.stream([bb.record(b"\xff", cigar="10M")] + r)[:-3]):
+        _bam_vs_oracle(ctx, buf)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_bam_random_streams_match_oracle(ctx, seed):
+    from test_oracle_bam import rand_stream
+
+    rng = random.Random(8000 + seed)
+    s = rand_stream(rng, rng.choice([1, 20, 200, 5000]))
+    for thr in [(0, 0.0, 0), (50, 0.5, 50), (100, 2.0, 0), (1 << 40, 0.75, 10)]:
+        _bam_vs_oracle(ctx, s, *thr)
+    for _ in range(6):
+        _bam_vs_oracle(ctx, s[: rng.randrange(0, len(s))], 50, 0.5, 50)
+    for _ in range(12):
+        b = bytearray(s)
+        for _ in range(rng.choice([1, 1, 3])):
+            b[rng.randrange(len(b))] = rng.choice([0, 1, 4, 0x44, 0x7F, 0x80, 0xFF])
+        _bam_vs_oracle(ctx, bytes(b), 50, 0.5, 50)
+
+
 def _paf_vs_oracle(ctx, buf: bytes, ml=0, mc=0.0, mq=0):
     try:
         o, oerr = orc.set_from_paf(buf, ml, mc, mq), None
