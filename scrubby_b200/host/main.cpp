@@ -1,7 +1,8 @@
 // main.cpp -- `scrubby` CLI host: same subcommands and flags as the reference's clap definition
 // (terminal.rs:8-50 App/Commands, :206-279 ClassifierArgs, :323-391 AlignmentArgs, :435-466 DiffArgs).
-// `reads` (external aligners / classifiers through `sh -c`, terminal.rs:57-157) is outside the hot
-// path and reports that instead of running.
+// `reads` (terminal.rs:57-157) runs the external aligner / classifier through `sh -c` with the reference's command
+// strings (cleaner.rs:255-649): kraken2 / metabuli outputs and minigraph's stdout PAF come back into the
+// GPU path; the SAM-emitting aligners are piped into samtools exactly as the reference does.
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -17,6 +18,7 @@ struct Flag {
     char short_name;
     const char *long_name;
     int arity;  // 0 = switch, 1 = one value, 2 = zero or more values (num_args(0..))
+    bool hyphen_ok = false;  // allow_hyphen_values: the value is taken verbatim even when it starts with '-'
 };
 
 struct Parsed {
@@ -47,6 +49,11 @@ Parsed parse(int argc, char **argv, int from, const std::vector<Flag> &flags) {
         const Flag *f = nullptr;
         std::string inline_val;
         bool has_inline = false;
+        if (cur && cur->arity == 1 && cur->hyphen_ok) {
+            p.values[cur->long_name].push_back(a);
+            cur = nullptr;
+            continue;
+        }
         if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
             std::string name = a.substr(2);
             size_t eq = name.find('=');
@@ -166,11 +173,45 @@ int main(int argc, char **argv) {
             ReadDifference d = ReadDifference::build(p.many("input"), p.many("output"), p.one("json"), p.one("read-ids"));
             d.device = device_from_env();
             d.compute();
-        } else if (cmd == "reads") {
-            fprintf(stderr, "Error: `scrubby reads` runs external aligners/classifiers (bowtie2, minimap2, kraken2, ...) through the shell; "
-                            "that orchestration is outside this build. Run the tool yourself and pass its output to "
-                            "`scrubby alignment` or `scrubby classifier`.\n");
-            return 1;
+        } else if (cmd == "reads") {  // terminal.rs:57-157, 176-202
+            std::vector<Flag> flags = {{'i', "input", 2}, {'o', "output", 2}, {'I', "index", 1}, {'a', "aligner", 1},
+                                       {'p', "preset", 1}, {'c', "classifier", 1}, {'T', "taxa", 2}, {'D', "taxa-direct", 2},
+                                       {'A', "aligner-args", 1, true}, {'C', "classifier-args", 1, true}, {'t', "threads", 1},
+                                       {'j', "json", 1}, {'w', "workdir", 1}, {'r', "read-ids", 1}, {'e', "extract", 0}};
+            Parsed p = parse(argc, argv, i, flags);
+            if (!p.one("index")) usage_error("the following required arguments were not provided: --index <INDEX>");
+            Scrubby s;
+            s.input = p.many("input");
+            s.output = p.many("output");
+            s.json = p.one("json");
+            s.workdir = p.one("workdir");
+            s.read_ids = p.one("read-ids");
+            s.extract = p.has("extract");
+            s.device = device_from_env();
+            s.config.command = join_args(argc, argv);
+            s.config.index = p.one("index");
+            if (auto a = p.one("aligner")) {
+                s.config.aligner = parse_aligner(*a);
+                if (!s.config.aligner) usage_error("invalid value '" + *a + "' for '--aligner' [possible values: bowtie2, minimap2, minigraph, strobealign]");
+            }
+            if (auto c = p.one("classifier")) {
+                s.config.classifier = parse_classifier(*c);
+                if (!s.config.classifier) usage_error("invalid value '" + *c + "' for '--classifier' [possible values: kraken2, metabuli]");
+            }
+            if (auto pr = p.one("preset")) {
+                s.config.preset = parse_preset(*pr);
+                if (!s.config.preset) usage_error("invalid value '" + *pr + "' for '--preset'");
+            }
+            s.config.taxa = p.many("taxa");
+            s.config.taxa_direct = p.many("taxa-direct");
+            s.config.aligner_args = p.one("aligner-args");
+            s.config.classifier_args = p.one("classifier-args");
+            try {
+                s.threads = (unsigned)std::stoul(p.one("threads").value_or("4"));
+            } catch (const std::exception &) {
+                usage_error("invalid value for '--threads'");
+            }
+            build(s).clean();
         } else {
             usage_error("unrecognized subcommand '" + cmd + "'");
         }

@@ -6,6 +6,9 @@
 
 #include <atomic>
 #include <thread>
+#include <fcntl.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -55,6 +58,25 @@ const char *serde_name(Preset p) {
     static const char *n[] = {"LrHq", "Splice", "SpliceHq", "Asm", "Asm5", "Asm10", "Asm20",
                               "Sr", "Lr", "MapPb", "MapHifi", "MapOnt", "AvaPb", "AvaOnt"};
     return n[(int)p];
+}
+const char *display_name(Preset p) {  // scrubby.rs:136-155
+    static const char *n[] = {"lr:hq", "splice", "splice:hq", "asm", "asm5", "asm10", "asm20",
+                              "sr", "lr", "map-pb", "map-hifi", "map-ont", "ava-pb", "ava-ont"};
+    return n[(int)p];
+}
+std::optional<Aligner> parse_aligner(const std::string &s) {
+    if (s == "bowtie2") return Aligner::Bowtie2;
+    if (s == "minimap2") return Aligner::Minimap2;
+    if (s == "minigraph") return Aligner::Minigraph;
+    if (s == "strobealign") return Aligner::Strobealign;
+    return std::nullopt;  // "minimap2-rs" exists only with the reference's `mm2` feature
+}
+std::optional<Preset> parse_preset(const std::string &s) {
+    static const char *n[] = {"lr-hq", "splice", "splice-hq", "asm", "asm5", "asm10", "asm20",
+                              "sr", "lr", "map-pb", "map-hifi", "map-ont", "ava-pb", "ava-ont"};
+    for (int i = 0; i < 14; i++)
+        if (s == n[i]) return (Preset)i;
+    return std::nullopt;
 }
 std::optional<Classifier> parse_classifier(const std::string &s) {
     if (s == "kraken2") return Classifier::Kraken2;
@@ -578,6 +600,189 @@ ReadIdSet Cleaner::parse_classifier_output(const GpuContext &g, const std::strin
                                                             : get_taxid_reads_metabuli(g, taxids, reads);
 }
 
+// ------------------------------------------------------------------------------------------ cleaner.rs external tools
+SamtoolsConfig SamtoolsConfig::from_scrubby(const Scrubby &s) {  // cleaner.rs:46-71
+    const unsigned threads = s.config.samtools_threads.value_or(4);
+    SamtoolsConfig c;
+    const char *flag = s.extract ? (s.config.paired_end ? "-F 12" : "-F 4") : (s.config.paired_end ? "-f 12" : "-f 4");
+    c.filter = std::string("samtools view -h ") + flag + " -";
+    const std::string t = std::to_string(threads);
+    if (s.config.paired_end)
+        c.fastq = "samtools fastq --threads " + t + " " + (s.config.unpaired ? "" : "-s /dev/null") + " -c 6 -n -1 '" +
+                  s.output[0] + "' -2 '" + s.output[1] + "'";
+    else
+        c.fastq = "samtools fastq --threads " + t + " -c 6 -n -0 '" + s.output[0] + "'";
+    return c;
+}
+
+// Command::new("sh").arg("-c").arg(cmd) with stderr (and optionally stdout) discarded: the exit code, or -1
+static int sh_status(const std::string &cmd, bool quiet_stdout) {
+    const pid_t pid = fork();
+    if (pid < 0) return -2;
+    if (pid == 0) {
+        const int nul = open("/dev/null", O_WRONLY);
+        if (nul >= 0) {
+            dup2(nul, 2);
+            if (quiet_stdout) dup2(nul, 1);
+        }
+        execl("/bin/sh", "sh", "-c", cmd.c_str(), (char *)nullptr);
+        _exit(127);
+    }
+    int st = 0;
+    if (waitpid(pid, &st, 0) < 0) return -2;
+    return WIFEXITED(st) ? WEXITSTATUS(st) : -1;
+}
+
+Cleaner Cleaner::from_scrubby(const Scrubby &s) {  // cleaner.rs:110-123, 255-291
+    Cleaner c{s, SamtoolsConfig::from_scrubby(s)};
+    if (s.config.aligner) {
+        static const char *ver[] = {"bowtie2 --version", "minimap2 --version", "minigraph --version", "strobealign --version"};
+        if (sh_status(ver[(int)*s.config.aligner], true) != 0)
+            throw ScrubbyError(ScrubbyError::AlignerDependencyMissing,
+                               std::string("Aligner `") + serde_name(*s.config.aligner) + "` cannot be executed - is it installed?");
+    } else if (s.config.classifier && !(s.config.reads && s.config.report)) {
+        // (the reference also probes the tool when only its OUTPUTS are given -- `scrubby classifier`, SURVEY F11;
+        //  there the tool is not needed and is not probed here)
+        const char *cmd = *s.config.classifier == Classifier::Kraken2 ? "kraken2 --version" : "metabuli";
+        if (sh_status(cmd, true) != 0)
+            throw ScrubbyError(ScrubbyError::ClassifierDependencyMissing,
+                               std::string("Classifier `") + serde_name(*s.config.classifier) + "` cannot be executed - is it installed?");
+    }
+    return c;
+}
+
+void Cleaner::run_command(const std::string &cmd) const {  // cleaner.rs:626-641 (stdout inherited, stderr discarded)
+    const int rc = sh_status(cmd, false);
+    if (rc == -2) throw ScrubbyError(ScrubbyError::CommandExecutionFailed, "Failed to execute command '" + cmd + "'");
+    if (rc != 0) throw ScrubbyError(ScrubbyError::CommandFailed, "Command '" + cmd + "' failed with exit code " + std::to_string(rc));
+}
+
+// cleaner.rs:651-687: the child's stdout is PAF; the reference parses it line by line while the child runs, here the
+// whole stream is collected and handed to the PAF kernel (same predicate, same errors; a PAF error wins over the
+// child's exit status because the reference returns it from inside the read loop)
+ReadIdSet Cleaner::run_command_stdout_paf(const GpuContext &g, const std::string &cmd) const {
+    int fds[2];
+    if (pipe(fds) != 0) throw ScrubbyError(ScrubbyError::CommandExecutionFailed, "Failed to execute command '" + cmd + "': pipe");
+    const pid_t pid = fork();
+    if (pid < 0) throw ScrubbyError(ScrubbyError::CommandExecutionFailed, "Failed to execute command '" + cmd + "': fork");
+    if (pid == 0) {
+        close(fds[0]);
+        dup2(fds[1], 1);
+        const int nul = open("/dev/null", O_WRONLY);
+        if (nul >= 0) dup2(nul, 2);
+        execl("/bin/sh", "sh", "-c", cmd.c_str(), (char *)nullptr);
+        _exit(127);
+    }
+    close(fds[1]);
+    std::vector<uint8_t> buf;
+    std::vector<uint8_t> chunk(1 << 20);
+    while (true) {
+        const ssize_t n = read(fds[0], chunk.data(), chunk.size());
+        if (n < 0 && errno == EINTR) continue;
+        if (n <= 0) break;
+        buf.insert(buf.end(), chunk.data(), chunk.data() + n);
+    }
+    close(fds[0]);
+    int st = 0;
+    waitpid(pid, &st, 0);
+    ReadIdSet ids;
+    uint64_t err = 0;
+    check(sgpu_idset_from_paf(g.get(), buf.data(), buf.size(), scrubby.config.min_query_length, scrubby.config.min_query_coverage,
+                              scrubby.config.min_mapq, ids.out(), &err),
+          err, "run_command_stdout_paf");
+    const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : -1;
+    if (rc != 0) throw ScrubbyError(ScrubbyError::CommandFailed, "Command '" + cmd + "' failed with exit code " + std::to_string(rc));
+    return ids;
+}
+
+static std::string temp_dir_of(const Scrubby &s) {  // workdir, else std::env::temp_dir()
+    if (s.workdir) {
+        mkdir(s.workdir->c_str(), 0755);
+        return *s.workdir;
+    }
+    const char *t = getenv("TMPDIR");
+    return (t && *t) ? t : "/tmp";
+}
+static std::string join_path(const std::string &dir, const std::string &name) {
+    return (!dir.empty() && dir.back() == '/') ? dir + name : dir + "/" + name;
+}
+
+std::string Cleaner::kraken_command(const std::string &reads_out, const std::string &report_out) const {  // cleaner.rs:300-322
+    const ScrubbyConfig &c = scrubby.config;
+    const std::string args = c.classifier_args.value_or("");
+    const std::string head = "kraken2 --threads " + std::to_string(scrubby.threads) + " --db " + *c.classifier_index + " " + args;
+    if (c.paired_end)
+        return head + " --paired " + scrubby.input[0] + " " + scrubby.input[1] + " --output " + reads_out + " --report " + report_out;
+    return head + " --single " + scrubby.input[0] + " --output " + reads_out + " --report " + report_out;
+}
+
+std::string Cleaner::metabuli_command(const std::string &dir) const {  // cleaner.rs:341-362
+    const ScrubbyConfig &c = scrubby.config;
+    const std::string args = c.classifier_args.value_or("");
+    const std::string t = std::to_string(scrubby.threads);
+    if (c.paired_end)
+        return "metabuli classify --seq-mode 2 --threads " + t + " " + args + " " + scrubby.input[0] + " " + scrubby.input[1] + " " +
+               *c.classifier_index + " " + dir + " metabuli";
+    return "metabuli classify --seq-mode 3 --threads " + t + " " + args + " " + scrubby.input[0] + " " + *c.classifier_index + " " +
+           dir + " metabuli";
+}
+
+void Cleaner::run_classifier() const {  // cleaner.rs:155-161, 293-376
+    const ScrubbyConfig &c = scrubby.config;
+    if (!c.classifier) throw ScrubbyError(ScrubbyError::MissingClassifier, "No classifier configured.");
+    if (!c.classifier_index) throw ScrubbyError(ScrubbyError::MissingClassifierIndex, "Classifier index must be set when classifier is configured.");
+    const std::string dir = temp_dir_of(scrubby);
+    GpuContext g(scrubby.device);
+    if (*c.classifier == Classifier::Kraken2) {
+        const std::string reads = join_path(dir, "kraken.reads"), report = join_path(dir, "kraken.report");
+        run_command(kraken_command(reads, report));
+        clean_reads(parse_classifier_output(g, report, reads));
+    } else {
+        run_command(metabuli_command(dir));
+        clean_reads(parse_classifier_output(g, join_path(dir, "metabuli_report.tsv"), join_path(dir, "metabuli_classifications.tsv")));
+    }
+}
+
+std::string Cleaner::aligner_command() const {  // cleaner.rs:385-470, 573-624
+    const ScrubbyConfig &c = scrubby.config;
+    const std::string args = c.aligner_args.value_or(""), t = std::to_string(scrubby.threads);
+    const std::string &idx = *c.aligner_index, &r1 = scrubby.input[0];
+    const std::string r2 = c.paired_end ? scrubby.input[1] : "";
+    auto q = [](const std::string &p) { return "'" + p + "'"; };
+    switch (*c.aligner) {
+    case Aligner::Minimap2:
+        if (!c.preset) throw ScrubbyError(ScrubbyError::MissingMinimap2Preset, "Minimap2 preset must be set.");
+        return std::string("minimap2 -ax ") + display_name(*c.preset) + " --secondary=no -t " + t + " " + args + " " + q(idx) + " " + q(r1) +
+               (c.paired_end ? " " + q(r2) : "") + " | " + samtools.get_pipeline();
+    case Aligner::Minigraph:
+        if (!c.preset) throw ScrubbyError(ScrubbyError::MissingMinigraphPreset, "Minigraph preset must be set.");
+        return std::string("minigraph -cx ") + display_name(*c.preset) + " -N 0 -t " + t + " " + args + " " + q(idx) + " " + q(r1) +
+               (c.paired_end ? " " + q(r2) : "");
+    case Aligner::Bowtie2:
+        if (c.paired_end)
+            return "bowtie2 -x " + q(idx) + " -1 " + q(r1) + " -2 " + q(r2) + " -k 1 --mm -p " + t + " " + args + " | " + samtools.get_pipeline();
+        return "bowtie2 -x " + q(idx) + " -U " + q(r1) + " -k 1 --mm -p " + t + " " + args + " | " + samtools.get_pipeline() + " ";
+    case Aligner::Strobealign:
+        return "strobealign -t " + t + " " + args + " " + q(idx) + " " + q(r1) + (c.paired_end ? " " + q(r2) : "") + " | " +
+               samtools.get_pipeline();
+    }
+    throw ScrubbyError(ScrubbyError::MissingAligner, "No aligner configured.");
+}
+
+void Cleaner::run_aligner() const {  // cleaner.rs:137-148
+    const ScrubbyConfig &c = scrubby.config;
+    if (!c.aligner) throw ScrubbyError(ScrubbyError::MissingAligner, "No aligner configured.");
+    if (!c.aligner_index) throw ScrubbyError(ScrubbyError::MissingAlignmentIndex, "Aligner index must be set when aligner is configured.");
+    const std::string cmd = aligner_command();
+    if (*c.aligner == Aligner::Minigraph) {
+        // the one aligner whose output comes back into the in-repo path: PAF on stdout -> id set -> clean_reads
+        GpuContext g(scrubby.device);
+        clean_reads(run_command_stdout_paf(g, cmd));
+    } else {
+        run_command(cmd);  // SAM-emitting aligners: samtools does the depletion and writes the outputs
+    }
+}
+
 void Cleaner::run_classifier_output() const {
     if (!scrubby.config.report)
         throw ScrubbyError(ScrubbyError::MissingClassifierClassificationReport,
@@ -626,6 +831,77 @@ static void validate_base_config(Scrubby &s) {  // scrubby.rs:760-799
         if (!file_exists(f)) throw ScrubbyError(ScrubbyError::MissingInputReadFile, "Read input file was not found: " + f);
     if (s.workdir) mkdir(s.workdir->c_str(), 0755);
     s.config.paired_end = s.input.size() == 2;
+    if (s.config.index) {  // scrubby.rs:787-796
+        if (s.config.aligner) s.config.aligner_index = s.config.index;
+        else if (s.config.classifier) s.config.classifier_index = s.config.index;
+        else s.config.aligner_index = s.config.index;
+    }
+}
+
+static bool dir_exists(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+static bool path_exists(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+// Path::with_extension: the text after the last '.' of the file name is replaced ("" removes it)
+static std::string with_extension(const std::string &path, const std::string &ext) {
+    const size_t slash = path.find_last_of('/');
+    const size_t name0 = slash == std::string::npos ? 0 : slash + 1;
+    const size_t dot = path.find_last_of('.');
+    std::string stem = (dot != std::string::npos && dot > name0) ? path.substr(0, dot) : path;
+    return ext.empty() ? stem : stem + "." + ext;
+}
+
+Scrubby build(Scrubby s) {  // scrubby.rs:813-975
+    validate_base_config(s);
+    ScrubbyConfig &c = s.config;
+    if (!c.aligner && !c.classifier) c.aligner = c.paired_end ? Aligner::Bowtie2 : Aligner::Minimap2;  // (no `mm2` feature)
+    if (c.aligner && c.classifier)
+        throw ScrubbyError(ScrubbyError::AlignerAndClassifierConfigured, "Unable to specify both aligner and classifier.");
+    if (c.aligner_index && c.classifier_index)
+        throw ScrubbyError(ScrubbyError::AlignerAndClassifierIndexConfigured, "Unable to specify both aligner and classifier index.");
+    if (c.classifier) {
+        if (!c.classifier_index) throw ScrubbyError(ScrubbyError::MissingClassifierIndex, "Classifier index must be set when classifier is configured.");
+        if (c.taxa.empty() && c.taxa_direct.empty())
+            throw ScrubbyError(ScrubbyError::MissingTaxa, "If classifier is set, `taxa` or `taxa_direct` must not be empty.");
+    }
+    if (c.aligner && !c.aligner_index)
+        throw ScrubbyError(ScrubbyError::MissingAlignmentIndex, "Aligner index must be set when aligner is configured.");
+    if (c.classifier_index && !dir_exists(*c.classifier_index))
+        throw ScrubbyError(ScrubbyError::MissingClassifierIndexDirectory, "Classifier index directory was not found: " + *c.classifier_index);
+    if (c.aligner && *c.aligner == Aligner::Strobealign && c.aligner_index) {
+        const std::string &f = *c.aligner_index;
+        if (f.size() > 4 && f.compare(f.size() - 4, 4, ".sti") == 0) {
+            const std::string base = with_extension(with_extension(f, ""), "");
+            if (!path_exists(base))
+                throw ScrubbyError(ScrubbyError::MissingStrobealignIndexBaseFile, "Strobealign index base file was not found: " + base);
+        }
+    }
+    if (c.aligner && *c.aligner == Aligner::Bowtie2) {
+        if (c.aligner_index) {
+            static const char *small[] = {"1.bt2", "2.bt2", "3.bt2", "4.bt2", "rev.1.bt2", "rev.2.bt2"};
+            static const char *large[] = {"1.bt21", "2.bt21", "3.bt21", "4.bt21", "rev.1.bt21", "rev.2.bt21"};
+            for (int i = 0; i < 6; i++)
+                if (!file_exists(with_extension(*c.aligner_index, small[i])) && !file_exists(with_extension(*c.aligner_index, large[i])))
+                    throw ScrubbyError(ScrubbyError::MissingBowtie2IndexFiles, "Bowtie2 index files were not found: " + *c.aligner_index);
+        }
+    } else if (c.aligner_index && !file_exists(*c.aligner_index)) {
+        throw ScrubbyError(ScrubbyError::MissingAlignmentIndexFile, "Alignment index file was not found: " + *c.aligner_index);
+    }
+    if (c.aligner && *c.aligner == Aligner::Minimap2) {
+        if (!c.preset) c.preset = c.paired_end ? Preset::Sr : Preset::MapOnt;
+        else if (*c.preset == Preset::Lr)
+            throw ScrubbyError(ScrubbyError::Minimap2PresetNotSupported, std::string("Preset not supported for minimap2: ") + display_name(*c.preset));
+    }
+    if (c.aligner && *c.aligner == Aligner::Minigraph) {
+        if (!c.preset) c.preset = c.paired_end ? Preset::Sr : Preset::Lr;
+        else if (*c.preset != Preset::Lr && *c.preset != Preset::Sr && *c.preset != Preset::Asm)
+            throw ScrubbyError(ScrubbyError::MinigraphPresetNotSupported, std::string("Preset not supported for minigraph: ") + display_name(*c.preset));
+    }
+    return s;
 }
 
 Scrubby build_classifier(Scrubby s) {  // scrubby.rs:978-1006
@@ -648,13 +924,13 @@ Scrubby build_alignment(Scrubby s) {  // scrubby.rs:1019-1038
 void Scrubby::clean() const {  // scrubby.rs:255-281
     Cleaner cleaner = Cleaner::from_scrubby(*this);
     if (config.aligner) {
-        throw ScrubbyError(ScrubbyError::Unsupported, "running external aligners is outside this build (SURVEY 8f.3)");
+        cleaner.run_aligner();
     } else if (config.reads && config.report) {
         // the reference's `classifier` subcommand reaches run_kraken and fails; the intended
-        // path is run_classifier_output, which is what runs here.
+        // path is run_classifier_output, which is what runs here (before the `classifier` arm for that reason).
         cleaner.run_classifier_output();
     } else if (config.classifier) {
-        throw ScrubbyError(ScrubbyError::MissingClassifierIndex, "Classifier index must be set when classifier is configured.");
+        cleaner.run_classifier();
     } else if (config.alignment) {
         cleaner.run_aligner_output();
     } else {

@@ -39,7 +39,12 @@ class ScrubbyError : public std::runtime_error {
         MissingClassifierReadClassfications, MissingClassifierClassificationReport, MissingAlignment,
         EmptyInputOutput, InputOutputLengthExceeded, MissingClassifier, MissingInputReadFile,
         KrakenReportTaxonParent, KrakenReportReadFieldConversion, KrakenReportDirectReadFieldConversion,
-        WouldPanic, Gpu, Unsupported
+        WouldPanic, Gpu, Unsupported,
+        // `scrubby reads` (scrubby.rs:813-975 build, cleaner.rs:255-649 external tools)
+        AlignerAndClassifierConfigured, AlignerAndClassifierIndexConfigured, MissingAlignmentIndex, MissingAlignmentIndexFile,
+        MissingBowtie2IndexFiles, MissingClassifierIndexDirectory, MissingStrobealignIndexBaseFile, Minimap2PresetNotSupported,
+        MinigraphPresetNotSupported, MissingMinimap2Preset, MissingMinigraphPreset, MissingAligner, AlignerDependencyMissing,
+        ClassifierDependencyMissing, CommandExecutionFailed, CommandFailed
     };
     ScrubbyError(Kind k, const std::string &msg, uint64_t index = 0) : std::runtime_error(msg), kind(k), index(index) {}
     Kind kind;
@@ -56,7 +61,10 @@ enum class AlignmentFormat { Sam, Bam, Cram, Paf, Txt, Gaf };
 const char *serde_name(Aligner);        // "bowtie2" ... (serde rename)
 const char *serde_name(Classifier);     // "kraken2", "metabuli"
 const char *serde_name(Preset);         // variant names: "Sr", "MapOnt", ... (no rename in the reference)
+const char *display_name(Preset);      // fmt::Display: "sr", "map-ont", "lr:hq", ... (what the aligner's -x gets)
 std::optional<Classifier> parse_classifier(const std::string &);
+std::optional<Aligner> parse_aligner(const std::string &);  // clap ValueEnum names
+std::optional<Preset> parse_preset(const std::string &);    // clap ValueEnum names: kebab-case of the variants
 std::optional<AlignmentFormat> parse_alignment_format(const std::string &);
 
 // ---------------------------------------------------------------- config (scrubby.rs:159-309)
@@ -64,6 +72,9 @@ struct ScrubbyConfig {
     std::optional<Aligner> aligner;
     std::optional<Classifier> classifier;
     std::optional<std::string> index, alignment, reads, report;
+    std::optional<std::string> aligner_index, classifier_index;  // set from `index` by validate_base_config (scrubby.rs:787-796)
+    bool unpaired = false;                                       // scrubby.rs:381
+    std::optional<unsigned> samtools_threads;                    // scrubby.rs:382 (None: 4, cleaner.rs:47)
     std::vector<std::string> taxa, taxa_direct;
     std::optional<std::string> classifier_args, aligner_args;
     std::optional<Preset> preset;
@@ -80,12 +91,14 @@ struct Scrubby {
     std::vector<std::string> input, output;
     std::optional<std::string> json, workdir, read_ids;
     bool extract = false;
+    unsigned threads = 4;  // terminal.rs:134-135
     ScrubbyConfig config;
     int device = 0;
     void clean() const;  // scrubby.rs:255-281
 };
 
 // validate_base_config (scrubby.rs:760-799) + build_classifier (:978-1006) / build_alignment (:1019-1038)
+Scrubby build(Scrubby s);  // ScrubbyBuilder::build, scrubby.rs:813-975 (`scrubby reads`)
 Scrubby build_classifier(Scrubby s);
 Scrubby build_alignment(Scrubby s);
 
@@ -149,9 +162,26 @@ struct FastqCleaner {
     void clean_reads(const GpuContext &, const ReadIdSet &read_ids, bool reverse) const;  // cleaner.rs:731-760
 };
 
+// cleaner.rs:29-87: the samtools stages behind the SAM-emitting aligners (the depletion of those pipelines is done by
+// samtools, not by the in-repo path)
+struct SamtoolsConfig {
+    std::string filter, fastq;
+    static SamtoolsConfig from_scrubby(const Scrubby &);
+    std::string get_pipeline() const { return filter + " | " + fastq; }
+};
+
 struct Cleaner {
     Scrubby scrubby;
-    static Cleaner from_scrubby(const Scrubby &s) { return {s}; }
+    SamtoolsConfig samtools;
+    static Cleaner from_scrubby(const Scrubby &s);  // cleaner.rs:110-123 (checks the external tool's presence)
+    // external tools through `sh -c` (cleaner.rs:137-161, 255-649): the command strings are the reference's
+    void run_aligner() const;
+    void run_classifier() const;
+    std::string kraken_command(const std::string &reads_out, const std::string &report_out) const;
+    std::string metabuli_command(const std::string &dir) const;
+    std::string aligner_command() const;
+    void run_command(const std::string &cmd) const;                              // cleaner.rs:626-641
+    ReadIdSet run_command_stdout_paf(const GpuContext &, const std::string &cmd) const;  // cleaner.rs:651-687
     void run_classifier_output() const;  // cleaner.rs:177-194
     void run_aligner_output() const;     // cleaner.rs:206-219
     void clean_reads(const ReadIdSet &read_ids) const;  // cleaner.rs:236-254 (two mate files on two threads)

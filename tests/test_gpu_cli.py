@@ -20,8 +20,8 @@ def cli():
     return hostlib.CLI
 
 
-def _run(cli, *args, ok=True):
-    r = subprocess.run([cli, *map(str, args)], capture_output=True, text=True, timeout=300)
+def _run(cli, *args, ok=True, env=None):
+    r = subprocess.run([cli, *map(str, args)], capture_output=True, text=True, timeout=300, env=env)
     assert (r.returncode == 0) == ok, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     return r
 
@@ -152,3 +152,126 @@ def test_cli_bam_alignment(cli, data):
     assert _run(cli, "alignment", "-i", data["r1"], "-o", d / "x.fq", "-a", tp, ok=False).returncode != 0
     cp = _write(d / "x.cram", b"CRAM\x03\x00" + b"\x00" * 40)
     assert _run(cli, "alignment", "-i", data["r1"], "-o", d / "x.fq", "-a", cp, ok=False).returncode != 0
+
+
+# ---------------------------------------------------------------------------- `scrubby reads` with stand-in tools
+FAKE_TOOL = r"""#!/bin/sh
+# stand-in for an external tool (TEST ONLY): logs its command line, then plays back prepared outputs
+name=$(basename "$0")
+echo "$name $*" >> "$FAKE_LOG"
+case "$name $1" in
+  "kraken2 --version"|"minigraph --version"|"minimap2 --version"|"bowtie2 --version"|"strobealign --version") exit 0;;
+esac
+case "$name" in
+  kraken2)
+    while [ $# -gt 0 ]; do
+      case "$1" in --output) cp "$FAKE_READS" "$2"; shift;; --report) cp "$FAKE_REPORT" "$2"; shift;; esac
+      shift
+    done;;
+  metabuli)
+    [ $# -eq 0 ] && exit 0
+    for a in "$@"; do prev2=$prev; prev=$a; done   # ... <index> <dir> metabuli
+    cp "$FAKE_REPORT" "$prev2/metabuli_report.tsv"; cp "$FAKE_READS" "$prev2/metabuli_classifications.tsv";;
+  minigraph) cat "$FAKE_PAF"; exit ${FAKE_EXIT:-0};;
+  minimap2|bowtie2|strobealign) echo "@HD	VN:1.6";;
+  samtools)
+    if [ "$1" = view ]; then cat; else
+      for a in "$@"; do case "$prev" in -0|-1) cat > "$a";; -2) : > "$a";; esac; prev=$a; done
+    fi;;
+esac
+"""
+
+
+@pytest.fixture(scope="module")
+def fake_tools(data):
+    d = data["d"] / "bin"
+    d.mkdir()
+    for name in ("kraken2", "metabuli", "minigraph", "minimap2", "bowtie2", "strobealign", "samtools"):
+        p = d / name
+        p.write_text(FAKE_TOOL)
+        p.chmod(0o755)
+    idx = data["d"] / "k2db"
+    idx.mkdir()
+    mmi = _write(data["d"] / "ref.mmi", b"x")
+    # Metabuli-style outputs: full-word ranks in the report, seven columns per read
+    mb_reads = b"".join(l + b"\t0.9\tspecies\n" for l in data["kr"].split(b"\n") if l)
+    env = dict(os.environ, PATH=f"{d}:{os.environ['PATH']}", FAKE_LOG=str(data["d"] / "tools.log"),
+               FAKE_READS=data["kr_p"], FAKE_REPORT=data["rep_p"], FAKE_PAF=data["paf_p"])
+    return dict(env=env, idx=str(idx), mmi=mmi, log=data["d"] / "tools.log", mb_reads=_write(data["d"] / "mb.tsv", mb_reads))
+
+
+def test_cli_reads_kraken2_and_metabuli(cli, data, fake_tools):
+    d, env = data["d"], fake_tools["env"]
+    tax = orc.taxids_from_report(data["rep"], ["Chordata"], ["9606"])
+    want = [orc.clean_fastq(f, orc.set_from_reads(data["kr"], 0, tax), False) for f in data["fq"]]
+    o1, o2, js = d / "k1.fq", d / "k2.fq", d / "k.json"
+    open(fake_tools["log"], "w").close()
+    _run(cli, "reads", "-i", data["r1"], data["r2"], "-o", o1, o2, "-I", fake_tools["idx"], "-c", "kraken2", "-T", "Chordata",
+         "-D", "9606", "-t", 7, "-C", "--confidence 0.1", "-w", d / "work", "-j", js, env=env)
+    assert open(o1, "rb").read() == want[0].written and open(o2, "rb").read() == want[1].written
+    log = open(fake_tools["log"]).read().split("\n")
+    assert log[0] == "kraken2 --version"                       # cleaner.rs:277-284
+    assert log[1] == (f"kraken2 --threads 7 --db {fake_tools['idx']} --confidence 0.1 --paired {data['r1']} {data['r2']} "
+                      f"--output {d / 'work' / 'kraken.reads'} --report {d / 'work' / 'kraken.report'}")  # cleaner.rs:300-311
+    rep = json.load(open(js))
+    assert rep["settings"]["classifier"] == "kraken2" and rep["settings"]["classifier_args"] == "--confidence 0.1"
+    assert rep["reads_in"] == 2 * data["n"] and rep["reads_out"] == want[0].reads_out + want[1].reads_out
+    # metabuli, single-end, extract
+    env2 = dict(env, FAKE_READS=fake_tools["mb_reads"])
+    o3 = d / "m1.fq"
+    open(fake_tools["log"], "w").close()
+    _run(cli, "reads", "-i", data["r1"], "-o", o3, "-I", fake_tools["idx"], "-c", "metabuli", "-T", "Chordata", "-D", "9606",
+         "-w", d / "work", "-e", env=env2)
+    mb = open(fake_tools["mb_reads"], "rb").read()
+    want_m = orc.clean_fastq(data["fq"][0], orc.set_from_reads(mb, 1, tax), True)
+    assert open(o3, "rb").read() == want_m.written and want_m.reads_out > 0
+    log = open(fake_tools["log"]).read().split("\n")
+    assert log[0] == "metabuli " and log[1] == (f"metabuli classify --seq-mode 3 --threads 4 {data['r1']} {fake_tools['idx']} "
+                                                f"{d / 'work'} metabuli")  # cleaner.rs:352-361
+    # validation (scrubby.rs:813-867): classifier without taxa; index that is not a directory; both tools at once
+    for extra in (["-c", "kraken2"], ["-c", "kraken2", "-T", "x", "-I", data["r1"]], ["-c", "kraken2", "-a", "minimap2", "-T", "x"]):
+        args = ["reads", "-i", data["r1"], "-o", d / "x.fq", "-I", fake_tools["idx"]] + extra
+        assert _run(cli, *args, ok=False, env=env).returncode != 0
+    # the tool is probed before anything runs (cleaner.rs:110-123)
+    bare = dict(env, PATH="/usr/bin:/bin")
+    r = _run(cli, "reads", "-i", data["r1"], "-o", d / "x.fq", "-I", fake_tools["idx"], "-c", "kraken2", "-T", "x", ok=False, env=bare)
+    assert "kraken2" in r.stderr
+
+
+def test_cli_reads_aligners(cli, data, fake_tools):
+    d, env = data["d"], fake_tools["env"]
+    # minigraph: stdout PAF comes back into the GPU path (cleaner.rs:651-687); defaults -l 0 -c 0 -q 0: every line's qname
+    want = orc.clean_fastq(data["fq"][0], orc.set_from_paf(data["paf"], 0, 0.0, 0), False)
+    o1 = d / "mg.fq"
+    open(fake_tools["log"], "w").close()
+    _run(cli, "reads", "-i", data["r1"], "-o", o1, "-I", fake_tools["mmi"], "-a", "minigraph", "-A", "-k 15", env=env)
+    assert open(o1, "rb").read() == want.written and 0 < want.reads_out < want.reads_in
+    log = open(fake_tools["log"]).read().split("\n")
+    assert log[:2] == ["minigraph --version", f"minigraph -cx lr -N 0 -t 4 -k 15 {fake_tools['mmi']} {data['r1']}"]  # single-end default: lr
+    # a failing child is CommandFailed even when its PAF parsed (cleaner.rs:681-684)
+    assert _run(cli, "reads", "-i", data["r1"], "-o", d / "x.fq", "-I", fake_tools["mmi"], "-a", "minigraph", ok=False,
+                env=dict(env, FAKE_EXIT="3")).returncode != 0
+    assert _run(cli, "reads", "-i", data["r1"], "-o", d / "x.fq", "-I", fake_tools["mmi"], "-a", "minigraph", "-p", "map-ont",
+                ok=False, env=env).returncode != 0  # MinigraphPresetNotSupported
+    # SAM-emitting aligners: the reference's shell pipeline, samtools does the depletion (cleaner.rs:46-71, 385-410)
+    open(fake_tools["log"], "w").close()
+    o2, o3 = d / "mm1.fq", d / "mm2.fq"
+    _run(cli, "reads", "-i", data["r1"], data["r2"], "-o", o2, o3, "-I", fake_tools["mmi"], "-a", "minimap2", "-t", 3, env=env)
+    log = open(fake_tools["log"]).read().split("\n")
+    assert log[0] == "minimap2 --version"
+    assert f"minimap2 -ax sr --secondary=no -t 3 {fake_tools['mmi']} {data['r1']} {data['r2']}" in log  # paired default: sr
+    assert "samtools view -h -f 12 -" in log
+    assert f"samtools fastq --threads 4 -s /dev/null -c 6 -n -1 {o2} -2 {o3}" in log
+    assert os.path.exists(o2) and os.path.exists(o3)
+    # defaults: single-end without -a / -c is minimap2 map-ont; minimap2 refuses the lr preset; bowtie2 wants its index files
+    open(fake_tools["log"], "w").close()
+    _run(cli, "reads", "-i", data["r1"], "-o", d / "mm3.fq", "-I", fake_tools["mmi"], "-e", env=env)
+    log = open(fake_tools["log"]).read().split("\n")
+    assert f"minimap2 -ax map-ont --secondary=no -t 4 {fake_tools['mmi']} {data['r1']}" in log and "samtools view -h -F 4 -" in log
+    for extra in (["-a", "minimap2", "-p", "lr"], ["-a", "bowtie2"], ["-a", "strobealign", "-I", d / "missing.fa"]):
+        assert _run(cli, "reads", "-i", data["r1"], "-o", d / "x.fq", "-I", fake_tools["mmi"], *extra, ok=False, env=env).returncode != 0
+    for ext in ("1.bt2", "2.bt2", "3.bt2", "4.bt2", "rev.1.bt2", "rev.2.bt2"):
+        _write(d / f"bt.{ext}", b"x")
+    open(fake_tools["log"], "w").close()
+    _run(cli, "reads", "-i", data["r1"], "-o", d / "bt.fq", "-I", d / "bt", "-a", "bowtie2", env=env)
+    assert f"bowtie2 -x {d / 'bt'} -U {data['r1']} -k 1 --mm -p 4\n" in open(fake_tools["log"]).read()
