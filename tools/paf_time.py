@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from scrubby_b200 import api, synth
 ctx = api.Context(0); dev = torch.device("cuda", 0)
