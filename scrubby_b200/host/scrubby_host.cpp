@@ -5,6 +5,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <fcntl.h>
 #include <sys/wait.h>
@@ -171,7 +172,9 @@ static bool inflate_bgzf_parallel(const std::vector<uint8_t> &raw, std::vector<u
         total += isize;
         p += bsize;
     }
+    const auto t0 = std::chrono::steady_clock::now();
     out.resize(total);
+    const auto t1 = std::chrono::steady_clock::now();
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, blks.size() / 16));
     std::atomic<size_t> next{0};
@@ -201,6 +204,12 @@ static bool inflate_bgzf_parallel(const std::vector<uint8_t> &raw, std::vector<u
     for (unsigned k = 1; k < nt; k++) th.emplace_back(work);
     work();
     for (auto &t : th) t.join();
+    if (getenv("SCRUBBY_DEBUG")) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[scrubby] BGZF: %zu blocks, %zu -> %zu bytes, %u threads: output allocated in %.1f ms, inflated in %.1f ms\n",
+                blks.size(), raw.size(), total, nt, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(t2 - t1).count());
+    }
     return !bad;
 }
 
