@@ -51,7 +51,7 @@ typedef enum {
     SGPU_ERR_KRAKEN_REPORT_READS = 12,  /* KrakenReportReadFieldConversion (error.rs:142) */
     SGPU_ERR_KRAKEN_REPORT_DIRECT = 13, /* KrakenReportDirectReadFieldConversion (error.rs:144) */
     SGPU_ERR_KRAKEN_REPORT_PARENT = 14, /* KrakenReportTaxonParent (error.rs:140) */
-    SGPU_ERR_FASTA_UNSUPPORTED = 15,    /* '>' input: needletail would switch to its FASTA reader; not built */
+    SGPU_ERR_FASTA_UNSUPPORTED = 15,    /* a SHARD of '>' input (sgpu_*_shard_dev): FASTA is handled on whole files only */
     SGPU_ERR_CUDA = 16,                 /* CUDA runtime failure / no device; sgpu_last_cuda_error() has the text */
     SGPU_ERR_NOMEM = 17,
     SGPU_ERR_INVALID_ARG = 18,

@@ -346,7 +346,8 @@ def fastq_records(buf: bytes):
     if len(buf) < 5:  # utils.rs:359-375 via niffler FileTooShort
         return
     if buf[:1] == b">":
-        raise RefError(E_FASTA)
+        yield from fasta_records(buf)
+        return
     if buf[:1] != b"@":
         raise RefError(E_FMT)
     start, idx, crlf = 0, 0, None
@@ -387,6 +388,32 @@ def fastq_records(buf: bytes):
         start = end + 1
 
 
+def fasta_records(buf: bytes):
+    """needletail 0.5.1 fasta Reader::next (second restatement: split on "\\n>" instead of walking newlines): yields
+    (index, id, raw_seq, None, crlf_known_so_far).  raw_seq keeps the inner line breaks of a multi-line sequence."""
+    chunks = buf.split(b"\n>")
+    crlf = None
+    for idx, ch in enumerate(chunks):
+        body = ch[1:] if idx == 0 else ch           # without the leading '>'
+        last_rec = idx == len(chunks) - 1
+        # the newline positions the reference records ("seq_pos"), relative to `body`
+        pos = [i for i, c in enumerate(body) if c == 10]
+        if last_rec:
+            if pos and pos[-1] == len(body) - 1:    # a newline on the input's last byte only counts after another one
+                pos = pos if len(pos) > 1 else []
+            elif pos:
+                pos.append(len(body))               # no trailing newline: the end of the input closes the last line
+        else:
+            pos.append(len(body))                   # the newline in front of the next '>'
+        if not pos:
+            raise RefError(E_END, idx)
+        rid = _trim_cr(body[: pos[0]])
+        raw = _trim_cr(body[pos[0] + 1: pos[-1]]) if len(pos) > 1 else b""
+        if crlf is None and 10 in body[: pos[-1]]:
+            crlf = body[: pos[-1]].find(b"\n") > 0 and body[body[: pos[-1]].find(b"\n") - 1] == 13
+        yield idx, rid, raw, None, bool(crlf)
+
+
 def clean_fastq(buf: bytes, ids: set[bytes], reverse=False):
     """cleaner.rs:731-760 -> (written, other, reads_in, reads_out).  Raises RefError."""
     w, o = bytearray(), bytearray()
@@ -397,7 +424,7 @@ def clean_fastq(buf: bytes, ids: set[bytes], reverse=False):
         except RefError as e:
             raise RefError(e.code, idx)
         e_ = b"\r\n" if crlf else b"\n"
-        rec = b"@" + rid + e_ + seq + e_ + b"+" + e_ + qual + e_
+        rec = b"@" + rid + e_ + seq + e_ + b"+" + e_ + qual + e_ if qual is not None else b">" + rid + e_ + seq + e_
         rin += 1
         hit = key in ids
         if (not reverse and not hit) or (reverse and hit):
@@ -414,11 +441,17 @@ def diff(pairs):
     rin = rout = d = 0
     for fin, fout in pairs:
         o_ids = set()
+        def key(rid, idx):
+            try:
+                return get_id(rid)
+            except RefError as e:  # the failing record's index within its file
+                raise RefError(e.code, idx)
+
         for idx, rid, *_ in fastq_records(fout):
-            o_ids.add(get_id(rid))
+            o_ids.add(key(rid, idx))
             rout += 1
         for idx, rid, *_ in fastq_records(fin):
-            k = get_id(rid)
+            k = key(rid, idx)
             if k not in o_ids:
                 diff_ids.add(k)
                 d += 1

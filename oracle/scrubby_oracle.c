@@ -848,6 +848,7 @@ typedef struct {
     int finished;
     int have_le, crlf; /* Reader.line_ending */
     uint64_t index;    /* records returned so far */
+    int fasta;         /* first byte '>': needletail's FASTA reader */
 } orc_reader;
 
 typedef struct {
@@ -872,8 +873,67 @@ static int rd_validate(const orc_reader *r, size_t start, size_t p1, size_t p2, 
     return ORC_OK;
 }
 
+/* needletail 0.5.1 fasta::Reader::next / find / _find (un-vendored; restated from the published source, parity
+ * unpinned).  A record runs from its '>' to the newline in front of the next "\n>"; `seq_pos` in the reference is the
+ * list of the record's newline positions, EXCEPT a newline that is the last byte of the input, which is only appended
+ * at end of input when an earlier one exists.  Hence:
+ *   id      = trim_cr(buf[start+1 .. first newline))
+ *   raw_seq = trim_cr(buf[first newline + 1 .. last seq_pos)) when there are two or more positions, else empty --
+ *             inner newlines (and inner CRs) of a multi-line sequence are kept verbatim (SequenceRecord::write passes
+ *             raw_seq to write_fasta);
+ *   a record without any position (a header with no newline, or whose only newline ends the input) is UnexpectedEnd;
+ *   the line ending is taken from the first record whose bytes [start, last seq_pos) hold a newline
+ *   (find_line_ending over BufferPosition::all); a record written before that uses LF.
+ * 1 = record (seq / seq_n = raw_seq, qual_n = 0), 0 = end, < 0 = -(error code). */
+static int fa_next(orc_reader *r, orc_rec *rec) {
+    if (r->finished || r->start >= r->n) return 0;
+    const uint8_t *b = r->buf;
+    const size_t s = r->start, n = r->n;
+    size_t first = (size_t)-1, last = 0, npos = 0, from = s, next_start = n;
+    int complete = 0;
+    while (from < n) {
+        const uint8_t *q = (const uint8_t *)memchr(b + from, '\n', n - from);
+        if (!q) break;
+        const size_t pos = (size_t)(q - b);
+        if (pos + 1 == n) { /* cannot look at the next byte: not pushed now; end of input appends it if others exist */
+            if (npos) { last = pos; npos++; }
+            from = n;
+            complete = 2;
+            break;
+        }
+        if (!npos) first = pos;
+        last = pos;
+        npos++;
+        if (b[pos + 1] == '>') {
+            next_start = pos + 1;
+            complete = 1;
+            break;
+        }
+        from = pos + 1;
+    }
+    if (complete == 0 && npos) { last = n; npos++; } /* no trailing newline: the end of the input is the last position */
+    if (complete != 1) r->finished = 1;
+    if (npos == 0) return -ORC_ERR_FASTQ_UNEXPECTED_END;
+    rec->id = s + 1;
+    rec->id_n = trim_cr_len(b + s + 1, first - (s + 1));
+    rec->seq = first + 1;
+    rec->seq_n = npos > 1 ? trim_cr_len(b + first + 1, last - (first + 1)) : 0;
+    rec->qual = rec->qual_n = 0;
+    if (!r->have_le) { /* find_line_ending(buf[start .. last)) */
+        const uint8_t *q = (const uint8_t *)memchr(b + s, '\n', last - s);
+        if (q) {
+            r->have_le = 1;
+            r->crlf = q > b + s && q[-1] == '\r';
+        }
+    }
+    r->start = next_start;
+    r->index++;
+    return 1;
+}
+
 /* Reader::next + find + check_end.  1 = record, 0 = end of records, <0 = -(error code) */
 static int rd_next(orc_reader *r, orc_rec *rec) {
+    if (r->fasta) return fa_next(r, rec);
     if (r->finished) return 0;
     const uint8_t *b = r->buf;
     size_t s = r->start, n = r->n;
@@ -920,13 +980,23 @@ static int rd_next(orc_reader *r, orc_rec *rec) {
     return 1;
 }
 
-/* needletail write_fastq: '@' id E seq E '+' E qual E */
-static size_t wr_record(uint8_t *o, size_t w, const uint8_t *b, const orc_rec *rec, int crlf) {
+/* needletail write_fastq: '@' id E seq E '+' E qual E;  write_fasta: '>' id E raw_seq E */
+static size_t wr_record(uint8_t *o, size_t w, const uint8_t *b, const orc_rec *rec, int crlf, int fasta) {
 #define PUT_E()                 \
     do {                        \
         if (crlf) o[w++] = '\r'; \
         o[w++] = '\n';          \
     } while (0)
+    if (fasta) {
+        o[w++] = '>';
+        memcpy(o + w, b + rec->id, rec->id_n);
+        w += rec->id_n;
+        PUT_E();
+        memcpy(o + w, b + rec->seq, rec->seq_n);
+        w += rec->seq_n;
+        PUT_E();
+        return w;
+    }
     o[w++] = '@';
     memcpy(o + w, b + rec->id, rec->id_n);
     w += rec->id_n;
@@ -954,7 +1024,10 @@ static int rd_open(orc_reader *r, const uint8_t *in, size_t n, orc_counts *c) {
         r->finished = 1;
         return ORC_OK;
     }
-    if (in[0] == '>') return ORC_ERR_FASTA_UNSUPPORTED;
+    if (in[0] == '>') {
+        r->fasta = 1;
+        return ORC_OK;
+    }
     if (in[0] != '@') return ORC_ERR_FASTQ_UNKNOWN_FORMAT;
     return ORC_OK;
 }
@@ -985,10 +1058,10 @@ int orc_clean_fastq(const uint8_t *in, size_t n_in, const orc_set *set, int reve
             c->reads_in++;
             int hit = orc_set_contains(set, in + rec.id + off, idn);
             if ((!reverse && !hit) || (reverse && hit)) {
-                w = wr_record(out_written, w, in, &rec, r.crlf);
+                w = wr_record(out_written, w, in, &rec, r.crlf, r.fasta);
                 c->reads_out++;
             } else if (out_other) {
-                wo = wr_record(out_other, wo, in, &rec, r.crlf);
+                wo = wr_record(out_other, wo, in, &rec, r.crlf, r.fasta);
             }
         }
     }

@@ -69,7 +69,10 @@ static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, s
     *n_records = *n_picked = 0;
     if (is_first) {
         bool empty;
-        SGPU_TRY(sniff(c, d_buf, n, &empty));
+        const sgpu_status src = sniff(c, d_buf, n, &empty);
+        if (src == SGPU_ERR_FASTA_UNSUPPORTED && is_last && own_len == n)  // a whole FASTA file
+            return fasta_ids_into(c, d_buf, n, probe, want_absent, into, n_records, n_picked, err_record);
+        if (src != SGPU_OK) return src;
         if (empty) return SGPU_OK;
     } else if (n == 0 || own_len == 0) {
         return SGPU_OK;
@@ -144,7 +147,12 @@ static sgpu_status clean_dev_locked(sgpu_ctx *c, const sgpu_idset *set, const ui
     if (n_o) *n_o = 0;
     if (n_in && ((uintptr_t)d_in & 15)) return SGPU_ERR_INVALID_ARG;
     bool empty;
-    SGPU_TRY(sniff(c, d_in, n_in, &empty));
+    {
+        const sgpu_status src = sniff(c, d_in, n_in, &empty);
+        if (src == SGPU_ERR_FASTA_UNSUPPORTED)  // '>': needletail's FASTA reader takes over (whole files only)
+            return clean_fasta(c, set, d_in, n_in, reverse, d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
+        if (src != SGPU_OK) return src;
+    }
     if (empty) {
         counts->empty_input = 1;
         return SGPU_OK;
@@ -203,7 +211,7 @@ const char *sgpu_strerror(int s) {
     case SGPU_ERR_KRAKEN_REPORT_READS: return "failed to convert the read field in the report from `Kraken2`";
     case SGPU_ERR_KRAKEN_REPORT_DIRECT: return "failed to convert the direct read field in the report from `Kraken2`";
     case SGPU_ERR_KRAKEN_REPORT_PARENT: return "failed to provide a parent taxon while parsing report from `Kraken2`";
-    case SGPU_ERR_FASTA_UNSUPPORTED: return "FASTA input is not supported by this build";
+    case SGPU_ERR_FASTA_UNSUPPORTED: return "FASTA input is not supported on this path (shards of a FASTA file)";
     case SGPU_ERR_CUDA: return "CUDA error (see sgpu_last_cuda_error)";
     case SGPU_ERR_NOMEM: return "out of memory";
     case SGPU_ERR_INVALID_ARG: return "invalid argument";

@@ -158,7 +158,6 @@ fastq_errors = [
          why="3 newlines reach SearchPosition::Quality, then validate sees '\\n' as start byte"),
     dict(name="blank_between_records", buf=L(b"@r0\nA\n+\nI\n\n@r1\nA\n+\nI\n"), error=3, error_record=1),
     dict(name="unknown_format", buf=L(b"hello world\n"), error=7, error_record=0),
-    dict(name="fasta", buf=L(b">s1\nACGT\n"), error=15, error_record=0),
     dict(name="invalid_utf8_header", buf=L(b"@r0 \xff\nA\n+\nI\n"), error=8, error_record=0),
     dict(name="overlong_utf8_header", buf=L(b"@r0 \xc0\xaf\nA\n+\nI\n"), error=8, error_record=0),
 ]

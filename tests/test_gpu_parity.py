@@ -737,6 +737,47 @@ def test_reads_tile_kernel_errors(ctx):
     _reads_vs_oracle(ctx, "".join(two).encode(), 0, ["9606"])  # the first error wins
 
 
+def test_fasta_input_matches_oracle(ctx_mode):
+    """'>' input: needletail's FASTA reader (multi-line sequences kept verbatim, line-ending rules, UnexpectedEnd);
+    clean in both modes, both outputs, error class and record index; diff on FASTA files"""
+    from test_oracle_differential import FASTA_CASES, rand_fasta
+
+    for buf, ids, rev, w, o in FASTA_CASES:
+        g = _same_clean(ctx_mode, buf, ids, rev)
+        assert (g.written, g.other) == (w, o)
+    for buf in (b">abcd", b">a\nAC\n>b\n", b">a\nAC\n>\nTT\n", b">a\nAC\n>\xff\nTT\n", b">a\n>b\n>c\n", b">a\nA"):
+        _same_clean(ctx_mode, buf, [b"a"])
+    rng = random.Random(9100)
+    ids = [b"b", b"q3", b"x" * 16]
+    for _ in range(120):
+        _same_clean(ctx_mode, rand_fasta(rng, rng.randrange(1, 9)), ids, rng.random() < 0.5)
+    # a larger file: 20 k records of 1-3 sequence lines, every third id in the set
+    recs = []
+    for i in range(20_000):
+        lines = [bytes(rng.choice(b"ACGT") for _ in range(60)) for _ in range(1 + i % 3)]
+        recs.append(b">ctg%d len=%d\n" % (i, 60 * len(lines)) + b"\n".join(lines) + b"\n")
+    big = b"".join(recs)
+    big_ids = [b"ctg%d" % i for i in range(0, 20_000, 3)]
+    g = _same_clean(ctx_mode, big, big_ids)
+    assert g.reads_in == 20_000 and g.reads_out == 20_000 - len(big_ids) and g.written + g.other != b""
+    _same_clean(ctx_mode, big[:-1], big_ids, True)
+    # diff (utils.rs:250-285) over FASTA files
+    pairs = [(big, g.written), (rand_fasta(random.Random(5), 40), b"")]
+    try:
+        o, oerr = orc.diff(pairs), None
+    except orc.OracleError as e:
+        o, oerr = None, (e.code, e.index)
+    try:
+        d, gerr = api.diff(ctx_mode, pairs), None
+    except api.ScrubbyGpuError as e:
+        d, gerr = None, (e.status, e.index)
+    assert gerr == oerr
+    if o is not None:
+        assert d[:3] == o[:3] and d[3].sorted_ids() == o[3].sorted_ids()
+    d1, o1 = api.diff(ctx_mode, pairs[:1]), orc.diff(pairs[:1])
+    assert d1[:3] == o1[:3] == (20_000, 20_000 - len(big_ids), len(big_ids)) and d1[3].sorted_ids() == o1[3].sorted_ids()
+
+
 def _bam_vs_oracle(ctx, buf: bytes, ml=0, mc=0.0, mq=0):
     try:
         o, oerr = orc.set_from_bam(buf, ml, mc, mq), None

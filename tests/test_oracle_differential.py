@@ -248,3 +248,68 @@ def test_host_report_state_machine_matches_oracle(seed):
         except hostlib.HostError as e:
             got = ("err", (kinds.get(e.kind, -e.kind), e.line))
         assert got == want, (taxa, direct)
+
+
+# ---------------------------------------------------------------------------------------------- FASTA input
+FASTA_CASES = [  # (input, ids in the set, reverse, written, other) -- derived by hand from needletail's fasta reader rules
+    (b">a x\nAC\nGT\n>b\nTT\n>c\n>d\nAA", [b"b"], False, b">a x\nAC\nGT\n>c\n\n>d\nAA\n", b">b\nTT\n"),   # multi-line kept verbatim
+    (b">a x\nAC\nGT\n>b\nTT\n>c\n>d\nAA", [b"b"], True, b">b\nTT\n", b">a x\nAC\nGT\n>c\n\n>d\nAA\n"),
+    (b">a\r\nAC\r\nGT\r\n>b\r\nTT\r\n", [b"b"], False, b">a\r\nAC\r\nGT\r\n", b">b\r\nTT\r\n"),               # CRLF file
+    (b">a\nAC\n\n", [], False, b">a\nAC\n\n", b""),                                                            # blank last line
+    (b">a\n>b\r\nAC\r\n", [], False, b">a\n\n>b\r\nAC\r\n", b""),          # the line ending is decided by the first record that holds a newline
+    (b">a\nAC\r\n>b\n\nTT\r", [b"a"], True, b">a\nAC\n", b">b\n\nTT\n"),   # one trailing CR trimmed from the id and from raw_seq
+    (b">  a b\nAC\n", [b"a"], False, b"", b">  a b\nAC\n"),                 # get_id: first whitespace-separated token
+]
+
+
+def test_fasta_hand_derived_cases():
+    for buf, ids, rev, w, o in FASTA_CASES:
+        r = orc.clean_fastq(buf, orc.OSet.from_ids(ids), rev)
+        assert (r.written, r.other) == (w, o), buf
+        p = po.clean_fastq(buf, set(ids), rev)
+        assert (p[0], p[1]) == (w, o), buf
+    for buf, err in ((b">abcd", (po.E_END, 0)), (b">a\nAC\n>b\n", (po.E_END, 1)), (b">a\nAC\n>\nTT\n", (po.E_HEADER, 1)),
+                     (b">a\nAC\n>\xff\nTT\n", (po.E_UTF8, 1))):
+        with pytest.raises(orc.OracleError) as ei:
+            orc.clean_fastq(buf, orc.OSet.from_ids([]))
+        assert _err_of(ei.value) == err, buf
+        with pytest.raises(po.RefError) as pi:
+            po.clean_fastq(buf, set())
+        assert (pi.value.code, pi.value.index) == err, buf
+
+
+def rand_fasta(rng, n):
+    parts = []
+    for i in range(n):
+        rid = rng.choice([b"q%d" % rng.randrange(6), b"b", b" x", b"a b", b"x" * 16, b"\xc3\xa9", b"", b"\xff"][: 8 if rng.random() < 0.03 else 6])
+        e_ = rng.choice([b"\n", b"\n", b"\r\n"])
+        lines = [bytes(rng.choice(b"ACGT>\r ") for _ in range(rng.choice([0, 1, 5, 60]))) for _ in range(rng.randrange(0, 4))]
+        parts.append(b">" + rid + e_ + b"".join(l + e_ for l in lines))
+    buf = b"".join(parts)
+    if rng.random() < 0.4:
+        buf = buf.rstrip(b"\n")
+    if rng.random() < 0.2:
+        buf = buf[: rng.randrange(1, len(buf) + 1)]
+    return buf
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fasta_two_restatements_agree(seed):
+    rng = random.Random(9000 + seed)
+    ids = [b"b", b"q3", b"x" * 16]
+    oset, pset = orc.OSet.from_ids(ids), set(ids)
+    for _ in range(150):
+        buf = rand_fasta(rng, rng.randrange(1, 9))
+        rev = rng.random() < 0.5
+        _both(lambda b: orc.clean_fastq(b, oset, rev), lambda b: po.clean_fastq(b, pset, rev), (buf,), (buf,),
+              lambda c: (c.written, c.other, c.reads_in, c.reads_out))
+    pairs = []
+    for _ in range(2):
+        fin = rand_fasta(rng, 30)
+        try:
+            fout = orc.clean_fastq(fin, oset).written
+        except orc.OracleError:
+            fout = b""
+        pairs.append((fin, fout))
+    _both(orc.diff, po.diff, (pairs,), (pairs,), lambda d: (d[0], d[1], d[2], d[3].sorted_ids()),
+          lambda d: (d[0], d[1], d[2], sorted(d[3])))
