@@ -172,6 +172,16 @@ void sgpu_idset_free(sgpu_idset *);
 void sgpu_free(void *);
 
 /* ---- FASTQ filter ---------------------------------------------------------------- */
+/* FASTA input.  When the first byte is '>' needletail switches to its FASTA reader (utils.rs:377-383) and the same
+ * clean_reads / get_difference loops run on those records; sgpu_clean_fastq{,_dev} and sgpu_diff{,_dev} follow (whole
+ * files; the shard entry points return SGPU_ERR_FASTA_UNSUPPORTED).  needletail 0.5.1 fasta::Reader restated (parity
+ * unpinned): a record runs from its '>' to the newline in front of the next "\n>" or to the end of the input; its
+ * positions are its newlines, except that a newline on the input's LAST byte is only counted after another one, and
+ * that without a trailing newline the end of the input closes the last line; id = trim_cr(start+1 .. first position),
+ * raw_seq = trim_cr(first position + 1 .. last position) when there are >= 2 positions, else empty -- the inner line
+ * breaks of a multi-line sequence are kept verbatim; a record without a position is SGPU_ERR_FASTQ_UNEXPECTED_END;
+ * the line ending E comes from the first record whose bytes before its last position hold a newline (CRLF when that
+ * newline follows a CR), records written before it use LF; output '>' id E raw_seq E. */
 /* FastqCleaner::clean_reads, cleaner.rs:731-760 (loop :742-754) including needletail's
  * framing and re-serialisation and get_id (utils.rs:91-103).
  *   out_written : the bytes the reference writes to its output file

@@ -2,8 +2,8 @@
 // '>' (utils.rs:377-383 parse_fastx_file), and FastqCleaner::clean_reads (cleaner.rs:731-760) / ReadDifference
 // (utils.rs:250-285) then run unchanged on those records.
 //
-// needletail 0.5.1 fasta::Reader::next / find / _find restated (un-vendored dependency; parity unpinned, the rules are
-// listed with the oracle's fa_next in oracle/scrubby_oracle.c):
+// needletail 0.5.1 fasta::Reader::next / find / _find restated (un-vendored dependency; parity unpinned; the same
+// rules are listed in include/scrubby_gpu.h):
 //   record  : from its '>' to the newline in front of the next "\n>" (or the end of the input);
 //   seq_pos : the record's newline positions, except a newline on the LAST byte of the input, which is appended at end
 //             of input only when an earlier one exists; without a trailing newline the end of the input is appended;
