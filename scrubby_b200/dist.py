@@ -193,17 +193,20 @@ def clean_fastq_sharded(ops, ids, file_bytes, dist=None, reverse: bool = False, 
         counts = _all_gather_ints(dist, [own_nl, int(crlf)], world)
         newlines_before = sum(c[0] for c in counts[:rank])
         crlf = bool(counts[0][1])
-        halo_short = 0
+        halo_short, failed = 0, None
         try:
             if sh.own_len == 0:
                 w, o, rin, rout = b"", b"", 0, 0
             else:
                 w, o, rin, rout = ops.clean_shard(ids, d_buf, sh, newlines_before, crlf, reverse, want_other)
         except Exception as e:  # SGPU_ERR_HALO == 21
-            if getattr(e, "status", None) != 21:
-                raise
-            halo_short, w, o, rin, rout = 1, b"", b"", 0, 0
-        res = _all_gather_ints(dist, [halo_short, len(w), len(o), rin, rout], world)
+            w, o, rin, rout = b"", b"", 0, 0
+            if getattr(e, "status", None) == 21:
+                halo_short = 1
+            else:
+                failed = e
+        res = _all_gather_ints(dist, [halo_short, len(w), len(o), rin, rout, _status_of(failed)], world)
+        _raise_collectively(res, 5, failed, rank)  # an error in one shard ends the run on EVERY rank (nobody is left waiting)
         if any(r[0] for r in res):
             if halo >= max_halo:
                 raise RuntimeError("a record is longer than the maximum shard halo")
@@ -235,16 +238,19 @@ def _ids_of_file_sharded(ops, file_bytes, dist, probe, collect, halo, max_halo):
         own_nl = ops.count_newlines(d_buf, sh.own_len)
         counts = _all_gather_ints(dist, [own_nl], world)
         newlines_before = sum(c[0] for c in counts[:rank])
-        halo_short, rec, picked = 0, 0, 0
+        halo_short, rec, picked, failed = 0, 0, 0, None
         scratch = ops.new_set()  # a retry must not leave ids of the failed attempt behind
         try:
             if sh.own_len:
                 rec, picked = ops.ids_shard(probe, d_buf, sh, newlines_before, scratch)
         except Exception as e:  # SGPU_ERR_HALO == 21
-            if getattr(e, "status", None) != 21:
-                raise
-            halo_short = 1
-        if any(r[0] for r in _all_gather_ints(dist, [halo_short], world)):
+            if getattr(e, "status", None) == 21:
+                halo_short = 1
+            else:
+                failed = e
+        res = _all_gather_ints(dist, [halo_short, _status_of(failed)], world)
+        _raise_collectively(res, 1, failed, rank)
+        if any(r[0] for r in res):
             if halo >= max_halo:
                 raise RuntimeError("a record is longer than the maximum shard halo")
             halo = min(max_halo, halo * 8)
@@ -290,6 +296,35 @@ def diff_sharded(ops, pairs, dist=None, halo: int = 1 << 20, max_halo: int = 1 <
             dist.all_gather_object(gathered, diff_local)
         ids = sorted(set(x for part in gathered for x in part))
     return ShardedDiff(sum(t[0] for t in tot), sum(t[1] for t in tot), sum(t[2] for t in tot), ids)
+
+
+class ShardError(RuntimeError):
+    """another rank's shard failed: every rank leaves the collective together (the lowest failing rank holds the
+    earliest record of the file, i.e. the error the reference would have stopped at)"""
+
+    def __init__(self, rank: int, status: int):
+        super().__init__(f"shard {rank} failed with status {status}")
+        self.rank, self.status = rank, status
+
+
+def _status_of(exc) -> int:
+    if exc is None:
+        return 0
+    st = getattr(exc, "status", None)
+    return int(st) if isinstance(st, int) and st > 0 else 1 << 20  # not a library status: still an error
+
+
+def _raise_collectively(res, col: int, mine, rank: int):
+    """res: the all-gathered rows; column `col` holds every rank's error status (0 = fine).  Raises on EVERY rank when
+    any shard failed: the first failing rank re-raises its own exception (it carries the record index), the others a
+    ShardError that names it."""
+    bad = [(r, row[col]) for r, row in enumerate(res) if row[col]]
+    if not bad:
+        return
+    first_rank, status = bad[0]
+    if mine is not None and rank == first_rank:
+        raise mine
+    raise ShardError(first_rank, status)
 
 
 def _all_gather_ints(dist, vals, world):

@@ -251,3 +251,42 @@ def test_sharded_diff_matches_unsharded(world, unite):
     for rank, rin, rout, d, dids in res:
         assert (rin, rout, d) == want[:3]
         assert dids == want[3].sorted_ids()
+
+
+def _error_worker(rank, world, port, fq, q):
+    from oracle import oracle as orc
+
+    from scrubby_b200.dist import ShardError
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        try:
+            clean_fastq_sharded(OracleOps(), orc.OSet(), fq, dist, halo=4096)
+            q.put((rank, "ok", 0))
+        except ShardError as e:
+            q.put((rank, "shard", e.rank))
+        except orc.OracleError as e:
+            q.put((rank, "own", e.code))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_error_in_one_shard_ends_every_rank():
+    """a corrupt record in the last third of the file: the owning rank raises its own error, the others a ShardError
+    naming it -- nobody is left waiting in a collective"""
+    n = 3000
+    fq = bytearray(synth.gen_fastq(n, 1).numpy().tobytes())
+    pos = fq.rfind(b"\n@syn.", 0, len(fq) - 1000)  # a header near the end: break its '@'
+    fq[pos + 1] = ord("X")
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_error_worker, args=(r, world, port, bytes(fq), q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, "shard", 2), (1, "shard", 2), (2, "own", 3)]  # FASTQ_INVALID_START on the owning rank
