@@ -14,3 +14,6 @@ tail -3 gpurun_out/ncu_full.log
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log
 
 timeout 300 python tools/config_times.py > gpurun_out/config_times.log 2>&1; grep -E "^C[1-5]" gpurun_out/config_times.log
+timeout 300 python tools/general_time.py > gpurun_out/general_time.log 2>&1; tail -3 gpurun_out/general_time.log
+timeout 300 python tools/bam_time.py > gpurun_out/bam_time.log 2>&1; tail -2 gpurun_out/bam_time.log
+timeout 400 python tools/c4_full.py > gpurun_out/c4_full.log 2>&1; tail -1 gpurun_out/c4_full.log | cut -c1-400
