@@ -1,0 +1,61 @@
+"""Host-side pieces of the C++ host that need no GPU: the serde_json / ryu float formatting used for `min_cov` in the
+report JSON (report.rs:60 `to_string_pretty`), checked against an independent statement of ryu's "pretty" layout on
+top of Python's shortest round-trip digits."""
+import math
+import random
+import struct
+from decimal import Decimal
+
+import pytest
+
+from scrubby_b200 import hostlib
+
+
+def ryu_pretty(v: float) -> str:
+    """ryu::Buffer::format_finite (what serde_json writes): shortest round-trip digits d1..dn with decimal exponent,
+    laid out as integer.0 / decimal / 0.00ddd for -5 < kk <= 16, else d.ddde±x"""
+    if v == 0:
+        return "-0.0" if math.copysign(1, v) < 0 else "0.0"
+    sign = "-" if v < 0 else ""
+    t = Decimal(repr(abs(v))).as_tuple()  # repr: the shortest digits that round-trip (like ryu)
+    digits = "".join(map(str, t.digits)).rstrip("0") or "0"
+    kk = len(t.digits) + t.exponent  # position of the decimal point relative to the first digit
+    n = len(digits)
+    if n <= kk <= 16:
+        return sign + digits + "0" * (kk - n) + ".0"
+    if 0 < kk <= 16:
+        return sign + digits[:kk] + "." + digits[kk:]
+    if -5 < kk <= 0:
+        return sign + "0." + "0" * (-kk) + digits
+    if n == 1:
+        return sign + digits + "e" + str(kk - 1)
+    return sign + digits[0] + "." + digits[1:] + "e" + str(kk - 1)
+
+
+def test_format_f64_known_values():
+    known = {0.5: "0.5", 0.0: "0.0", 1.0: "1.0", 0.1: "0.1", 0.75: "0.75", 100.0: "100.0", 1e16: "1e16", 1e15: "1000000000000000.0",
+             1e-5: "0.00001", 1e-6: "1e-6", 1.5e-7: "1.5e-7", 123456.789: "123456.789", 1.2345678901234568e17: "1.2345678901234568e17",
+             0.30000000000000004: "0.30000000000000004", 5e-324: "5e-324", 1.7976931348623157e308: "1.7976931348623157e308",
+             -2.5: "-2.5"}
+    for v, s in known.items():
+        assert ryu_pretty(v) == s, v        # the independent statement reproduces ryu's documented outputs
+        assert hostlib.format_f64(v) == s, v
+    assert hostlib.format_f64(float("nan")) == "null" and hostlib.format_f64(float("inf")) == "null"  # serde_json
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_format_f64_random_doubles(seed):
+    rng = random.Random(seed)
+    for _ in range(3000):
+        kind = rng.randrange(4)
+        if kind == 0:
+            v = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0]
+        elif kind == 1:
+            v = round(rng.random(), rng.randrange(1, 6))        # what a user types for --min-cov
+        elif kind == 2:
+            v = rng.random() * 10 ** rng.randrange(-12, 22)
+        else:
+            v = float(rng.randrange(0, 10 ** rng.randrange(1, 19)))
+        if not math.isfinite(v):
+            continue
+        assert hostlib.format_f64(v) == ryu_pretty(v), repr(v)
