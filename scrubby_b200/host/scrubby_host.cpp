@@ -1000,7 +1000,7 @@ void Difference::to_json(const std::string &output) const {
     write_file(output, (const uint8_t *)s.data(), s.size(), 6);
 }
 
-static std::string csv_field(const std::string &f) {  // csv crate, QuoteStyle::Necessary, delimiter '\t'
+std::string csv_field(const std::string &f) {  // csv crate, QuoteStyle::Necessary, delimiter '\t'
     bool q = f.empty();
     for (char c : f)
         if (c == '\t' || c == '"' || c == '\n' || c == '\r') q = true;
@@ -1190,6 +1190,15 @@ int scrubby_host_read_file(const char *path, uint8_t **out, size_t *out_n) {
     } catch (const scrubby::ScrubbyError &e) {
         return 100 + (int)e.kind;
     }
+}
+
+// the two string encoders of the report writers (serde_json string escaping, report.rs:60; csv crate quoting with
+// QuoteStyle::Necessary and a tab delimiter, utils.rs:207-216): which = 0 JSON, 1 TSV field.  Returns the length or -1.
+int scrubby_host_encode_string(int which, const char *in, size_t n, char *out, size_t cap) {
+    const std::string s = which == 0 ? scrubby::json_escape(std::string(in, n)) : scrubby::csv_field(std::string(in, n));
+    if (s.size() > cap) return -1;
+    memcpy(out, s.data(), s.size());
+    return (int)s.size();
 }
 
 // report JSON of a classifier / alignment run with the given counts (date passed in): layout test

@@ -217,6 +217,7 @@ struct ScrubbyReport {
     std::string to_json_string() const;  // serde_json::to_string_pretty layout
 };
 
+std::string csv_field(const std::string &);  // csv crate, QuoteStyle::Necessary, tab delimiter
 std::string json_escape(const std::string &);
 std::string format_f64(double);  // serde_json (ryu) formatting of f64
 

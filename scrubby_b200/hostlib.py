@@ -41,6 +41,7 @@ def load():
         H.scrubby_host_free.argtypes = [C.c_void_p]
         H.scrubby_host_free.restype = None
         H.scrubby_host_format_f64.argtypes = [C.c_double, C.c_char_p, C.c_size_t]
+        H.scrubby_host_encode_string.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         H.scrubby_host_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         _h = H
     return _h
@@ -87,3 +88,11 @@ def read_file(path: str) -> bytes:
     raw = C.string_at(out, n.value)
     load().scrubby_host_free(out)
     return raw
+
+
+def encode_string(which: int, raw: bytes) -> bytes:
+    """which = 0: serde_json string escaping (report JSON); 1: csv field with a tab delimiter (read-id TSV)"""
+    buf = C.create_string_buffer(6 * len(raw) + 8)
+    n = load().scrubby_host_encode_string(which, raw, len(raw), buf, len(buf))
+    assert n >= 0
+    return buf.raw[:n]

@@ -59,3 +59,22 @@ def test_format_f64_random_doubles(seed):
         if not math.isfinite(v):
             continue
         assert hostlib.format_f64(v) == ryu_pretty(v), repr(v)
+
+
+def test_report_string_encoders_match_independent_writers():
+    """serde_json escaping against json.dumps(ensure_ascii=False); the csv crate's QuoteStyle::Necessary with a tab
+    delimiter against Python's csv writer (QUOTE_MINIMAL)"""
+    import csv
+    import io
+    import json
+
+    rng = random.Random(1)
+    alphabet = ["a", "Z", "0", " ", "\t", "\n", "\r", '"', "\\", "/", ",", "\x00", "\x01", "\x1f", "\x7f", "\b", "\f", "é", "あ", "\u2028"]
+    cases = ["", "syn.1", 'a"b', "a\tb", "a\nb", "a,b", "tab\there", "\x1f"] + \
+        ["".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 12))) for _ in range(2000)]
+    for sx in cases:
+        raw = sx.encode("utf-8")
+        assert hostlib.encode_string(0, raw).decode("utf-8") == json.dumps(sx, ensure_ascii=False), repr(sx)
+        out = io.StringIO()
+        csv.writer(out, delimiter="\t", quoting=csv.QUOTE_MINIMAL, lineterminator="\n").writerow([sx])
+        assert hostlib.encode_string(1, raw).decode("utf-8") + "\n" == out.getvalue(), repr(sx)
