@@ -275,3 +275,28 @@ def test_cli_reads_aligners(cli, data, fake_tools):
     open(fake_tools["log"], "w").close()
     _run(cli, "reads", "-i", data["r1"], "-o", d / "bt.fq", "-I", d / "bt", "-a", "bowtie2", env=env)
     assert f"bowtie2 -x {d / 'bt'} -U {data['r1']} -k 1 --mm -p 4\n" in open(fake_tools["log"]).read()
+
+
+def test_cli_fasta_reads(cli, data):
+    """FASTA input through the CLI (needletail's FASTA reader under the same clean_reads loop): multi-line records,
+    TXT id list, deplete and extract, report JSON from the diff over the FASTA files"""
+    import random
+
+    d = data["d"]
+    rng = random.Random(4)
+    recs = []
+    for i in range(3000):
+        lines = [bytes(rng.choice(b"ACGT") for _ in range(70)) for _ in range(1 + i % 4)]
+        recs.append(b">read%d runid=x\n" % i + b"\n".join(lines) + b"\n")
+    fa = b"".join(recs)
+    ids = b"".join(b"read%d\n" % i for i in range(0, 3000, 4))
+    fp, ip = _write(d / "reads.fasta", fa), _write(d / "ids.txt", ids)
+    for extract in (False, True):
+        o, js = d / f"fa_{extract}.fasta", d / f"fa_{extract}.json"
+        args = ["alignment", "-i", fp, "-o", o, "-a", ip, "-j", js] + (["-e"] if extract else [])
+        _run(cli, *args)
+        want = orc.clean_fastq(fa, orc.set_from_txt(ids), extract)
+        assert open(o, "rb").read() == want.written and 0 < want.reads_out < want.reads_in
+        rep = json.load(open(js))
+        assert (rep["reads_in"], rep["reads_out"]) == (3000, want.reads_out)
+        assert (rep["reads_removed"], rep["reads_extracted"]) == ((0, 3000 - want.reads_out) if extract else (3000 - want.reads_out, 0))
