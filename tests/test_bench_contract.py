@@ -40,3 +40,35 @@ def test_ours_arm_needs_a_gpu():
         return
     r = _run("--steps", "1", "--warmup", "3", "--pairs", "1000")
     assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """the bench lines committed under profiles/ (the evidence of the round) carry every key of the contract, and
+    their derived numbers are consistent (value = reads / time, frac = achieved / peak, e2e counted from real bytes)"""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v36*.json")))
+    assert files
+    for f in files:
+        j = json.load(open(f))
+        if j.get("impl") == "reference":
+            assert j["cpu_baseline"]["kind"] in ("port", "reference") and j["e2e"]["h2d_bytes_per_step"] == 0
+            continue
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+            assert k in j, (f, k)
+        assert j["metric"] == "reads_per_s_depleted" and j["unit"] == "reads/s" and j["dtype"] == "u8"
+        assert j["scaling"] == "weak" and j["vs_baseline"] is None and j["data"] == "synthetic" and j["warmup"] >= 3
+        assert "workload" in j["config"] and "model" not in j["config"]
+        reads = 2 * j["config"]["pairs_per_gpu"] * j["n_gpus"]
+        assert abs(j["value"] - reads / (j["ms_per_step"] * 1e-3)) / j["value"] < 1e-6
+        r = j["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["avg_ms"] * 1e-3) / 1e9) / r["achieved"] < 1e-6
+        e = j["e2e"]
+        assert e["h2d_bytes_per_step"] > j["config"]["fastq_bytes_per_gpu"] and e["d2h_bytes_per_step"] > 0
+        assert e["value"] < j["value"] and abs(e["value"] - reads / (e["ms_per_step"] * 1e-3)) / e["value"] < 1e-6
+        assert j["gpu_launches"] > 0 and j["clocks"]["sm_mhz"] and not set(j["clocks"]["reasons"]) & {
+            "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        c = j["cpu_baseline"]
+        assert c["kind"] == "port" and c["cores"] == 2 and c["value"] > 0 and c["sample"]
