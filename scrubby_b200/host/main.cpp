@@ -36,6 +36,62 @@ struct Parsed {
     }
 };
 
+// `--help` / `-h` (clap prints the help and exits 0): the flags of terminal.rs, per subcommand
+const char *HELP_TOP =
+    "scrubby 1.0.2 (B200 host)\nRemove or extract background reads (host depletion) from FASTQ / FASTA files\n\n"
+    "Usage: scrubby [--log-file <FILE>] <COMMAND>\n\nCommands:\n"
+    "  reads       Deplete or extract reads using aligners or classifiers (runs the external tool)\n"
+    "  classifier  Deplete or extract reads from classifier outputs (Kraken2 / Metabuli style)\n"
+    "  alignment   Deplete or extract reads from an alignment (.paf / .gaf / .sam / .bam) or a read-id list (.txt)\n"
+    "  diff        Difference between input and output read files, with optional JSON summary and read-id TSV\n\n"
+    "Options:\n  -l, --log-file <FILE>  Output logs to file instead of the terminal\n  -h, --help     Print help\n"
+    "  -V, --version  Print version\n\nEnvironment: SCRUBBY_GPU_DEVICE=<index> selects the GPU (default 0)\n";
+const char *help_of(const std::string &cmd) {
+    if (cmd == "reads")
+        return "Usage: scrubby reads [OPTIONS] --index <INDEX>\n\nOptions:\n"
+               "  -i, --input [<INPUT>...]            Input read files (one, or two for paired-end; .gz accepted)\n"
+               "  -o, --output [<OUTPUT>...]          Output read files (.gz by extension)\n"
+               "  -I, --index <INDEX>                 Aligner index file or classifier database directory\n"
+               "  -a, --aligner <ALIGNER>             [possible values: bowtie2, minimap2, minigraph, strobealign]\n"
+               "  -p, --preset <PRESET>               minimap2 / minigraph preset [lr-hq, splice, splice-hq, asm, asm5, asm10, asm20, sr, lr,\n"
+               "                                      map-pb, map-hifi, map-ont, ava-pb, ava-ont]\n"
+               "  -c, --classifier <CLASSIFIER>       [possible values: kraken2, metabuli]\n"
+               "  -T, --taxa [<TAXA>...]              Taxa and all sub-taxa to deplete (names or taxids)\n"
+               "  -D, --taxa-direct [<TAXA_DIRECT>...]  Taxa to deplete directly (names or taxids)\n"
+               "  -A, --aligner-args <ARGS>           Additional aligner arguments\n"
+               "  -C, --classifier-args <ARGS>        Additional classifier arguments\n"
+               "  -t, --threads <THREADS>             Threads for the external tool [default: 4]\n"
+               "  -j, --json <JSON>                   Summary report (JSON)\n  -w, --workdir <WORKDIR>             Working directory\n"
+               "  -r, --read-ids <READ_IDS>           Read identifiers of depleted / extracted reads (TSV)\n"
+               "  -e, --extract                       Extract instead of deplete\n  -h, --help                          Print help\n";
+    if (cmd == "classifier")
+        return "Usage: scrubby classifier [OPTIONS] --report <REPORT> --reads <READS> --classifier <CLASSIFIER>\n\nOptions:\n"
+               "  -i, --input [<INPUT>...]     Input read files\n  -o, --output [<OUTPUT>...]   Output read files\n"
+               "  -k, --report <REPORT>        Kraken-style report of the classifier\n"
+               "      --reads <READS>          Kraken-style per-read classifications\n"
+               "  -c, --classifier <CLASSIFIER>  Output style [possible values: kraken2, metabuli]\n"
+               "  -T, --taxa [<TAXA>...]       Taxa and all sub-taxa to deplete\n  -D, --taxa-direct [<TAXA_DIRECT>...]  Taxa to deplete directly\n"
+               "  -j, --json <JSON>            Summary report (JSON)\n  -w, --workdir <WORKDIR>      Working directory\n"
+               "  -r, --read-ids <READ_IDS>    Read identifiers (TSV)\n  -e, --extract                Extract instead of deplete\n"
+               "  -h, --help                   Print help\n";
+    if (cmd == "alignment")
+        return "Usage: scrubby alignment [OPTIONS] --alignment <ALIGNMENT>\n\nOptions:\n"
+               "  -i, --input [<INPUT>...]     Input read files\n  -o, --output [<OUTPUT>...]   Output read files\n"
+               "  -a, --alignment <ALIGNMENT>  Alignment (.paf, .gaf, .sam, .bam) or read-id list (.txt)\n"
+               "  -f, --format <FORMAT>        Explicit format [possible values: sam, bam, cram, paf, txt, gaf]\n"
+               "  -l, --min-len <MIN_LEN>      Minimum query alignment length [default: 0]\n"
+               "  -c, --min-cov <MIN_COV>      Minimum query alignment coverage [default: 0]\n"
+               "  -q, --min-mapq <MIN_MAPQ>    Minimum mapping quality [default: 0]\n"
+               "  -j, --json <JSON>            Summary report (JSON)\n  -w, --workdir <WORKDIR>      Working directory\n"
+               "  -r, --read-ids <READ_IDS>    Read identifiers (TSV)\n  -e, --extract                Extract instead of deplete\n"
+               "  -h, --help                   Print help\n";
+    if (cmd == "diff")
+        return "Usage: scrubby diff [OPTIONS]\n\nOptions:\n  -i, --input [<INPUT>...]    Input read files\n"
+               "  -o, --output [<OUTPUT>...]  Output read files of a previous run\n  -j, --json <JSON>           Counts (JSON)\n"
+               "  -r, --read-ids <READ_IDS>   Read identifiers missing from the output (TSV)\n  -h, --help                  Print help\n";
+    return nullptr;
+}
+
 [[noreturn]] void usage_error(const std::string &msg) {
     fprintf(stderr, "error: %s\n\nUsage: scrubby [--log-file <FILE>] <reads|classifier|alignment|diff> [OPTIONS]\n", msg.c_str());
     exit(2);
@@ -108,6 +164,21 @@ int main(int argc, char **argv) {
         if (cmd == "--version" || cmd == "-V") {
             printf("scrubby %s\n", CRATE_VERSION);
             return 0;
+        }
+        if (cmd == "--help" || cmd == "-h" || cmd == "help") {
+            fputs(HELP_TOP, stdout);
+            return 0;
+        }
+        for (int k = i; k < argc; k++) {
+            if (!strcmp(argv[k], "-A") || !strcmp(argv[k], "--aligner-args") || !strcmp(argv[k], "-C") ||
+                !strcmp(argv[k], "--classifier-args")) {
+                k++;  // allow_hyphen_values: the next argument is a value, whatever it looks like
+                continue;
+            }
+            if ((!strcmp(argv[k], "--help") || !strcmp(argv[k], "-h")) && help_of(cmd)) {
+                fputs(help_of(cmd), stdout);
+                return 0;
+            }
         }
         if (cmd == "classifier") {
             // note: in the reference both --reads and --json claim -j (terminal.rs:235,259); as in clap's

@@ -78,3 +78,21 @@ def test_report_string_encoders_match_independent_writers():
         out = io.StringIO()
         csv.writer(out, delimiter="\t", quoting=csv.QUOTE_MINIMAL, lineterminator="\n").writerow([sx])
         assert hostlib.encode_string(1, raw).decode("utf-8") + "\n" == out.getvalue(), repr(sx)
+
+
+def test_cli_help_and_version_need_no_gpu():
+    """clap prints help / version and exits 0 before anything is built; usage errors exit 2"""
+    import subprocess
+
+    hostlib.build()
+    run = lambda *a: subprocess.run([hostlib.CLI, *a], capture_output=True, text=True, timeout=60)
+    r = run("--version")
+    assert r.returncode == 0 and r.stdout.strip() == "scrubby 1.0.2"
+    r = run("--help")
+    assert r.returncode == 0 and all(c in r.stdout for c in ("reads", "classifier", "alignment", "diff"))
+    for cmd, flag in (("reads", "--index"), ("classifier", "--report"), ("alignment", "--min-mapq"), ("diff", "--read-ids")):
+        r = run(cmd, "--help")
+        assert r.returncode == 0 and flag in r.stdout and r.stdout.startswith(f"Usage: scrubby {cmd}")
+    assert run("reads", "-i", "x", "-A", "-h").returncode == 2       # "-h" is the VALUE of --aligner-args; --index is missing
+    assert run("nonsense").returncode == 2 and run().returncode == 2
+    assert run("alignment", "-i", "a", "-o", "b").returncode == 2    # --alignment is required
