@@ -273,13 +273,35 @@ sam_errors = [
     dict(name="qname_not_utf8", buf=L(b"\xff" + (sam("e", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()), error=8),
 ]
 
+# --- FASTA input: needletail 0.5.1 fasta reader + write_fasta under cleaner.rs:742-754 (hand-derived) -------------
+fasta_cases = [
+    dict(name="multi_line_verbatim", buf=L(b">a x\nAC\nGT\n>b\nTT\n>c\n>d\nAA"), ids=["b"], reverse=False,
+         written=L(b">a x\nAC\nGT\n>c\n\n>d\nAA\n"), other=L(b">b\nTT\n")),
+    dict(name="extract", buf=L(b">a x\nAC\nGT\n>b\nTT\n>c\n>d\nAA"), ids=["b"], reverse=True,
+         written=L(b">b\nTT\n"), other=L(b">a x\nAC\nGT\n>c\n\n>d\nAA\n")),
+    dict(name="crlf_file", buf=L(b">a\r\nAC\r\nGT\r\n>b\r\nTT\r\n"), ids=["b"], reverse=False,
+         written=L(b">a\r\nAC\r\nGT\r\n"), other=L(b">b\r\nTT\r\n")),
+    dict(name="blank_last_line", buf=L(b">a\nAC\n\n"), ids=[], reverse=False, written=L(b">a\nAC\n\n"), other=""),
+    dict(name="line_ending_from_first_record_with_a_newline", buf=L(b">a\n>b\r\nAC\r\n"), ids=[], reverse=False,
+         written=L(b">a\n\n>b\r\nAC\r\n"), other=""),
+    dict(name="one_trailing_cr_trimmed", buf=L(b">a\nAC\r\n>b\n\nTT\r"), ids=["a"], reverse=True,
+         written=L(b">a\nAC\n"), other=L(b">b\n\nTT\n")),
+    dict(name="id_is_first_token", buf=L(b">  a b\nAC\n"), ids=["a"], reverse=False, written="", other=L(b">  a b\nAC\n")),
+]
+fasta_errors = [
+    dict(name="header_without_newline", buf=L(b">abcd"), error=6, error_record=0),
+    dict(name="last_header_without_sequence_line", buf=L(b">a\nAC\n>b\n"), error=6, error_record=1),
+    dict(name="empty_id", buf=L(b">a\nAC\n>\nTT\n"), error=9, error_record=1),
+    dict(name="id_not_utf8", buf=L(b">a\nAC\n>\xff\nTT\n"), error=8, error_record=1),
+]
+
 doc = dict(
     provenance="hand-derived from /root/reference/src (see make_golden.py); reference has no fixtures; parity unpinned",
     report_kraken=L(report(REPORT_ROWS)), report_metabuli=L(report(REPORT_ROWS, True)),
     taxon_cases=taxon_cases, taxon_metabuli=taxon_metabuli, paf_cases=paf_cases, paf_errors=paf_errors,
     fastq_cases=fastq_cases, fastq_errors=fastq_errors, diff_cases=diff_cases, report_case=report_case,
     reads_cases=reads_cases, reads_errors=reads_errors, txt_cases=txt_cases, get_id_cases=get_id_cases,
-    sam_cases=sam_cases, sam_errors=sam_errors)
+    sam_cases=sam_cases, sam_errors=sam_errors, fasta_cases=fasta_cases, fasta_errors=fasta_errors)
 
 if __name__ == "__main__":
     with open(os.path.join(HERE, "vectors.json"), "w") as f:

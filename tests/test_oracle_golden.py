@@ -172,3 +172,19 @@ def test_txt_and_get_id(golden):
         else:
             assert orc.get_id(B(c["header"])) == B(c["expect"])
             assert pyo.get_id(B(c["header"])) == B(c["expect"])
+
+
+def test_fasta_cases(golden):
+    """FASTA input (first byte '>'): both restatements against the hand-derived vectors"""
+    for c in golden["fasta_cases"]:
+        ids = [B(i) for i in c["ids"]]
+        r = orc.clean_fastq(B(c["buf"]), orc.OSet.from_ids(ids), c["reverse"])
+        assert (r.written, r.other) == (B(c["written"]), B(c["other"])), c["name"]
+        w, o, _, _ = pyo.clean_fastq(B(c["buf"]), set(ids), c["reverse"])
+        assert (w, o) == (B(c["written"]), B(c["other"])), c["name"]
+    for c in golden["fasta_errors"]:
+        r = orc.clean_fastq(B(c["buf"]), orc.OSet(), False, raise_on_error=False)
+        assert (r.error, r.error_record) == (c["error"], c["error_record"]), c["name"]
+        with pytest.raises(pyo.RefError) as e:
+            pyo.clean_fastq(B(c["buf"]), set())
+        assert (e.value.code, e.value.index) == (c["error"], c["error_record"]), c["name"]
