@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SGPU_ABI_VERSION 1
+#define SGPU_ABI_VERSION 2
 
 typedef enum {
     SGPU_OK = 0,
@@ -59,8 +59,13 @@ typedef enum {
     SGPU_ERR_KEY_TOO_LONG = 20,         /* a read id of 16 MiB or more */
     SGPU_ERR_HALO = 21,                 /* shard: the last owned record does not end inside the buffer */
     SGPU_ERR_SAM_RECORD = 22,           /* a SAM line htslib's sam_parse1 rejects (rust_htslib error through `result?`, alignment.rs:131) */
-    SGPU_ERR_BAM_RECORD = 23            /* a BAM header / record htslib's bam_hdr_read / bam_read1 rejects (bad magic, truncated or inconsistent) */
+    SGPU_ERR_BAM_RECORD = 23,           /* a BAM header / record htslib's bam_hdr_read / bam_read1 rejects (bad magic, truncated or inconsistent) */
+    SGPU_ERR_PHASE_UNKNOWN = 24         /* shard called with SGPU_NEWLINES_UNKNOWN that the single-pass kernel cannot take (not canonical FASTQ,
+                                           no "\n+\n" in sight ...): nothing was produced, call again with the exact newlines_before / crlf */
 } sgpu_status;
+
+/* `newlines_before` of a shard whose line phase has not been exchanged yet (see sgpu_clean_fastq_shard_dev) */
+#define SGPU_NEWLINES_UNKNOWN UINT64_MAX
 
 typedef struct sgpu_ctx sgpu_ctx;     /* device, stream, scratch arena */
 typedef struct sgpu_idset sgpu_idset; /* exact read-id set (HashSet<String>) resident in HBM */
@@ -73,7 +78,9 @@ typedef struct {
     uint32_t crlf;          /* 1: first record ends its header with CRLF, output uses CRLF     */
     uint32_t empty_input;   /* 1: fewer than 5 bytes => "empty" (utils.rs:359-375); no output  */
     uint32_t path;          /* 1: fused single-pass kernel produced the result, 2: general path */
-    uint32_t reserved;
+    uint32_t speculated;    /* 1: the shard's line phase was speculated (SGPU_NEWLINES_UNKNOWN): verify it  */
+    uint64_t own_newlines;  /* speculated shards: '\n' bytes in the owned range [0, own_len)                */
+    uint64_t lead_newlines; /* speculated shards: '\n' bytes before the first record the shard produced    */
 } sgpu_counts;
 
 /* ---- context ------------------------------------------------------------------- */
@@ -204,13 +211,29 @@ sgpu_status sgpu_clean_fastq_dev(sgpu_ctx *, const sgpu_idset *, const uint8_t *
  * records that START inside [0, own_len).  `newlines_before` is the number of '\n' bytes in
  * the file before this shard (allgathered by the caller), `crlf` the file-level line ending
  * (decided by the first record, i.e. by shard 0), `is_last` marks the shard that holds EOF.
- * Concatenating the shards' outputs in order is byte-identical to the unsharded call. */
+ * Concatenating the shards' outputs in order is byte-identical to the unsharded call.
+ *
+ * One pass without a prior newline count (round 2): pass newlines_before = SGPU_NEWLINES_UNKNOWN (and crlf = -1) on
+ * every shard but the first.  The shard then SPECULATES its line phase from the first "\n+\n" among its first four
+ * newlines, runs the single-pass kernel and returns counts->{speculated = 1, own_newlines, lead_newlines}.  The caller
+ * all-gathers own_newlines (a few bytes per shard, AFTER the kernels instead of a pass over the file before them) and
+ * accepts shard r iff (sum of own_newlines of the shards before r + lead_newlines_r) % 4 == 0 and shard 0 reported
+ * crlf == 0; otherwise -- or when the call returned SGPU_ERR_PHASE_UNKNOWN -- the shard is run again with the exact
+ * values.  The first shard may also be called with crlf = -1: it decides the line ending itself (counts->crlf). */
 sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *, const sgpu_idset *, const uint8_t *d_in,
                                        size_t n_in, size_t own_len, uint64_t newlines_before,
                                        int is_first, int is_last, int crlf, int reverse,
                                        uint8_t *d_out_written, size_t cap_written,
                                        size_t *n_written, uint8_t *d_out_other, size_t cap_other,
                                        size_t *n_other, sgpu_counts *counts);
+/* The same shard contract on HOST buffers (pinned memory for full PCIe rate): the shard goes through the device in
+ * chunks, the host->device copy of chunk k+1, the kernels of chunk k and the device->host copy of chunk k-1 overlapped
+ * (what sgpu_clean_fastq does for a whole file).  With SGPU_NEWLINES_UNKNOWN the first chunk speculates, the later chunks
+ * continue from its phase; counts->{own_newlines, lead_newlines} cover the whole shard. */
+sgpu_status sgpu_clean_fastq_shard(sgpu_ctx *, const sgpu_idset *, const uint8_t *in, size_t n_in, size_t own_len,
+                                   uint64_t newlines_before, int is_first, int is_last, int crlf, int reverse,
+                                   uint8_t *out_written, size_t cap_written, size_t *n_written,
+                                   uint8_t *out_other, size_t cap_other, size_t *n_other, sgpu_counts *counts);
 /* '\n' count of a device buffer (the per-shard figure that is allgathered) */
 sgpu_status sgpu_count_newlines_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, uint64_t *count);
 
@@ -234,11 +257,11 @@ sgpu_status sgpu_diff_dev(sgpu_ctx *, const uint8_t *d_in, size_t n_in, const ui
 
 /* ---- multi-GPU plumbing: replicate a set over NCCL ---------------------------------- */
 typedef struct {
-    void *d_table;        /* device pointer: capacity 16-byte slots           */
+    void *d_table;        /* device pointer: capacity 16-byte slots, 128-byte aligned */
     uint64_t table_bytes;
     void *d_arena;        /* device pointer: key bytes of ids longer than 15  */
     uint64_t arena_bytes;
-    uint64_t capacity;    /* slots (power of two)                             */
+    uint64_t capacity;    /* slots (a multiple of 8: 128-byte buckets)        */
     uint64_t count;       /* distinct ids                                     */
     uint64_t has_empty;   /* the empty string is a member (txt blank line)    */
 } sgpu_idset_image;

@@ -15,17 +15,19 @@ STATUS = {
     12: "SGPU_ERR_KRAKEN_REPORT_READS", 13: "SGPU_ERR_KRAKEN_REPORT_DIRECT", 14: "SGPU_ERR_KRAKEN_REPORT_PARENT",
     15: "SGPU_ERR_FASTA_UNSUPPORTED", 16: "SGPU_ERR_CUDA", 17: "SGPU_ERR_NOMEM", 18: "SGPU_ERR_INVALID_ARG",
     19: "SGPU_ERR_CAPACITY", 20: "SGPU_ERR_KEY_TOO_LONG", 21: "SGPU_ERR_HALO", 22: "SGPU_ERR_SAM_RECORD",
-    23: "SGPU_ERR_BAM_RECORD",
+    23: "SGPU_ERR_BAM_RECORD", 24: "SGPU_ERR_PHASE_UNKNOWN",
 }
 SGPU_ERR_CAPACITY = 19
 SGPU_ERR_HALO = 21
+SGPU_ERR_PHASE_UNKNOWN = 24
+NEWLINES_UNKNOWN = (1 << 64) - 1
 
 
 class Counts(C.Structure):
     _fields_ = [
         ("reads_in", C.c_uint64), ("reads_out", C.c_uint64), ("difference", C.c_uint64),
         ("error_record", C.c_uint64), ("crlf", C.c_uint32), ("empty_input", C.c_uint32),
-        ("path", C.c_uint32), ("reserved", C.c_uint32),
+        ("path", C.c_uint32), ("speculated", C.c_uint32), ("own_newlines", C.c_uint64), ("lead_newlines", C.c_uint64),
     ]
 
 
@@ -45,7 +47,7 @@ SYMBOLS = [
     "sgpu_idset_from_txt", "sgpu_idset_from_txt_dev",
     "sgpu_idset_from_reads", "sgpu_idset_from_reads_dev", "sgpu_idset_from_ids", "sgpu_idset_new",
     "sgpu_idset_len", "sgpu_idset_contains", "sgpu_idset_dump", "sgpu_idset_free", "sgpu_free",
-    "sgpu_clean_fastq", "sgpu_clean_fastq_dev", "sgpu_clean_fastq_shard_dev", "sgpu_count_newlines_dev",
+    "sgpu_clean_fastq", "sgpu_clean_fastq_dev", "sgpu_clean_fastq_shard_dev", "sgpu_clean_fastq_shard", "sgpu_count_newlines_dev",
     "sgpu_diff", "sgpu_diff_dev", "sgpu_fastq_ids_shard_dev", "sgpu_idset_export", "sgpu_idset_import",
     "sgpu_idset_keys_dev", "sgpu_idset_from_bam",
 ]
@@ -107,6 +109,7 @@ def load():
         getattr(L, name).argtypes = [vp, vp, vp, sz, i32, vp, sz, P(sz), vp, sz, P(sz), P(Counts)]
     L.sgpu_clean_fastq_shard_dev.argtypes = [vp, vp, vp, sz, sz, u64, i32, i32, i32, i32, vp, sz, P(sz), vp, sz,
                                              P(sz), P(Counts)]
+    L.sgpu_clean_fastq_shard.argtypes = L.sgpu_clean_fastq_shard_dev.argtypes
     L.sgpu_count_newlines_dev.argtypes = [vp, vp, sz, P(u64)]
     L.sgpu_fastq_ids_shard_dev.argtypes = [vp, vp, vp, sz, sz, u64, i32, i32, vp, P(Counts)]
     for name in ("sgpu_diff", "sgpu_diff_dev"):

@@ -289,6 +289,10 @@ class DevCleanResult:
     crlf: bool
     empty_input: bool
     path: int
+    status: int = 0          # 0, or SGPU_ERR_PHASE_UNKNOWN from a speculative shard call (nothing was produced)
+    speculated: bool = False
+    own_newlines: int = 0    # speculative shards: newlines of the owned range / before the first produced record
+    lead_newlines: int = 0
 
 
 def clean_fastq_dev(ctx: Context, ids: IdSet, d_in, n_in: int, d_out, d_other=None, reverse: bool = False
@@ -303,17 +307,39 @@ def clean_fastq_dev(ctx: Context, ids: IdSet, d_in, n_in: int, d_out, d_other=No
     return DevCleanResult(n1.value, n2.value, c.reads_in, c.reads_out, bool(c.crlf), bool(c.empty_input), c.path)
 
 
-def clean_fastq_shard_dev(ctx: Context, ids: IdSet, d_in, n_in: int, own_len: int, newlines_before: int,
-                          is_first: bool, is_last: bool, crlf: bool, d_out, d_other=None, reverse: bool = False
-                          ) -> DevCleanResult:
+def clean_fastq_shard_dev(ctx: Context, ids: IdSet, d_in, n_in: int, own_len: int, newlines_before, is_first: bool,
+                          is_last: bool, crlf, d_out, d_other=None, reverse: bool = False) -> DevCleanResult:
+    """sgpu_clean_fastq_shard_dev.  newlines_before=None / crlf=None: not exchanged yet -- the shard speculates its line
+    phase (one pass, no newline count before it); the result then carries own_newlines / lead_newlines for the caller's
+    check, or status == SGPU_ERR_PHASE_UNKNOWN when the exact protocol has to take over."""
     n1, n2, c = C.c_size_t(), C.c_size_t(), _lib.Counts()
+    nb = _lib.NEWLINES_UNKNOWN if (newlines_before is None and not is_first) else int(newlines_before or 0)
     rc = ctx.L.sgpu_clean_fastq_shard_dev(
-        ctx.h, ids.h, C.c_void_p(d_in.data_ptr()), n_in, own_len, newlines_before, int(is_first), int(is_last),
-        int(crlf), int(reverse), C.c_void_p(d_out.data_ptr()), d_out.numel(), C.byref(n1),
+        ctx.h, ids.h, C.c_void_p(d_in.data_ptr()), n_in, own_len, nb, int(is_first), int(is_last),
+        -1 if crlf is None else int(crlf), int(reverse), C.c_void_p(d_out.data_ptr()), d_out.numel(), C.byref(n1),
         C.c_void_p(d_other.data_ptr()) if d_other is not None else None,
         d_other.numel() if d_other is not None else 0, C.byref(n2), C.byref(c))
-    _check(rc, c.error_record, "clean_fastq_shard_dev")
-    return DevCleanResult(n1.value, n2.value, c.reads_in, c.reads_out, bool(c.crlf), bool(c.empty_input), c.path)
+    if rc != _lib.SGPU_ERR_PHASE_UNKNOWN:
+        _check(rc, c.error_record, "clean_fastq_shard_dev")
+    return DevCleanResult(n1.value, n2.value, c.reads_in, c.reads_out, bool(c.crlf), bool(c.empty_input), c.path, rc,
+                          bool(c.speculated), c.own_newlines, c.lead_newlines)
+
+
+def clean_fastq_shard_host(ctx: Context, ids: IdSet, h_in, n_in: int, own_len: int, newlines_before, is_first: bool,
+                           is_last: bool, crlf, h_out, h_other=None, reverse: bool = False) -> DevCleanResult:
+    """sgpu_clean_fastq_shard: the shard contract of clean_fastq_shard_dev on caller-owned HOST tensors (pinned for full
+    PCIe rate); the chunked H2D / kernel / D2H pipeline runs inside the call"""
+    n1, n2, c = C.c_size_t(), C.c_size_t(), _lib.Counts()
+    nb = _lib.NEWLINES_UNKNOWN if (newlines_before is None and not is_first) else int(newlines_before or 0)
+    rc = ctx.L.sgpu_clean_fastq_shard(
+        ctx.h, ids.h, C.c_void_p(h_in.data_ptr()), n_in, own_len, nb, int(is_first), int(is_last),
+        -1 if crlf is None else int(crlf), int(reverse), C.c_void_p(h_out.data_ptr()), h_out.numel(), C.byref(n1),
+        C.c_void_p(h_other.data_ptr()) if h_other is not None else None,
+        h_other.numel() if h_other is not None else 0, C.byref(n2), C.byref(c))
+    if rc != _lib.SGPU_ERR_PHASE_UNKNOWN:
+        _check(rc, c.error_record, "clean_fastq_shard")
+    return DevCleanResult(n1.value, n2.value, c.reads_in, c.reads_out, bool(c.crlf), bool(c.empty_input), c.path, rc,
+                          bool(c.speculated), c.own_newlines, c.lead_newlines)
 
 
 def count_newlines_dev(ctx: Context, d_buf, n: int) -> int:

@@ -11,11 +11,12 @@ sgpu_status clean_fused(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in,
                         sgpu_counts *counts, int *used);
 sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, size_t own_len,
                       uint64_t newlines_before, int is_first, int is_last, uint64_t *span_off, uint32_t *span_len,
-                      uint64_t cap, uint64_t *n_spans, uint64_t *span_base, uint64_t *n_records, int *used);
+                      uint64_t cap, uint64_t *n_spans, uint64_t *span_base, uint64_t *n_records, int *used,
+                      sgpu_counts *spec_out);
 sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
                               uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
                               size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
-                              sgpu_counts *counts, int *used);
+                              sgpu_counts *counts, int *used, bool want_nl);
 
 // ids of every record of a FASTQ buffer (diff): span + validity
 __global__ void __launch_bounds__(128)
@@ -65,8 +66,10 @@ static sgpu_status sniff(sgpu_ctx *c, const uint8_t *d_in, size_t n_in, bool *em
 // -> ids (all, or only those absent from `probe`) inserted into `into`
 static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, size_t own_len, uint64_t newlines_before,
                                   int is_first, int is_last, const sgpu_idset *probe, int want_absent, sgpu_idset *into,
-                                  uint64_t *n_records, uint64_t *n_picked, uint64_t *err_record) {
+                                  uint64_t *n_records, uint64_t *n_picked, uint64_t *err_record,
+                                  sgpu_counts *spec_out = nullptr) {
     *n_records = *n_picked = 0;
+    const bool spec = !is_first && newlines_before == SGPU_NEWLINES_UNKNOWN;
     if (is_first) {
         bool empty;
         const sgpu_status src = sniff(c, d_buf, n, &empty);
@@ -88,7 +91,7 @@ static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, s
         uint64_t n_spans = 0, n_rec = 0, base = 0;
         int used = 0;
         SGPU_TRY(ids_fused(c, want_absent ? probe : nullptr, d_buf, n, own_len, newlines_before, is_first, is_last,
-                           s_off.p, s_len.p, cap, &n_spans, &base, &n_rec, &used));
+                           s_off.p, s_len.p, cap, &n_spans, &base, &n_rec, &used, spec_out));
         if (used) {
             *n_records = n_rec;
             *n_picked = n_spans;
@@ -97,6 +100,7 @@ static sgpu_status fastq_ids_into(sgpu_ctx *c, const uint8_t *d_buf, size_t n, s
             return SGPU_OK;
         }
     }
+    if (spec) return SGPU_ERR_PHASE_UNKNOWN;
     DevBuf<uint64_t> nlpos, key_off, scratch;
     DevBuf<uint32_t> key_len;
     DevBuf<uint8_t> sel;
@@ -220,6 +224,7 @@ const char *sgpu_strerror(int s) {
     case SGPU_ERR_HALO: return "shard halo too small: last owned record does not end inside the buffer";
     case SGPU_ERR_SAM_RECORD: return "failed to parse a SAM record";
     case SGPU_ERR_BAM_RECORD: return "failed to read a BAM header or record";
+    case SGPU_ERR_PHASE_UNKNOWN: return "shard needs the exact newlines_before / crlf (speculation not applicable)";
     default: return "unknown status";
     }
 }
@@ -340,50 +345,60 @@ sgpu_status sgpu_clean_fastq_dev(sgpu_ctx *c, const sgpu_idset *set, const uint8
 static sgpu_status clean_shard_locked(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in,
                                       size_t own_len, uint64_t newlines_before, int is_first, int is_last, int crlf,
                                       int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o,
-                                      size_t cap_o, size_t *n_o, sgpu_counts *counts);
+                                      size_t cap_o, size_t *n_o, sgpu_counts *counts, bool want_nl);
 
 sgpu_status sgpu_clean_fastq_shard_dev(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in,
                                        size_t own_len, uint64_t newlines_before, int is_first, int is_last, int crlf,
                                        int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o,
                                        size_t cap_o, size_t *n_o, sgpu_counts *counts) {
     if (!c || !set || !n_w || !counts || (n_in && !d_in) || own_len > n_in || (is_last && own_len != n_in) ||
-        (is_first && newlines_before != 0))
+        (is_first && newlines_before != 0) || crlf < -1 || crlf > 1 || (!is_first && crlf < 0 && newlines_before != SGPU_NEWLINES_UNKNOWN))
         return SGPU_ERR_INVALID_ARG;
     if (n_in && ((uintptr_t)d_in & 15)) return SGPU_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     SGPU_CUDA(cudaSetDevice(c->device));
     return clean_shard_locked(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, crlf, reverse, d_out_w,
-                              cap_w, n_w, d_out_o, cap_o, n_o, counts);
+                              cap_w, n_w, d_out_o, cap_o, n_o, counts, crlf < 0);
 }
 
-// shard body shared by sgpu_clean_fastq_shard_dev and the pipelined host path (context locked, device set)
+// shard body shared by sgpu_clean_fastq_shard_dev and the pipelined host path (context locked, device set).
+// want_nl: when the single-pass kernel produces the result, counts->own_newlines is filled from its per-tile counts
 static sgpu_status clean_shard_locked(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in,
                                       size_t own_len, uint64_t newlines_before, int is_first, int is_last, int crlf,
                                       int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w, uint8_t *d_out_o,
-                                      size_t cap_o, size_t *n_o, sgpu_counts *counts) {
+                                      size_t cap_o, size_t *n_o, sgpu_counts *counts, bool want_nl) {
     memset(counts, 0, sizeof(*counts));
     *n_w = 0;
     if (n_o) *n_o = 0;
-    if (c->mode == 0 && !crlf && n_in >= 5) {
+    // crlf == -1: not exchanged yet.  The single-pass kernel only takes LF input, so whatever it produces is right for a
+    // file whose first record is LF (the caller checks shard 0's counts->crlf); the first shard decides it itself.
+    const bool spec = !is_first && (newlines_before == SGPU_NEWLINES_UNKNOWN || crlf < 0);
+    if (spec && newlines_before != SGPU_NEWLINES_UNKNOWN) return SGPU_ERR_INVALID_ARG;
+    if (c->mode == 0 && crlf <= 0 && n_in >= 5) {
         int used = 0;
         SGPU_TRY(clean_fused_shard(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, reverse, d_out_w,
-                                   cap_w, n_w, d_out_o, cap_o, n_o, counts, &used));
+                                   cap_w, n_w, d_out_o, cap_o, n_o, counts, &used, want_nl));
         if (used) return SGPU_OK;
         memset(counts, 0, sizeof(*counts));
         *n_w = 0;
         if (n_o) *n_o = 0;
     }
-    return clean_general(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, crlf ? 1 : 0, reverse,
-                         d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
+    if (spec) return SGPU_ERR_PHASE_UNKNOWN;  // the exact protocol (newline counts exchanged first) takes over
+    return clean_general(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, is_first && crlf < 0 ? -1 : (crlf ? 1 : 0),
+                         reverse, d_out_w, cap_w, n_w, d_out_o, cap_o, n_o, counts);
 }
 
-// Host buffers, large input: the file goes through the GPU in chunks (shards of one device) so that the
-// host->device copy of chunk k+1.., the kernels of chunk k and the device->host copy of chunk k-1 overlap on
+// Host buffers, large input: the file (or one shard of it) goes through the GPU in chunks (shards of one device) so
+// that the host->device copy of chunk k+1.., the kernels of chunk k and the device->host copy of chunk k-1 overlap on
 // three streams -- the end-to-end time approaches the PCIe time of the larger direction instead of the sum.
 // Results are identical to the one-shot path (the same shard logic the multi-GPU driver uses: line phase
 // from the running newline count, the record that straddles a cut belongs to the chunk where it starts).
+// The buffer is a shard in the sense of sgpu_clean_fastq_shard_dev: own bytes [0, own_len) + halo; a whole file is the
+// shard (n_in, n_in, 0, first, last).  newlines_before == SGPU_NEWLINES_UNKNOWN: chunk 0 speculates the line phase, the
+// later chunks continue from it, counts->{own_newlines, lead_newlines} let the caller verify it.
 // *done = 0: not applicable here (small input, halo too small for a record ...), take the one-shot path.
-static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *in, size_t n_in, int reverse,
+static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *in, size_t n_in, size_t own_len,
+                                        uint64_t newlines_before, int is_first, int is_last, int crlf_in, int reverse,
                                         uint8_t *out_w, size_t cap_w, size_t *n_w, uint8_t *out_o, size_t cap_o,
                                         size_t *n_o, sgpu_counts *counts, int *done) {
     *done = 0;
@@ -391,18 +406,23 @@ static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, cons
     const size_t CHUNK = getenv("SGPU_PIPE_CHUNK") ? (size_t)atoll(getenv("SGPU_PIPE_CHUNK")) & ~(size_t)15
                                                    : (size_t)128 << 20;
     const size_t HALO = getenv("SGPU_PIPE_HALO") ? (size_t)atoll(getenv("SGPU_PIPE_HALO")) : (size_t)8 << 20;
-    if (CHUNK < 4096 || n_in < 2 * CHUNK || c->mode != 0) return SGPU_OK;
-    if (in[0] != '@') return SGPU_OK;  // FASTA / unknown format: the one-shot path reports it
-    // needletail decides the line ending on the first record's first line
-    const uint8_t *nl = (const uint8_t *)memchr(in, '\n', n_in);
-    const int crlf = nl && nl > in && nl[-1] == '\r';
+    if (CHUNK < 4096 || own_len < 2 * CHUNK || c->mode != 0) return SGPU_OK;
+    if (is_first && in[0] != '@') return SGPU_OK;  // FASTA / unknown format: the one-shot path reports it
+    const bool spec = !is_first && newlines_before == SGPU_NEWLINES_UNKNOWN;
+    int crlf = crlf_in > 0;
+    if (is_first) {  // needletail decides the line ending on the first record's first line
+        const uint8_t *nl = (const uint8_t *)memchr(in, '\n', n_in);
+        crlf = nl && nl > in && nl[-1] == '\r';
+    }
     if (!c->s_in) {
         SGPU_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         SGPU_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     }
     cudaStream_t st = c->stream;
-    const size_t K = ceil_div(n_in, CHUNK);
-    const size_t obuf = CHUNK + HALO + 64;
+    const size_t K = ceil_div(own_len, CHUNK);  // kernel chunks: the owned range
+    const size_t U = ceil_div(n_in, CHUNK);     // upload pieces: the whole buffer (own range + halo)
+    const size_t tail_halo = n_in - own_len;
+    const size_t obuf = CHUNK + std::max(HALO, tail_halo) + 64;
     // context-owned staging (the context is locked): 0 the file, 1-2 kept chunks, 3-4 removed chunks
     auto staging = [&](int i, size_t bytes, uint8_t **p) -> sgpu_status {
         if (c->pipe_cap[i] < bytes) {
@@ -430,9 +450,9 @@ static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, cons
         if (out_o) SGPU_TRY(staging(3 + r, obuf, &d_o[r].p));
     }
     SGPU_CUDA(cudaStreamSynchronize(st));  // earlier work on `st` that used the staging is done
-    std::vector<cudaEvent_t> ev_in(K);
+    std::vector<cudaEvent_t> ev_in(U);
     cudaEvent_t ev_k[2], ev_out[2];
-    for (size_t k = 0; k < K; k++) SGPU_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+    for (size_t k = 0; k < U; k++) SGPU_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
     for (int r = 0; r < 2; r++) {
         SGPU_CUDA(cudaEventCreateWithFlags(&ev_k[r], cudaEventDisableTiming));
         SGPU_CUDA(cudaEventCreateWithFlags(&ev_out[r], cudaEventDisableTiming));
@@ -445,30 +465,41 @@ static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, cons
     };
     sgpu_status rc = SGPU_OK;
     size_t off_w = 0, off_o = 0;
-    uint64_t newlines_before = 0;
-    bool bail = false;
+    uint64_t nb = spec ? 0 : newlines_before;  // running count: exact, or relative to the speculated phase
+    uint64_t own_nl_total = 0, lead_nl = 0;
+    bool bail = false, unknown = false;
     sgpu_counts total;
     memset(&total, 0, sizeof(total));
     total.path = 1;
     cudaError_t ce = cudaSuccess;
-    for (size_t k = 0; k < std::min<size_t>(K, 3) && ce == cudaSuccess; k++) ce = upload(k);
+    size_t up_next = 0;
+    for (; up_next < std::min<size_t>(U, 3) && ce == cudaSuccess; up_next++) ce = upload(up_next);
     for (size_t k = 0; k < K && ce == cudaSuccess && rc == SGPU_OK && !bail; k++) {
-        if (k + 3 < K) ce = upload(k + 3);  // keep the copy engine three chunks ahead
         const int r = (int)(k & 1);
-        const size_t a = k * CHUNK, own = std::min(CHUNK, n_in - a);
-        const int is_last = k + 1 == K;
-        const size_t buf_len = is_last ? own : std::min(n_in - a, own + HALO);
-        // the chunk and its halo (inside the next chunks) are on the device; the output buffer is free again
-        for (size_t j = k; j < K && j * CHUNK < a + buf_len; j++) cudaStreamWaitEvent(st, ev_in[j], 0);
+        const size_t a = k * CHUNK, own = std::min(CHUNK, own_len - a);
+        const bool last_chunk = k + 1 == K;
+        const size_t buf_len = last_chunk ? n_in - a : std::min(n_in - a, own + HALO);
+        // keep the copy engine three pieces ahead, and at least as far as this chunk's halo reaches
+        while (up_next < U && ce == cudaSuccess && (up_next < k + 4 || up_next * CHUNK < a + buf_len)) ce = upload(up_next++);
+        if (ce != cudaSuccess) break;
+        // the chunk and its halo (inside the next pieces) are on the device; the output buffer is free again
+        for (size_t j = k; j < U && j * CHUNK < a + buf_len; j++) cudaStreamWaitEvent(st, ev_in[j], 0);
         if (k >= 2) cudaStreamWaitEvent(st, ev_out[r], 0);
         size_t nw = 0, no = 0;
         sgpu_counts ck;
-        rc = clean_shard_locked(c, set, d_in.p + a, buf_len, own, newlines_before, k == 0, is_last, crlf, reverse,
-                                d_w[r].p, obuf, &nw, out_o ? d_o[r].p : nullptr, obuf, &no, &ck);
+        const bool spec0 = spec && k == 0;
+        rc = clean_shard_locked(c, set, d_in.p + a, buf_len, own, spec0 ? SGPU_NEWLINES_UNKNOWN : nb, is_first && k == 0,
+                                last_chunk && is_last, spec0 ? -1 : crlf, reverse, d_w[r].p, obuf, &nw,
+                                out_o ? d_o[r].p : nullptr, obuf, &no, &ck, true);
         if (getenv("SGPU_DEBUG"))
             fprintf(stderr, "[sgpu] pipe chunk %zu/%zu a=%zu own=%zu buf=%zu nlb=%llu -> rc=%d nw=%zu no=%zu in=%llu out=%llu path=%u\n",
-                    k, K, a, own, buf_len, (unsigned long long)newlines_before, (int)rc, nw, no,
+                    k, K, a, own, buf_len, (unsigned long long)nb, (int)rc, nw, no,
                     (unsigned long long)ck.reads_in, (unsigned long long)ck.reads_out, ck.path);
+        if (rc == SGPU_ERR_PHASE_UNKNOWN || (spec && rc == SGPU_OK && ck.path != 1)) {
+            rc = SGPU_OK;  // speculation not applicable: the caller comes back with the exact phase
+            unknown = true;
+            break;
+        }
         if (rc == SGPU_ERR_HALO) {  // a record longer than the halo: the one-shot path handles any length
             rc = SGPU_OK;
             bail = true;
@@ -498,16 +529,20 @@ static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, cons
             rc = parse_rc;
             break;
         }
-        if (!is_last) {
-            uint64_t cnt = 0;
-            rc = count_newlines(c, d_in.p + a, own, &cnt);
-            newlines_before += cnt;
+        // this chunk's newlines: a by-product of the single-pass kernel, else one counting pass
+        uint64_t cnt = ck.own_newlines;
+        if (ck.path != 1 && (!last_chunk || crlf_in < 0)) rc = count_newlines(c, d_in.p + a, own, &cnt);
+        if (spec0) {
+            lead_nl = ck.lead_newlines;
+            nb = (4 - (lead_nl & 3)) & 3;  // the phase the speculation stands for
         }
+        nb += cnt;
+        own_nl_total += cnt;
     }
     cudaStreamSynchronize(c->s_in);
     cudaStreamSynchronize(c->s_out);
     cudaStreamSynchronize(st);
-    for (size_t k = 0; k < K; k++) cudaEventDestroy(ev_in[k]);
+    for (size_t k = 0; k < U; k++) cudaEventDestroy(ev_in[k]);
     for (int r = 0; r < 2; r++) {
         cudaEventDestroy(ev_k[r]);
         cudaEventDestroy(ev_out[r]);
@@ -516,9 +551,19 @@ static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, cons
         set_cuda_error(ce, __FILE__, __LINE__);
         return SGPU_ERR_CUDA;
     }
+    if (unknown) {
+        *done = 1;
+        memset(counts, 0, sizeof(*counts));
+        *n_w = 0;
+        if (n_o) *n_o = 0;
+        return SGPU_ERR_PHASE_UNKNOWN;
+    }
     if (bail) return SGPU_OK;  // *done stays 0
     *done = 1;
     *counts = total;
+    counts->own_newlines = own_nl_total;
+    counts->lead_newlines = lead_nl;
+    counts->speculated = spec ? 1 : 0;
     *n_w = off_w;
     if (n_o) *n_o = out_o ? off_o : 0;
     return rc;
@@ -533,18 +578,63 @@ sgpu_status sgpu_clean_fastq(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *
     cudaStream_t st = c->stream;
     {
         int done = 0;
-        sgpu_status prc =
-            clean_host_pipelined(c, set, in, n_in, reverse, out_w, cap_w, n_w, out_o, cap_o, n_o, counts, &done);
+        sgpu_status prc = clean_host_pipelined(c, set, in, n_in, n_in, 0, 1, 1, -1, reverse, out_w, cap_w, n_w, out_o,
+                                               cap_o, n_o, counts, &done);
         if (done || prc != SGPU_OK) return prc;
     }
     DevBuf<uint8_t> d_in, d_w, d_o;
     SGPU_TRY(d_in.alloc(n_in + 16, st));
-    SGPU_TRY(d_w.alloc(cap_w + 16, st));
-    if (out_o) SGPU_TRY(d_o.alloc(cap_o + 16, st));
     if (n_in) SGPU_CUDA(cudaMemcpyAsync(d_in.p, in, n_in, cudaMemcpyHostToDevice, st));
-    sgpu_status rc = clean_dev_locked(c, set, d_in.p, n_in, reverse, d_w.p, cap_w, n_w, out_o ? d_o.p : nullptr, cap_o,
-                                      n_o, counts);
+    // write_fastq's output is the input re-serialised: larger only when LF records follow a CRLF first record (every
+    // record is then written with CRLF, +4 bytes each).  Device buffers are sized for the common case first.
+    sgpu_status rc = SGPU_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const size_t want = attempt ? ~(size_t)0 : n_in + n_in / 16 + 4096;
+        const size_t dcap_w = std::min(cap_w, want), dcap_o = std::min(cap_o, want);
+        SGPU_TRY(d_w.alloc(dcap_w + 16, st));
+        if (out_o) SGPU_TRY(d_o.alloc(dcap_o + 16, st));
+        rc = clean_dev_locked(c, set, d_in.p, n_in, reverse, d_w.p, dcap_w, n_w, out_o ? d_o.p : nullptr, dcap_o, n_o,
+                              counts);
+        if (rc != SGPU_ERR_CAPACITY || (dcap_w == cap_w && (!out_o || dcap_o == cap_o))) break;
+    }
     if (rc == SGPU_ERR_CAPACITY || rc == SGPU_ERR_CUDA || rc == SGPU_ERR_NOMEM) return rc;
+    if (*n_w) SGPU_CUDA(cudaMemcpyAsync(out_w, d_w.p, *n_w, cudaMemcpyDeviceToHost, st));
+    if (out_o && n_o && *n_o) SGPU_CUDA(cudaMemcpyAsync(out_o, d_o.p, *n_o, cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+sgpu_status sgpu_clean_fastq_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *in, size_t n_in, size_t own_len,
+                                   uint64_t newlines_before, int is_first, int is_last, int crlf, int reverse,
+                                   uint8_t *out_w, size_t cap_w, size_t *n_w, uint8_t *out_o, size_t cap_o, size_t *n_o,
+                                   sgpu_counts *counts) {
+    if (!c || !set || !n_w || !counts || (n_in && !in) || (cap_w && !out_w) || own_len > n_in ||
+        (is_last && own_len != n_in) || (is_first && newlines_before != 0) || crlf < -1 || crlf > 1 ||
+        (!is_first && crlf < 0 && newlines_before != SGPU_NEWLINES_UNKNOWN))
+        return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    {
+        int done = 0;
+        sgpu_status prc = clean_host_pipelined(c, set, in, n_in, own_len, newlines_before, is_first, is_last, crlf, reverse,
+                                               out_w, cap_w, n_w, out_o, cap_o, n_o, counts, &done);
+        if (done || prc != SGPU_OK) return prc;
+    }
+    DevBuf<uint8_t> d_in, d_w, d_o;
+    SGPU_TRY(d_in.alloc(n_in + 16, st));
+    if (n_in) SGPU_CUDA(cudaMemcpyAsync(d_in.p, in, n_in, cudaMemcpyHostToDevice, st));
+    sgpu_status rc = SGPU_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const size_t want = attempt ? ~(size_t)0 : n_in + n_in / 16 + 4096;
+        const size_t dcap_w = std::min(cap_w, want), dcap_o = std::min(cap_o, want);
+        SGPU_TRY(d_w.alloc(dcap_w + 16, st));
+        if (out_o) SGPU_TRY(d_o.alloc(dcap_o + 16, st));
+        rc = clean_shard_locked(c, set, d_in.p, n_in, own_len, newlines_before, is_first, is_last, crlf, reverse, d_w.p,
+                                dcap_w, n_w, out_o ? d_o.p : nullptr, dcap_o, n_o, counts, crlf < 0);
+        if (rc != SGPU_ERR_CAPACITY || (dcap_w == cap_w && (!out_o || dcap_o == cap_o))) break;
+    }
+    if (rc == SGPU_ERR_CAPACITY || rc == SGPU_ERR_CUDA || rc == SGPU_ERR_NOMEM || rc == SGPU_ERR_PHASE_UNKNOWN) return rc;
     if (*n_w) SGPU_CUDA(cudaMemcpyAsync(out_w, d_w.p, *n_w, cudaMemcpyDeviceToHost, st));
     if (out_o && n_o && *n_o) SGPU_CUDA(cudaMemcpyAsync(out_o, d_o.p, *n_o, cudaMemcpyDeviceToHost, st));
     SGPU_CUDA(cudaStreamSynchronize(st));
@@ -585,11 +675,16 @@ sgpu_status sgpu_fastq_ids_shard_dev(sgpu_ctx *c, const sgpu_idset *probe, const
     std::lock_guard<std::mutex> lk(c->mu);
     SGPU_CUDA(cudaSetDevice(c->device));
     uint64_t n_rec = 0, n_pick = 0, err = 0;
+    sgpu_counts spec;
+    memset(&spec, 0, sizeof(spec));
     sgpu_status rc = fastq_ids_into(c, d_buf, n_buf, own_len, newlines_before, is_first, is_last, probe, probe != nullptr,
-                                    into, &n_rec, &n_pick, &err);
+                                    into, &n_rec, &n_pick, &err, &spec);
     if (rc == SGPU_OK) {
         counts->reads_in += n_rec;
         counts->difference += n_pick;
+        counts->speculated = spec.speculated;
+        counts->own_newlines = spec.own_newlines;
+        counts->lead_newlines = spec.lead_newlines;
     } else {
         counts->error_record = err;
     }

@@ -109,7 +109,8 @@ struct sgpu_idset {
     sgpu_ctx *ctx = nullptr;  // owner of the stream the buffers were allocated on
     int device = 0;
     Slot *d_table = nullptr;
-    uint64_t capacity = 0;  // slots, power of two (0 = no table yet)
+    uint64_t n_buckets = 0;  // 128-byte buckets of eight slots, any number (0 = no table yet)
+    uint64_t slots() const { return n_buckets * 8; }
     uint8_t *d_arena = nullptr;
     uint64_t arena_used = 0, arena_cap = 0;
     uint64_t count = 0;      // distinct non-empty ids

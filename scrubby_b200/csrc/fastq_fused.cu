@@ -110,6 +110,8 @@ struct FusedResult {
     unsigned long long reason;      // first fallback reason (diagnostics)
     unsigned long long owned_end;   // end of the last owned record (shards); ~0 when no foreign record was seen
     unsigned long long n_spans;     // ids mode: id tokens emitted
+    unsigned long long overflow;    // != 0: an output buffer was too small (nothing is written past its capacity)
+    unsigned long long own_newlines;  // shards: '\n' bytes in the owned range (fused_own_newlines_kernel)
 };
 
 struct FusedParams {
@@ -120,6 +122,7 @@ struct FusedParams {
     uint32_t lead;     // bytes before the first record start (< 16; they belong to the previous shard)
     int is_last;       // the buffer ends at the end of the file
     uint8_t *out_w, *out_o;
+    uint64_t cap_w, cap_o;  // capacities of the two outputs: a copy item that would end past one raises `overflow`
     int reverse;
     IdSetView set;
     unsigned long long *desc1, *desc2;  // per tile look-back descriptors (zero initialised)
@@ -453,9 +456,6 @@ __device__ __forceinline__ RecPrep record_prepare(uint32_t tile_s, uint32_t sp, 
     R.mode = 1;
     return R;
 }
-__device__ __forceinline__ uint64_t inline_home(uint64_t lo, uint64_t hi) {
-    return mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL));
-}
 // general token scan + probe: skip leading blanks, run to the next blank / newline
 __device__ __forceinline__ bool record_probe_scan(const IdSetView &set, const uint8_t *tile, uint32_t sp, uint32_t avail,
                                                   uint32_t *why, uint32_t *tok_a, uint32_t *tok_len) {
@@ -481,33 +481,40 @@ __device__ __noinline__ bool record_probe_slow_span(const IdSetView &set, const 
                                                     uint32_t avail, uint32_t *why, uint32_t *tok_a, uint32_t *tok_len) {
     return record_probe_scan(set, tile, sp, avail, why, tok_a, tok_len);
 }
-// the home bucket of an inline key: four slots, one 64-byte burst, four independent loads
+// the first HALF of the home bucket of an inline key: four independent 16-byte loads of one 128-byte line.  The
+// occupied slots of a bucket are a prefix of it, so the second half is only looked at when the first is full of
+// other keys (the line is in L1 by then: ld.global.nc allocates)
+constexpr int HALF = 4;
 struct Bucket {
-    Slot s[IDSET_BUCKET];
+    Slot s[HALF];
 };
 __device__ __forceinline__ Bucket load_bucket(const IdSetView &set, uint64_t lo, uint64_t hi) {
-    const Slot *bp = set.table + home_slot(inline_home(lo, hi), set.mask);
+    const Slot *bp = set.table + home_bucket(inline_hash(lo, hi), set.n_buckets) * IDSET_BUCKET;
     Bucket B;
 #pragma unroll
-    for (int q = 0; q < (int)IDSET_BUCKET; q++) B.s[q] = load_slot(bp + q);
+    for (int q = 0; q < HALF; q++) B.s[q] = load_slot(bp + q);
     return B;
 }
-// exact membership given the home bucket; the probe sequence only leaves it when all four slots are taken
-// by other keys (< 1 % of the lookups at load <= 0.2)
+// exact membership given the first half of the home bucket
 __device__ __forceinline__ bool probe_bucket(const IdSetView &set, const Bucket &B, uint64_t lo, uint64_t hi) {
     bool hit = false, open = false;
 #pragma unroll
-    for (int q = 0; q < (int)IDSET_BUCKET; q++) {
+    for (int q = 0; q < HALF; q++) {
         hit |= B.s[q].lo == lo && B.s[q].hi == hi;
         open |= (B.s[q].lo | B.s[q].hi) == 0;
     }
     if (hit || open) return hit;
-    uint64_t idx = home_slot(inline_home(lo, hi), set.mask) + (IDSET_BUCKET - 1);
+    uint64_t b = home_bucket(inline_hash(lo, hi), set.n_buckets);
+    int q = HALF;
     while (true) {
-        idx = (idx + 1) & set.mask;
-        const Slot sl = load_slot(set.table + idx);
-        if ((sl.lo | sl.hi) == 0) return false;
-        if (sl.lo == lo && sl.hi == hi) return true;
+        const Slot *bp = set.table + b * IDSET_BUCKET;
+        for (; q < (int)IDSET_BUCKET; q++) {
+            const Slot sl = load_slot(bp + q);
+            if ((sl.lo | sl.hi) == 0) return false;
+            if (sl.lo == lo && sl.hi == hi) return true;
+        }
+        q = 0;
+        b = next_bucket(b, set.n_buckets);
     }
 }
 
@@ -904,7 +911,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                             const bool inl = R.mode == 1 && !why && P.set.table != nullptr;
                             Bucket first;
 #pragma unroll
-                            for (int q = 0; q < (int)IDSET_BUCKET; q++) first.s[q].lo = first.s[q].hi = 0;
+                            for (int q = 0; q < HALF; q++) first.s[q].lo = first.s[q].hi = 0;
 #ifndef SGPU_ABL_NOPROBE
                             if (inl) first = load_bucket(P.set, R.lo, R.hi);
 #endif
@@ -1093,14 +1100,21 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                 const Item itm = S->items[i];
                 const uint32_t tag = itm.rel & (3u << 30), rel = itm.rel & 0x3FFFFFFFu;
                 uint8_t *dst;
+                bool to_w = true;
                 if (tag == TAG_KEPT) {
                     dst = base_w + head_kept + rel;
                 } else if (tag == TAG_OTHER) {
                     dst = base_o + head_other + rel;
+                    to_w = false;
                 } else {
                     if (carry == F_KEPT) dst = base_w + rel;
-                    else if (carry == F_OTHER && base_o) dst = base_o + rel;
+                    else if (carry == F_OTHER && base_o) dst = base_o + rel, to_w = false;
                     else continue;
+                }
+                // the outputs are sized by the caller (a depleted file is smaller than its input): never write past them
+                if ((uint64_t)(dst - (to_w ? P.out_w : P.out_o)) + itm.len > (to_w ? P.cap_w : P.cap_o)) {
+                    if (lane == 0) P.res->overflow = 1;
+                    continue;
                 }
 #ifndef SGPU_ABL_NOCOPY  // ablation (timing only): nothing is written
                 copy_piece(tile_s + itm.src, itm.len, dst, lane);
@@ -1158,14 +1172,39 @@ struct IdsOut {
     uint64_t base;     // out: the spans' offsets are relative to d_in + base
 };
 
+// '\n' bytes in [lead, own_len) of the range the fused kernel ran over, from its per-tile counts (whole tiles below
+// own_len: the exclusive prefix) plus the bytes of the one tile own_len cuts.  One CTA.
+__global__ void fused_own_newlines_kernel(const uint8_t *in, uint32_t lead, uint64_t own_len, const uint64_t *nl_prefix,
+                                          const uint32_t *nl_count, uint64_t n_tiles, FusedResult *res) {
+    const uint64_t tb = own_len / (uint64_t)TILE;
+    uint64_t a = own_len;
+    if (tb < n_tiles) a = tb * (uint64_t)TILE;  // (16-byte aligned)
+    uint32_t cnt = 0;
+    for (uint64_t pos = a + (uint64_t)threadIdx.x * 16; pos < own_len; pos += (uint64_t)blockDim.x * 16) {
+        uint32_t m = nl_mask16_v2(ld_nc_u4(in + pos));  // (the buffer is readable up to a multiple of 16 past n_in)
+        if (own_len - pos < 16) m &= (1u << (own_len - pos)) - 1u;
+        if (pos < lead) m &= ~((1u << (lead - pos)) - 1u);
+        cnt += __popc(m);
+    }
+    __shared__ unsigned int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t whole = tb < n_tiles ? nl_prefix[tb] : nl_prefix[n_tiles - 1] + nl_count[n_tiles - 1];
+        res->own_newlines = whole + s_cnt;
+    }
+}
+
+// want_own_nl: also count the '\n' bytes of [lead, own_len) into counts->own_newlines (speculative shards)
 sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, uint32_t lead,
                               size_t own_len, int is_last, int reverse, uint8_t *d_out_w, size_t cap_w, size_t *n_w,
                               uint8_t *d_out_o, size_t cap_o, size_t *n_o, sgpu_counts *counts, int *used,
-                              IdsOut *ids = nullptr) {
+                              IdsOut *ids = nullptr, bool want_own_nl = false) {
     *used = 0;
-    // the fused kernel writes a byte partition of the input: both outputs must be able to hold it
     if (n_in == 0 || lead >= 16) return SGPU_OK;
-    if (!ids && (cap_w < n_in || (d_out_o && cap_o < n_in))) return SGPU_OK;
+    // (the outputs may be smaller than the input: the kernel never writes past cap_w / cap_o and reports it)
     cudaStream_t st = c->stream;
     static bool attr_done[64] = {false};
     const size_t smem = sizeof(CtaSmem);
@@ -1205,6 +1244,8 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     P.is_last = is_last;
     P.out_w = d_out_w;
     P.out_o = d_out_o;
+    P.cap_w = cap_w;
+    P.cap_o = d_out_o ? cap_o : 0;
     P.reverse = reverse;
     P.set = view_of(set);
     P.desc1 = desc.p;
@@ -1259,6 +1300,10 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
                                                                          prefix.p + n_tiles, nl_count.p, P.phase_used,
                                                                          n_tiles, is_last, res.p);
     SGPU_LAUNCH(c);
+    if (want_own_nl) {
+        fused_own_newlines_kernel<<<1, 1024, 0, st>>>(d_in, lead, own_len, prefix.p + n_tiles, nl_count.p, n_tiles, res.p);
+        SGPU_LAUNCH(c);
+    }
     SGPU_CUDA(cudaGetLastError());
     FusedResult h;
     SGPU_TRY(read_u64s(c, res.p, (uint64_t *)&h, sizeof(FusedResult) / 8));
@@ -1295,7 +1340,9 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
         if (getenv("SGPU_DEBUG")) fprintf(stderr, "[sgpu] fused kernel fell back, reason %llu\n", h.reason);
         return SGPU_OK;
     }
+    if (h.overflow) return SGPU_ERR_CAPACITY;
     *used = 1;
+    counts->own_newlines = want_own_nl ? h.own_newlines : 0;
     if (ids) {
         ids->n_spans = h.n_spans;
         counts->reads_in = h.reads_in;
@@ -1314,12 +1361,12 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     return SGPU_OK;
 }
 
-// position of the (k+1)-th '\n' of buf[0..n), or ~0: one warp, 512 bytes per step (shards: the first record
-// boundary lies within the first record's length of the cut)
-__global__ void kth_newline_kernel(const uint8_t *buf, uint64_t n, uint32_t k, unsigned long long *out) {
+// positions of the first four '\n' bytes of buf[0..n) (~0 where there is none): one warp, 512 bytes per step (shards:
+// the first record boundary lies within the first record's length of the cut)
+__global__ void first_newlines_kernel(const uint8_t *buf, uint64_t n, unsigned long long *out) {
     const int lane = threadIdx.x;
     uint32_t seen = 0;
-    for (uint64_t base = 0; base < n; base += 512) {
+    for (uint64_t base = 0; base < n && seen < 4; base += 512) {
         const uint64_t pos = base + (uint64_t)lane * 16;
         uint32_t m = 0;
         if (pos < n) {
@@ -1332,57 +1379,79 @@ __global__ void kth_newline_kernel(const uint8_t *buf, uint64_t n, uint32_t k, u
             const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += x;
         }
-        const uint32_t before = seen + inc - __popc(m);
-        if (before <= k && k < before + __popc(m)) {
-            uint32_t mm = m;
-            for (uint32_t i = before; i < k; i++) mm &= mm - 1;
-            *out = pos + (uint64_t)(__ffs(mm) - 1);
-        }
+        uint32_t idx = seen + inc - __popc(m);  // index of this lane's first newline
+        for (uint32_t mm = m; mm && idx < 4; mm &= mm - 1, idx++) out[idx] = pos + (uint64_t)(__ffs(mm) - 1);
         seen += __shfl_sync(0xffffffffu, inc, 31);
-        if (seen > k) return;
+    }
+    // out[4 + i] = 1 when newline i is followed by "+\n" (the end of a sequence line of canonical FASTQ)
+    __syncwarp();
+    if (lane < 4) {
+        const unsigned long long p = *((volatile unsigned long long *)out + lane);
+        out[4 + lane] = (p != ~0ull && p + 2 < n && buf[p + 1] == '+' && buf[p + 2] == '\n') ? 1ull : 0ull;
     }
 }
 
 // one shard (see sgpu_clean_fastq_shard_dev): locate the first owned record start, then run the fused kernel
 // from the 16-byte aligned address below it.  *used = 0: take the general path.
+// newlines_before == SGPU_NEWLINES_UNKNOWN: the line phase is SPECULATED from the first "\n+\n" among the shard's first
+// four newlines (it ends a sequence line, so the newline two places before / behind it ends a record); the caller
+// verifies (true newlines_before + counts->lead_newlines) % 4 == 0 once the shards' own_newlines are exchanged.
 static sgpu_status fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
                                uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
                                size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
-                               sgpu_counts *counts, int *used, IdsOut *ids) {
+                               sgpu_counts *counts, int *used, IdsOut *ids, bool want_nl = false) {
     *used = 0;
-    uint64_t s0 = 0;
+    const bool spec = newlines_before == SGPU_NEWLINES_UNKNOWN;
+    want_nl = want_nl || spec;
+    uint64_t s0 = 0, lead_nl = 0;
     if (!is_first) {
-        // the newline that ends the previous shard's last record has global index == 3 (mod 4)
-        const uint32_t k = (uint32_t)((3 - (newlines_before & 3)) & 3);
         DevBuf<unsigned long long> pos;
-        SGPU_TRY(pos.alloc(1, c->stream));
-        SGPU_CUDA(cudaMemsetAsync(pos.p, 0xFF, 8, c->stream));
-        kth_newline_kernel<<<1, 32, 0, c->stream>>>(d_in, n_in, k, pos.p);
+        SGPU_TRY(pos.alloc(8, c->stream));
+        SGPU_CUDA(cudaMemsetAsync(pos.p, 0xFF, 64, c->stream));
+        first_newlines_kernel<<<1, 32, 0, c->stream>>>(d_in, n_in, pos.p);
         SGPU_LAUNCH(c);
-        uint64_t p;
-        SGPU_TRY(read_u64s(c, pos.p, &p, 1));
-        if (p == ~0ull) return SGPU_OK;  // no record boundary in the buffer: the general path sorts it out
-        s0 = p + 1;
+        uint64_t h[8];
+        SGPU_TRY(read_u64s(c, pos.p, h, 8));
+        uint32_t k;  // index of the first newline that ends a record
+        if (spec) {
+            uint32_t j = 0;
+            while (j < 4 && !(h[j] != ~0ull && h[4 + j] == 1)) j++;
+            if (j == 4) return SGPU_OK;  // no "\n+\n" in sight: not canonical here, the exact protocol decides
+            k = (2 + j) & 3;             // newline j has role 1 => newline j + 2 (mod 4) has role 3
+        } else {
+            // the newline that ends the previous shard's last record has global index == 3 (mod 4)
+            k = (uint32_t)((3 - (newlines_before & 3)) & 3);
+        }
+        if (h[k] == ~0ull) return SGPU_OK;  // no record boundary in the buffer: the general path sorts it out
+        s0 = h[k] + 1;
+        lead_nl = k + 1;
         if (s0 >= n_in || s0 > own_len) return SGPU_OK;  // owns nothing (general path: zero records / errors)
     }
     const uint32_t lead = (uint32_t)(s0 & 15);
     const uint64_t skip = s0 - lead;
+    sgpu_status rc;
     if (ids) {  // span offsets are relative to the range the kernel sees: rebase them to d_in afterwards
-        sgpu_status rc = clean_fused_range(c, set, d_in + skip, n_in - skip, lead, own_len - skip, is_last, reverse,
-                                           nullptr, 0, nullptr, nullptr, 0, nullptr, counts, used, ids);
+        rc = clean_fused_range(c, set, d_in + skip, n_in - skip, lead, own_len - skip, is_last, reverse, nullptr, 0,
+                               nullptr, nullptr, 0, nullptr, counts, used, ids, want_nl);
         ids->base = skip;
-        return rc;
+    } else {
+        rc = clean_fused_range(c, set, d_in + skip, n_in - skip, lead, own_len - skip, is_last, reverse, d_out_w, cap_w,
+                               n_w, d_out_o, cap_o, n_o, counts, used, nullptr, want_nl);
     }
-    return clean_fused_range(c, set, d_in + skip, n_in - skip, lead, own_len - skip, is_last, reverse, d_out_w, cap_w,
-                             n_w, d_out_o, cap_o, n_o, counts, used);
+    if (want_nl && *used) {
+        counts->lead_newlines = lead_nl;
+        counts->own_newlines += lead_nl;  // [0, s0) + [s0, own_len)
+        counts->speculated = spec ? 1 : 0;
+    }
+    return rc;
 }
 
 sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t *d_in, size_t n_in, size_t own_len,
                               uint64_t newlines_before, int is_first, int is_last, int reverse, uint8_t *d_out_w,
                               size_t cap_w, size_t *n_w, uint8_t *d_out_o, size_t cap_o, size_t *n_o,
-                              sgpu_counts *counts, int *used) {
+                              sgpu_counts *counts, int *used, bool want_nl) {
     return fused_shard(c, set, d_in, n_in, own_len, newlines_before, is_first, is_last, reverse, d_out_w, cap_w, n_w,
-                       d_out_o, cap_o, n_o, counts, used, nullptr);
+                       d_out_o, cap_o, n_o, counts, used, nullptr, want_nl);
 }
 
 // ReadDifference::get_difference's two loops (utils.rs:259-267, 269-283) over canonical FASTQ: the id tokens of
@@ -1390,12 +1459,14 @@ sgpu_status clean_fused_shard(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
 // (shards as in clean_fused_shard; *span_base: the offsets are relative to d_in + *span_base)
 sgpu_status ids_fused(sgpu_ctx *c, const sgpu_idset *probe, const uint8_t *d_in, size_t n_in, size_t own_len,
                       uint64_t newlines_before, int is_first, int is_last, uint64_t *span_off, uint32_t *span_len,
-                      uint64_t cap, uint64_t *n_spans, uint64_t *span_base, uint64_t *n_records, int *used) {
+                      uint64_t cap, uint64_t *n_spans, uint64_t *span_base, uint64_t *n_records, int *used,
+                      sgpu_counts *spec_out) {
     IdsOut ids{span_off, span_len, cap, 0, 0};
     sgpu_counts counts;
     memset(&counts, 0, sizeof(counts));
     SGPU_TRY(fused_shard(c, probe, d_in, n_in, own_len, newlines_before, is_first, is_last, 0, nullptr, 0, nullptr,
                          nullptr, 0, nullptr, &counts, used, &ids));
+    if (spec_out) *spec_out = counts;
     *n_spans = ids.n_spans;
     *span_base = ids.base;
     *n_records = counts.reads_in;

@@ -65,7 +65,33 @@ __global__ void idset_arena_copy_kernel(const uint8_t *src, const uint64_t *off,
     warp_copy(arena + arena_base + arena_off[w], src + off[w], L, lane);
 }
 
-__global__ void idset_insert_kernel(Slot *table, uint64_t mask, const uint8_t *arena, uint64_t arena_base,
+// walks the probe sequence of (lo, hi) from its home bucket and claims the first empty slot with a 128-bit CAS;
+// returns true when the key was new.  Slots are read first (an L2 load brings the 128-byte bucket in from DRAM
+// without occupying the L2 atomic unit for the whole miss) and the CAS is issued only on a slot seen empty.
+template <typename SameKey>
+__device__ __forceinline__ bool idset_claim(Slot *table, uint64_t n_buckets, uint64_t home, uint64_t lo, uint64_t hi,
+                                            SameKey same_key) {
+    const unsigned __int128 mine = pack128(lo, hi);
+    uint64_t b = home_bucket(home, n_buckets);
+    while (true) {
+        Slot *bp = table + b * IDSET_BUCKET;
+        for (int q = 0; q < (int)IDSET_BUCKET; q++) {
+            const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2 *>(bp + q));
+            uint64_t olo = cur.x, ohi = cur.y;
+            if ((olo | ohi) == 0) {
+                unsigned __int128 old =
+                    atomicCAS(reinterpret_cast<unsigned __int128 *>(bp + q), (unsigned __int128)0, mine);
+                if (old == 0) return true;
+                olo = (uint64_t)old;
+                ohi = (uint64_t)(old >> 64);
+            }
+            if (olo == lo && same_key(ohi)) return false;  // duplicate
+        }
+        b = next_bucket(b, n_buckets);
+    }
+}
+
+__global__ void idset_insert_kernel(Slot *table, uint64_t n_buckets, const uint8_t *arena, uint64_t arena_base,
                                     const uint8_t *src, const uint64_t *off, const uint32_t *len, const uint8_t *sel,
                                     const uint64_t *arena_off, size_t n, InsertStats *st) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,33 +104,10 @@ __global__ void idset_insert_kernel(Slot *table, uint64_t mask, const uint8_t *a
             key_image(key, L, &lo, &hi, &home);
             const bool is_inline = L <= IDSET_INLINE_MAX;
             if (!is_inline) hi = ((arena_base + arena_off[i]) << 24) | L;
-            unsigned __int128 mine = pack128(lo, hi);
-            uint64_t idx = home_slot(home, mask);
-            // Read first (an L2 load brings the 64-byte bucket in from DRAM without occupying the L2 atomic
-            // unit for the whole miss), walk occupied slots without atomics, and issue the 128-bit CAS only
-            // on a slot that was seen empty.
-            while (true) {
-                const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2 *>(table + idx));
-                uint64_t olo = cur.x, ohi = cur.y;
-                if ((olo | ohi) == 0) {
-                    unsigned __int128 old =
-                        atomicCAS(reinterpret_cast<unsigned __int128 *>(table + idx), (unsigned __int128)0, mine);
-                    if (old == 0) {
-                        fresh = true;
-                        break;
-                    }
-                    olo = (uint64_t)old;
-                    ohi = (uint64_t)(old >> 64);
-                }
-                if (olo == lo) {
-                    if (is_inline) {
-                        if (ohi == hi) break;  // duplicate
-                    } else if ((ohi & 0xFFFFFFull) == L && bytes_equal(arena + (ohi >> 24), key, L)) {
-                        break;  // duplicate (bytes verified)
-                    }
-                }
-                idx = (idx + 1) & mask;
-            }
+            fresh = idset_claim(table, n_buckets, home, lo, hi, [&](uint64_t ohi) {
+                if (is_inline) return ohi == hi;
+                return (ohi & 0xFFFFFFull) == L && bytes_equal(arena + (ohi >> 24), key, L);  // bytes verified
+            });
         }
     }
     __shared__ unsigned int s_fresh;
@@ -116,15 +119,13 @@ __global__ void idset_insert_kernel(Slot *table, uint64_t mask, const uint8_t *a
     if (threadIdx.x == 0 && s_fresh) atomicAdd(&st->inserted, (unsigned long long)s_fresh);
 }
 
-__global__ void idset_rehash_kernel(const Slot *old_table, uint64_t old_cap, Slot *table, uint64_t mask) {
+// every stored key is distinct: no comparison needed, only an empty slot
+__global__ void idset_rehash_kernel(const Slot *old_table, uint64_t old_slots, Slot *table, uint64_t n_buckets) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= old_cap) return;
+    if (i >= old_slots) return;
     Slot s = old_table[i];
     if ((s.lo | s.hi) == 0) return;
-    unsigned __int128 mine = pack128(s.lo, s.hi);
-    uint64_t idx = home_slot(slot_home(s.lo, s.hi), mask);
-    while (atomicCAS(reinterpret_cast<unsigned __int128 *>(table + idx), (unsigned __int128)0, mine) != 0)
-        idx = (idx + 1) & mask;
+    idset_claim(table, n_buckets, slot_home(s.lo, s.hi), s.lo, s.hi, [](uint64_t) { return false; });
 }
 
 // dump: per-slot byte length (id + '\n'), then flat copy
@@ -170,23 +171,25 @@ sgpu_status idset_create(sgpu_ctx *c, sgpu_idset **out) {
 
 static sgpu_status idset_reserve(sgpu_ctx *c, sgpu_idset *s, uint64_t n_new, uint64_t new_long_bytes) {
     cudaStream_t st = c->stream;
-    uint64_t need = next_pow2(std::max<uint64_t>(1024, IDSET_INV_LOAD * (s->count + n_new)));
-    if (need > s->capacity) {
+    // sized exactly for its keys at the target load; a set that grows again (diff accumulators, evidence in several
+    // calls) at least doubles, so the rehash cost stays amortised
+    uint64_t need = idset_buckets_for(s->count + n_new);
+    if (need > s->n_buckets) {
+        if (s->n_buckets) need = std::max(need, 2 * s->n_buckets);
         Slot *nt = nullptr;
-        cudaError_t e = cudaMallocAsync((void **)&nt, need * sizeof(Slot), st);
+        cudaError_t e = cudaMallocAsync((void **)&nt, need * IDSET_BUCKET * sizeof(Slot), st);  // (256-byte aligned)
         if (e != cudaSuccess) {
             set_cuda_error(e, __FILE__, __LINE__);
             return SGPU_ERR_NOMEM;
         }
-        SGPU_CUDA(cudaMemsetAsync(nt, 0, need * sizeof(Slot), st));
-        if (s->capacity && s->count) {
-            idset_rehash_kernel<<<(unsigned)ceil_div(s->capacity, 256), 256, 0, st>>>(s->d_table, s->capacity, nt,
-                                                                                      need - 1);
+        SGPU_CUDA(cudaMemsetAsync(nt, 0, need * IDSET_BUCKET * sizeof(Slot), st));
+        if (s->n_buckets && s->count) {
+            idset_rehash_kernel<<<(unsigned)ceil_div(s->slots(), 256), 256, 0, st>>>(s->d_table, s->slots(), nt, need);
             SGPU_LAUNCH(c);
         }
         if (s->d_table) SGPU_CUDA(cudaFreeAsync(s->d_table, st));
         s->d_table = nt;
-        s->capacity = need;
+        s->n_buckets = need;
     }
     if (s->arena_used + new_long_bytes > s->arena_cap) {
         uint64_t ncap = std::max<uint64_t>(s->arena_cap * 2, s->arena_used + new_long_bytes);
@@ -232,7 +235,7 @@ sgpu_status idset_insert_spans(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src,
                                                                                  s->d_arena, s->arena_used);
         SGPU_LAUNCH(c);
     }
-    idset_insert_kernel<<<grid, 256, 0, st>>>(s->d_table, s->capacity - 1, s->d_arena, s->arena_used, d_src, d_off,
+    idset_insert_kernel<<<grid, 256, 0, st>>>(s->d_table, s->n_buckets, s->d_arena, s->arena_used, d_src, d_off,
                                               d_len, d_sel, aoff.p, n, stats.p);
     SGPU_LAUNCH(c);
     SGPU_CUDA(cudaGetLastError());
@@ -330,7 +333,7 @@ sgpu_status sgpu_idset_contains(sgpu_ctx *c, const sgpu_idset *s, const char *id
         *found = s->has_empty;
         return SGPU_OK;
     }
-    if (len > IDSET_MAX_KEY || s->capacity == 0) {
+    if (len > IDSET_MAX_KEY || s->n_buckets == 0) {
         *found = 0;
         return SGPU_OK;
     }
@@ -353,21 +356,21 @@ sgpu_status sgpu_idset_dump(sgpu_ctx *c, const sgpu_idset *s, uint8_t **out, siz
     SGPU_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     std::vector<uint8_t> flat;
-    if (s->capacity && s->count) {
+    if (s->n_buckets && s->count) {
         DevBuf<uint32_t> len;
         DevBuf<uint64_t> off, total;
-        SGPU_TRY(len.alloc(s->capacity, st));
-        SGPU_TRY(off.alloc(s->capacity, st));
+        SGPU_TRY(len.alloc(s->slots(), st));
+        SGPU_TRY(off.alloc(s->slots(), st));
         SGPU_TRY(total.alloc(1, st));
-        unsigned grid = (unsigned)ceil_div(s->capacity, 256);
-        idset_dump_len_kernel<<<grid, 256, 0, st>>>(s->d_table, s->capacity, len.p);
+        unsigned grid = (unsigned)ceil_div(s->slots(), 256);
+        idset_dump_len_kernel<<<grid, 256, 0, st>>>(s->d_table, s->slots(), len.p);
         SGPU_LAUNCH(c);
-        SGPU_TRY(exclusive_scan_u32_to_u64(c, len.p, off.p, s->capacity, total.p));
+        SGPU_TRY(exclusive_scan_u32_to_u64(c, len.p, off.p, s->slots(), total.p));
         uint64_t bytes;
         SGPU_TRY(read_u64s(c, total.p, &bytes, 1));
         DevBuf<uint8_t> d_out;
         SGPU_TRY(d_out.alloc(bytes, st));
-        idset_dump_copy_kernel<<<grid, 256, 0, st>>>(s->d_table, s->capacity, s->d_arena, off.p, d_out.p);
+        idset_dump_copy_kernel<<<grid, 256, 0, st>>>(s->d_table, s->slots(), s->d_arena, off.p, d_out.p);
         SGPU_LAUNCH(c);
         flat.resize(bytes);
         SGPU_CUDA(cudaMemcpyAsync(flat.data(), d_out.p, bytes, cudaMemcpyDeviceToHost, st));
@@ -416,21 +419,21 @@ sgpu_status sgpu_idset_keys_dev(sgpu_ctx *c, const sgpu_idset *s, uint8_t *d_out
     uint64_t bytes = 0;
     DevBuf<uint32_t> len;
     DevBuf<uint64_t> off, total;
-    const unsigned grid = (unsigned)ceil_div(s->capacity, 256);
-    if (s->capacity && s->count) {
-        SGPU_TRY(len.alloc(s->capacity, st));
-        SGPU_TRY(off.alloc(s->capacity, st));
+    const unsigned grid = (unsigned)ceil_div(s->slots(), 256);
+    if (s->n_buckets && s->count) {
+        SGPU_TRY(len.alloc(s->slots(), st));
+        SGPU_TRY(off.alloc(s->slots(), st));
         SGPU_TRY(total.alloc(1, st));
-        idset_dump_len_kernel<<<grid, 256, 0, st>>>(s->d_table, s->capacity, len.p);
+        idset_dump_len_kernel<<<grid, 256, 0, st>>>(s->d_table, s->slots(), len.p);
         SGPU_LAUNCH(c);
-        SGPU_TRY(exclusive_scan_u32_to_u64(c, len.p, off.p, s->capacity, total.p));
+        SGPU_TRY(exclusive_scan_u32_to_u64(c, len.p, off.p, s->slots(), total.p));
         SGPU_TRY(read_u64s(c, total.p, &bytes, 1));
     }
     *n = (size_t)bytes + (s->has_empty ? 1 : 0);
     if (*n == 0) return SGPU_OK;
     if (!d_out || cap < *n) return SGPU_ERR_CAPACITY;  // *n tells the size to come back with
     if (bytes) {
-        idset_dump_copy_kernel<<<grid, 256, 0, st>>>(s->d_table, s->capacity, s->d_arena, off.p, d_out);
+        idset_dump_copy_kernel<<<grid, 256, 0, st>>>(s->d_table, s->slots(), s->d_arena, off.p, d_out);
         SGPU_LAUNCH(c);
     }
     if (s->has_empty) SGPU_CUDA(cudaMemsetAsync(d_out + bytes, '\n', 1, st));  // the empty id: a blank line
@@ -441,10 +444,10 @@ sgpu_status sgpu_idset_keys_dev(sgpu_ctx *c, const sgpu_idset *s, uint8_t *d_out
 sgpu_status sgpu_idset_export(const sgpu_idset *s, sgpu_idset_image *img) {
     if (!s || !img) return SGPU_ERR_INVALID_ARG;
     img->d_table = s->d_table;
-    img->table_bytes = s->capacity * sizeof(Slot);
+    img->table_bytes = s->slots() * sizeof(Slot);
     img->d_arena = s->d_arena;
     img->arena_bytes = s->arena_used;
-    img->capacity = s->capacity;
+    img->capacity = s->slots();
     img->count = s->count;
     img->has_empty = s->has_empty ? 1 : 0;
     return SGPU_OK;
@@ -452,7 +455,7 @@ sgpu_status sgpu_idset_export(const sgpu_idset *s, sgpu_idset_image *img) {
 
 sgpu_status sgpu_idset_import(sgpu_ctx *c, const sgpu_idset_image *img, sgpu_idset **out) {
     if (!c || !img || !out) return SGPU_ERR_INVALID_ARG;
-    if (img->capacity && (img->capacity & (img->capacity - 1))) return SGPU_ERR_INVALID_ARG;
+    if (img->capacity % IDSET_BUCKET) return SGPU_ERR_INVALID_ARG;
     if (img->table_bytes != img->capacity * sizeof(Slot)) return SGPU_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     SGPU_CUDA(cudaSetDevice(c->device));
@@ -465,7 +468,7 @@ sgpu_status sgpu_idset_import(sgpu_ctx *c, const sgpu_idset_image *img, sgpu_ids
             return SGPU_ERR_NOMEM;
         }
         cudaMemcpyAsync(s->d_table, img->d_table, img->table_bytes, cudaMemcpyDeviceToDevice, st);
-        s->capacity = img->capacity;
+        s->n_buckets = img->capacity / IDSET_BUCKET;
     }
     if (img->arena_bytes) {
         uint64_t cap = (img->arena_bytes + 255) & ~255ull;

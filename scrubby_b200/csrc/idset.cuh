@@ -4,45 +4,54 @@
 // classifier.rs:135,274 and utils.rs:251,257, and `read_ids.contains(&id)` at
 // cleaner.rs:747,751.
 //
-// Layout in HBM: open addressing, 16-byte slots in 64-byte BUCKETS of four; a key's probe sequence starts
-// at the first slot of its home bucket and runs linearly from there (no deletions, so the occupied slots
-// of a bucket are always a prefix of it).  Load factor <= 0.2: a lookup is then decided by the home
-// bucket alone -- four independent 16-byte loads, one DRAM burst -- in > 99 % of the cases, which is
-// what keeps a warp of 32 lookups to a single memory round trip (with slot-granular homes and load 0.5
-// the longest of 32 chains is 5-6 dependent loads).
+// Layout in HBM (round 2): open addressing over 128-byte BUCKETS of eight 16-byte slots -- one L2 line, which
+// is what a random DRAM miss costs on B200 whatever is asked for (measured in round 1: 124 B per lookup with
+// 16-, 32- and 64-byte buckets alike).  The number of buckets is ARBITRARY (not a power of two): the home
+// bucket is the multiply-shift range reduction mulhi64(hash, n_buckets), so the table is sized exactly for its
+// keys at load 0.5 (C4's 50 M ids: 1.6 GB, was 4.3 GB at load <= 0.2 in 64-byte buckets).  A key's probe
+// sequence starts at slot 0 of its home bucket and runs linearly, bucket after bucket; there are no deletions,
+// so the occupied slots of a bucket are a prefix of it and a lookup ends at the first empty slot.  With a mean
+// of four keys per bucket 95 % of the lookups are decided by the home bucket, i.e. one line, one round trip.
 //   empty  : lo == 0 && hi == 0
 //   inline : ids of 1..15 bytes live IN the slot: byte0 = len, bytes 1..15 = id (zero padded).
 //            One 16-byte load and a 128-bit compare decide membership exactly.
 //   long   : ids of >= 16 bytes: byte0 = 0x80, bytes 1..7 = top 56 bits of a 64-bit hash,
 //            hi = (arena offset << 24) | len.  A fingerprint hit is verified against the
 //            id bytes in the arena, so there are no false positives.
-// A bucket is two 32-byte sectors of one 64-byte DRAM burst.
 #pragma once
 #include "common.cuh"
 
 namespace sgpu {
 
 constexpr uint32_t IDSET_INLINE_MAX = 15;
-#ifndef SGPU_IDSET_BUCKET
-#define SGPU_IDSET_BUCKET 4
+#ifndef SGPU_IDSET_LOAD_PCT
+#define SGPU_IDSET_LOAD_PCT 50
 #endif
-#ifndef SGPU_IDSET_INV_LOAD
-#define SGPU_IDSET_INV_LOAD 5
-#endif
-constexpr uint64_t IDSET_BUCKET = SGPU_IDSET_BUCKET;      // slots per bucket
-constexpr uint64_t IDSET_INV_LOAD = SGPU_IDSET_INV_LOAD;  // capacity >= IDSET_INV_LOAD * keys
+constexpr uint64_t IDSET_BUCKET = 8;                      // slots per bucket: 8 x 16 B = one 128-byte line
+constexpr uint64_t IDSET_LOAD_PCT = SGPU_IDSET_LOAD_PCT;  // keys <= LOAD_PCT % of the slots
 constexpr uint64_t IDSET_MAX_KEY = (1ull << 24) - 1;
 
 struct IdSetView {
-    const Slot *table;
-    uint64_t mask;  // capacity - 1 (capacity == 0 -> table == nullptr)
+    const Slot *table;   // n_buckets * 8 slots, 128-byte aligned (n_buckets == 0 -> table == nullptr)
+    uint64_t n_buckets;
     const uint8_t *arena;
 };
 
+// buckets for `keys` ids at the target load
+static inline uint64_t idset_buckets_for(uint64_t keys) {
+    const uint64_t slots = (keys * 100 + IDSET_LOAD_PCT - 1) / IDSET_LOAD_PCT;
+    const uint64_t b = (slots + IDSET_BUCKET - 1) / IDSET_BUCKET;
+    return b < 16 ? 16 : b;
+}
+
 #ifdef __CUDACC__
 
-// first slot of the home bucket of a key whose hash is h
-__device__ __forceinline__ uint64_t home_slot(uint64_t h, uint64_t mask) { return h & mask & ~(IDSET_BUCKET - 1); }
+// home bucket of a key whose (well mixed) 64-bit hash is h: multiply-shift range reduction
+__device__ __forceinline__ uint64_t home_bucket(uint64_t h, uint64_t n_buckets) { return __umul64hi(h, n_buckets); }
+__device__ __forceinline__ uint64_t next_bucket(uint64_t b, uint64_t n_buckets) { return b + 1 == n_buckets ? 0 : b + 1; }
+__device__ __forceinline__ uint64_t inline_hash(uint64_t lo, uint64_t hi) {
+    return mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL));
+}
 
 __device__ __forceinline__ uint64_t hash_bytes(const uint8_t *p, uint32_t len) {
     uint64_t h = 0x9E3779B97F4A7C15ULL ^ ((uint64_t)len * 0xD6E8FEB86659FD93ULL);
@@ -60,7 +69,7 @@ __device__ __forceinline__ uint64_t hash_bytes(const uint8_t *p, uint32_t len) {
     return mix64(h);
 }
 
-// builds the slot image of a key and its home index hash.  For long keys `hi` is left 0
+// builds the slot image of a key and its home hash (home_bucket() turns it into a bucket).  For long keys `hi` is left 0
 // (the caller fills offset/len when inserting).
 __device__ __forceinline__ void key_image(const uint8_t *p, uint32_t len, uint64_t *lo, uint64_t *hi,
                                           uint64_t *home) {
@@ -74,19 +83,19 @@ __device__ __forceinline__ void key_image(const uint8_t *p, uint32_t len, uint64
             if (i < len) b |= (uint64_t)p[i] << (8 * (i - 7));
         *lo = a;
         *hi = b;
-        *home = mix64(a ^ mix64(b + 0x9E3779B97F4A7C15ULL));
+        *home = inline_hash(a, b);
     } else {
         uint64_t h = hash_bytes(p, len);
         *lo = 0x80ull | (h & ~0xFFull);
         *hi = 0;
-        *home = h >> 8;
+        *home = mix64(*lo);
     }
 }
 
-// home index recomputed from a stored slot (rehash without touching key bytes)
+// home hash recomputed from a stored slot (rehash without touching key bytes)
 __device__ __forceinline__ uint64_t slot_home(uint64_t lo, uint64_t hi) {
-    if ((lo & 0xFF) == 0x80) return lo >> 8;
-    return mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL));
+    if ((lo & 0xFF) == 0x80) return mix64(lo);
+    return inline_hash(lo, hi);
 }
 
 __device__ __forceinline__ bool bytes_equal(const uint8_t *a, const uint8_t *b, uint32_t n) {
@@ -108,32 +117,22 @@ __device__ __forceinline__ bool idset_contains(const IdSetView &v, const uint8_t
     if (v.table == nullptr || len > IDSET_MAX_KEY) return false;
     uint64_t lo, hi, home;
     key_image(key, len, &lo, &hi, &home);
-    uint64_t idx = home_slot(home, v.mask);
+    uint64_t b = home_bucket(home, v.n_buckets);
     const bool is_inline = len <= IDSET_INLINE_MAX;
     while (true) {
-        Slot s = load_slot(v.table + idx);
-        if ((s.lo | s.hi) == 0) return false;
-        if (s.lo == lo) {
-            if (is_inline) {
-                if (s.hi == hi) return true;
-            } else if ((s.hi & 0xFFFFFFull) == len && bytes_equal(v.arena + (s.hi >> 24), key, len)) {
-                return true;
+        const Slot *bp = v.table + b * IDSET_BUCKET;
+        for (int q = 0; q < (int)IDSET_BUCKET; q++) {
+            Slot s = load_slot(bp + q);
+            if ((s.lo | s.hi) == 0) return false;
+            if (s.lo == lo) {
+                if (is_inline) {
+                    if (s.hi == hi) return true;
+                } else if ((s.hi & 0xFFFFFFull) == len && bytes_equal(v.arena + (s.hi >> 24), key, len)) {
+                    return true;
+                }
             }
         }
-        idx = (idx + 1) & v.mask;
-    }
-}
-
-// exact membership of an INLINE key (1..15 bytes) whose slot image (lo, hi) the caller has already built
-// (byte0 = len, bytes 1..15 = id, zero padded) -- identical to key_image() + idset_contains()
-__device__ __forceinline__ bool idset_contains_inline(const IdSetView &v, uint64_t lo, uint64_t hi) {
-    if (v.table == nullptr) return false;
-    uint64_t idx = home_slot(mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL)), v.mask);
-    while (true) {
-        const Slot s = load_slot(v.table + idx);
-        if ((s.lo | s.hi) == 0) return false;
-        if (s.lo == lo && s.hi == hi) return true;
-        idx = (idx + 1) & v.mask;
+        b = next_bucket(b, v.n_buckets);
     }
 }
 
@@ -141,8 +140,8 @@ __device__ __forceinline__ bool idset_contains_inline(const IdSetView &v, uint64
 
 static inline IdSetView view_of(const sgpu_idset *s) {
     IdSetView v;
-    v.table = s && s->capacity ? s->d_table : nullptr;
-    v.mask = s && s->capacity ? s->capacity - 1 : 0;
+    v.table = s && s->n_buckets ? s->d_table : nullptr;
+    v.n_buckets = s ? s->n_buckets : 0;
     v.arena = s ? s->d_arena : nullptr;
     return v;
 }

@@ -340,3 +340,185 @@ def _all_gather_ints(dist, vals, world):
     out = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(out, t)
     return [[int(x) for x in o.tolist()] for o in out]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Device-resident data plane (round 2): nothing below goes through host `bytes`.  Inputs are device tensors holding this
+# rank's byte range (+ halo) of every file, outputs stay in caller-owned device tensors; the exchanges are NCCL
+# collectives on device tensors (bench.py times exactly these calls).
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass
+class DevShardResult:
+    n_written: int          # bytes this rank produced (in its d_out / d_other)
+    n_other: int
+    offset_written: int     # where they start in the concatenated output (shards are concatenated in rank order)
+    offset_other: int
+    total_written: int
+    total_other: int
+    reads_in: int           # whole file (summed over ranks)
+    reads_out: int
+    crlf: bool
+    one_pass: bool          # the speculative single pass was accepted on every rank (no newline count before it)
+    path: int
+
+
+def evidence_shard_len(total: int, world: int, align: int = 16) -> int:
+    """bytes per rank when an evidence file is cut into `world` EQUAL byte ranges (the last one padded): equal sizes
+    make the all-gather's output buffer a contiguous image of the file"""
+    per = -(-total // world)
+    return max(align, -(-per // align) * align)
+
+
+def replicate_file_dev(d_shard, per: int, total: int, dist=None, out=None):
+    """all-gather of the `world` equal byte ranges of a file (NCCL over NVLink): every rank ends up with the whole file
+    in HBM, contiguous.  For a one-column id list this IS the replication of the depletion set in its most compact
+    form (alignment.rs:60-82 then runs on every rank over the same bytes -- one global set, cleaner.rs:236-254)."""
+    import torch
+
+    world = dist.get_world_size() if dist is not None else 1
+    if world == 1:
+        return d_shard[:total]
+    assert d_shard.numel() >= per
+    if out is None:
+        out = torch.empty(world * per + 16, dtype=torch.uint8, device=d_shard.device)
+    dist.all_gather_into_tensor(out[: world * per], d_shard[:per])
+    return out[:total]
+
+
+def _gather_rows(dist, vals, world, device):
+    """all_gather of a short int64 row per rank, on the device the ranks compute on"""
+    import torch
+
+    if dist is None or world == 1:
+        return [list(vals)]
+    t = torch.tensor(vals, dtype=torch.int64, device=device)
+    out = torch.empty(world * len(vals), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, t)
+    flat = out.tolist()
+    return [flat[r * len(vals): (r + 1) * len(vals)] for r in range(world)]
+
+
+def _clean_files_sharded(call, count_own_newlines, first_line_crlf, shards, dist, device, ShardFailure):
+    """the one-pass protocol over several files; `call(f, newlines_before, crlf)` runs file f's shard of this rank
+    (None, None = speculate), `count_own_newlines(f)` / `first_line_crlf(f)` serve the exact protocol"""
+    from . import _lib
+
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    W = 10  # integers per file in the exchange
+    row, failures = [], {}
+    for f, sh in enumerate(shards):
+        st, r = 0, None
+        if sh.own_len:
+            try:
+                r = call(f, 0 if sh.is_first else None, None)
+                st = r.status
+            except ShardFailure as e:
+                st, r = e.status, None
+                failures[f] = e
+        if r is None or st:
+            row += [st, 0, 0, 0, 0, 0, 0, 0, 0, int(bool(sh.own_len))]
+        else:
+            row += [0, r.path, r.own_newlines, r.lead_newlines, int(r.crlf), r.n_written, r.n_other, r.reads_in,
+                    r.reads_out, 1]
+    rows = _gather_rows(dist, row, world, device)
+    results = []
+    for f, sh in enumerate(shards):
+        col = [rw[f * W: (f + 1) * W] for rw in rows]
+        hard = [(q, c[0]) for q, c in enumerate(col) if c[0] not in (0, _lib.SGPU_ERR_PHASE_UNKNOWN)]
+        if hard:  # a parse error / halo / capacity problem in one shard ends the run on EVERY rank
+            if f in failures and hard[0][0] == rank:
+                raise failures[f]
+            raise ShardError(hard[0][0], hard[0][1])
+        ok = col[0][4] == 0
+        before = 0
+        for q, c in enumerate(col):
+            if not c[9]:
+                continue  # owns nothing
+            ok = ok and c[0] == 0 and c[1] == 1 and (q == 0 or (before + c[3]) % 4 == 0)
+            before += c[2]
+        if ok:
+            results.append(DevShardResult(col[rank][5], col[rank][6], sum(c[5] for c in col[:rank]),
+                                          sum(c[6] for c in col[:rank]), sum(c[5] for c in col), sum(c[6] for c in col),
+                                          sum(c[7] for c in col), sum(c[8] for c in col), False, True, 1))
+            continue
+        # ---- exact protocol for this file: newline counts and shard 0's line ending first
+        own_nl = count_own_newlines(f) if sh.own_len else 0
+        crlf = int(first_line_crlf(f)) if (rank == 0 and sh.buf_len) else 0
+        cnt = _gather_rows(dist, [own_nl, crlf], world, device)
+        nb, crlf = sum(c[0] for c in cnt[:rank]), bool(cnt[0][1])
+        st, r, exc = 0, None, None
+        if sh.own_len:
+            try:
+                r = call(f, nb, crlf)
+            except ShardFailure as e:
+                st, exc = e.status, e
+        fin = _gather_rows(dist, [st, r.n_written if r else 0, r.n_other if r else 0, r.reads_in if r else 0,
+                                  r.reads_out if r else 0, r.path if r else 0], world, device)
+        _raise_collectively(fin, 0, exc, rank)
+        results.append(DevShardResult(fin[rank][1], fin[rank][2], sum(c[1] for c in fin[:rank]),
+                                      sum(c[2] for c in fin[:rank]), sum(c[1] for c in fin), sum(c[2] for c in fin),
+                                      sum(c[3] for c in fin), sum(c[4] for c in fin), crlf, False,
+                                      max(c[5] for c in fin)))
+    return results
+
+
+def _crlf_of_head(head: bytes, fetch_all):
+    p = head.find(b"\n")
+    if p < 0:
+        head = fetch_all()
+        p = head.find(b"\n")
+    return p > 0 and head[p - 1: p] == b"\r"
+
+
+def clean_files_sharded_dev(api, ctx, ids, jobs, dist=None, reverse: bool = False):
+    """FastqCleaner::clean_reads (cleaner.rs:731-760) for several files at once (the mate files of cleaner.rs:238-248),
+    each cut into one byte range per rank.  jobs: [(d_buf, Shard, d_out, d_other_or_None), ...], all DEVICE tensors.
+
+    ONE pass per file: every rank runs the single-pass kernel on its range with a speculated line phase
+    (SGPU_NEWLINES_UNKNOWN), then ONE all-gather of a few integers per file carries the own-range newline counts that
+    prove (or refute) every speculation, the file-level CRLF decision of shard 0, the output sizes (-> write offsets
+    of the concatenation) and the read counters.  A refuted speculation, a non-canonical shard or a CRLF file takes the
+    exact protocol: newline counts first, then the shard call with the exact phase (two passes over the range)."""
+    import torch
+
+    device = torch.device("cuda", ctx.device)
+
+    def call(f, nb, crlf):
+        d_buf, sh, d_out, d_oth = jobs[f]
+        return api.clean_fastq_shard_dev(ctx, ids, d_buf, sh.buf_len, sh.own_len, nb, sh.is_first, sh.is_last, crlf,
+                                         d_out, d_oth, reverse)
+
+    def count(f):
+        return api.count_newlines_dev(ctx, jobs[f][0], jobs[f][1].own_len)
+
+    def crlf(f):
+        d_buf, sh = jobs[f][0], jobs[f][1]
+        return _crlf_of_head(bytes(d_buf[: min(sh.buf_len, 1 << 16)].cpu().numpy()),
+                             lambda: bytes(d_buf[: sh.buf_len].cpu().numpy()))
+
+    return _clean_files_sharded(call, count, crlf, [j[1] for j in jobs], dist, device, api.ScrubbyGpuError)
+
+
+def clean_files_sharded_host(api, ctx, ids, jobs, dist=None, reverse: bool = False):
+    """the same protocol on HOST buffers (pinned for full PCIe rate): jobs = [(h_buf, Shard, h_out, h_other_or_None)],
+    torch CPU uint8 tensors; every shard goes through sgpu_clean_fastq_shard (chunked H2D / kernels / D2H overlapped
+    inside the call).  The exchanges are the same few integers, on the device the rank computes on."""
+    import torch
+
+    device = torch.device("cuda", ctx.device)
+
+    def call(f, nb, crlf):
+        h_buf, sh, h_out, h_oth = jobs[f]
+        return api.clean_fastq_shard_host(ctx, ids, h_buf, sh.buf_len, sh.own_len, nb, sh.is_first, sh.is_last, crlf,
+                                          h_out, h_oth, reverse)
+
+    def count(f):
+        h_buf, sh = jobs[f][0], jobs[f][1]
+        return int((h_buf[: sh.own_len] == 10).sum())
+
+    def crlf(f):
+        h_buf, sh = jobs[f][0], jobs[f][1]
+        return _crlf_of_head(bytes(h_buf[: min(sh.buf_len, 1 << 16)].numpy()), lambda: bytes(h_buf[: sh.buf_len].numpy()))
+
+    return _clean_files_sharded(call, count, crlf, [j[1] for j in jobs], dist, device, api.ScrubbyGpuError)

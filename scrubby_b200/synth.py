@@ -243,8 +243,9 @@ def gen_txt_ids(n: int, seed: int = SEED, device="cpu", start: int = 0) -> torch
 
 
 def gen_ont_fastq(n: int, seed: int = SEED, device="cpu", mean_log: float = 8.6, sigma: float = 0.8,
-                  min_len: int = 200, max_len: int = 500_000):
-    """ONT-like long reads: lognormal lengths, 36-char UUID-style ids.  Returns (fastq bytes, lengths, ids hex)"""
+                  min_len: int = 200, max_len: int = 500_000, group_bytes: int = 1 << 28):
+    """ONT-like long reads: lognormal lengths, 36-char UUID-style ids.  Returns (fastq bytes, lengths, ids hex).
+    Records are rendered in groups of about `group_bytes` so that the temporaries stay bounded (2 M reads = 30 GB)."""
     g = torch.Generator(device="cpu")
     g.manual_seed(seed & 0x7FFFFFFF)
     lens = torch.empty(n).log_normal_(mean_log, sigma, generator=g).clamp(min_len, max_len).long()
@@ -252,15 +253,9 @@ def gen_ont_fastq(n: int, seed: int = SEED, device="cpu", mean_log: float = 8.6,
     off = torch.zeros(n + 1, dtype=torch.int64)
     off[1:] = torch.cumsum(rec, 0)
     total = int(off[-1])
-    gd = torch.Generator(device=device)
-    gd.manual_seed((seed + 17) & 0x7FFFFFFF)
-    out = torch.randint(0, 4, (total,), dtype=torch.uint8, device=device, generator=gd)
-    out = _bytes("ACGT", device)[out.long()]
-    # quality halves: overwrite with '5'..'I'
+    out = torch.empty(total, dtype=torch.uint8, device=device)
     hexd = _bytes("0123456789abcdef", device)
     idx = torch.arange(n, dtype=torch.int64, device=device)
-    offd = off.to(device)
-    lensd = lens.to(device)
     uu = torch.empty((n, 36), dtype=torch.uint8, device=device)
     col = 0
     for k in range(36):
@@ -269,19 +264,82 @@ def gen_ont_fastq(n: int, seed: int = SEED, device="cpu", mean_log: float = 8.6,
         else:
             uu[:, k] = hexd[(_lsr(splitmix64(idx * 2 + (col // 16) + _i64(seed)), 4 * (col % 16)) & 15)]
             col += 1
-    start = offd[:-1]
-    out[start] = 64
-    for k in range(36):
-        out[start + 1 + k] = uu[:, k]
-    out[start + 37] = 10
-    out[start + 38 + lensd] = 10
-    out[start + 39 + lensd] = 43
-    out[start + 40 + lensd] = 10
-    out[start + 41 + 2 * lensd] = 10
-    # qualities: any printable; make them distinct from bases so that framing bugs show up
-    qmask = torch.zeros(total + 1, dtype=torch.int8, device=device)
-    qmask[start + 41 + lensd] += 1
-    qmask[start + 41 + 2 * lensd] -= 1
-    inq = torch.cumsum(qmask[:total], 0).bool()
-    out[inq] = out[inq] // 2 + 20  # 'A','C','G','T' -> 52,53,55,62 ('4','5','7','>')
+    del idx
+    # group boundaries: consecutive records of about group_bytes
+    g0 = 0
+    grp = 0
+    while g0 < n:
+        g1 = int(torch.searchsorted(off, off[g0] + group_bytes, right=True))
+        g1 = max(g0 + 1, min(n, g1 - 1 if g1 > g0 + 1 else g1))
+        base = int(off[g0])
+        size = int(off[g1]) - base
+        gd = torch.Generator(device=device)
+        gd.manual_seed((seed + 17 + 7919 * grp) & 0x7FFFFFFF)
+        r = torch.randint(0, 4, (size,), dtype=torch.uint8, device=device, generator=gd)
+        # 'A','C','G','T' = 65, 67, 71, 84 from r = 0..3 without an index tensor
+        o = 65 + r * 2 + (r == 2).to(torch.uint8) * 2 + (r == 3).to(torch.uint8) * 13
+        del r
+        start = (off[g0:g1] - base).to(device)
+        lensd = lens[g0:g1].to(device)
+        o[start] = 64
+        for k in range(36):
+            o[start + 1 + k] = uu[g0:g1, k]
+        o[start + 37] = 10
+        o[start + 38 + lensd] = 10
+        o[start + 39 + lensd] = 43
+        o[start + 40 + lensd] = 10
+        o[start + 41 + 2 * lensd] = 10
+        # qualities: any printable; make them distinct from bases so that framing bugs show up
+        qmask = torch.zeros(size + 1, dtype=torch.int32, device=device)
+        qmask[start + 41 + lensd] += 1
+        qmask[start + 41 + 2 * lensd] -= 1
+        inq = torch.cumsum(qmask[:size], 0, dtype=torch.int32).bool()
+        del qmask
+        o[inq] = o[inq] // 2 + 20  # 'A','C','G','T' -> 52,53,55,62 ('4','5','7','>')
+        out[base: base + size] = o
+        del o, inq
+        g0 = g1
+        grp += 1
     return out, lens, uu
+
+
+def gen_ont_paf(lens: torch.Tensor, uu: torch.Tensor, seed: int = SEED, device="cpu", chunk: int = 1 << 18,
+                max_lines: int = 15) -> torch.Tensor:
+    """map-ont-style PAF for the reads of gen_ont_fastq: 1..max_lines alignments per read (mean 8), grouped by qname in
+    read order -- the "many alignments per read" shape of BASELINE configs[2].  A read is host iff splitmix64(i ^ seed)
+    & 1: its first line passes -l 50 -c 0.5 -q 50 (80 % of the read aligned, mapq 60), its other lines are random
+    sub-alignments; every line of a non-host read has mapq < 50 and therefore fails whatever its length."""
+    n = lens.numel()
+    parts = []
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        idx = torch.arange(a, b, dtype=torch.int64, device=device)
+        L = lens[a:b].to(device)
+        host = is_host(idx, seed)
+        k = 1 + _lsr(splitmix64(idx * 3 + _i64(seed ^ 0x0A7)), 17) % max_lines
+        rid = torch.repeat_interleave(torch.arange(b - a, device=device), k)  # local read index per line
+        first = torch.ones_like(rid, dtype=torch.bool)
+        first[1:] = rid[1:] != rid[:-1]
+        ln = torch.arange(rid.numel(), dtype=torch.int64, device=device)
+        h = splitmix64((idx[rid] << 5) + ln + _i64(seed ^ 0xBEEF))
+        Lr = L[rid]
+        sure = first & host[rid]
+        qs = torch.where(sure, Lr // 10, _lsr(h, 8) % (Lr - 60))
+        span = torch.where(sure, Lr * 8 // 10, 30 + _lsr(h, 30) % (Lr - qs - 29))
+        qe = qs + span
+        mapq = torch.where(sure, torch.full_like(h, 60),
+                           torch.where(host[rid], _lsr(h, 50) % 61, _lsr(h, 50) % 50))
+        ts = 10_000 + _lsr(h, 20) % 100_000_000
+        m = rid.numel()
+        fields = [
+            (uu[a:b].to(device)[rid], torch.ones((m, 36), dtype=torch.bool, device=device)),
+            _const_field("\t", m, device), _num_field(Lr, 7), _const_field("\t", m, device), _num_field(qs, 7),
+            _const_field("\t", m, device), _num_field(qe, 7),
+            _choice_field(["\t+\tchr1\t248956422\t", "\t-\tchr7\t159345973\t"], (_lsr(h, 3) & 1)),
+            _num_field(ts, 9), _const_field("\t", m, device), _num_field(ts + span, 9), _const_field("\t", m, device),
+            _num_field(span - span // 12, 7), _const_field("\t", m, device), _num_field(span, 7),
+            _const_field("\t", m, device), _num_field(mapq, 2),
+            _const_field("\ttp:A:P\tcm:i:412\ts1:i:3301\ts2:i:0\tdv:f:0.0712\trl:i:57\n", m, device),
+        ]
+        parts.append(_render(fields))
+    return torch.cat(parts) if len(parts) != 1 else parts[0]

@@ -25,7 +25,7 @@ def test_header_symbols_all_exported():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/scrubby_gpu.h but not exported"
     assert sorted(_lib.SYMBOLS) == declared
-    assert L.sgpu_abi_version() == 1
+    assert L.sgpu_abi_version() == 2
 
 
 def test_strerror_covers_every_status():

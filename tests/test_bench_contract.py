@@ -23,9 +23,17 @@ def test_reference_arm_line():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "reads_per_s_depleted" and j["unit"] == "reads/s"
     assert j["higher_is_better"] is True and j["steps"] == 2 and j["warmup"] == 1 and j["value"] > 0
-    assert j["config"]["workload"].startswith("classifier: synthetic 10M 2x150 pairs")
+    assert j["config"]["workload"].startswith("C4: 100M 2x150 pairs") and j["scaling"] == "strong"
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] == 2 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_c2_line():
+    r = _run("--impl", "reference", "--config", "c2", "--steps", "1", "--warmup", "0", "--cpu-pairs", "20000",
+             "--cpu-step-seconds", "0.05")
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert j["config"]["workload"].startswith("classifier: synthetic 10M 2x150 pairs") and j["scaling"] == "weak"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

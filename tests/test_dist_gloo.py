@@ -41,16 +41,18 @@ class OracleOps:
         from oracle import oracle as orc
 
         # records that START inside [0, own_len): a record starts after a newline whose global index is 3 mod 4
-        pos, line = 0, newlines_before
+        # (a record that starts exactly at a cut belongs to the shard BEFORE the cut: the next one cannot know that its
+        # byte 0 follows a newline)
+        pos = 0
         if not sh.is_first:
-            while line % 4 != 0:
+            for _ in range((3 - newlines_before % 4) % 4 + 1):
                 p = buf.find(b"\n", pos)
                 if p < 0:
                     return b"", b"", 0, 0
-                pos, line = p + 1, line + 1
+                pos = p + 1
         start = pos
         end = start
-        while end < sh.own_len:
+        while end < sh.own_len or (end == sh.own_len and not sh.is_last and end < len(buf)):
             e = end
             for _ in range(4):
                 p = buf.find(b"\n", e)
@@ -61,7 +63,7 @@ class OracleOps:
                     raise HaloError()
                 e = p + 1
             end = e
-        if start >= sh.own_len:
+        if start >= end:
             return b"", b"", 0, 0
         r = orc.clean_fastq(buf[start:end], ids, reverse)
         return r.written, (r.other if want_other else b""), r.reads_in, r.reads_out
@@ -79,13 +81,13 @@ class OracleOps:
     def ids_shard(self, probe, buf, sh: Shard, newlines_before, into):
         from oracle import oracle as orc
 
-        pos, line = 0, newlines_before
+        pos = 0
         if not sh.is_first:
-            while line % 4 != 0:
+            for _ in range((3 - newlines_before % 4) % 4 + 1):
                 p = buf.find(b"\n", pos)
                 if p < 0:
                     return 0, 0
-                pos, line = p + 1, line + 1
+                pos = p + 1
         rec = picked = 0
         while pos < len(buf) and (pos < sh.own_len or (pos == sh.own_len and not sh.is_last)):
             lines = []
@@ -290,3 +292,130 @@ def test_error_in_one_shard_ends_every_rank():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, "shard", 2), (1, "shard", 2), (2, "own", 3)]  # FASTQ_INVALID_START on the owning rank
+
+
+# ------------------------------------------------------------------------------------------ one-pass protocol (round 2)
+class _SpecResult:
+    def __init__(self, status=0, path=1, own_newlines=0, lead_newlines=0, crlf=False, written=b"", other=b"", reads_in=0,
+                 reads_out=0):
+        self.status, self.path, self.own_newlines, self.lead_newlines, self.crlf = status, path, own_newlines, lead_newlines, crlf
+        self.written, self.other = written, other
+        self.n_written, self.n_other, self.reads_in, self.reads_out = len(written), len(other), reads_in, reads_out
+
+
+def _spec_call(ops, ids, buf, sh, nb, crlf, reverse):
+    """CPU stand-in (TEST ONLY) for sgpu_clean_fastq_shard_dev incl. SGPU_NEWLINES_UNKNOWN: the speculation rule of
+    fastq_fused.cu::fused_shard restated -- among the first four newlines the first one followed by "+\\n" ends a
+    sequence line; canonical LF input only, anything else answers SGPU_ERR_PHASE_UNKNOWN (24)"""
+    own_nl = buf[: sh.own_len].count(b"\n")
+    if nb is None:
+        if b"\r" in buf or not sh.own_len:
+            return _SpecResult(status=24)
+        pos, p = [], -1
+        for _ in range(4):
+            p = buf.find(b"\n", p + 1)
+            if p < 0:
+                break
+            pos.append(p)
+        j = next((i for i, p in enumerate(pos) if buf[p + 1: p + 3] == b"+\n"), None)
+        if j is None:
+            return _SpecResult(status=24)
+        k = (2 + j) & 3
+        if k >= len(pos) or pos[k] + 1 > sh.own_len or pos[k] + 1 >= len(buf):
+            return _SpecResult(status=24)
+        lead = k + 1
+        try:
+            w, o, rin, rout = ops.clean_shard(ids, buf, sh, (4 - lead % 4) % 4, False, reverse, True)
+        except Exception:  # a wrong phase makes the records malformed: the single-pass kernel falls back -> 24
+            return _SpecResult(status=24)
+        return _SpecResult(0, 1, own_nl, lead, False, w, o, rin, rout)
+    first_crlf = ops.first_line_crlf(buf, len(buf)) if sh.is_first and crlf is None else bool(crlf)
+    if first_crlf or b"\r" in buf:
+        # (the oracle's whole-file cleaner normalises line endings; shards of CRLF files are not needed by these tests)
+        w, o, rin, rout = ops.clean_shard(ids, buf, sh, nb, first_crlf, reverse, True)
+        return _SpecResult(0, 2, own_nl, 0, first_crlf, w, o, rin, rout)
+    w, o, rin, rout = ops.clean_shard(ids, buf, sh, nb, False, reverse, True)
+    return _SpecResult(0, 1, own_nl, 0, False, w, o, rin, rout)
+
+
+def _onepass_worker(rank, world, port, files, ids_txt, halo, q):
+    from oracle import oracle as orc
+
+    from scrubby_b200.dist import _clean_files_sharded
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        ids = orc.set_from_txt(ids_txt)
+        ops = OracleOps()
+        shards = [plan_shards(len(f), world, halo)[rank] for f in files]
+        bufs = [f[sh.start: sh.start + sh.buf_len] for f, sh in zip(files, shards)]
+        last = {}
+
+        def call(f, nb, crlf):
+            last[f] = _spec_call(ops, ids, bufs[f], shards[f], nb, crlf, False)
+            return last[f]
+
+        rs = _clean_files_sharded(call, lambda f: bufs[f][: shards[f].own_len].count(b"\n"),
+                                  lambda f: ops.first_line_crlf(bufs[f], len(bufs[f])), shards, dist, "cpu", HaloError)
+        q.put((rank, [(last[f].written if f in last and last[f].status == 0 else b"", r.offset_written, r.total_written,
+                       r.reads_in, r.reads_out, r.one_pass) for f, r in enumerate(rs)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_onepass(world, files, ids_txt, halo=4096):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_onepass_worker, args=(r, world, port, files, ids_txt, halo, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_one_pass_protocol_accepts_canonical_files(world):
+    """both mate files in one exchange: every speculation is accepted, offsets and counters equal the unsharded run"""
+    from oracle import oracle as orc
+
+    n = 3000
+    files = [synth.gen_fastq(n, m, start=3).numpy().tobytes() for m in (1, 2)]
+    ids_txt = synth.gen_txt_ids(n + 10).numpy().tobytes()
+    res = _run_onepass(world, files, ids_txt)
+    for f, fq in enumerate(files):
+        whole = orc.clean_fastq(fq, orc.set_from_txt(ids_txt))
+        assert b"".join(r[1][f][0] for r in res) == whole.written
+        off = 0
+        for r in res:
+            w, offset, total, rin, rout, one_pass = r[1][f]
+            assert one_pass and offset == off and total == len(whole.written)
+            assert (rin, rout) == (whole.reads_in, whole.reads_out)
+            off += len(w)
+
+
+def test_one_pass_protocol_refutes_wrong_speculation():
+    """one-base reads whose quality line is "+": the first "\\n+\\n" of a shard may be a QUALITY line, the speculated phase
+    is then wrong, the exchanged newline counts refute it and the exact protocol produces the right bytes"""
+    from oracle import oracle as orc
+
+    fq = None
+    for pad in range(64):  # shift the file until the world-2 cut lands on the '+' of a separator before a "+" quality line
+        recs = [b"@r%d%s\nA\n+\n%s\n" % (i, b"x" * pad if i == 0 else b"", b"+" if i % 3 else b"I") for i in range(4000)]
+        cand = b"".join(recs)
+        cut = plan_shards(len(cand), 2, 256)[1].start
+        if cand[cut - 1: cut + 4] == b"\n+\n+\n":
+            fq = cand
+            break
+    assert fq is not None
+    ids_txt = b"".join(b"r%d\n" % i for i in range(0, 4000, 2))
+    whole = orc.clean_fastq(fq, orc.set_from_txt(ids_txt))
+    for world in (2, 3):
+        res = _run_onepass(world, [fq], ids_txt, halo=256)
+        assert b"".join(r[1][0][0] for r in res) == whole.written
+        assert all(r[1][0][3:5] == (whole.reads_in, whole.reads_out) for r in res)
+        if world == 2:
+            assert not res[0][1][0][5], "the cut was built to refute the speculation"
