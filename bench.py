@@ -135,14 +135,25 @@ def bind_to_gpu_numa_node(device: int):
 
 
 def mem_available_gb() -> float:
+    """host memory this job may still take: MemAvailable, capped by the container's cgroup limit when there is one"""
+    avail = 0.0
     try:
         with open("/proc/meminfo") as f:
             for line in f:
                 if line.startswith("MemAvailable:"):
-                    return int(line.split()[1]) / 1e6
+                    avail = int(line.split()[1]) / 1e6
     except OSError:
         pass
-    return 0.0
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            v = open(lim).read().strip()
+            if v != "max" and int(v) < (1 << 60):
+                left = (int(v) - int(open(cur).read().strip())) / 1e9
+                avail = min(avail, left) if avail else left
+        except (OSError, ValueError):
+            pass
+    return avail
 
 
 def taxids_for_config():
@@ -404,6 +415,8 @@ def run_ours(args):
             ph.begin()
         if c4:
             ev = sdist.replicate_file_dev(d_ev, per, ev_total, D, d_ev_all)
+            if os.environ.get("SGPU_BENCH_SYNC"):
+                torch.cuda.synchronize()
             if timed:
                 ph.mark()
             ids = api.IdSet.from_txt(ctx, ev)
@@ -455,7 +468,8 @@ def run_ours(args):
     ctx.fused_stats()
     sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    if not os.environ.get("SGPU_BENCH_NOSAMPLER"):
+        sampler.start()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` lists exactly the timed launches
@@ -478,11 +492,15 @@ def run_ours(args):
     assert (reads_job == 2 * pairs) if (c4 or world == 1) else True
 
     # ---- end-to-end arm: pinned host buffers through the host-pointer C ABI (H2D + D2H inside)
-    e2e = run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, shards, d_r, n_r, d_ev, n_k,
-                  taxids, cap, barrier, (per, ev_total) if c4 else None, written_job)
+    if args.e2e_steps > 0:
+        e2e = run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, shards, d_r, n_r, d_ev, n_k,
+                      taxids, cap, barrier, (per, ev_total) if c4 else None, written_job, d_out, d_oth)
+    else:
+        e2e = {"t": float("nan"), "h2d": 0, "d2h": 0, "steps": 0, "each": [], "warm": [], "pairs": 0, "scale": 1.0,
+               "mem_gb": round(mem_available_gb(), 1), "note": "skipped (--e2e-steps 0)"}
 
     # ---- max over ranks
-    ms_t = torch.tensor([ms, e2e["t"] * 1e3, f_ms / max(f_n, 1)] + [phases[n] for n in names], dtype=torch.float64,
+    ms_t = torch.tensor([ms, e2e["t"] * 1e3 if e2e["steps"] else 0.0, f_ms / max(f_n, 1)] + [phases[n] for n in names], dtype=torch.float64,
                         device=dev)
     cnt = torch.tensor([reads_job, kept_job, own_bytes, launches], dtype=torch.int64, device=dev)
     fmin = torch.tensor([f_bytes / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0], dtype=torch.float64, device=dev)
@@ -527,10 +545,11 @@ def run_ours(args):
                 "fastq_gb_per_s": bytes_all / (ms * 1e-3) / 1e9,
             },
             "phases_ms": phases_max,
-            "e2e": {"value": reads_all / (e2e_ms * 1e-3) * e2e["scale"], "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+            "e2e": {"value": (reads_all / (e2e_ms * 1e-3) * e2e["scale"]) if e2e["steps"] else None, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_ms, "steps": e2e["steps"],
                     "ms_each_rank0": e2e["each"], "warmup_ms_each_rank0": e2e["warm"], "pairs": e2e["pairs"],
-                    "h2d_gb_per_s_rank0": e2e["h2d"] / e2e["t"] / 1e9, "d2h_gb_per_s_rank0": e2e["d2h"] / e2e["t"] / 1e9,
+                    "h2d_gb_per_s_rank0": (e2e["h2d"] / e2e["t"] / 1e9) if e2e["steps"] else None,
+                    "d2h_gb_per_s_rank0": (e2e["d2h"] / e2e["t"] / 1e9) if e2e["steps"] else None,
                     "host_mem_available_gb": e2e["mem_gb"], "note": e2e["note"],
                     "timing": "host wall clock around the host-buffer C ABI calls of one step on pinned host "
                               "buffers (evidence upload + set build + both mate files), stream synchronised, max over ranks"},
@@ -550,19 +569,28 @@ def run_ours(args):
 
 
 def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, shards, d_r, n_r, d_ev, n_k, taxids, cap,
-            barrier, evinfo, written_job):
+            barrier, evinfo, written_job, d_out, d_oth):
     """the step through HOST buffers: inputs in pinned host memory, outputs into pinned host memory"""
-    # the pinned copies of this rank's inputs and outputs must fit the host: otherwise the arm runs on a prefix of the
-    # rank's records (a rate is still a rate; `pairs` / `note` say so)
+    # the pinned copies of every rank's inputs and outputs must fit the host (with room to spare: pinned pages cannot be
+    # reclaimed and an exhausted box kills the job).  A single-GPU run that does not fit runs on a prefix of whole
+    # records (a rate is still a rate; `pairs` / `note` say so); a multi-GPU run that does not fit is not run.
     need_gb = (sum(n_r) + sum(cap) + n_k) / 1e9
     avail = mem_available_gb()
+    if world > 1:
+        a_t = torch.tensor([avail], dtype=torch.float64, device=dev)
+        dist.all_reduce(a_t, op=dist.ReduceOp.MIN)
+        avail = float(a_t[0])
+    sys.stderr.write(f"[bench] rank {rank}: e2e needs {need_gb:.1f} GB of pinned host memory per rank x {world}, "
+                     f"{avail:.0f} GB available\n")
     note = "full workload"
     frac = 1.0
-    if avail and need_gb * world > 0.6 * avail:
-        frac = max(0.05, 0.6 * avail / (need_gb * world))
-        note = f"host memory: {avail:.0f} GB available, {need_gb * world:.0f} GB needed -> the first {frac:.2f} of every shard"
-    if c4 and world > 1 and frac < 1.0:
-        frac = 1.0  # (shards of a strong-scaling run are small enough in practice; keep the protocol whole)
+    if avail and need_gb * world > 0.55 * avail:
+        if world > 1:
+            return {"t": float("nan"), "h2d": 0, "d2h": 0, "steps": 0, "each": [], "warm": [], "pairs": 0, "scale": 1.0,
+                    "mem_gb": round(avail, 1),
+                    "note": f"not run: {need_gb * world:.0f} GB of pinned host memory needed, {avail:.0f} GB available"}
+        frac = max(0.05, 0.55 * avail / need_gb)
+        note = f"host memory: {avail:.0f} GB available, {need_gb:.0f} GB needed -> the first {frac:.2f} of every file"
     e_n = []
     for i in range(2):
         if frac >= 1.0:
@@ -572,21 +600,33 @@ def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, 
             tail = bytes(d_r[i][k: k + 4096].cpu().numpy())
             at = tail.find(b"\n@syn.")
             e_n.append(k + at + 1)
-    h_r = [torch.empty(n + 16, dtype=torch.uint8).pin_memory() for n in e_n]
-    h_k = torch.empty(n_k + 16, dtype=torch.uint8).pin_memory()
+    h_r = [torch.empty(n + 16, dtype=torch.uint8, pin_memory=True) for n in e_n]
+    h_k = torch.empty(n_k + 16, dtype=torch.uint8, pin_memory=True)
     for i in range(2):
         h_r[i][: e_n[i]].copy_(d_r[i][: e_n[i]])
     h_k[:n_k].copy_(d_ev[:n_k])
+    # the device-resident arm is over: its buffers go back to the driver (the host-buffer path stages on the device)
+    d_r.clear()
+    d_out.clear()
+    d_oth.clear()
+    if not (c4 and world > 1):
+        del d_ev
+    torch.cuda.empty_cache()
     e_cap = [int(c * min(1.0, frac * 1.05)) + (1 << 20) for c in cap]
-    h_out = [torch.empty(c, dtype=torch.uint8).pin_memory() for c in e_cap]
-    h_oth = [torch.empty(c, dtype=torch.uint8).pin_memory() for c in e_cap] if args.split else [None, None]
+    h_out = [torch.empty(c, dtype=torch.uint8, pin_memory=True) for c in e_cap]
+    h_oth = [torch.empty(c, dtype=torch.uint8, pin_memory=True) for c in e_cap] if args.split else [None, None]
     torch.cuda.synchronize()
+    sys.stderr.write(f"[bench] rank {rank}: pinned buffers ready, {mem_available_gb():.0f} GB of host memory left\n")
     if c4 and world > 1:
         per, ev_total = evinfo
         d_ev2 = torch.empty(per + 16, dtype=torch.uint8, device=dev)
         d_ev_all = torch.empty(world * per + 16, dtype=torch.uint8, device=dev)
 
+    dbg = os.environ.get("SGPU_BENCH_DEBUG")
+
     def step_host():
+        if dbg:
+            sys.stderr.write(f"[bench] rank {rank}: host step, {mem_available_gb():.0f} GB of host memory left\n")
         if c4 and world > 1:
             d_ev2[:per].copy_(h_k[:per], non_blocking=True)
             ev = sdist.replicate_file_dev(d_ev2, per, ev_total, D, d_ev_all)

@@ -105,12 +105,16 @@ struct Slot {
     unsigned long long lo, hi;
 };
 
+#ifndef SGPU_IDSET_BUCKET
+#define SGPU_IDSET_BUCKET 8  // slots per bucket (idset.cuh)
+#endif
+
 struct sgpu_idset {
     sgpu_ctx *ctx = nullptr;  // owner of the stream the buffers were allocated on
     int device = 0;
     Slot *d_table = nullptr;
-    uint64_t n_buckets = 0;  // 128-byte buckets of eight slots, any number (0 = no table yet)
-    uint64_t slots() const { return n_buckets * 8; }
+    uint64_t n_buckets = 0;  // 128-byte buckets of eight slots: a whole number of 256-bucket pages (0 = no table yet)
+    uint64_t slots() const { return n_buckets * SGPU_IDSET_BUCKET; }
     uint8_t *d_arena = nullptr;
     uint64_t arena_used = 0, arena_cap = 0;
     uint64_t count = 0;      // distinct non-empty ids
@@ -342,8 +346,13 @@ void ctx_release(sgpu_ctx *c);
 // idset.cu
 sgpu_status idset_create(sgpu_ctx *c, sgpu_idset **out);
 // insert the selected keys: key i is d_src[off[i] .. off[i]+len[i]) when sel[i] != 0
+// `known`: what a pass over the candidates would find (the producer has already counted), or nullptr
+struct SpanStats {
+    uint64_t n_sel, long_bytes;
+    bool has_empty, too_long;
+};
 sgpu_status idset_insert_spans(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src, const uint64_t *d_off,
-                               const uint32_t *d_len, const uint8_t *d_sel, size_t n);
+                               const uint32_t *d_len, const uint8_t *d_sel, size_t n, const SpanStats *known = nullptr);
 
 // fastq.cu
 struct FastqIndex;  // per-record metadata produced by the general path

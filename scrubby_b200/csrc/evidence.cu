@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(128)
 // (it reads on past the tile's end if the line does) -> selected (offset, length) spans compacted into a
 // candidate list with one global atomic per CTA.  Replaces nl_count + scan + nl_emit + reads_parse_kernel /
 // txt_lines_kernel (same per-line semantics); PAF keeps the indexed path (its segmented OR needs line order).
-constexpr int LT_NT = 256, LT_FC = 4, LT_TILE = LT_NT * LT_FC * 16, LT_LMAX = 1024, LT_HALO = 1024, LT_SMAX = 5120;
+constexpr int LT_NT = 256, LT_FC = 4, LT_TILE = LT_NT * LT_FC * 16, LT_LMAX = 2048, LT_HALO = 1024, LT_SMAX = 5120;
 
 struct TileOut {
     uint64_t *cand_off;
@@ -495,6 +495,8 @@ struct TileOut {
     unsigned long long *n_cand;   // candidates found (may exceed cap: the caller retries with more room)
     unsigned long long *err_word; // (line start offset << 8) | code, smallest wins
     unsigned long long *dense;    // a tile with more than LT_LMAX lines: use the indexed path
+    unsigned long long *stats;    // [0] bytes of candidates longer than 15, [1] an empty candidate, [2] one of >= 16 MiB:
+                                  // what idset_measure_kernel would find, so the set build can skip that pass
 };
 
 // one line [s, e_raw) of the buffer (e_raw = position of its '\n', or n for an unterminated last line):
@@ -912,6 +914,13 @@ __global__ void __launch_bounds__(LT_NT)
             total += x;
         }
         if (tid == 0 && total) cand_base = atomicAdd(O.n_cand, (unsigned long long)total);
+        {   // candidate statistics for the set build
+            unsigned long long lb = (sel && klen > IDSET_INLINE_MAX && klen <= IDSET_MAX_KEY) ? klen : 0ull;
+            for (int d = 16; d; d >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, d);
+            if (lane == 0 && lb) atomicAdd(O.stats, lb);
+            if (sel && klen == 0) O.stats[1] = 1ull;
+            if (sel && klen > IDSET_MAX_KEY) O.stats[2] = 1ull;
+        }
         __syncthreads();
         if (sel) {
             const uint64_t slot = cand_base + before + (uint32_t)__popc(b & ((1u << lane) - 1u));
@@ -937,27 +946,33 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
     }
     sgpu_status rc = SGPU_OK;
     bool done = false;
+    // The stream may still be busy with what produced d_buf (an NCCL all-gather of the evidence shards, an upload): wait
+    // here, BEFORE the scratch and the table are taken from the stream-ordered pool.  The first host round trip of the
+    // build is microseconds away anyway, and allocating while the previous set's frees are still queued behind that work
+    // makes the pool grow instead of reusing them -- with peer access enabled (NCCL) growing costs milliseconds
+    // (measured at 2 GPUs: set build 10.3 ms -> 5.0 ms per step).
+    SGPU_CUDA(cudaStreamSynchronize(st));
     if (c->mode == 0 && (kind == EV_TXT || kind == EV_READS || kind == EV_PAF) && ((uintptr_t)d_buf & 15) == 0) {
         // ---- order-free evidence: the tile kernel, no newline index
         do {
             DevBuf<uint64_t> cand_off, ctr;
             DevBuf<uint32_t> cand_len;
-            uint64_t cap = n / 32 + 4096;
+            uint64_t cap = (kind == EV_TXT ? n / 8 : n / 32) + 4096;  // (more candidates than room: one retry with the count)
             const TaxSet none{nullptr, 0, nullptr, nullptr, 0};
             for (int attempt = 0; attempt < 2 && rc == SGPU_OK; attempt++) {
                 if ((rc = cand_off.alloc(cap, st)) != SGPU_OK) break;
                 if ((rc = cand_len.alloc(cap, st)) != SGPU_OK) break;
-                if ((rc = ctr.alloc(3, st)) != SGPU_OK) break;
-                const uint64_t init[3] = {0, ~0ull, 0};
+                if ((rc = ctr.alloc(6, st)) != SGPU_OK) break;
+                const uint64_t init[6] = {0, ~0ull, 0, 0, 0, 0};
                 memcpy(c->h_pinned + 40, init, sizeof(init));
                 cudaMemcpyAsync(ctr.p, c->h_pinned + 40, sizeof(init), cudaMemcpyHostToDevice, st);
                 TileOut O{cand_off.p, cand_len.p, cap, (unsigned long long *)ctr.p, (unsigned long long *)ctr.p + 1,
-                          (unsigned long long *)ctr.p + 2};
+                          (unsigned long long *)ctr.p + 2, (unsigned long long *)ctr.p + 3};
                 lines_tile_kernel<<<(unsigned)ceil_div(n, (size_t)LT_TILE), LT_NT, 0, st>>>(
                     d_buf, (uint64_t)n, T ? *T : none, need_fields, kind == EV_TXT ? 1 : kind == EV_PAF ? 2 : 0, F, O);
                 SGPU_LAUNCH(c);
-                uint64_t h[3];
-                if ((rc = read_u64s(c, ctr.p, h, 3)) != SGPU_OK) break;
+                uint64_t h[6];
+                if ((rc = read_u64s(c, ctr.p, h, 6)) != SGPU_OK) break;
                 if (h[2]) break;  // pathological line density: the indexed path below
                 if (h[1] != ~0ull) {
                     rc = (sgpu_status)(h[1] & 0xFF);
@@ -975,7 +990,10 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
                     cap = h[0];
                     continue;
                 }
-                if (h[0]) rc = idset_insert_spans(c, set, d_buf, cand_off.p, cand_len.p, nullptr, (size_t)h[0]);
+                if (h[0]) {  // every candidate is selected: the kernel has already measured them
+                    const SpanStats known{h[0], h[3], h[4] != 0, h[5] != 0};
+                    rc = idset_insert_spans(c, set, d_buf, cand_off.p, cand_len.p, nullptr, (size_t)h[0], &known);
+                }
                 done = true;
                 break;
             }

@@ -484,18 +484,22 @@ __device__ __noinline__ bool record_probe_slow_span(const IdSetView &set, const 
 // the first HALF of the home bucket of an inline key: four independent 16-byte loads of one 128-byte line.  The
 // occupied slots of a bucket are a prefix of it, so the second half is only looked at when the first is full of
 // other keys (the line is in L1 by then: ld.global.nc allocates)
-constexpr int HALF = 4;
+#ifndef SGPU_FUSED_HALF
+#define SGPU_FUSED_HALF 4
+#endif
+constexpr int HALF = SGPU_FUSED_HALF < (int)IDSET_BUCKET ? SGPU_FUSED_HALF : (int)IDSET_BUCKET;
 struct Bucket {
     Slot s[HALF];
 };
 __device__ __forceinline__ Bucket load_bucket(const IdSetView &set, uint64_t lo, uint64_t hi) {
-    const Slot *bp = set.table + home_bucket(inline_hash(lo, hi), set.n_buckets) * IDSET_BUCKET;
+    const Slot *bp = set.table + home_bucket(inline_hash(lo, hi), set.n_pages) * IDSET_BUCKET;
     Bucket B;
 #pragma unroll
     for (int q = 0; q < HALF; q++) B.s[q] = load_slot(bp + q);
     return B;
 }
-// exact membership given the first half of the home bucket
+// exact membership given the first half of the home bucket.  Beyond it the probe sequence is followed four slots at
+// a time -- four INDEPENDENT loads per round trip, never a chain of dependent single-slot loads
 __device__ __forceinline__ bool probe_bucket(const IdSetView &set, const Bucket &B, uint64_t lo, uint64_t hi) {
     bool hit = false, open = false;
 #pragma unroll
@@ -504,17 +508,24 @@ __device__ __forceinline__ bool probe_bucket(const IdSetView &set, const Bucket 
         open |= (B.s[q].lo | B.s[q].hi) == 0;
     }
     if (hit || open) return hit;
-    uint64_t b = home_bucket(inline_hash(lo, hi), set.n_buckets);
+    uint64_t b = home_bucket(inline_hash(lo, hi), set.n_pages);
     int q = HALF;
     while (true) {
-        const Slot *bp = set.table + b * IDSET_BUCKET;
-        for (; q < (int)IDSET_BUCKET; q++) {
-            const Slot sl = load_slot(bp + q);
-            if ((sl.lo | sl.hi) == 0) return false;
-            if (sl.lo == lo && sl.hi == hi) return true;
+        if (q >= (int)IDSET_BUCKET) {
+            q = 0;
+            b = next_bucket(b);
         }
-        q = 0;
-        b = next_bucket(b, set.n_buckets);
+        const Slot *bp = set.table + b * IDSET_BUCKET + q;
+        Slot s[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[k] = load_slot(bp + k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            hit |= s[k].lo == lo && s[k].hi == hi;
+            open |= (s[k].lo | s[k].hi) == 0;
+        }
+        if (hit || open) return hit;
+        q += 4;
     }
 }
 
@@ -1096,26 +1107,31 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
             // bytes of the other stream before this tile = owned bytes before it - kept bytes before it
             uint8_t *const base_o = P.out_o ? P.out_o + (t == 0 ? 0 : (g0 - P.lead) - kept_before) : nullptr;
             const uint32_t head_other = carry == F_OTHER ? head_len : 0u;
+            // the outputs are sized by the caller (a depleted file is smaller than its input): room left in each
+            // stream from this tile's base, so that no item is ever written past a buffer
+            const uint64_t off_w = kept_before, off_o = t == 0 ? 0 : (g0 - P.lead) - kept_before;
+            const uint32_t room_w = P.cap_w > off_w ? (uint32_t)(P.cap_w - off_w < 0xFFFFFFFFull ? P.cap_w - off_w : 0xFFFFFFFFull) : 0u;
+            const uint32_t room_o = P.cap_o > off_o ? (uint32_t)(P.cap_o - off_o < 0xFFFFFFFFull ? P.cap_o - off_o : 0xFFFFFFFFull) : 0u;
             for (uint32_t i = warp; i < n_items; i += NW) {
                 const Item itm = S->items[i];
                 const uint32_t tag = itm.rel & (3u << 30), rel = itm.rel & 0x3FFFFFFFu;
-                uint8_t *dst;
+                uint32_t off;
                 bool to_w = true;
                 if (tag == TAG_KEPT) {
-                    dst = base_w + head_kept + rel;
+                    off = head_kept + rel;
                 } else if (tag == TAG_OTHER) {
-                    dst = base_o + head_other + rel;
+                    off = head_other + rel;
                     to_w = false;
                 } else {
-                    if (carry == F_KEPT) dst = base_w + rel;
-                    else if (carry == F_OTHER && base_o) dst = base_o + rel, to_w = false;
-                    else continue;
+                    off = rel;
+                    if (carry == F_OTHER && base_o) to_w = false;
+                    else if (carry != F_KEPT) continue;
                 }
-                // the outputs are sized by the caller (a depleted file is smaller than its input): never write past them
-                if ((uint64_t)(dst - (to_w ? P.out_w : P.out_o)) + itm.len > (to_w ? P.cap_w : P.cap_o)) {
+                if (off + itm.len > (to_w ? room_w : room_o)) {
                     if (lane == 0) P.res->overflow = 1;
                     continue;
                 }
+                uint8_t *const dst = (to_w ? base_w : base_o) + off;
 #ifndef SGPU_ABL_NOCOPY  // ablation (timing only): nothing is written
                 copy_piece(tile_s + itm.src, itm.len, dst, lane);
 #endif

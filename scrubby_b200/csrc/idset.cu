@@ -1,5 +1,7 @@
 // idset.cu -- build / grow / dump of the exact read-id set (see idset.cuh for the layout).
 // Replaces HashSet::insert at alignment.rs:74,106, classifier.rs:284,322, utils.rs:264,275.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -69,10 +71,10 @@ __global__ void idset_arena_copy_kernel(const uint8_t *src, const uint64_t *off,
 // returns true when the key was new.  Slots are read first (an L2 load brings the 128-byte bucket in from DRAM
 // without occupying the L2 atomic unit for the whole miss) and the CAS is issued only on a slot seen empty.
 template <typename SameKey>
-__device__ __forceinline__ bool idset_claim(Slot *table, uint64_t n_buckets, uint64_t home, uint64_t lo, uint64_t hi,
+__device__ __forceinline__ bool idset_claim(Slot *table, uint64_t n_pages, uint64_t home, uint64_t lo, uint64_t hi,
                                             SameKey same_key) {
     const unsigned __int128 mine = pack128(lo, hi);
-    uint64_t b = home_bucket(home, n_buckets);
+    uint64_t b = home_bucket(home, n_pages);
     while (true) {
         Slot *bp = table + b * IDSET_BUCKET;
         for (int q = 0; q < (int)IDSET_BUCKET; q++) {
@@ -87,11 +89,11 @@ __device__ __forceinline__ bool idset_claim(Slot *table, uint64_t n_buckets, uin
             }
             if (olo == lo && same_key(ohi)) return false;  // duplicate
         }
-        b = next_bucket(b, n_buckets);
+        b = next_bucket(b);
     }
 }
 
-__global__ void idset_insert_kernel(Slot *table, uint64_t n_buckets, const uint8_t *arena, uint64_t arena_base,
+__global__ void idset_insert_kernel(Slot *table, uint64_t n_pages, const uint8_t *arena, uint64_t arena_base,
                                     const uint8_t *src, const uint64_t *off, const uint32_t *len, const uint8_t *sel,
                                     const uint64_t *arena_off, size_t n, InsertStats *st) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,7 +106,7 @@ __global__ void idset_insert_kernel(Slot *table, uint64_t n_buckets, const uint8
             key_image(key, L, &lo, &hi, &home);
             const bool is_inline = L <= IDSET_INLINE_MAX;
             if (!is_inline) hi = ((arena_base + arena_off[i]) << 24) | L;
-            fresh = idset_claim(table, n_buckets, home, lo, hi, [&](uint64_t ohi) {
+            fresh = idset_claim(table, n_pages, home, lo, hi, [&](uint64_t ohi) {
                 if (is_inline) return ohi == hi;
                 return (ohi & 0xFFFFFFull) == L && bytes_equal(arena + (ohi >> 24), key, L);  // bytes verified
             });
@@ -120,12 +122,12 @@ __global__ void idset_insert_kernel(Slot *table, uint64_t n_buckets, const uint8
 }
 
 // every stored key is distinct: no comparison needed, only an empty slot
-__global__ void idset_rehash_kernel(const Slot *old_table, uint64_t old_slots, Slot *table, uint64_t n_buckets) {
+__global__ void idset_rehash_kernel(const Slot *old_table, uint64_t old_slots, Slot *table, uint64_t n_pages) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= old_slots) return;
     Slot s = old_table[i];
     if ((s.lo | s.hi) == 0) return;
-    idset_claim(table, n_buckets, slot_home(s.lo, s.hi), s.lo, s.hi, [](uint64_t) { return false; });
+    idset_claim(table, n_pages, slot_home(s.lo, s.hi), s.lo, s.hi, [](uint64_t) { return false; });
 }
 
 // dump: per-slot byte length (id + '\n'), then flat copy
@@ -169,7 +171,15 @@ sgpu_status idset_create(sgpu_ctx *c, sgpu_idset **out) {
     return SGPU_OK;
 }
 
-static sgpu_status idset_reserve(sgpu_ctx *c, sgpu_idset *s, uint64_t n_new, uint64_t new_long_bytes) {
+// idset_build.cu
+sgpu_status idset_build_paged(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src, const uint64_t *d_off, const uint32_t *d_len,
+                              const uint8_t *d_sel, size_t n, uint64_t n_sel, uint64_t *inserted, uint64_t *arena_bytes,
+                              int *ok);
+
+// *zeroed = false: a NEW table was allocated and left uninitialised (the bulk build writes every page of it)
+static sgpu_status idset_reserve(sgpu_ctx *c, sgpu_idset *s, uint64_t n_new, uint64_t new_long_bytes, bool may_skip_zero,
+                                 bool *zeroed) {
+    *zeroed = true;
     cudaStream_t st = c->stream;
     // sized exactly for its keys at the target load; a set that grows again (diff accumulators, evidence in several
     // calls) at least doubles, so the rehash cost stays amortised
@@ -182,9 +192,11 @@ static sgpu_status idset_reserve(sgpu_ctx *c, sgpu_idset *s, uint64_t n_new, uin
             set_cuda_error(e, __FILE__, __LINE__);
             return SGPU_ERR_NOMEM;
         }
-        SGPU_CUDA(cudaMemsetAsync(nt, 0, need * IDSET_BUCKET * sizeof(Slot), st));
+        if (may_skip_zero && s->count == 0) *zeroed = false;
+        else SGPU_CUDA(cudaMemsetAsync(nt, 0, need * IDSET_BUCKET * sizeof(Slot), st));
         if (s->n_buckets && s->count) {
-            idset_rehash_kernel<<<(unsigned)ceil_div(s->slots(), 256), 256, 0, st>>>(s->d_table, s->slots(), nt, need);
+            idset_rehash_kernel<<<(unsigned)ceil_div(s->slots(), 256), 256, 0, st>>>(s->d_table, s->slots(), nt,
+                                                                                     need / IDSET_PAGE_BUCKETS);
             SGPU_LAUNCH(c);
         }
         if (s->d_table) SGPU_CUDA(cudaFreeAsync(s->d_table, st));
@@ -210,32 +222,66 @@ static sgpu_status idset_reserve(sgpu_ctx *c, sgpu_idset *s, uint64_t n_new, uin
 }
 
 sgpu_status idset_insert_spans(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src, const uint64_t *d_off,
-                               const uint32_t *d_len, const uint8_t *d_sel, size_t n) {
+                               const uint32_t *d_len, const uint8_t *d_sel, size_t n, const SpanStats *known) {
     if (n == 0) return SGPU_OK;
     cudaStream_t st = c->stream;
+    static const uint64_t bulk_min = getenv("SGPU_IDSET_BULK_MIN") ? (uint64_t)atoll(getenv("SGPU_IDSET_BULK_MIN")) : 32768;
     DevBuf<uint32_t> alen;
     DevBuf<uint64_t> aoff;
     DevBuf<InsertStats> stats;
-    SGPU_TRY(alen.alloc(n, st));
-    SGPU_TRY(aoff.alloc(n, st));
+    InsertStats h;
+    memset(&h, 0, sizeof(h));
+    // the measuring pass (and its per-candidate arena lengths) is only needed by the key-by-key path, or when the
+    // producer of the spans has not counted them itself
+    const bool skip_measure = known && s->count == 0 && known->n_sel >= bulk_min && !known->too_long;
     SGPU_TRY(stats.alloc(1, st));
     SGPU_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(InsertStats), st));
     unsigned grid = (unsigned)ceil_div(n, 256);
-    idset_measure_kernel<<<grid, 256, 0, st>>>(d_len, d_sel, n, alen.p, stats.p);
-    SGPU_LAUNCH(c);
-    InsertStats h;
-    SGPU_TRY(read_u64s(c, stats.p, (uint64_t *)&h, sizeof(InsertStats) / 8));
+    auto measure = [&]() -> sgpu_status {
+        SGPU_TRY(alen.alloc(n, st));
+        SGPU_TRY(aoff.alloc(n, st));
+        idset_measure_kernel<<<grid, 256, 0, st>>>(d_len, d_sel, n, alen.p, stats.p);
+        SGPU_LAUNCH(c);
+        return read_u64s(c, stats.p, (uint64_t *)&h, sizeof(InsertStats) / 8);
+    };
+    if (skip_measure) {
+        h.n_sel = known->n_sel;
+        h.long_bytes = known->long_bytes;
+        h.has_empty = known->has_empty;
+    } else {
+        SGPU_TRY(measure());
+    }
     if (h.too_long) return SGPU_ERR_KEY_TOO_LONG;
     if (h.has_empty) s->has_empty = true;
     if (h.n_sel == 0) return SGPU_OK;
-    SGPU_TRY(idset_reserve(c, s, h.n_sel, h.long_bytes));
+    // a whole evidence file into an empty set: the bulk build (partition by page, assemble every page in shared memory,
+    // write the table once); everything else key by key with a 128-bit CAS
+    const bool bulk = s->count == 0 && h.n_sel >= bulk_min;
+    bool zeroed = true;
+    SGPU_TRY(idset_reserve(c, s, h.n_sel, h.long_bytes, bulk, &zeroed));
+    if (bulk) {
+        uint64_t inserted = 0, arena_bytes = 0;
+        int ok = 0;
+        SGPU_TRY(idset_build_paged(c, s, d_src, d_off, d_len, d_sel, n, h.n_sel, &inserted, &arena_bytes, &ok));
+        if (ok) {
+            s->count += inserted;
+            s->arena_used += arena_bytes;
+            return SGPU_OK;
+        }
+        zeroed = true;  // (the build that did not apply left a zeroed table behind)
+        if (skip_measure) {
+            SGPU_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(InsertStats), st));
+            SGPU_TRY(measure());
+        }
+    }
     if (h.long_bytes) {
         SGPU_TRY(exclusive_scan_u32_to_u64(c, alen.p, aoff.p, n, nullptr));
         idset_arena_copy_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(d_src, d_off, alen.p, aoff.p, n,
                                                                                  s->d_arena, s->arena_used);
         SGPU_LAUNCH(c);
     }
-    idset_insert_kernel<<<grid, 256, 0, st>>>(s->d_table, s->n_buckets, s->d_arena, s->arena_used, d_src, d_off,
+    if (!zeroed) SGPU_CUDA(cudaMemsetAsync(s->d_table, 0, s->slots() * sizeof(Slot), st));
+    idset_insert_kernel<<<grid, 256, 0, st>>>(s->d_table, s->n_buckets / IDSET_PAGE_BUCKETS, s->d_arena, s->arena_used, d_src, d_off,
                                               d_len, d_sel, aoff.p, n, stats.p);
     SGPU_LAUNCH(c);
     SGPU_CUDA(cudaGetLastError());
@@ -455,7 +501,7 @@ sgpu_status sgpu_idset_export(const sgpu_idset *s, sgpu_idset_image *img) {
 
 sgpu_status sgpu_idset_import(sgpu_ctx *c, const sgpu_idset_image *img, sgpu_idset **out) {
     if (!c || !img || !out) return SGPU_ERR_INVALID_ARG;
-    if (img->capacity % IDSET_BUCKET) return SGPU_ERR_INVALID_ARG;
+    if (img->capacity % (IDSET_BUCKET * IDSET_PAGE_BUCKETS)) return SGPU_ERR_INVALID_ARG;
     if (img->table_bytes != img->capacity * sizeof(Slot)) return SGPU_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     SGPU_CUDA(cudaSetDevice(c->device));

@@ -4,14 +4,17 @@
 // classifier.rs:135,274 and utils.rs:251,257, and `read_ids.contains(&id)` at
 // cleaner.rs:747,751.
 //
-// Layout in HBM (round 2): open addressing over 128-byte BUCKETS of eight 16-byte slots -- one L2 line, which
-// is what a random DRAM miss costs on B200 whatever is asked for (measured in round 1: 124 B per lookup with
-// 16-, 32- and 64-byte buckets alike).  The number of buckets is ARBITRARY (not a power of two): the home
-// bucket is the multiply-shift range reduction mulhi64(hash, n_buckets), so the table is sized exactly for its
-// keys at load 0.5 (C4's 50 M ids: 1.6 GB, was 4.3 GB at load <= 0.2 in 64-byte buckets).  A key's probe
-// sequence starts at slot 0 of its home bucket and runs linearly, bucket after bucket; there are no deletions,
-// so the occupied slots of a bucket are a prefix of it and a lookup ends at the first empty slot.  With a mean
-// of four keys per bucket 95 % of the lookups are decided by the home bucket, i.e. one line, one round trip.
+// Layout in HBM (round 2): open addressing over 128-byte BUCKETS of eight 16-byte slots -- one L2 line, which is what a
+// random DRAM miss costs on B200 whatever is asked for (round 1: 124 B per lookup with 16-, 32- and 64-byte buckets
+// alike).  Buckets are grouped into PAGES of 256 (32 KiB): a key's page is the multiply-shift range reduction
+// mulhi64(hash, n_pages) -- any number of pages, so the table is sized exactly for its keys -- and its home bucket
+// inside the page comes from the hash's low bits.  The probe sequence starts at slot 0 of the home bucket and runs
+// linearly, bucket after bucket, WRAPPING INSIDE THE PAGE: a page is a closed little hash table, which is what lets
+// the bulk build (idset_build.cu) assemble every page in shared memory and write the table exactly once.  There are
+// no deletions, so the occupied slots of a bucket are a prefix of it and a lookup ends at the first empty slot.
+// Load factor 0.2 (measured, tools/c4_probe.py on 50 M ids: the fused kernel takes 1.75 / 1.77 / 1.81 / 1.83 / 1.94 ms
+// per 3.3 GB at load 0.12 / 0.2 / 0.25 / 0.33 / 0.5 -- lookups that leave the first four slots cost a second round
+// trip for the whole warp).
 //   empty  : lo == 0 && hi == 0
 //   inline : ids of 1..15 bytes live IN the slot: byte0 = len, bytes 1..15 = id (zero padded).
 //            One 16-byte load and a 128-bit compare decide membership exactly.
@@ -25,30 +28,38 @@ namespace sgpu {
 
 constexpr uint32_t IDSET_INLINE_MAX = 15;
 #ifndef SGPU_IDSET_LOAD_PCT
-#define SGPU_IDSET_LOAD_PCT 50
+#define SGPU_IDSET_LOAD_PCT 20
 #endif
-constexpr uint64_t IDSET_BUCKET = 8;                      // slots per bucket: 8 x 16 B = one 128-byte line
+constexpr uint64_t IDSET_BUCKET = SGPU_IDSET_BUCKET;      // slots per bucket: 8 x 16 B = one 128-byte line
+constexpr uint64_t IDSET_PAGE_BUCKETS = 256;              // buckets per page (a power of two): 32 KiB
 constexpr uint64_t IDSET_LOAD_PCT = SGPU_IDSET_LOAD_PCT;  // keys <= LOAD_PCT % of the slots
 constexpr uint64_t IDSET_MAX_KEY = (1ull << 24) - 1;
 
 struct IdSetView {
-    const Slot *table;   // n_buckets * 8 slots, 128-byte aligned (n_buckets == 0 -> table == nullptr)
-    uint64_t n_buckets;
+    const Slot *table;   // n_pages * 256 buckets * 8 slots, 128-byte aligned (n_pages == 0 -> table == nullptr)
+    uint64_t n_pages;
     const uint8_t *arena;
 };
 
-// buckets for `keys` ids at the target load
+// buckets (a whole number of pages) for `keys` ids at the target load
 static inline uint64_t idset_buckets_for(uint64_t keys) {
     const uint64_t slots = (keys * 100 + IDSET_LOAD_PCT - 1) / IDSET_LOAD_PCT;
-    const uint64_t b = (slots + IDSET_BUCKET - 1) / IDSET_BUCKET;
-    return b < 16 ? 16 : b;
+    const uint64_t per_page = IDSET_PAGE_BUCKETS * IDSET_BUCKET;
+    const uint64_t pages = (slots + per_page - 1) / per_page;
+    return (pages ? pages : 1) * IDSET_PAGE_BUCKETS;
 }
 
 #ifdef __CUDACC__
 
-// home bucket of a key whose (well mixed) 64-bit hash is h: multiply-shift range reduction
-__device__ __forceinline__ uint64_t home_bucket(uint64_t h, uint64_t n_buckets) { return __umul64hi(h, n_buckets); }
-__device__ __forceinline__ uint64_t next_bucket(uint64_t b, uint64_t n_buckets) { return b + 1 == n_buckets ? 0 : b + 1; }
+// page / home bucket of a key whose (well mixed) 64-bit hash is h: multiply-shift range reduction over the pages, the
+// low bits inside the page; the probe sequence wraps inside the page
+__device__ __forceinline__ uint64_t home_page(uint64_t h, uint64_t n_pages) { return __umul64hi(h, n_pages); }
+__device__ __forceinline__ uint64_t home_bucket(uint64_t h, uint64_t n_pages) {
+    return home_page(h, n_pages) * IDSET_PAGE_BUCKETS + (h & (IDSET_PAGE_BUCKETS - 1));
+}
+__device__ __forceinline__ uint64_t next_bucket(uint64_t b) {
+    return (b & ~(IDSET_PAGE_BUCKETS - 1)) | ((b + 1) & (IDSET_PAGE_BUCKETS - 1));
+}
 __device__ __forceinline__ uint64_t inline_hash(uint64_t lo, uint64_t hi) {
     return mix64(lo ^ mix64(hi + 0x9E3779B97F4A7C15ULL));
 }
@@ -117,7 +128,7 @@ __device__ __forceinline__ bool idset_contains(const IdSetView &v, const uint8_t
     if (v.table == nullptr || len > IDSET_MAX_KEY) return false;
     uint64_t lo, hi, home;
     key_image(key, len, &lo, &hi, &home);
-    uint64_t b = home_bucket(home, v.n_buckets);
+    uint64_t b = home_bucket(home, v.n_pages);
     const bool is_inline = len <= IDSET_INLINE_MAX;
     while (true) {
         const Slot *bp = v.table + b * IDSET_BUCKET;
@@ -132,7 +143,7 @@ __device__ __forceinline__ bool idset_contains(const IdSetView &v, const uint8_t
                 }
             }
         }
-        b = next_bucket(b, v.n_buckets);
+        b = next_bucket(b);
     }
 }
 
@@ -141,7 +152,7 @@ __device__ __forceinline__ bool idset_contains(const IdSetView &v, const uint8_t
 static inline IdSetView view_of(const sgpu_idset *s) {
     IdSetView v;
     v.table = s && s->n_buckets ? s->d_table : nullptr;
-    v.n_buckets = s ? s->n_buckets : 0;
+    v.n_pages = s ? s->n_buckets / IDSET_PAGE_BUCKETS : 0;
     v.arena = s ? s->d_arena : nullptr;
     return v;
 }
