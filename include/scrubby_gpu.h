@@ -122,10 +122,12 @@ sgpu_status sgpu_idset_from_paf_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, 
  *     MAPQ decimal 0..255; CIGAR "*" or (count op)+ with op in MIDNSHP=XB, count < 2^28;
  *   - SEQ "*" (length 0) or its byte length; with a CIGAR and a SEQ the CIGAR's query length (M I S = X)
  *     must equal it; QUAL "*" or as long as SEQ; any violation -> SGPU_ERR_SAM_RECORD at that line;
- *   - unmapped = FLAG & 4, or RNAME "*", or POS < 1 (htslib sets BAM_FUNMAP for both): skipped;
+ *   - RNAME other than "*" is looked up among the SN: names of the header's @SQ lines (bam_name2id): with no @SQ
+ *     line at all that is htslib's parse error "no SQ lines present in the header" -> SGPU_ERR_SAM_RECORD; a name the
+ *     header does not declare makes the record unmapped ("unrecognized reference name; treated as unmapped");
+ *   - unmapped = FLAG & 4, or RNAME "*" / undeclared, or POS < 1 (htslib sets BAM_FUNMAP for all of them): skipped;
  *   - QNAME must be valid UTF-8 (alignment.rs:187) -> SGPU_ERR_RECORD_NAME_UTF8.
- * Not restated: textual FLAG strings, and RNAME values missing from the @SQ header (htslib warns and treats
- * the record as unmapped; aligners always declare their references). */
+ * Not restated: textual FLAG strings; @SQ lines without LN: (htslib rejects the header). */
 sgpu_status sgpu_idset_from_sam(sgpu_ctx *, const uint8_t *buf, size_t n, uint64_t min_len,
                                 double min_cov, uint8_t min_mapq, sgpu_idset **out,
                                 uint64_t *err_line);

@@ -131,6 +131,18 @@ def ids_from_sam(buf: bytes, min_len=0, min_cov=0.0, min_mapq=0) -> set[bytes]:
         terminated = [True] * len(raw)
     else:
         terminated = [True] * (len(raw) - 1) + [False]
+    # the reference names the header declares (SN: of every @SQ line): htslib looks RNAME up among them
+    refs = set()
+    for line, term in zip(raw, terminated):
+        if term and line.endswith(b"\r"):
+            line = line[:-1]
+        if line.startswith(b"@SQ\t"):
+            sn = [x[3:] for x in line.split(b"\t")[1:] if x.startswith(b"SN:")]
+            if sn:
+                refs.add(sn[0])
+    have_sq = any((l[:-1] if (t and l.endswith(b"\r")) else l).startswith(b"@SQ\t") and
+                  any(x.startswith(b"SN:") for x in (l[:-1] if (t and l.endswith(b"\r")) else l).split(b"\t")[1:])
+                  for l, t in zip(raw, terminated))
     for no, (line, term) in enumerate(zip(raw, terminated)):
         if term and line.endswith(b"\r"):
             line = line[:-1]
@@ -145,7 +157,8 @@ def ids_from_sam(buf: bytes, min_len=0, min_cov=0.0, min_mapq=0) -> set[bytes]:
         ops = re.findall(rb"([0-9]+)([MIDNSHP=XB])", cigar)
         cigar_ok = cigar == b"*" or (ops and b"".join(a + b for a, b in ops) == cigar and
                                      all(int(a) < (1 << 28) for a, _ in ops))
-        if not (q and m and rname and sint(pos) and re.fullmatch(rb"[0-9]{1,18}", mapq) and int(mapq) <= 255 and
+        if not (q and m and rname and (rname == b"*" or have_sq) and sint(pos) and
+                re.fullmatch(rb"[0-9]{1,18}", mapq) and int(mapq) <= 255 and
                 cigar_ok and rnext and sint(pnext) and sint(tlen) and seq and qual):
             raise RefError(E_SAM, no)
         fl = int(m.group(1), 16) if m.group(1) else int(m.group(2), 8) if m.group(2) else int(m.group(3))
@@ -162,7 +175,7 @@ def ids_from_sam(buf: bytes, min_len=0, min_cov=0.0, min_mapq=0) -> set[bytes]:
             q.decode("utf-8")
         except UnicodeDecodeError:
             raise RefError(E_UTF8, no)
-        if (fl & 4) or rname == b"*" or int(pos) < 1:
+        if (fl & 4) or rname == b"*" or rname not in refs or int(pos) < 1:
             continue
         cov = 0.0 if qlen == 0 else float(qalen) / float(qlen)
         if (qalen >= min_len or cov >= min_cov) and int(mapq) >= min_mapq:

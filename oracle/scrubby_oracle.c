@@ -429,7 +429,10 @@ int orc_set_from_paf(const uint8_t *buf, size_t n, uint64_t min_len, double min_
  *     MAPQ decimal 0..255; CIGAR "*" or (count op)+ with op in MIDNSHP=XB, count < 2^28;
  *   - SEQ "*" (length 0) or its byte length; with a CIGAR and a SEQ the CIGAR's query length (M I S = X) must
  *     equal it; QUAL "*" or as long as SEQ;  any violation -> ORC_ERR_SAM_RECORD at that line;
- *   - unmapped = FLAG & 4, or RNAME "*", or POS < 1 (htslib sets BAM_FUNMAP for both): skipped
+ *   - RNAME other than "*" is looked up among the SN: names of the header's @SQ lines (bam_name2id): with NO @SQ line
+ *     at all that is a parse error ("no SQ lines present in the header") -> ORC_ERR_SAM_RECORD; a name that is not
+ *     declared makes the record unmapped ("unrecognized reference name; treated as unmapped");
+ *   - unmapped = FLAG & 4, or RNAME "*" / undeclared, or POS < 1 (htslib sets BAM_FUNMAP for all of them): skipped
  *     (alignment.rs:132-134);
  *   - qalen = sum of M and I counts (u32), qlen = SEQ length; pass iff (qalen >= min_len || cov >= min_cov)
  *     && mapq >= min_mapq with cov = qlen == 0 ? 0 : qalen / qlen (alignment.rs:136-140, :204-209);
@@ -504,6 +507,30 @@ int orc_set_from_sam(const uint8_t *buf, size_t n, uint64_t min_len, double min_
     size_t pos = 0;
     uint64_t line_no = 0;
     int rc = ORC_OK;
+    /* the reference names the header declares: SN: of every @SQ line */
+    orc_set *refs = orc_set_new();
+    uint64_t n_targets = 0;
+    while (pos < n) {
+        const uint8_t *s = buf + pos;
+        const uint8_t *nl = (const uint8_t *)memchr(s, '\n', n - pos);
+        size_t len = nl ? (size_t)(nl - s) : n - pos;
+        pos += len + (nl ? 1 : 0);
+        if (nl && len && s[len - 1] == '\r') len--;
+        if (len >= 4 && s[0] == '@' && s[1] == 'S' && s[2] == 'Q' && s[3] == '\t') {
+            size_t a = 4;
+            while (a < len) {
+                size_t b = a;
+                while (b < len && s[b] != '\t') b++;
+                if (b - a >= 3 && s[a] == 'S' && s[a + 1] == 'N' && s[a + 2] == ':') {
+                    orc_set_insert(refs, s + a + 3, b - a - 3);
+                    n_targets++;
+                    break;
+                }
+                a = b + 1;
+            }
+        }
+    }
+    pos = 0;
     while (pos < n && rc == ORC_OK) {
         const uint8_t *s = buf + pos;
         const uint8_t *nl = (const uint8_t *)memchr(s, '\n', n - pos);
@@ -519,7 +546,9 @@ int orc_set_from_sam(const uint8_t *buf, size_t n, uint64_t min_len, double min_
         }
         uint32_t flag = 0, n_ops = 0, cq = 0, qalen = 0;
         int64_t p = 0, mapq = 0, t = 0;
-        if (f[0].len == 0 || sam_flag(f[1].p, f[1].len, &flag) || f[2].len == 0 || sam_int(f[3].p, f[3].len, 1, &p) ||
+        const int rname_star = f[2].len == 1 && f[2].p[0] == '*';
+        if (f[0].len == 0 || sam_flag(f[1].p, f[1].len, &flag) || f[2].len == 0 || (!rname_star && n_targets == 0) ||
+            sam_int(f[3].p, f[3].len, 1, &p) ||
             sam_int(f[4].p, f[4].len, 0, &mapq) || mapq > 255 || sam_cigar(f[5].p, f[5].len, &n_ops, &cq, &qalen) ||
             f[6].len == 0 || sam_int(f[7].p, f[7].len, 1, &t) || sam_int(f[8].p, f[8].len, 1, &t) || f[9].len == 0 ||
             f[10].len == 0) {
@@ -537,12 +566,13 @@ int orc_set_from_sam(const uint8_t *buf, size_t n, uint64_t min_len, double min_
             rc = ORC_ERR_RECORD_NAME_UTF8;
             break;
         }
-        const int unmapped = (flag & 4) || (f[2].len == 1 && f[2].p[0] == '*') || p < 1;
+        const int unmapped = (flag & 4) || rname_star || !orc_set_contains(refs, f[2].p, f[2].len) || p < 1;
         if (unmapped) continue;
         const double cov = qlen == 0 ? 0.0 : (double)qalen / (double)qlen;
         if (((uint64_t)qalen >= min_len || cov >= min_cov) && (uint8_t)mapq >= min_mapq)
             orc_set_insert(set, f[0].p, f[0].len);
     }
+    orc_set_free(refs);
     if (rc != ORC_OK) {
         if (err_line) *err_line = line_no - 1;
         orc_set_free(set);

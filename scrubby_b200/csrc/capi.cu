@@ -492,9 +492,10 @@ static sgpu_status clean_host_pipelined(sgpu_ctx *c, const sgpu_idset *set, cons
                                 last_chunk && is_last, spec0 ? -1 : crlf, reverse, d_w[r].p, obuf, &nw,
                                 out_o ? d_o[r].p : nullptr, obuf, &no, &ck, true);
         if (getenv("SGPU_DEBUG"))
-            fprintf(stderr, "[sgpu] pipe chunk %zu/%zu a=%zu own=%zu buf=%zu nlb=%llu -> rc=%d nw=%zu no=%zu in=%llu out=%llu path=%u\n",
+            fprintf(stderr, "[sgpu] pipe chunk %zu/%zu a=%zu own=%zu buf=%zu nlb=%llu -> rc=%d nw=%zu no=%zu in=%llu out=%llu path=%u own_nl=%llu lead_nl=%llu\n",
                     k, K, a, own, buf_len, (unsigned long long)nb, (int)rc, nw, no,
-                    (unsigned long long)ck.reads_in, (unsigned long long)ck.reads_out, ck.path);
+                    (unsigned long long)ck.reads_in, (unsigned long long)ck.reads_out, ck.path,
+                    (unsigned long long)ck.own_newlines, (unsigned long long)ck.lead_newlines);
         if (rc == SGPU_ERR_PHASE_UNKNOWN || (spec && rc == SGPU_OK && ck.path != 1)) {
             rc = SGPU_OK;  // speculation not applicable: the caller comes back with the exact phase
             unknown = true;

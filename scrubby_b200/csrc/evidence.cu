@@ -208,9 +208,39 @@ __device__ __forceinline__ bool sam_cigar(const uint8_t *s, uint64_t n, uint32_t
     return true;
 }
 
+// the reference names the header declares: SN: of every "@SQ" line (htslib's bam_name2id looks RNAME up among them)
 __global__ void __launch_bounds__(128)
-    sam_parse_kernel(LineParams P, PafParams F, uint64_t n_lines, uint64_t *key_off, uint32_t *key_len, uint8_t *sel,
-                     unsigned long long *err_word) {
+    sam_sq_kernel(LineParams P, uint64_t n_lines, uint64_t *key_off, uint32_t *key_len, uint8_t *sel) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    uint64_t s, e, koff = 0;
+    uint32_t klen = 0;
+    uint8_t ok = 0;
+    if (line_span(P, i, &s, &e)) {
+        const uint8_t *in = P.in;
+        if (i < P.n_nl && e > s && in[e - 1] == '\r') e--;
+        if (e - s >= 4 && in[s] == '@' && in[s + 1] == 'S' && in[s + 2] == 'Q' && in[s + 3] == '\t') {
+            uint64_t a = s + 4;
+            while (a < e && !ok) {
+                uint64_t b = a;
+                while (b < e && in[b] != '\t') b++;
+                if (b - a >= 3 && in[a] == 'S' && in[a + 1] == 'N' && in[a + 2] == ':') {
+                    koff = a + 3;
+                    klen = (uint32_t)(b - a - 3);
+                    ok = 1;
+                }
+                a = b + 1;
+            }
+        }
+    }
+    key_off[i] = koff;
+    key_len[i] = klen;
+    sel[i] = ok;
+}
+
+__global__ void __launch_bounds__(128)
+    sam_parse_kernel(LineParams P, PafParams F, IdSetView refs, int have_sq, uint64_t n_lines, uint64_t *key_off,
+                     uint32_t *key_len, uint8_t *sel, unsigned long long *err_word) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lines) return;
     uint64_t s, e;
@@ -240,7 +270,9 @@ __global__ void __launch_bounds__(128)
                 code = SGPU_ERR_SAM_RECORD;
             } else {
 #define FLEN(k) (fe[k] - fs[k])
-                const bool good = FLEN(0) && sam_flag(in + fs[1], FLEN(1), &flag) && FLEN(2) &&
+                // RNAME other than "*" with no @SQ line at all: htslib's "no SQ lines present in the header" parse error
+                const bool rname_star = FLEN(2) == 1 && in[fs[2]] == '*';
+                const bool good = FLEN(0) && sam_flag(in + fs[1], FLEN(1), &flag) && FLEN(2) && (rname_star || have_sq) &&
                                   sam_int(in + fs[3], FLEN(3), true, &p) && sam_int(in + fs[4], FLEN(4), false, &mapq) &&
                                   mapq <= 255 && sam_cigar(in + fs[5], FLEN(5), &n_ops, &cq, &qalen) && FLEN(6) &&
                                   sam_int(in + fs[7], FLEN(7), true, &t) && sam_int(in + fs[8], FLEN(8), true, &t) &&
@@ -256,7 +288,10 @@ __global__ void __launch_bounds__(128)
                     } else if (!utf8_valid(in + fs[0], FLEN(0))) {
                         code = SGPU_ERR_RECORD_NAME_UTF8;
                     } else {
-                        const bool unmapped = (flag & 4u) || (FLEN(2) == 1 && in[fs[2]] == '*') || p < 1;
+                        // an undeclared RNAME: "unrecognized reference name; treated as unmapped" (tid -1 -> BAM_FUNMAP)
+                        const bool declared = !rname_star && (FLEN(2) == 0 ? false : (FLEN(2) <= IDSET_MAX_KEY &&
+                                                              idset_contains(refs, in + fs[2], (uint32_t)FLEN(2))));
+                        const bool unmapped = (flag & 4u) || rname_star || !declared || p < 1;
                         if (!unmapped) {
                             const double cov = qlen == 0 ? 0.0 : (double)qalen / (double)qlen;
                             ok = (((uint64_t)qalen >= F.min_len || cov >= F.min_cov) && (uint32_t)mapq >= F.min_mapq) ? 1 : 0;
@@ -999,6 +1034,7 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
             }
         } while (0);
     }
+    sgpu_idset *sam_refs = nullptr;
     if (!done && rc == SGPU_OK) do {
         DevBuf<uint64_t> nlpos, key_off, errw;
         DevBuf<uint32_t> key_len;
@@ -1022,8 +1058,13 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
             paf_segment_kernel<<<(unsigned)ceil_div(n_lines, 256), 256, 0, st>>>(pass.p, head.p, n_lines, sel.p);
             SGPU_LAUNCH(c);
         } else if (kind == EV_SAM) {
-            sam_parse_kernel<<<grid, 128, 0, st>>>(P, F, n_lines, key_off.p, key_len.p, sel.p,
-                                                   (unsigned long long *)errw.p);
+            // the header's @SQ names first (a small exact set of their own), then the records
+            sam_sq_kernel<<<grid, 128, 0, st>>>(P, n_lines, key_off.p, key_len.p, sel.p);
+            SGPU_LAUNCH(c);
+            if ((rc = idset_create(c, &sam_refs)) != SGPU_OK) break;
+            if ((rc = idset_insert_spans(c, sam_refs, d_buf, key_off.p, key_len.p, sel.p, n_lines)) != SGPU_OK) break;
+            sam_parse_kernel<<<grid, 128, 0, st>>>(P, F, view_of(sam_refs), sgpu_idset_len(sam_refs) != 0, n_lines, key_off.p,
+                                                   key_len.p, sel.p, (unsigned long long *)errw.p);
             SGPU_LAUNCH(c);
         } else if (kind == EV_TXT) {
             txt_lines_kernel<<<grid, 128, 0, st>>>(P, n_lines, key_off.p, key_len.p, sel.p,
@@ -1045,6 +1086,10 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
         // txt: a blank line is the empty id; the tail thread of a '\n'-terminated buffer offers
         // nothing because its sel is 0
     } while (0);
+    if (sam_refs) {
+        cudaStreamSynchronize(st);  // the record pass reads the reference names
+        sgpu_idset_free(sam_refs);
+    }
     if (rc != SGPU_OK) {
         sgpu_idset_free(set);
         return rc;

@@ -647,12 +647,20 @@ __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
 
 // CR / "+\n" checks of one newline by its role (the newlines of whole records are checked by the record's thread)
-__device__ __forceinline__ uint32_t check_newline(const uint8_t *tile, uint32_t p, uint32_t role, uint32_t avail) {
+// (a sequence line whose "+\n" lies beyond the last byte of a buffer that does not end the file -- p + 2 >= avail only
+// happens at the end of the buffer -- belongs to a record that starts in the halo, the next shard's)
+// A buffer that ends within two bytes of a sequence line's newline used to send the whole shard to the general path
+// (one chunk in 165 of a 2x150 file): only the file's last buffer (is_last) has to hold the separator line.
+__device__ __forceinline__ uint32_t check_newline(const FusedParams &P, const uint8_t *tile, uint32_t p, uint32_t role,
+                                                  uint32_t avail) {
     uint32_t fb = 0;
     if (tile[(int)p - 1] == '\r') fb = 3;  // CRLF: not canonical
     if (role == 1) {                       // end of the sequence line: "+\n" must follow
-        if (p + 2 >= avail) fb = 4;
-        else if (tile[p + 1] != '+' || tile[p + 2] != '\n') fb = 4;
+        if (p + 2 >= avail) {
+            if (P.is_last) fb = 4;
+        } else if (tile[p + 1] != '+' || tile[p + 2] != '\n') {
+            fb = 4;
+        }
     }
     return fb;
 }
@@ -1026,7 +1034,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                             const uint32_t role = (c0 + r) & 3, p = S->nlp[r];
                             const long long pp = (long long)(g0 + p);
                             total += (role == 0 || role == 3) ? -pp : pp;
-                            const uint32_t f = check_newline(tile, p, role, avail);
+                            const uint32_t f = check_newline(P, tile, p, role, avail);
                             if (f) fb = f;
                         }
                     } else {
@@ -1034,7 +1042,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                             const uint32_t role = (c0 + r) & 3, p = S->nlp[r];
                             const long long pp = (long long)(g0 + p);
                             head += (role == 0 || role == 3) ? -pp : pp;
-                            const uint32_t f = check_newline(tile, p, role, avail);
+                            const uint32_t f = check_newline(P, tile, p, role, avail);
                             if (f) fb = f;
                         }
                         total = head;
@@ -1042,7 +1050,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
                             const uint32_t role = (c0 + r) & 3, p = S->nlp[r];
                             const long long pp = (long long)(g0 + p);
                             total += (role == 0 || role == 3) ? -pp : pp;
-                            const uint32_t f = check_newline(tile, p, role, avail);
+                            const uint32_t f = check_newline(P, tile, p, role, avail);
                             if (f) fb = f;
                         }
                     }

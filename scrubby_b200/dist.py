@@ -16,6 +16,8 @@ file's host logic with the gloo backend at world_size 2.
 """
 from __future__ import annotations
 
+import os
+import sys
 from dataclasses import dataclass
 
 
@@ -437,6 +439,9 @@ def _clean_files_sharded(call, count_own_newlines, first_line_crlf, shards, dist
                 continue  # owns nothing
             ok = ok and c[0] == 0 and c[1] == 1 and (q == 0 or (before + c[3]) % 4 == 0)
             before += c[2]
+        if not ok and os.environ.get("SGPU_DIST_DEBUG") and rank == 0:
+            sys.stderr.write(f"[dist] file {f}: one pass not accepted; rows (status, path, own_nl, lead_nl, crlf, n_w, n_o, "
+                             f"reads_in, reads_out, owns) = {col}\n")
         if ok:
             results.append(DevShardResult(col[rank][5], col[rank][6], sum(c[5] for c in col[:rank]),
                                           sum(c[6] for c in col[:rank]), sum(c[5] for c in col), sum(c[6] for c in col),
@@ -515,7 +520,8 @@ def clean_files_sharded_host(api, ctx, ids, jobs, dist=None, reverse: bool = Fal
 
     def count(f):
         h_buf, sh = jobs[f][0], jobs[f][1]
-        return int((h_buf[: sh.own_len] == 10).sum())
+        step = 1 << 28  # (bounded temporaries: the comparison makes a byte per byte)
+        return sum(int((h_buf[a: min(sh.own_len, a + step)] == 10).sum()) for a in range(0, sh.own_len, step))
 
     def crlf(f):
         h_buf, sh = jobs[f][0], jobs[f][1]

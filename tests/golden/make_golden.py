@@ -254,9 +254,19 @@ sam_cases = [
                                                 + "\r\n" + sam("b", 0, "chr1", 5, 60, "10M", 10)).encode()),
          min_len=50, min_cov=0.5, min_mapq=0, expect=["a", "b"], why="b: qalen 10 < 50 but cov 1.0"),
     dict(name="header_only", buf=L(SAM_HDR.encode()), min_len=0, min_cov=0.0, min_mapq=0, expect=[]),
-    dict(name="octal_flag", buf=L((sam("o", "04", "chr1", 5, 60, "150M", 150) + "\n"
+    dict(name="octal_flag", buf=L((SAM_HDR + sam("o", "04", "chr1", 5, 60, "150M", 150) + "\n"
                                   + sam("p", "020", "chr1", 5, 60, "150M", 150) + "\n").encode()),
          min_len=0, min_cov=0.0, min_mapq=0, expect=["p"], why="04 = unmapped; 020 = 16 reverse strand"),
+    dict(name="undeclared_rname_is_unmapped",
+         buf=L((SAM_HDR + sam("k", 0, "chr1", 5, 60, "150M", 150) + "\n" + sam("u", 0, "chr2", 5, 60, "150M", 150) + "\n"
+                + sam("v", 0, "chr", 5, 60, "150M", 150) + "\n").encode()),
+         min_len=0, min_cov=0.0, min_mapq=0, expect=["k"],
+         why="htslib sam_parse1: 'unrecognized reference name; treated as unmapped' (tid -1 -> BAM_FUNMAP), "
+             "rust-htslib is_unmapped() skips it (alignment.rs:132-134)"),
+    dict(name="two_sq_lines", buf=L((SAM_HDR + "@SQ\tLN:5\tSN:chr2\n" + sam("u", 0, "chr2", 5, 60, "150M", 150) + "\n").encode()),
+         min_len=0, min_cov=0.0, min_mapq=0, expect=["u"], why="SN: may be any field of the @SQ line"),
+    dict(name="no_header_only_unmapped", buf=L((sam("s5", 4, "*", 0, 0, "*", 150) + "\n").encode()),
+         min_len=0, min_cov=0.0, min_mapq=0, expect=[], why="RNAME '*' needs no header"),
 ]
 sam_errors = [
     dict(name="ten_fields", buf=L(("\t".join(sam("e", 0, "chr1", 5, 60, "150M", 150).split("\t")[:10]) + "\n").encode()), error=22),
@@ -266,11 +276,14 @@ sam_errors = [
     dict(name="cigar_seq_mismatch", buf=L((sam("e", 0, "chr1", 5, 60, "149M", 150) + "\n").encode()), error=22),
     dict(name="qual_len_mismatch", buf=L((sam("e", 0, "chr1", 5, 60, "150M", 150, qual="I" * 149) + "\n").encode()), error=22),
     dict(name="flag_text", buf=L((sam("e", "abc", "chr1", 5, 60, "150M", 150) + "\n").encode()), error=22),
-    dict(name="blank_line", buf=L((sam("a", 0, "chr1", 5, 60, "150M", 150) + "\n\n"
-                                  + sam("b", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()), error=22, error_line=1),
+    dict(name="blank_line", buf=L((SAM_HDR + sam("a", 0, "chr1", 5, 60, "150M", 150) + "\n\n"
+                                  + sam("b", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()), error=22, error_line=4),
     dict(name="error_after_header", buf=L((SAM_HDR + sam("a", 0, "chr1", 5, 60, "150M", 150) + "\n"
                                           + sam("e", 0, "chr1", "x", 60, "150M", 150) + "\n").encode()), error=22, error_line=4),
-    dict(name="qname_not_utf8", buf=L(b"\xff" + (sam("e", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()), error=8),
+    dict(name="qname_not_utf8", buf=L(SAM_HDR.encode() + b"\xff" + (sam("e", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()),
+         error=8, error_line=3),
+    dict(name="no_sq_lines", buf=L((sam("a", 4, "*", 0, 0, "*", 150) + "\n" + sam("b", 0, "chr1", 5, 60, "150M", 150) + "\n").encode()),
+         error=22, error_line=1, why="htslib sam_parse1: 'no SQ lines present in the header' for any RNAME other than '*'"),
 ]
 
 # --- FASTA input: needletail 0.5.1 fasta reader + write_fasta under cleaner.rs:742-754 (hand-derived) -------------

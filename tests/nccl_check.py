@@ -1,4 +1,5 @@
-"""Real NCCL check of the multi-GPU driver (run under torchrun on >= 2 GPUs; not collected by pytest):
+"""Real NCCL check of the multi-GPU driver (run under torchrun on >= 2 GPUs; tests/test_gpu_multi.py launches it from
+pytest and self-skips below two devices):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
         tests/nccl_check.py
@@ -16,6 +17,7 @@ import torch.distributed as dist
 
 from bench import taxids_for_config
 from scrubby_b200 import api, synth
+from scrubby_b200 import dist as sdist
 from scrubby_b200.dist import GpuOps, clean_fastq_sharded, diff_sharded
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -56,6 +58,49 @@ if rank == 0:
     print(f"diff: world {world} reads_in {sd.reads_in} reads_out {sd.reads_out} difference {sd.difference} "
           f"unique ids {len(sd.diff_ids)} -> {'identical' if good else 'MISMATCH'}")
     ok = ok and good
+# ---- the device-resident plane bench.py times (round 2): the id list all-gathered as equal byte ranges, the set built
+#      on every rank, both mate files in ONE pass with a speculated line phase and one exchange of a few integers;
+#      device buffers and host (pinned) buffers; concatenation in rank order == the single-GPU output
+txt = synth.gen_txt_ids(n, device=dev)
+total = int(txt.numel())
+per = sdist.evidence_shard_len(total, world)
+d_ev = torch.zeros(per + 16, dtype=torch.uint8, device=dev)
+mine = txt[rank * per: min(total, (rank + 1) * per)]
+d_ev[: mine.numel()] = mine
+ev = sdist.replicate_file_dev(d_ev, per, total, dist)
+assert torch.equal(ev, txt), "the all-gathered byte ranges are the file"
+ids2 = api.IdSet.from_txt(ctx, ev)
+files = [synth.gen_fastq(n, mate, device=dev) for mate in (1, 2)]
+whole = [api.clean_fastq(ctx, ids2, f.cpu().numpy().tobytes()) for f in files]
+for host in (False, True):
+    jobs, keep = [], []
+    for f in files:
+        sh = sdist.plan_shards(int(f.numel()), world, halo=1 << 16)[rank]
+        buf = torch.zeros(sh.buf_len + 16, dtype=torch.uint8, device=dev)
+        buf[: sh.buf_len] = f[sh.start: sh.start + sh.buf_len]
+        if host:
+            hb = torch.empty(sh.buf_len + 16, dtype=torch.uint8, pin_memory=True)
+            hb.copy_(buf)
+            jobs.append((hb, sh, torch.empty(sh.buf_len + 64, dtype=torch.uint8, pin_memory=True),
+                         torch.empty(sh.buf_len + 64, dtype=torch.uint8, pin_memory=True)))
+        else:
+            jobs.append((buf, sh, torch.empty(sh.buf_len + 64, dtype=torch.uint8, device=dev),
+                         torch.empty(sh.buf_len + 64, dtype=torch.uint8, device=dev)))
+    rs = (sdist.clean_files_sharded_host if host else sdist.clean_files_sharded_dev)(api, ctx, ids2, jobs, dist)
+    for k, (r, job) in enumerate(zip(rs, jobs)):
+        mine_w = bytes(job[2][: r.n_written].cpu().numpy())
+        mine_o = bytes(job[3][: r.n_other].cpu().numpy())
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine_w, mine_o, r.offset_written))
+        if rank == 0:
+            cat_w, cat_o = b"".join(p[0] for p in parts), b"".join(p[1] for p in parts)
+            offs = [p[2] for p in parts]
+            good = cat_w == whole[k].written and cat_o == whole[k].other and r.one_pass and \
+                (r.reads_in, r.reads_out) == (whole[k].reads_in, whole[k].reads_out) and \
+                offs == [sum(len(p[0]) for p in parts[:q]) for q in range(world)]
+            print(f"one-pass {'host' if host else 'device'} buffers, mate {k + 1}: world {world} reads_in {r.reads_in} "
+                  f"reads_out {r.reads_out} one_pass {r.one_pass} -> {'identical' if good else 'MISMATCH'}")
+            ok = ok and good
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()

@@ -266,6 +266,38 @@ def test_host_shard_pipeline_small_chunks(ctx, monkeypatch):
     assert b"".join(outs) == whole.written
 
 
+def test_host_shard_pipeline_default_chunks(ctx):
+    """the host shard entry point with its real 128 MiB chunks: a 1 GB file in two shards, each pipelined over several
+    chunks; newline counts, speculation check and bytes as for the unsharded call"""
+    n = int(os.environ.get("SGPU_TEST_PIPE_RECORDS", "3000000"))
+    d_fq = synth.gen_fastq(n, 1, device="cuda")
+    fq_t = d_fq.cpu()
+    gs = api.IdSet.from_txt(ctx, synth.gen_txt_ids(n, device="cuda"))
+    size = int(fq_t.numel())
+    d_all = torch.zeros(size + 16, dtype=torch.uint8, device="cuda")
+    d_all[:size] = d_fq
+    del d_fq
+    d_w = torch.empty(size + 64, dtype=torch.uint8, device="cuda")
+    whole = api.clean_fastq_dev(ctx, gs, d_all, size, d_w, None)
+    cut = (size // 2) & ~15
+    halo = 1 << 20
+    before, off = 0, 0
+    for s, (a, b) in enumerate([(0, cut), (cut, size)]):
+        end = size if s == 1 else b + halo
+        h_in = torch.zeros(end - a + 16, dtype=torch.uint8, pin_memory=True)
+        h_in[: end - a] = fq_t[a:end]
+        h_out = torch.empty(int((end - a) * 0.6), dtype=torch.uint8, pin_memory=True)
+        r = api.clean_fastq_shard_host(ctx, gs, h_in, end - a, b - a, 0 if s == 0 else None, s == 0, s == 1, None, h_out, None)
+        assert r.status == 0 and r.path == 1
+        assert r.own_newlines == int((fq_t[a:b] == 10).sum()), "own-range newline count over several chunks"
+        if s:
+            assert r.speculated and (before + r.lead_newlines) % 4 == 0
+        before += r.own_newlines
+        assert torch.equal(h_out[: r.n_written].cuda(), d_w[off: off + r.n_written])
+        off += r.n_written
+    assert off == whole.n_written
+
+
 # ------------------------------------------------------------------------------------------------ full-size parity
 N_THREADS = max(2, min(12, (os.cpu_count() or 4) - 2))
 

@@ -58,7 +58,7 @@ def _random_sam(seed: int, n: int = 400) -> bytes:
     import random
 
     rnd = random.Random(seed)
-    out = ["@HD\tVN:1.6", "@SQ\tSN:chr1\tLN:1000000"]
+    out = ["@HD\tVN:1.6", "@SQ\tSN:chr1\tLN:1000000", "@SQ\tLN:5000\tSN:chrM"]
     for i in range(n):
         ops, qlen = [], 0
         if rnd.random() < 0.9:
@@ -75,7 +75,7 @@ def _random_sam(seed: int, n: int = 400) -> bytes:
         seq = "*" if star else "".join(rnd.choice("ACGTN") for _ in range(qlen))
         qual = "*" if star or rnd.random() < 0.2 else "".join(chr(rnd.randint(33, 73)) for _ in range(qlen))
         flag = rnd.choice([0, 16, 4, 256, 2048, 83, 163, 77, "0x10", "0x904", "020", "04"])
-        rname = rnd.choice(["chr1", "chr1", "chr1", "*"])
+        rname = rnd.choice(["chr1", "chr1", "chrM", "*", "chr2", "chr"])  # chr2 / chr: not declared -> unmapped
         pos = rnd.choice([0, 1, 5, 99999])
         mapq = rnd.choice([0, 1, 30, 49, 50, 60, 255])
         q = f"read{rnd.randint(0, n // 2)}"

@@ -3,7 +3,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 (nvidia-smi topo -m; free -g; nproc; cat /sys/fs/cgroup/memory.max /sys/fs/cgroup/memory.current 2>/dev/null; ulimit -l) > gpurun_out/topo_n$N.txt 2>&1
-timeout 200 python tools/c4_probe.py 2>&1 | tail -1
+true
 if [ "$N" = "1" ]; then
   timeout 900 python bench.py --steps 5 > gpurun_out/bench_c4_n1.log 2> gpurun_out/bench_c4_n1.err
 else
