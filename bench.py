@@ -386,6 +386,19 @@ def run_ours(args):
         d_ev[: mine.numel()] = mine
         del ev_full, mine
         d_ev_all = torch.empty(world * per + 16, dtype=torch.uint8, device=dev) if world > 1 else None
+        # the evidence shards live in symmetric memory: every rank pulls the others' ranges over NVLink (no rendezvous
+        # per step); --gather nccl keeps the NCCL all-gather
+        peer_ev = None
+        gather_how = "nccl all-gather"
+        if world > 1 and args.gather == "pull":
+            try:
+                peer_ev = sdist.PeerFile(per, dist, dev)
+                peer_ev.local[: per + 16].copy_(d_ev)
+                peer_ev.publish(dist)
+                gather_how = "peer pull (symmetric memory, NVLink P2P copies)"
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] rank {rank}: symmetric memory unavailable ({type(e).__name__}: {e}); NCCL all-gather\n")
+                peer_ev = None
         taxids = None
         n_k = per if world > 1 else ev_total
         # a depleted file is smaller than its input: the outputs are sized for the expected kept fraction + slack
@@ -414,7 +427,10 @@ def run_ours(args):
         if timed:
             ph.begin()
         if c4:
-            ev = sdist.replicate_file_dev(d_ev, per, ev_total, D, d_ev_all)
+            if peer_ev is not None:
+                ev = peer_ev.pull(ev_total, d_ev_all)
+            else:
+                ev = sdist.replicate_file_dev(d_ev, per, ev_total, D, d_ev_all)
             if os.environ.get("SGPU_BENCH_SYNC"):
                 torch.cuda.synchronize()
             if timed:
@@ -497,7 +513,7 @@ def run_ours(args):
                       taxids, cap, barrier, (per, ev_total) if c4 else None, written_job, d_out, d_oth)
     else:
         e2e = {"t": float("nan"), "h2d": 0, "d2h": 0, "steps": 0, "each": [], "warm": [], "pairs": 0, "scale": 1.0,
-               "mem_gb": round(mem_available_gb(), 1), "note": "skipped (--e2e-steps 0)"}
+               "mem_gb": round(mem_available_gb(), 1), "note": "skipped (--e2e-steps 0)", "h2d_rank": 0, "d2h_rank": 0}
 
     # ---- max over ranks
     ms_t = torch.tensor([ms, e2e["t"] * 1e3 if e2e["steps"] else 0.0, f_ms / max(f_n, 1)] + [phases[n] for n in names], dtype=torch.float64,
@@ -537,8 +553,8 @@ def run_ours(args):
                 "fastq_bytes_total": bytes_all, "evidence_bytes": ev_total if c4 else n_k * world,
                 "outputs": "kept+removed" if args.split else "kept (reference-equivalent single output)",
                 "fraction_kept": kept_all / reads_all,
-                "parallelism": (f"byte-range shards x{world}; id list all-gathered (NCCL), set built on every rank; "
-                                "one-pass filter with speculated line phase; counters all-reduced") if c4
+                "parallelism": (f"byte-range shards x{world}; id list replicated by {gather_how}, set built on every rank; "
+                                "one-pass filter with speculated line phase; counters all-reduced (NCCL)") if c4
                 else f"chunk-sharded x{world} (co-partitioned evidence, no collective in the step)",
                 "host_cpus_rank0": cpulist, "setup_s_rank0": round(t_setup, 1),
                 "l2": "inputs (>= 8 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
@@ -548,8 +564,8 @@ def run_ours(args):
             "e2e": {"value": (reads_all / (e2e_ms * 1e-3) * e2e["scale"]) if e2e["steps"] else None, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e_ms, "steps": e2e["steps"],
                     "ms_each_rank0": e2e["each"], "warmup_ms_each_rank0": e2e["warm"], "pairs": e2e["pairs"],
-                    "h2d_gb_per_s_rank0": (e2e["h2d"] / e2e["t"] / 1e9) if e2e["steps"] else None,
-                    "d2h_gb_per_s_rank0": (e2e["d2h"] / e2e["t"] / 1e9) if e2e["steps"] else None,
+                    "h2d_gb_per_s_rank0": (e2e["h2d_rank"] / e2e["t"] / 1e9) if e2e["steps"] else None,
+                    "d2h_gb_per_s_rank0": (e2e["d2h_rank"] / e2e["t"] / 1e9) if e2e["steps"] else None,
                     "host_mem_available_gb": e2e["mem_gb"], "note": e2e["note"],
                     "timing": "host wall clock around the host-buffer C ABI calls of one step on pinned host "
                               "buffers (evidence upload + set build + both mate files), stream synchronised, max over ranks"},
@@ -587,7 +603,7 @@ def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, 
     if avail and need_gb * world > 0.55 * avail:
         if world > 1:
             return {"t": float("nan"), "h2d": 0, "d2h": 0, "steps": 0, "each": [], "warm": [], "pairs": 0, "scale": 1.0,
-                    "mem_gb": round(avail, 1),
+                    "mem_gb": round(avail, 1), "h2d_rank": 0, "d2h_rank": 0,
                     "note": f"not run: {need_gb * world:.0f} GB of pinned host memory needed, {avail:.0f} GB available"}
         frac = max(0.05, 0.55 * avail / need_gb)
         note = f"host memory: {avail:.0f} GB available, {need_gb:.0f} GB needed -> the first {frac:.2f} of every file"
@@ -671,15 +687,20 @@ def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, 
     h2d = sum(e_n) + n_k
     reads_e2e = sum(r.reads_in for r in rh)
     tot = torch.tensor([reads_e2e], dtype=torch.int64, device=dev)
-    if world > 1:
+    if world > 1 and not c4:  # (the sharded C4 results already carry the whole file's counters)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    io = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)  # bytes of the whole job per step (every rank moves its own shard)
+    h2d_rank, d2h_rank = h2d, d2h
+    h2d, d2h = int(io[0]), int(io[1])
     total_reads = 2 * pairs if c4 else 2 * pairs * world
     scale = int(tot[0]) / total_reads  # 1.0 unless the arm ran on a prefix
     if frac >= 1.0 and world == 1:
         assert sum(r.n_written for r in rh) == written_job, "host and device arms disagree"
     return {"t": t_e2e, "h2d": h2d, "d2h": d2h, "steps": e2e_steps, "each": [round(x * 1e3, 2) for x in e2e_each],
             "warm": [round(x * 1e3, 2) for x in warm_each], "pairs": int(tot[0]) // 2, "scale": scale,
-            "mem_gb": round(avail, 1), "note": note}
+            "mem_gb": round(avail, 1), "note": note, "h2d_rank": h2d_rank, "d2h_rank": d2h_rank}
 
 
 def main():
@@ -692,6 +713,8 @@ def main():
                     help="c4: 100M pairs + 50M-id list, strong scaling (BASELINE configs[3]); c2: classifier, 10M pairs per GPU")
     ap.add_argument("--pairs", type=int, default=0, help="c4: pairs of the whole job (default 100M); c2: pairs per GPU (10M)")
     ap.add_argument("--halo", type=int, default=1 << 20, help="c4: bytes of halo after a shard's own range")
+    ap.add_argument("--gather", default="pull", choices=["pull", "nccl"],
+                    help="c4, N > 1: how the id list's byte ranges reach every rank (peer pull over NVLink, or NCCL all-gather)")
     ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="bounded CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work timed for cpu_baseline")
     ap.add_argument("--cpu-step-seconds", type=float, default=3.0, help="--impl reference: CPU work per step")

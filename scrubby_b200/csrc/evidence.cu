@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(LT_NT)
         }
         if (tid == 0 && total) cand_base = atomicAdd(O.n_cand, (unsigned long long)total);
         {   // candidate statistics for the set build
-            unsigned long long lb = (sel && klen > IDSET_INLINE_MAX && klen <= IDSET_MAX_KEY) ? klen : 0ull;
+            unsigned long long lb = (sel && klen > IDSET_INLINE_MAX && klen <= IDSET_MAX_KEY) ? arena_padded(klen) : 0ull;
             for (int d = 16; d; d >>= 1) lb += __shfl_xor_sync(0xffffffffu, lb, d);
             if (lane == 0 && lb) atomicAdd(O.stats, lb);
             if (sel && klen == 0) O.stats[1] = 1ull;

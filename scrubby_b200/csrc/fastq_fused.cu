@@ -148,10 +148,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+#ifdef SGPU_LD_EF  // experiment: the input is read once -- evict-first in L2
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -179,7 +188,11 @@ __device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long 
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_global_v4(void *p, uint4 v) {
+#ifdef SGPU_ST_CS  // experiment: streaming (evict-first) output stores
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 __device__ __forceinline__ void st_global_u8(void *p, uint32_t v) {
     asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -456,9 +469,73 @@ __device__ __forceinline__ RecPrep record_prepare(uint32_t tile_s, uint32_t sp, 
     R.mode = 1;
     return R;
 }
+// Ids of 16..64 bytes (Illumina / ONT read names) without byte loops: the token's end from 16-byte windows, the hash
+// word-wise from shared memory (hash_words == hash_bytes), four independent slot loads per round, and a fingerprint
+// hit verified word-wise against the 16-byte aligned arena entry -- only HITS touch the arena.  It runs inside the
+// (not inlined) scanning routines below: its registers stay out of the kernel's budget, the inline-id path is the
+// tuned one.
+// Returns (token length << 1) | member, or LONG_NA: not applicable (leading blank, longer than 64 bytes, a stop byte
+// that is not white space, too close to the end of the buffer) -- the scanning routine decides.
+constexpr uint32_t LONG_NA = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t record_probe_long(const IdSetView &set, uint32_t tile_s, uint32_t sp, uint32_t avail) {
+    const uint32_t a = sp + 1;
+    if (a + 84 > avail) return LONG_NA;
+    const uint32_t sa = tile_s + a;
+    const uint32_t wa = sa & ~3u, sh = (sa & 3u) * 8u;
+    auto word = [&](uint32_t k) { return __funnelshift_r(lds_u32(wa + 4 * k), lds_u32(wa + 4 * k + 4), sh); };
+    uint32_t len = 0, cb = 0;
+    bool found = false;
+#pragma unroll 1
+    for (uint32_t w = 0; w < 5 && !found; w++) {
+        const uint32_t w0 = word(4 * w), w1 = word(4 * w + 1), w2 = word(4 * w + 2), w3 = word(4 * w + 3);
+        const uint32_t stop = gather16(le20_flags(w0), le20_flags(w1), le20_flags(w2), le20_flags(w3));
+        if (stop) {
+            const uint32_t k = (uint32_t)(__ffs(stop) - 1);
+            len = 16 * w + k;
+            const uint32_t cw = k < 4 ? w0 : k < 8 ? w1 : k < 12 ? w2 : w3;
+            cb = (cw >> (8 * (k & 3))) & 0xFFu;
+            found = true;
+        }
+    }
+    if (!found || len <= IDSET_INLINE_MAX || len > 64 || !(cb == 0x20u || (cb - 9u) < 5u)) return LONG_NA;
+    if (set.table == nullptr) return len << 1;
+    const uint64_t lo = 0x80ull | (hash_words(word, len) & ~0xFFull);
+    uint64_t b = home_bucket(mix64(lo), set.n_pages);
+    int q = 0;
+    while (true) {
+        const Slot *bp = set.table + b * IDSET_BUCKET + q;
+        Slot s[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[k] = load_slot(bp + k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if ((s[k].lo | s[k].hi) == 0) return len << 1;
+            if (s[k].lo == lo && (s[k].hi & 0xFFFFFFull) == len && arena_equal_words(set.arena + (s[k].hi >> 24), word, len))
+                return (len << 1) | 1u;
+        }
+        q += 4;
+        if (q >= (int)IDSET_BUCKET) {
+            q = 0;
+            b = next_bucket(b);
+        }
+    }
+}
+
 // general token scan + probe: skip leading blanks, run to the next blank / newline
+// LONG: the set holds ids of 16 bytes and more (it has a key arena): the vectorised long-id probe goes first.  A set of
+// inline ids only cannot hold a long id, and the kernel variant for it keeps these routines (and the registers the
+// calls cost around them) as light as they were.
+template <bool LONG>
 __device__ __forceinline__ bool record_probe_scan(const IdSetView &set, const uint8_t *tile, uint32_t sp, uint32_t avail,
                                                   uint32_t *why, uint32_t *tok_a, uint32_t *tok_len) {
+    if (LONG) {
+        const uint32_t lr = record_probe_long(set, smem_u32(tile), sp, avail);
+        if (lr != LONG_NA) {
+            *tok_a = sp + 1;
+            *tok_len = lr >> 1;
+            return (lr & 1u) != 0;
+        }
+    }
     uint32_t a = sp + 1;
     while (a < avail && is_ws_ascii(tile[a]) && tile[a] != '\n') a++;
     uint32_t q = a;
@@ -471,15 +548,17 @@ __device__ __forceinline__ bool record_probe_scan(const IdSetView &set, const ui
     *tok_len = q - a;
     return idset_contains(set, tile + a, q - a);
 }
+template <bool LONG>
 __device__ __noinline__ bool record_probe_slow(const IdSetView &set, const uint8_t *tile, uint32_t sp, uint32_t avail,
                                                uint32_t *why) {
     uint32_t ta, tl;
-    return record_probe_scan(set, tile, sp, avail, why, &ta, &tl);
+    return record_probe_scan<LONG>(set, tile, sp, avail, why, &ta, &tl);
 }
 // ids mode: the token's span as well
+template <bool LONG>
 __device__ __noinline__ bool record_probe_slow_span(const IdSetView &set, const uint8_t *tile, uint32_t sp,
                                                     uint32_t avail, uint32_t *why, uint32_t *tok_a, uint32_t *tok_len) {
-    return record_probe_scan(set, tile, sp, avail, why, tok_a, tok_len);
+    return record_probe_scan<LONG>(set, tile, sp, avail, why, tok_a, tok_len);
 }
 // the first HALF of the home bucket of an inline key: four independent 16-byte loads of one 128-byte line.  The
 // occupied slots of a bucket are a prefix of it, so the second half is only looked at when the first is full of
@@ -494,8 +573,22 @@ struct Bucket {
 __device__ __forceinline__ Bucket load_bucket(const IdSetView &set, uint64_t lo, uint64_t hi) {
     const Slot *bp = set.table + home_bucket(inline_hash(lo, hi), set.n_pages) * IDSET_BUCKET;
     Bucket B;
+#ifndef SGPU_NO_LD256  // two 256-bit loads (sm_100: LDG.E.256) instead of four 128-bit ones: half the L1 wavefronts per
+                       // lookup (measured: 1.827 -> 1.810 ms per 3.3 GB against a 50 M-id set)
+    static_assert(HALF == 4, "two slots per 256-bit load");
+#pragma unroll
+    for (int q = 0; q < HALF; q += 2) {
+        unsigned long long a, b, c, d;
+        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(bp + q));
+        B.s[q].lo = a;
+        B.s[q].hi = b;
+        B.s[q + 1].lo = c;
+        B.s[q + 1].hi = d;
+    }
+#else
 #pragma unroll
     for (int q = 0; q < HALF; q++) B.s[q] = load_slot(bp + q);
+#endif
     return B;
 }
 // exact membership given the first half of the home bucket.  Beyond it the probe sequence is followed four slots at
@@ -665,7 +758,7 @@ __device__ __forceinline__ uint32_t check_newline(const FusedParams &P, const ui
     return fb;
 }
 
-template <bool IDS>
+template <bool IDS, bool LONG>
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(FusedParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     CtaSmem *S = reinterpret_cast<CtaSmem *>(smem_raw);
@@ -941,8 +1034,8 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fastq_fused_kernel(Fuse
 #else
                                 if (R.mode == 1) hit = inl && probe_bucket(P.set, first, R.lo, R.hi);
 #endif
-                                else if (IDS) hit = record_probe_slow_span(P.set, tile, sp, avail, &why, &tok_a, &tok_len);
-                                else hit = record_probe_slow(P.set, tile, sp, avail, &why);
+                                else if (IDS) hit = record_probe_slow_span<LONG>(P.set, tile, sp, avail, &why, &tok_a, &tok_len);
+                                else hit = record_probe_slow<LONG>(P.set, tile, sp, avail, &why);
                                 if (IDS && R.mode == 1) {
                                     tok_a = sp + 1;
                                     tok_len = (uint32_t)(R.lo & 0xFFu);
@@ -1233,10 +1326,12 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     static bool attr_done[64] = {false};
     const size_t smem = sizeof(CtaSmem);
     if (!attr_done[c->device & 63]) {
-        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SGPU_CUDA(cudaFuncSetAttribute(fastq_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        const void *variants[4] = {(const void *)fastq_fused_kernel<false, false>, (const void *)fastq_fused_kernel<false, true>,
+                                   (const void *)fastq_fused_kernel<true, false>, (const void *)fastq_fused_kernel<true, true>};
+        for (const void *k : variants) {
+            SGPU_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SGPU_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
         attr_done[c->device & 63] = true;
     }
     uint64_t n_tiles = ceil_div(n_in, (size_t)TILE);
@@ -1287,7 +1382,7 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     static int occ[64] = {0};
     if (!occ[c->device & 63]) {
         int o = 0;
-        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fastq_fused_kernel<false>, NTHREADS, smem));
+        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fastq_fused_kernel<false, false>, NTHREADS, smem));
         occ[c->device & 63] = o > 0 ? o : 1;
         if (getenv("SGPU_DEBUG"))
             fprintf(stderr, "[sgpu] fused kernel: tile %d B, %zu B shared memory per CTA, %d CTAs per SM\n", TILE, smem, o);
@@ -1314,8 +1409,15 @@ sgpu_status clean_fused_range(sgpu_ctx *c, const sgpu_idset *set, const uint8_t 
     }
     cudaMemcpyToSymbol(g_trace, &d_trace, sizeof(d_trace));
 #endif
-    if (ids) fastq_fused_kernel<true><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
-    else fastq_fused_kernel<false><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
+    // a set with a key arena holds ids of 16 bytes and more: the variant with the vectorised long-id probe
+    const bool long_ids = set && set->arena_used > 0;
+    if (ids) {
+        if (long_ids) fastq_fused_kernel<true, true><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
+        else fastq_fused_kernel<true, false><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
+    } else {
+        if (long_ids) fastq_fused_kernel<false, true><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
+        else fastq_fused_kernel<false, false><<<(unsigned)grid, NTHREADS, smem, st>>>(P);
+    }
     SGPU_LAUNCH(c);
     if (c->profiling) SGPU_CUDA(cudaEventRecord(c->prof_events[c->prof_used++].second, st));
     SGPU_TRY(exclusive_scan_u64(c, (const uint64_t *)P.sum_total, prefix.p, n_tiles, nullptr));

@@ -31,7 +31,7 @@ __global__ void idset_measure_kernel(const uint32_t *len, const uint8_t *sel, si
     if (i < n) {
         s = sel ? sel[i] != 0 : true;
         uint32_t L = len[i];
-        l = (s && L > IDSET_INLINE_MAX && L <= IDSET_MAX_KEY) ? L : 0;
+        l = (s && L > IDSET_INLINE_MAX && L <= IDSET_MAX_KEY) ? arena_padded(L) : 0;  // (entries are 16-byte aligned)
         arena_len[i] = l;
         if (s && L > IDSET_MAX_KEY) st->too_long = 1;
         if (s && L == 0) st->has_empty = 1;
@@ -56,15 +56,14 @@ __global__ void idset_measure_kernel(const uint32_t *len, const uint8_t *sel, si
     }
 }
 
-__global__ void idset_arena_copy_kernel(const uint8_t *src, const uint64_t *off, const uint32_t *arena_len,
+__global__ void idset_arena_copy_kernel(const uint8_t *src, const uint64_t *off, const uint32_t *len, const uint32_t *arena_len,
                                         const uint64_t *arena_off, size_t n, uint8_t *arena, uint64_t arena_base) {
     // one warp per candidate
     size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (w >= n) return;
-    uint32_t L = arena_len[w];
-    if (L == 0) return;
-    warp_copy(arena + arena_base + arena_off[w], src + off[w], L, lane);
+    if (arena_len[w] == 0) return;
+    warp_copy(arena + arena_base + arena_off[w], src + off[w], len[w], lane);
 }
 
 // walks the probe sequence of (lo, hi) from its home bucket and claims the first empty slot with a 128-bit CAS;
@@ -276,7 +275,7 @@ sgpu_status idset_insert_spans(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src,
     }
     if (h.long_bytes) {
         SGPU_TRY(exclusive_scan_u32_to_u64(c, alen.p, aoff.p, n, nullptr));
-        idset_arena_copy_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(d_src, d_off, alen.p, aoff.p, n,
+        idset_arena_copy_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(d_src, d_off, d_len, alen.p, aoff.p, n,
                                                                                  s->d_arena, s->arena_used);
         SGPU_LAUNCH(c);
     }

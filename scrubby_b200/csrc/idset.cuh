@@ -14,7 +14,8 @@
 // no deletions, so the occupied slots of a bucket are a prefix of it and a lookup ends at the first empty slot.
 // Load factor 0.2 (measured, tools/c4_probe.py on 50 M ids: the fused kernel takes 1.75 / 1.77 / 1.81 / 1.83 / 1.94 ms
 // per 3.3 GB at load 0.12 / 0.2 / 0.25 / 0.33 / 0.5 -- lookups that leave the first four slots cost a second round
-// trip for the whole warp).
+// trip for the whole warp; the bulk build's page kernel is bound by the keys it places per page, not by the bytes it
+// writes: 1.28 ms at load 0.2, 1.59 ms at 0.25).
 //   empty  : lo == 0 && hi == 0
 //   inline : ids of 1..15 bytes live IN the slot: byte0 = len, bytes 1..15 = id (zero padded).
 //            One 16-byte load and a 128-bit compare decide membership exactly.
@@ -31,7 +32,10 @@ constexpr uint32_t IDSET_INLINE_MAX = 15;
 #define SGPU_IDSET_LOAD_PCT 20
 #endif
 constexpr uint64_t IDSET_BUCKET = SGPU_IDSET_BUCKET;      // slots per bucket: 8 x 16 B = one 128-byte line
-constexpr uint64_t IDSET_PAGE_BUCKETS = 256;              // buckets per page (a power of two): 32 KiB
+#ifndef SGPU_IDSET_PAGE_BUCKETS
+#define SGPU_IDSET_PAGE_BUCKETS 256
+#endif
+constexpr uint64_t IDSET_PAGE_BUCKETS = SGPU_IDSET_PAGE_BUCKETS;  // buckets per page (a power of two): 256 = 32 KiB
 constexpr uint64_t IDSET_LOAD_PCT = SGPU_IDSET_LOAD_PCT;  // keys <= LOAD_PCT % of the slots
 constexpr uint64_t IDSET_MAX_KEY = (1ull << 24) - 1;
 
@@ -80,6 +84,60 @@ __device__ __forceinline__ uint64_t hash_bytes(const uint8_t *p, uint32_t len) {
     return mix64(h);
 }
 
+// hash_bytes() over a key delivered as little-endian 32-bit words: word(k) = bytes 4k .. 4k+3 of the key (bytes past
+// the key's end may hold anything).  Same value as hash_bytes(), a fraction of the loads (keys of 16 bytes and more:
+// Illumina / ONT read names).
+template <typename Words>
+__device__ __forceinline__ uint64_t hash_words(Words word, uint32_t len) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL ^ ((uint64_t)len * 0xD6E8FEB86659FD93ULL);
+    uint32_t i = 0;
+    for (; i + 8 <= len; i += 8) {
+        const uint64_t w = (uint64_t)word(i >> 2) | ((uint64_t)word((i >> 2) + 1) << 32);
+        h = (h ^ w) * 0xFF51AFD7ED558CCDULL;
+        h ^= h >> 29;
+    }
+    const uint32_t rem = len - i;
+    uint64_t w = 0;
+    if (rem) {
+        w = (uint64_t)word(i >> 2);
+        if (rem > 4) w |= (uint64_t)word((i >> 2) + 1) << 32;
+        w &= (1ull << (8 * rem)) - 1ull;
+    }
+    h = (h ^ w) * 0xC4CEB9FE1A85EC53ULL;
+    return mix64(h);
+}
+// the words of a key at an arbitrarily aligned GLOBAL address; only words that hold key bytes are read
+struct GlobalKeyWords {
+    const uint32_t *w;
+    uint32_t sh, need;  // misalignment in bits; bytes from the aligned base that belong to the key
+    __device__ __forceinline__ GlobalKeyWords(const uint8_t *p, uint32_t len) {
+        const uint32_t mis = (uint32_t)((uintptr_t)p & 3u);
+        w = reinterpret_cast<const uint32_t *>(p - mis);
+        sh = mis * 8u;
+        need = mis + len;
+    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const {
+        const uint32_t a = 4u * k < need ? __ldg(w + k) : 0u;
+        const uint32_t b = (sh && 4u * (k + 1) < need) ? __ldg(w + k + 1) : 0u;
+        return __funnelshift_r(a, b, sh);
+    }
+};
+// key bytes == the arena entry at `e` (16-byte aligned: arena entries are padded to 16)?  word-wise
+template <typename Words>
+__device__ __forceinline__ bool arena_equal_words(const uint8_t *e, Words word, uint32_t len) {
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(e);
+    const uint32_t nw = len >> 2, rem = len & 3u;
+    for (uint32_t k = 0; k < nw; k++)
+        if (__ldg(a + k) != word(k)) return false;
+    if (rem) {
+        const uint32_t m = (1u << (8 * rem)) - 1u;
+        if ((__ldg(a + nw) & m) != (word(nw) & m)) return false;
+    }
+    return true;
+}
+constexpr uint32_t IDSET_ARENA_ALIGN = 16;  // arena entries start on 16-byte boundaries (their lengths are padded)
+__host__ __device__ __forceinline__ uint32_t arena_padded(uint32_t len) { return (len + IDSET_ARENA_ALIGN - 1) & ~(IDSET_ARENA_ALIGN - 1); }
+
 // builds the slot image of a key and its home hash (home_bucket() turns it into a bucket).  For long keys `hi` is left 0
 // (the caller fills offset/len when inserting).
 __device__ __forceinline__ void key_image(const uint8_t *p, uint32_t len, uint64_t *lo, uint64_t *hi,
@@ -116,7 +174,12 @@ __device__ __forceinline__ bool bytes_equal(const uint8_t *a, const uint8_t *b, 
 }
 
 __device__ __forceinline__ Slot load_slot(const Slot *p) {
+#ifdef SGPU_TBL_NA  // experiment: table lines are used once -- no L1 allocation
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+#else
     ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+#endif
     Slot s;
     s.lo = v.x;
     s.hi = v.y;

@@ -57,36 +57,58 @@ __global__ void __launch_bounds__(256)
     idset_count_kernel(const uint8_t *src, const uint64_t *off, const uint32_t *len, const uint8_t *sel, size_t n,
                        uint64_t n_pages, uint64_t arena_base, uint32_t *page_of, uint64_t *arena_at, uint32_t *page_count,
                        BuildStats *st) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        uint32_t page = NO_PAGE;
-        if (sel ? sel[i] != 0 : true) {
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // (whole warps stay in the loop: the arena reservation below is a warp-wide step)
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+        const size_t i = i0 + lane;
+        uint32_t page = NO_PAGE, need = 0;
+        if (i < n && (sel ? sel[i] != 0 : true)) {
             const uint32_t L = len[i];
             if (L >= 1 && L <= IDSET_MAX_KEY) {
                 uint64_t lo, hi, home;
                 if (L <= IDSET_INLINE_MAX) {
                     inline_image_global(src + off[i], L, &lo, &hi);
                     home = inline_hash(lo, hi);
-                } else {
-                    key_image(src + off[i], L, &lo, &hi, &home);
-                    arena_at[i] = arena_base + atomicAdd(&st->arena_used, (unsigned long long)L);
+                } else {  // fingerprint of the word-wise hash; the key's bytes get (16-byte aligned) arena space
+                    const uint64_t h = hash_words(GlobalKeyWords(src + off[i], L), L);
+                    lo = 0x80ull | (h & ~0xFFull);
+                    home = mix64(lo);
+                    need = arena_padded(L);
                 }
                 page = (uint32_t)home_page(home, n_pages);
                 atomicAdd(&page_count[page], 1u);
             }
         }
-        page_of[i] = page;
+        // arena space for the warp's long ids: one atomic per warp (a cursor every key bumps is a single hot word:
+        // 5 M long ids took 1.6 ms that way)
+        if (__any_sync(0xffffffffu, need != 0)) {
+            uint32_t inc = need;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += x;
+            }
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(&st->arena_used, (unsigned long long)inc);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            if (need) arena_at[i] = arena_base + base + (inc - need);
+        }
+        if (i < n) page_of[i] = page;
     }
 }
 
-// long ids: key bytes into the arena, one warp per candidate
+// long ids: key bytes into the arena (16-byte aligned entries), one thread per candidate, word-wise
 __global__ void idset_arena_fill_kernel(const uint8_t *src, const uint64_t *off, const uint32_t *len, const uint32_t *page_of,
                                         const uint64_t *arena_at, size_t n, uint8_t *arena) {
-    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= n || page_of[w] == NO_PAGE) return;
-    const uint32_t L = len[w];
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || page_of[i] == NO_PAGE) return;
+    const uint32_t L = len[i];
     if (L <= IDSET_INLINE_MAX) return;
-    warp_copy(arena + arena_at[w], src + off[w], L, lane);
+    const GlobalKeyWords word(src + off[i], L);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(arena + arena_at[i]);
+    const uint32_t nw = (L + 3) >> 2;
+    for (uint32_t k = 0; k < nw; k++) dst[k] = word(k);
 }
 
 // scatter: every selected candidate's slot image into its page's list.  Four candidates per thread and round: the
@@ -109,8 +131,8 @@ __global__ void __launch_bounds__(256)
                 if (L <= IDSET_INLINE_MAX) {
                     inline_image_global(src + off[i], L, &lo[k], &hi[k]);
                 } else {
-                    uint64_t home;
-                    key_image(src + off[i], L, &lo[k], &hi[k], &home);
+                    const uint64_t h = hash_words(GlobalKeyWords(src + off[i], L), L);
+                    lo[k] = 0x80ull | (h & ~0xFFull);
                     hi[k] = (arena_at[i] << 24) | L;
                 }
             }
@@ -132,7 +154,11 @@ struct PageSmem {
     uint32_t fresh;
 };
 __device__ __forceinline__ uint32_t page_slot(uint32_t b, uint32_t q) { return b * IDSET_BUCKET + ((q + b) & (IDSET_BUCKET - 1)); }
-__global__ void __launch_bounds__(256)
+#ifndef SGPU_PAGE_THREADS
+#define SGPU_PAGE_THREADS 256
+#endif
+constexpr int PAGE_THREADS = SGPU_PAGE_THREADS;
+__global__ void __launch_bounds__(PAGE_THREADS)
     idset_page_kernel(const ulonglong2 *in, const uint32_t *in_count, const uint64_t *in_start, uint64_t n_pages,
                       const uint8_t *arena, Slot *table, BuildStats *st) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -140,12 +166,18 @@ __global__ void __launch_bounds__(256)
     constexpr uint32_t SLOTS = IDSET_PAGE_BUCKETS * IDSET_BUCKET;
     static_assert(IDSET_BUCKET == 8, "the bank rotation assumes 8 slots of 16 bytes per bucket");
     uint32_t fresh = 0;
+    // (the next page's list is looked up while this one is assembled: two dependent loads less per page)
+    uint64_t n_next = blockIdx.x < n_pages ? in_count[blockIdx.x] : 0, start_next = blockIdx.x < n_pages ? in_start[blockIdx.x] : 0;
     for (uint64_t page = blockIdx.x; page < n_pages; page += gridDim.x) {
+        const uint64_t n = n_next;
+        const ulonglong2 *recs = in + start_next;
+        if (page + gridDim.x < n_pages) {
+            n_next = in_count[page + gridDim.x];
+            start_next = in_start[page + gridDim.x];
+        }
         for (uint32_t i = threadIdx.x; i < SLOTS; i += blockDim.x) S->slot[i] = make_ulonglong2(0ull, 0ull);
         for (uint32_t i = threadIdx.x; i < IDSET_PAGE_BUCKETS; i += blockDim.x) S->lock[i] = 0;
         __syncthreads();
-        const uint64_t n = in_count[page];
-        const ulonglong2 *recs = in + in_start[page];
         for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
             const ulonglong2 r = recs[i];
             const bool is_long = (r.x & 0xFF) == 0x80;
@@ -171,7 +203,9 @@ __global__ void __launch_bounds__(256)
                             bool same;
                             if (!is_long) same = ohi == r.y;
                             else same = (ohi & 0xFFFFFFull) == (r.y & 0xFFFFFFull) &&
-                                        bytes_equal(arena + (ohi >> 24), arena + (r.y >> 24), (uint32_t)(r.y & 0xFFFFFFull));
+                                        arena_equal_words(arena + (ohi >> 24),
+                                                          GlobalKeyWords(arena + (r.y >> 24), (uint32_t)(r.y & 0xFFFFFFull)),
+                                                          (uint32_t)(r.y & 0xFFFFFFull));
                             if (same) {
                                 done = true;
                                 full = false;
@@ -236,15 +270,17 @@ sgpu_status idset_build_paged(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src, 
     SGPU_LAUNCH(c);
     SGPU_TRY(exclusive_scan_u32_to_u64(c, counts.p, starts.p, n_pages, nullptr));
     if (any_long) {
-        idset_arena_fill_kernel<<<(unsigned)ceil_div(n * 32, (size_t)256), 256, 0, st>>>(d_src, d_off, d_len, page_of.p,
-                                                                                         arena_at.p, n, s->d_arena);
+        idset_arena_fill_kernel<<<(unsigned)ceil_div(n, (size_t)256), 256, 0, st>>>(d_src, d_off, d_len, page_of.p, arena_at.p, n,
+                                                                                    s->d_arena);
         SGPU_LAUNCH(c);
     }
     idset_scatter_kernel<<<grid, 256, 0, st>>>(d_src, d_off, d_len, n, page_of.p, arena_at.p, starts.p, counts.p + n_pages,
                                                recs.p);
     SGPU_LAUNCH(c);
-    const unsigned g3 = (unsigned)std::min<uint64_t>(n_pages, (uint64_t)c->sm_count * 6);
-    idset_page_kernel<<<g3, 256, sizeof(PageSmem), st>>>(recs.p, counts.p, starts.p, n_pages, s->d_arena, s->d_table, stats.p);
+    // resident CTAs per SM by shared memory (a page + its locks), at most 16
+    const unsigned per_sm = (unsigned)std::min<size_t>(16, (size_t)(220 * 1024) / (sizeof(PageSmem) + 1024));
+    const unsigned g3 = (unsigned)std::min<uint64_t>(n_pages, (uint64_t)c->sm_count * per_sm);
+    idset_page_kernel<<<g3, PAGE_THREADS, sizeof(PageSmem), st>>>(recs.p, counts.p, starts.p, n_pages, s->d_arena, s->d_table, stats.p);
     SGPU_LAUNCH(c);
     SGPU_CUDA(cudaGetLastError());
     BuildStats h;

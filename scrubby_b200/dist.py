@@ -387,6 +387,52 @@ def replicate_file_dev(d_shard, per: int, total: int, dist=None, out=None):
     return out[:total]
 
 
+class PeerFile:
+    """The byte ranges of a file in SYMMETRIC memory (torch.distributed._symmetric_memory): every rank's range is mapped
+    into every other rank's address space over NVLink / NVSwitch, so a rank PULLS the ranges it needs with plain
+    device-to-device copies -- no rendezvous per use.  An NCCL all-gather makes every rank wait until the slowest one
+    has arrived (measured at 8 GPUs: 3.2 ms per step for a 0.8 ms transfer); ranges that are resident and immutable
+    (the evidence shards, uploaded once) need no such hand-shake."""
+
+    def __init__(self, per: int, dist, device):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+
+        self.per, self.world, self.rank = per, dist.get_world_size(), dist.get_rank()
+        self.local = symm.empty(per + 16, dtype=torch.uint8, device=device)
+        self.local.zero_()
+        self.handle = symm.rendezvous(self.local, dist.group.WORLD)
+        self.peers = [self.handle.get_buffer(r, (per,), torch.uint8) for r in range(self.world)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(min(4, self.world - 1))]
+        self.ready = torch.cuda.Event()
+
+    def publish(self, dist):
+        """after the local range has been (re)written: every rank's range is final before anyone pulls"""
+        import torch
+
+        torch.cuda.current_stream().synchronize()
+        dist.barrier()
+
+    def pull(self, total: int, out):
+        """the whole file, contiguous, in `out`: the other ranks' ranges are copied over NVLink (up to four peers at a
+        time on side streams), the own range locally; the current stream continues when all of it has landed"""
+        import torch
+
+        cur = torch.cuda.current_stream()
+        self.ready.record(cur)
+        per = self.per
+        for k in range(1, self.world):
+            r = (self.rank + k) % self.world
+            st = self.streams[(k - 1) % len(self.streams)]
+            st.wait_event(self.ready)
+            with torch.cuda.stream(st):
+                out[r * per: (r + 1) * per].copy_(self.peers[r], non_blocking=True)
+        out[self.rank * per: (self.rank + 1) * per].copy_(self.local[:per], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return out[:total]
+
+
 def _gather_rows(dist, vals, world, device):
     """all_gather of a short int64 row per rank, on the device the ranks compute on"""
     import torch

@@ -168,12 +168,19 @@ static bool inflate_bgzf_parallel(const std::vector<uint8_t> &raw, std::vector<u
         const uint8_t *t = raw.data() + p + bsize - 4;
         const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
         const uint32_t crc = (uint32_t)t[-4] | ((uint32_t)t[-3] << 8) | ((uint32_t)t[-2] << 16) | ((uint32_t)t[-1] << 24);
+        // the BGZF specification caps a block's payload at 64 KiB: a member that claims more is not BGZF (and must not
+        // size the output: 28-byte members claiming 4 GiB each would ask for terabytes) -- the serial path decides
+        if (isize > 65536) return false;
         blks.push_back(Blk{p + 12 + xlen, bsize - 12 - xlen - 8, total, isize, crc});
         total += isize;
         p += bsize;
     }
     const auto t0 = std::chrono::steady_clock::now();
-    out.resize(total);
+    try {
+        out.resize(total);
+    } catch (const std::bad_alloc &) {
+        return false;
+    }
     const auto t1 = std::chrono::steady_clock::now();
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, blks.size() / 16));
@@ -213,8 +220,18 @@ static bool inflate_bgzf_parallel(const std::vector<uint8_t> &raw, std::vector<u
     return !bad;
 }
 
-std::vector<uint8_t> read_file(const std::string &path) {
+// is_file_empty (utils.rs:359-375): niffler's FileTooShort rule applies to the RAW file (fewer than 5 bytes), after that
+// only "one decompressed byte can be read" counts -- a .gz whose content is "r1\n" is NOT empty
+std::vector<uint8_t> read_file(const std::string &path, bool *empty) {
+    size_t raw_size = 0;
+    std::vector<uint8_t> v = read_file(path, &raw_size);
+    *empty = raw_size < 5 || v.empty();
+    return v;
+}
+
+std::vector<uint8_t> read_file(const std::string &path, size_t *raw_size) {
     std::vector<uint8_t> raw = slurp(path);
+    if (raw_size) *raw_size = raw.size();
     if (raw.size() < 5) return raw;  // FileTooShort => callers treat it as empty (utils.rs:365)
     if (raw[0] == 0x1f && raw[1] == 0x8b) {
         std::vector<uint8_t> out;
@@ -350,10 +367,11 @@ ReadAlignment ReadAlignment::from(const GpuContext &g, const std::string &path, 
 
 ReadAlignment ReadAlignment::from_paf(const GpuContext &g, const std::string &path, uint64_t min_len, double min_cov,
                                       uint8_t min_mapq) {
-    std::vector<uint8_t> buf = read_file(path);
+    bool empty = false;
+    std::vector<uint8_t> buf = read_file(path, &empty);
     ReadAlignment r;
     uint64_t err = 0;
-    if (buf.size() < 5) buf.clear();  // is_file_empty => empty set (alignment.rs:93)
+    if (empty) buf.clear();  // is_file_empty => empty set (alignment.rs:93)
     check(sgpu_idset_from_paf(g.get(), buf.data(), buf.size(), min_len, min_cov, min_mapq, r.aligned_reads.out(), &err),
           err, "from_paf");
     return r;
@@ -382,10 +400,11 @@ ReadAlignment ReadAlignment::from_sam(const GpuContext &g, const std::string &pa
 }
 
 ReadAlignment ReadAlignment::from_txt(const GpuContext &g, const std::string &path) {
-    std::vector<uint8_t> buf = read_file(path);
+    bool empty = false;
+    std::vector<uint8_t> buf = read_file(path, &empty);
     ReadAlignment r;
     uint64_t err = 0;
-    if (buf.size() < 5) buf.clear();
+    if (empty) buf.clear();
     check(sgpu_idset_from_txt(g.get(), buf.data(), buf.size(), r.aligned_reads.out(), &err), err, "from_txt");
     return r;
 }
@@ -585,19 +604,30 @@ ReadIdSet get_taxid_reads_metabuli(const GpuContext &g, const std::vector<std::s
 
 // ------------------------------------------------------------------------------------------ cleaner.rs
 void FastqCleaner::clean_reads(const GpuContext &g, const ReadIdSet &read_ids, bool reverse) const {
-    std::vector<uint8_t> in = read_file(input);
-    if (in.size() < 5) {  // parse_fastx_file_with_check => None: warn, create nothing (cleaner.rs:755-757)
+    bool empty = false;
+    std::vector<uint8_t> in = read_file(input, &empty);
+    if (empty) {  // parse_fastx_file_with_check => None: warn, create nothing (cleaner.rs:755-757)
         fprintf(stderr, "[WARN] - Input file is empty: %s\n", input.c_str());
         return;
     }
-    std::vector<uint8_t> out(2 * in.size() + 64);
+    // write_fastq re-serialises the input: the output only outgrows it when LF records follow a CRLF first record (+4
+    // bytes per record); uninitialised storage (a zero-filled vector of twice a 33 GB mate file is seconds of memset)
+    size_t cap = in.size() + in.size() / 16 + 4096;
+    std::unique_ptr<uint8_t[]> out(new uint8_t[cap]);
     size_t n_out = 0;
     sgpu_counts counts;
-    int st = sgpu_clean_fastq(g.get(), read_ids.get(), in.data(), in.size(), reverse ? 1 : 0, out.data(), out.size(), &n_out,
-                              nullptr, 0, nullptr, &counts);
-    if (st == SGPU_OK || (st >= SGPU_ERR_FASTQ_INVALID_START && st <= SGPU_ERR_FASTQ_HEADER)) {
-        // on a parse error the reference has already written the records before it
-        write_file(output, out.data(), n_out, 6);  // niffler::compression::Level::Six
+    int st = sgpu_clean_fastq(g.get(), read_ids.get(), in.data(), in.size(), reverse ? 1 : 0, out.get(), cap, &n_out, nullptr, 0,
+                              nullptr, &counts);
+    if (st == SGPU_ERR_CAPACITY) {
+        cap = 2 * in.size() + 64;
+        out.reset(new uint8_t[cap]);
+        st = sgpu_clean_fastq(g.get(), read_ids.get(), in.data(), in.size(), reverse ? 1 : 0, out.get(), cap, &n_out, nullptr, 0,
+                              nullptr, &counts);
+    }
+    // on a parse error the reference has already written the records before it; an input that is neither FASTQ nor
+    // FASTA fails before the writer exists (utils.rs:377-383), so nothing is created for it
+    if (st == SGPU_OK || (st >= SGPU_ERR_FASTQ_INVALID_START && st <= SGPU_ERR_FASTQ_HEADER && st != SGPU_ERR_FASTQ_UNKNOWN_FORMAT)) {
+        write_file(output, out.get(), n_out, 6);  // niffler::compression::Level::Six
     }
     check(st, counts.error_record, "clean_reads");
 }
@@ -971,8 +1001,9 @@ Difference ReadDifference::get_difference() const {
     memset(&c, 0, sizeof(c));
     for (size_t i = 0; i < input_reads.size() && i < output_reads.size(); i++) {  // zip, utils.rs:256
         std::vector<uint8_t> out = read_file(output_reads[i]);  // a missing output is an I/O error (utils.rs:259,360)
-        std::vector<uint8_t> in = read_file(input_reads[i]);
-        if (in.size() < 5) fprintf(stderr, "[WARN] - Input file is empty: %s\n", input_reads[i].c_str());
+        bool in_empty = false;
+        std::vector<uint8_t> in = read_file(input_reads[i], &in_empty);
+        if (in_empty) fprintf(stderr, "[WARN] - Input file is empty: %s\n", input_reads[i].c_str());
         check(sgpu_diff(g.get(), in.data(), in.size(), out.data(), out.size(), &c, diff_ids.out()), c.error_record, "get_difference");
     }
     Difference d;

@@ -133,7 +133,8 @@ class ReadIdSet {
 // ---------------------------------------------------------------- host I/O stage (niffler / needletail open)
 enum class Compression { No, Gzip, Bzip, Lzma };
 Compression compression_from_path(const std::string &path);         // utils.rs:27-36 (by extension, for writing)
-std::vector<uint8_t> read_file(const std::string &path);            // magic-byte sniffing + inflate (niffler::get_reader)
+std::vector<uint8_t> read_file(const std::string &path, size_t *raw_size = nullptr);  // magic-byte sniffing + inflate (niffler::get_reader)
+std::vector<uint8_t> read_file(const std::string &path, bool *empty);  // + is_file_empty (utils.rs:359-375)
 void write_file(const std::string &path, const uint8_t *data, size_t n, int gz_level);  // get_fastx_writer
 
 // ---------------------------------------------------------------- alignment.rs

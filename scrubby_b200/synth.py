@@ -343,3 +343,56 @@ def gen_ont_paf(lens: torch.Tensor, uu: torch.Tensor, seed: int = SEED, device="
         ]
         parts.append(_render(fields))
     return torch.cat(parts) if len(parts) != 1 else parts[0]
+
+
+def gen_fastq_illumina(n: int, mate: int = 1, seed: int = SEED, device="cpu", start: int = 0, read_len: int = 150
+                       ) -> torch.Tensor:
+    """2x150 records with Illumina-style 40-byte names `A00123:0456:H7ABCDEFG:1:TTTT:XXXXX:YYYYY` (instrument : run :
+    flowcell : lane : tile : x : y, fixed width, unique per index) -- ids longer than the 15 bytes a slot holds inline,
+    i.e. the fingerprint + key-arena path of the id set.  Record = 40 + 24 + 2 * read_len bytes."""
+    g = torch.Generator(device=device)
+    g.manual_seed((seed * 2 + mate + 77) & 0x7FFFFFFF)
+    head = _bytes("@A00123:0456:H7ABCDEFG:1:", device)
+    tail = _bytes(f" {mate}:N:0:ATCACG\n", device)
+    L = head.numel() + 16 + tail.numel() + 2 * read_len + 4
+    out = torch.empty(n * L, dtype=torch.uint8, device=device)
+    CH = 1 << 20
+    for a in range(0, n, CH):
+        b = min(n, a + CH)
+        m = b - a
+        buf = out[a * L: b * L].view(m, L)
+        idx = torch.arange(start + a, start + b, dtype=torch.int64, device=device)
+        p = 0
+        buf[:, p: p + head.numel()] = head
+        p += head.numel()
+        for val, width in ((1101 + idx // 10_000_000_000, 4), ((idx // 100_000) % 100_000, 5), (idx % 100_000, 5)):
+            for k in range(width):
+                buf[:, p + k] = ((val // (10 ** (width - 1 - k))) % 10 + 48).to(torch.uint8)
+            p += width
+            if width == 4 or p == head.numel() + 10:
+                buf[:, p] = 58  # ':'
+                p += 1
+        buf[:, p: p + tail.numel()] = tail
+        p += tail.numel()
+        r = torch.randint(0, 4, (m, read_len), dtype=torch.uint8, device=device, generator=g)
+        buf[:, p: p + read_len] = 65 + r * 2 + (r == 2).to(torch.uint8) * 2 + (r == 3).to(torch.uint8) * 13
+        p += read_len
+        buf[:, p] = 10
+        buf[:, p + 1] = 43
+        buf[:, p + 2] = 10
+        p += 3
+        buf[:, p: p + read_len] = torch.randint(33, 74, (m, read_len), dtype=torch.uint8, device=device, generator=g)
+        buf[:, p + read_len] = 10
+    return out
+
+
+def gen_txt_ids_illumina(n: int, seed: int = SEED, device="cpu", start: int = 0) -> torch.Tensor:
+    """the id list of the host reads (is_host) of gen_fastq_illumina"""
+    idx = torch.arange(start, start + n, dtype=torch.int64, device=device)
+    idx = idx[is_host(idx, seed)]
+    k = idx.numel()
+    w = lambda v, width: (torch.stack([(v // (10 ** (width - 1 - j))) % 10 + 48 for j in range(width)], 1).to(torch.uint8),
+                          torch.ones((k, width), dtype=torch.bool, device=device))
+    return _render([_const_field("A00123:0456:H7ABCDEFG:1:", k, device), w(1101 + idx // 10_000_000_000, 4),
+                    _const_field(":", k, device), w((idx // 100_000) % 100_000, 5), _const_field(":", k, device),
+                    w(idx % 100_000, 5), _const_field("\n", k, device)])

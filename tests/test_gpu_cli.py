@@ -300,3 +300,24 @@ def test_cli_fasta_reads(cli, data):
         rep = json.load(open(js))
         assert (rep["reads_in"], rep["reads_out"]) == (3000, want.reads_out)
         assert (rep["reads_removed"], rep["reads_extracted"]) == ((0, 3000 - want.reads_out) if extract else (3000 - want.reads_out, 0))
+
+
+def test_cli_tiny_gz_id_list_is_not_empty(cli, data, tmp_path):
+    """ADVICE r01 / utils.rs:359-375: niffler's 5-byte FileTooShort rule applies to the RAW file; a .gz id list whose
+    decompressed content is "syn.5\\n" (6 bytes) or even 3 bytes is read, only a raw file under 5 bytes is empty"""
+    ids_gz = tmp_path / "ids.gz"
+    with gzip.open(ids_gz, "wb") as f:
+        f.write(b"s\n")  # 2 bytes decompressed: matches nothing, but is NOT "empty"
+    o1 = tmp_path / "o1.fq"
+    js = tmp_path / "r.json"
+    _run(cli, "alignment", "-i", data["r1"], "-o", o1, "-a", ids_gz, "--format", "txt", "-j", js)
+    assert open(o1, "rb").read() == data["fq"][0]
+    one = tmp_path / "one.gz"
+    with gzip.open(one, "wb") as f:
+        f.write(b"syn.5\n")
+    _run(cli, "alignment", "-i", data["r1"], "-o", o1, "-a", one, "--format", "txt", "-j", js)
+    want = orc.clean_fastq(data["fq"][0], orc.OSet.from_ids([b"syn.5"])).written
+    assert open(o1, "rb").read() == want and len(want) < len(data["fq"][0])
+    raw3 = _write(tmp_path / "tiny.txt", b"s\n")  # raw file of 2 bytes: empty by the FileTooShort rule
+    _run(cli, "alignment", "-i", data["r1"], "-o", o1, "-a", raw3, "--format", "txt", "-j", js)
+    assert open(o1, "rb").read() == data["fq"][0]

@@ -450,3 +450,42 @@ def test_c4_c5_full_size_oracle_parity(ctx):
             again.free()
             del keys
         d[3].free()
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_long_ids_oracle_parity(ctx, reverse):
+    """40-byte Illumina-style read names (fingerprint slot + key arena, the vectorised long-id probe of the fused kernel and
+    the word-wise bulk build): set, kept / removed bytes and counters equal the oracle's; ids of 16, 17, 63, 64 and 65
+    bytes sit on the edges of that fast path"""
+    n = 300_000
+    fq = synth.gen_fastq_illumina(n, 1, device="cuda")
+    txt = synth.gen_txt_ids_illumina(n, device="cuda")
+    gs = api.IdSet.from_txt(ctx, txt)
+    oset = orc.set_from_txt(txt.cpu().numpy())
+    assert gs.sorted_ids() == oset.sorted_ids()
+    n_in = int(fq.numel())
+    pad = torch.zeros(n_in + 16, dtype=torch.uint8, device="cuda")
+    pad[:n_in] = fq
+    d_w = torch.empty(n_in + 64, dtype=torch.uint8, device="cuda")
+    d_o = torch.empty(n_in + 64, dtype=torch.uint8, device="cuda")
+    r = api.clean_fastq_dev(ctx, gs, pad, n_in, d_w, d_o, reverse)
+    o = orc.clean_fastq(fq.cpu().numpy(), oset, reverse, want_bytes=False)
+    assert r.path == 1 and (r.reads_in, r.reads_out) == (o.reads_in, o.reads_out)
+    assert torch.equal(d_w[: r.n_written].cpu(), torch.from_numpy(o.written))
+    assert torch.equal(d_o[: r.n_other].cpu(), torch.from_numpy(o.other))
+    # edge lengths, hits and misses, ids that differ only in their last byte
+    rng = random.Random(3)
+    recs, members = [], []
+    for i in range(4000):
+        L = rng.choice([15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 90])
+        rid = (b"%06d" % i) + bytes(rng.randrange(48, 123) for _ in range(L - 6))
+        twin = rid[:-1] + bytes([rid[-1] ^ 1])
+        recs.append(b"@" + rid + b" c\n" + b"ACGT" * 30 + b"\n+\n" + b"I" * 120 + b"\n")
+        recs.append(b"@" + twin + b"\tc\n" + b"ACGT" * 30 + b"\n+\n" + b"I" * 120 + b"\n")
+        if i % 2:
+            members.append(rid)
+    buf = b"".join(recs)
+    g2 = api.IdSet.from_ids(ctx, members)
+    got = api.clean_fastq(ctx, g2, buf, reverse)
+    want = orc.clean_fastq(buf, orc.OSet.from_ids(members), reverse)
+    assert got.path == 1 and got.written == want.written and got.other == want.other

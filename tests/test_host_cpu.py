@@ -96,3 +96,28 @@ def test_cli_help_and_version_need_no_gpu():
     assert run("reads", "-i", "x", "-A", "-h").returncode == 2       # "-h" is the VALUE of --aligner-args; --index is missing
     assert run("nonsense").returncode == 2 and run().returncode == 2
     assert run("alignment", "-i", "a", "-o", "b").returncode == 2    # --alignment is required
+
+
+def test_bgzf_member_that_claims_a_huge_payload_is_not_trusted(tmp_path):
+    """a crafted BGZF file of tiny members whose ISIZE trailers claim 4 GiB each must not size an allocation:
+    the parallel BGZF reader refuses it (the spec caps a block at 64 KiB) and the serial gzip path reports the corrupt
+    stream as an error instead of the process dying on bad_alloc"""
+    import struct
+    import zlib
+
+    def member(payload: bytes, claim: int) -> bytes:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(payload) + co.flush()
+        bsize = 12 + 6 + len(body) + 8
+        hdr = b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        return hdr + body + struct.pack("<II", zlib.crc32(payload), claim)
+
+    good = member(b"r1\nr2\n", 6) * 40
+    p = tmp_path / "ok.gz"
+    p.write_bytes(good)
+    assert hostlib.read_file(str(p)) == b"r1\nr2\n" * 40
+    bad = member(b"r1\n", 0xFFFFFFF0) * 64
+    q = tmp_path / "bad.gz"
+    q.write_bytes(bad)
+    with pytest.raises(Exception):
+        hostlib.read_file(str(q))

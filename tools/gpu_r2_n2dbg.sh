@@ -1,10 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=${1:-2}
-(while true; do free -g | sed -n 2p; sleep 3; done) > gpurun_out/mem_n$N.txt 2>&1 &
-MP=$!
-SGPU_DIST_DEBUG=1 SGPU_BENCH_DEBUG=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 5 > gpurun_out/bench_c4_n$N.log 2> gpurun_out/bench_c4_n$N.err
-echo "full rc=$?"; kill $MP
-grep -E "dist\]|bench\]|Assertion|Signal" gpurun_out/bench_c4_n$N.err | head -30; cat gpurun_out/bench_c4_n$N.log | cut -c1-3000
-tail -25 gpurun_out/mem_n$N.txt | awk '{print $3, $7}' | tr '\n' ';'
-dmesg 2>/dev/null | grep -i -E "oom|killed" | tail -5
+run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $2 bench.py --gpus $N --steps 5 --e2e-steps 0 --cpu-seconds 0.5 --gather $1 2> gpurun_out/gather_$1.err | python -c "import sys,json; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', j['ms_per_step'], j['phases_ms'], j['config']['parallelism'][:90])"; grep -E "bench\]" gpurun_out/gather_$1.err | head -3; }
+run pull 29551
+run nccl 29552
