@@ -7,8 +7,11 @@ Default workload = BASELINE.json configs[3] (C4, the configuration the metric is
 100 M 2x150 pairs (2 x 33.1 GB of FASTQ) against a 50 M-id depletion set delivered as a one-column id list.
 `--gpus N` is STRONG scaling: the SAME input is cut into N byte ranges per file (shards), one per rank.  One step =
 
-    evidence   all-gather of the N byte ranges of the id list over NCCL (the replication of the depletion set in its
-               most compact form), then ReadAlignment::from_txt on every rank      -> exact id set in HBM
+    evidence   every rank turns ITS byte range of the id list into slot images grouped by table page (parse, hash,
+    set_build  partition: done once per key across the box), one barrier, then every rank assembles the whole table from
+               all ranks' lists, read over NVLink out of symmetric memory            -> the same exact id set in every HBM
+               (--setbuild replicated: the id list itself is replicated -- peer pull or NCCL all-gather -- and
+               ReadAlignment::from_txt runs on every rank over the whole list)
     filter     R1 and R2 shards: ONE pass of the fused parse -> probe -> compact kernel each, line phase speculated
     exchange   one all-gather of a few integers per file (own-range newline counts that prove the speculation, output
                sizes -> write offsets of the concatenation) and an all-reduce of the report counters
@@ -384,13 +387,26 @@ def run_ours(args):
         d_ev = torch.zeros(per + 16, dtype=torch.uint8, device=dev)
         mine = ev_full[rank * per: min(ev_total, (rank + 1) * per)]
         d_ev[: mine.numel()] = mine
-        del ev_full, mine
+        del mine
+        # sharded set build (N > 1): this rank's byte range + a halo; every rank parses / hashes / partitions only its own
+        # range, the page-sorted slot images are read over NVLink, every rank assembles the whole table
+        sharded = None
+        if world > 1 and args.setbuild == "sharded":
+            try:
+                evs = sdist.evidence_shard_with_halo(ev_full, rank, world, per)
+                sharded = sdist.ShardedTxtSet(api, ctx, dist, ev_total, per, dev, direct=not args.pull_lists)
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] rank {rank}: sharded set build unavailable ({type(e).__name__}: {e})\n")
+                sharded = None
         d_ev_all = torch.empty(world * per + 16, dtype=torch.uint8, device=dev) if world > 1 else None
         # the evidence shards live in symmetric memory: every rank pulls the others' ranges over NVLink (no rendezvous
         # per step); --gather nccl keeps the NCCL all-gather
         peer_ev = None
         gather_how = "nccl all-gather"
-        if world > 1 and args.gather == "pull":
+        if sharded is not None:
+            gather_how = ("sharded set build: page-sorted slot images " +
+                          ("read from peer memory by the page kernel" if not args.pull_lists else "pulled over NVLink"))
+        elif world > 1 and args.gather == "pull":
             try:
                 peer_ev = sdist.PeerFile(per, dist, dev)
                 peer_ev.local[: per + 16].copy_(d_ev)
@@ -399,6 +415,7 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001
                 sys.stderr.write(f"[bench] rank {rank}: symmetric memory unavailable ({type(e).__name__}: {e}); NCCL all-gather\n")
                 peer_ev = None
+        del ev_full
         taxids = None
         n_k = per if world > 1 else ev_total
         # a depleted file is smaller than its input: the outputs are sized for the expected kept fraction + slack
@@ -419,7 +436,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
-    names = ["evidence_allgather", "set_build", "filter", "exchange"] if c4 else ["set_build", "filter"]
+    names = ["evidence", "set_build", "filter", "exchange"] if c4 else ["set_build", "filter"]
     ph = Phases(torch, names)
 
     def step_dev(timed=False):
@@ -427,15 +444,18 @@ def run_ours(args):
         if timed:
             ph.begin()
         if c4:
-            if peer_ev is not None:
-                ev = peer_ev.pull(ev_total, d_ev_all)
-            else:
-                ev = sdist.replicate_file_dev(d_ev, per, ev_total, D, d_ev_all)
-            if os.environ.get("SGPU_BENCH_SYNC"):
-                torch.cuda.synchronize()
-            if timed:
-                ph.mark()
-            ids = api.IdSet.from_txt(ctx, ev)
+            ids = None
+            if sharded is not None:  # evidence = partition of the own range + barrier + offset tables; set_build = assembly
+                ids = sharded.build(*evs, mark=ph.mark if timed else None)
+                assert ids is not None, "the id list of this workload takes the sharded build"
+            else:  # evidence = replication of the id list; set_build = from_txt over the whole list
+                if peer_ev is not None:
+                    ev = peer_ev.pull(ev_total, d_ev_all)
+                else:
+                    ev = sdist.replicate_file_dev(d_ev, per, ev_total, D, d_ev_all)
+                if timed:
+                    ph.mark()
+                ids = api.IdSet.from_txt(ctx, ev)
             if timed:
                 ph.mark()
             if world == 1:
@@ -510,7 +530,8 @@ def run_ours(args):
     # ---- end-to-end arm: pinned host buffers through the host-pointer C ABI (H2D + D2H inside)
     if args.e2e_steps > 0:
         e2e = run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, shards, d_r, n_r, d_ev, n_k,
-                      taxids, cap, barrier, (per, ev_total) if c4 else None, written_job, d_out, d_oth)
+                      taxids, cap, barrier, (per, ev_total) if c4 else None, written_job, d_out, d_oth,
+                      (sharded, evs) if (c4 and sharded is not None) else None)
     else:
         e2e = {"t": float("nan"), "h2d": 0, "d2h": 0, "steps": 0, "each": [], "warm": [], "pairs": 0, "scale": 1.0,
                "mem_gb": round(mem_available_gb(), 1), "note": "skipped (--e2e-steps 0)", "h2d_rank": 0, "d2h_rank": 0}
@@ -567,6 +588,7 @@ def run_ours(args):
                     "h2d_gb_per_s_rank0": (e2e["h2d_rank"] / e2e["t"] / 1e9) if e2e["steps"] else None,
                     "d2h_gb_per_s_rank0": (e2e["d2h_rank"] / e2e["t"] / 1e9) if e2e["steps"] else None,
                     "host_mem_available_gb": e2e["mem_gb"], "note": e2e["note"],
+                    "host_copy_ceiling_all_ranks": e2e.get("ceiling"),
                     "timing": "host wall clock around the host-buffer C ABI calls of one step on pinned host "
                               "buffers (evidence upload + set build + both mate files), stream synchronised, max over ranks"},
             "gpu_launches": launches_all,
@@ -584,8 +606,37 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def host_copy_ceiling(torch, dist, dev, world, h_src, h_dst, n_bytes: int, reps: int = 3):
+    """aggregate pinned-memory copy rate of the box with every rank copying at once (GB/s: H2D alone, D2H alone, both
+    directions together) -- the ceiling of the end-to-end arm, whatever the kernels do"""
+    n = min(n_bytes, int(h_src.numel()), int(h_dst.numel()), 4 << 30)
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    s2 = torch.cuda.Stream(device=dev)
+    out = []
+    for mode in ("h2d", "d2h", "both"):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if mode in ("h2d", "both"):
+                d.copy_(h_src[:n], non_blocking=True)
+            if mode in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    h_dst[:n].copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        moved = n * reps * (2 if mode == "both" else 1) * world
+        out.append(round(moved / float(t[0]) / 1e9, 1))
+    del d
+    return {"h2d_gb_per_s": out[0], "d2h_gb_per_s": out[1], "both_gb_per_s": out[2], "bytes_per_rank_and_copy": n}
+
+
 def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, shards, d_r, n_r, d_ev, n_k, taxids, cap,
-            barrier, evinfo, written_job, d_out, d_oth):
+            barrier, evinfo, written_job, d_out, d_oth, sharded_ev=None):
     """the step through HOST buffers: inputs in pinned host memory, outputs into pinned host memory"""
     # the pinned copies of every rank's inputs and outputs must fit the host (with room to spare: pinned pages cannot be
     # reclaimed and an exhausted box kills the job).  A single-GPU run that does not fit runs on a prefix of whole
@@ -637,13 +688,21 @@ def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, 
         per, ev_total = evinfo
         d_ev2 = torch.empty(per + 16, dtype=torch.uint8, device=dev)
         d_ev_all = torch.empty(world * per + 16, dtype=torch.uint8, device=dev)
+        if sharded_ev is not None:  # the rank's id-list range + halo from pinned host memory, then the sharded build
+            sharded, evs = sharded_ev
+            h_evs = torch.empty(evs[0].numel(), dtype=torch.uint8, pin_memory=True)
+            h_evs.copy_(evs[0])
+            d_evs = torch.empty_like(evs[0])
 
     dbg = os.environ.get("SGPU_BENCH_DEBUG")
 
     def step_host():
         if dbg:
             sys.stderr.write(f"[bench] rank {rank}: host step, {mem_available_gb():.0f} GB of host memory left\n")
-        if c4 and world > 1:
+        if c4 and world > 1 and sharded_ev is not None:
+            d_evs.copy_(h_evs, non_blocking=True)
+            ids = sharded.build(d_evs, *evs[1:])
+        elif c4 and world > 1:
             d_ev2[:per].copy_(h_k[:per], non_blocking=True)
             ev = sdist.replicate_file_dev(d_ev2, per, ev_total, D, d_ev_all)
             ids = api.IdSet.from_txt(ctx, ev)
@@ -698,7 +757,8 @@ def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, 
     scale = int(tot[0]) / total_reads  # 1.0 unless the arm ran on a prefix
     if frac >= 1.0 and world == 1:
         assert sum(r.n_written for r in rh) == written_job, "host and device arms disagree"
-    return {"t": t_e2e, "h2d": h2d, "d2h": d2h, "steps": e2e_steps, "each": [round(x * 1e3, 2) for x in e2e_each],
+    ceiling = host_copy_ceiling(torch, dist, dev, world, h_r[0], h_out[0], int(h_out[0].numel()))
+    return {"ceiling": ceiling, "t": t_e2e, "h2d": h2d, "d2h": d2h, "steps": e2e_steps, "each": [round(x * 1e3, 2) for x in e2e_each],
             "warm": [round(x * 1e3, 2) for x in warm_each], "pairs": int(tot[0]) // 2, "scale": scale,
             "mem_gb": round(avail, 1), "note": note, "h2d_rank": h2d_rank, "d2h_rank": d2h_rank}
 
@@ -713,6 +773,11 @@ def main():
                     help="c4: 100M pairs + 50M-id list, strong scaling (BASELINE configs[3]); c2: classifier, 10M pairs per GPU")
     ap.add_argument("--pairs", type=int, default=0, help="c4: pairs of the whole job (default 100M); c2: pairs per GPU (10M)")
     ap.add_argument("--halo", type=int, default=1 << 20, help="c4: bytes of halo after a shard's own range")
+    ap.add_argument("--setbuild", default="sharded", choices=["sharded", "replicated"],
+                    help="c4, N > 1: every rank partitions its own byte range of the id list and all ranks assemble the table "
+                         "from everybody's lists (sharded), or the id list is replicated and every rank builds alone")
+    ap.add_argument("--pull-lists", action="store_true", help="sharded set build: pull the other ranks' lists into local "
+                                                              "buffers instead of reading them from peer memory")
     ap.add_argument("--gather", default="pull", choices=["pull", "nccl"],
                     help="c4, N > 1: how the id list's byte ranges reach every rank (peer pull over NVLink, or NCCL all-gather)")
     ap.add_argument("--cpu-pairs", type=int, default=1_000_000, help="bounded CPU-baseline sample")

@@ -60,6 +60,8 @@ typedef enum {
     SGPU_ERR_HALO = 21,                 /* shard: the last owned record does not end inside the buffer */
     SGPU_ERR_SAM_RECORD = 22,           /* a SAM line htslib's sam_parse1 rejects (rust_htslib error through `result?`, alignment.rs:131) */
     SGPU_ERR_BAM_RECORD = 23,           /* a BAM header / record htslib's bam_hdr_read / bam_read1 rejects (bad magic, truncated or inconsistent) */
+    SGPU_ERR_NOT_SHARDABLE = 25,        /* sgpu_idset_assemble_dev: the evidence holds ids of 16 bytes and more, or more keys than the virtual
+                                           pages were sized for: replicate the evidence and build the set on every rank instead */
     SGPU_ERR_PHASE_UNKNOWN = 24         /* shard called with SGPU_NEWLINES_UNKNOWN that the single-pass kernel cannot take (not canonical FASTQ,
                                            no "\n+\n" in sight ...): nothing was produced, call again with the exact newlines_before / crlf */
 } sgpu_status;
@@ -267,6 +269,25 @@ typedef struct {
     uint64_t count;       /* distinct ids                                     */
     uint64_t has_empty;   /* the empty string is a member (txt blank line)    */
 } sgpu_idset_image;
+/* Sharded set build (round 2): every rank turns ITS byte range of the evidence into slot images grouped by virtual page
+ * (step 1), the ranks pull each other's lists over NVLink (symmetric memory: plain device pointers here), and every
+ * rank assembles the whole table from all lists (step 2) -- the parse, the hashing and the partition are done once per
+ * key across the box, only the 16-byte images travel, and ReadAlignment::from_txt's result (alignment.rs:60-82) is
+ * the same set on every rank (cleaner.rs:236-254: one global set).
+ *   d_buf      : the shard's own bytes [0, own_len) followed by a halo (the start of the next shard: a line of this
+ *                shard may end there); 16-byte aligned.  starts_line: the byte before the buffer is '\n' (or the buffer
+ *                starts the file) -- otherwise the first, partial line belongs to the previous shard.
+ *   log2_vpages: virtual pages = 2^log2_vpages, the same on every rank (>= total keys / 410 for load 0.2).
+ *   d_recs     : cap_recs x 16 bytes; d_vstart: (2^log2_vpages + 2) x u64 (exclusive starts, count, flags).
+ * The call returns when the lists are final (stream synchronised): signal the other ranks then. */
+sgpu_status sgpu_idset_partition_txt_dev(sgpu_ctx *, const uint8_t *d_buf, size_t n, size_t own_len, int starts_line,
+                                         int is_last, uint32_t log2_vpages, void *d_recs, size_t cap_recs,
+                                         uint64_t *d_vstart, uint64_t *n_recs, uint64_t *err_line);
+/* step 2: n_parts (<= 8) lists, as device pointers valid on this device.  SGPU_ERR_NOT_SHARDABLE: fall back to the
+ * replicated build. */
+sgpu_status sgpu_idset_assemble_dev(sgpu_ctx *, int n_parts, const void *const *d_recs, const uint64_t *const *d_vstart,
+                                    uint32_t log2_vpages, sgpu_idset **out);
+
 /* the set's keys as an unsorted one-column list ("id\n" per key; a blank line for the empty id) written to a
  * caller-owned DEVICE buffer.  *n = bytes needed / written; SGPU_ERR_CAPACITY (with *n set) when d_out is NULL
  * or cap < *n.  Exchange format of the multi-GPU diff: ReadDifference::get_difference (utils.rs:250-285) keeps

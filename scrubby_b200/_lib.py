@@ -15,11 +15,12 @@ STATUS = {
     12: "SGPU_ERR_KRAKEN_REPORT_READS", 13: "SGPU_ERR_KRAKEN_REPORT_DIRECT", 14: "SGPU_ERR_KRAKEN_REPORT_PARENT",
     15: "SGPU_ERR_FASTA_UNSUPPORTED", 16: "SGPU_ERR_CUDA", 17: "SGPU_ERR_NOMEM", 18: "SGPU_ERR_INVALID_ARG",
     19: "SGPU_ERR_CAPACITY", 20: "SGPU_ERR_KEY_TOO_LONG", 21: "SGPU_ERR_HALO", 22: "SGPU_ERR_SAM_RECORD",
-    23: "SGPU_ERR_BAM_RECORD", 24: "SGPU_ERR_PHASE_UNKNOWN",
+    23: "SGPU_ERR_BAM_RECORD", 24: "SGPU_ERR_PHASE_UNKNOWN", 25: "SGPU_ERR_NOT_SHARDABLE",
 }
 SGPU_ERR_CAPACITY = 19
 SGPU_ERR_HALO = 21
 SGPU_ERR_PHASE_UNKNOWN = 24
+SGPU_ERR_NOT_SHARDABLE = 25
 NEWLINES_UNKNOWN = (1 << 64) - 1
 
 
@@ -49,7 +50,7 @@ SYMBOLS = [
     "sgpu_idset_len", "sgpu_idset_contains", "sgpu_idset_dump", "sgpu_idset_free", "sgpu_free",
     "sgpu_clean_fastq", "sgpu_clean_fastq_dev", "sgpu_clean_fastq_shard_dev", "sgpu_clean_fastq_shard", "sgpu_count_newlines_dev",
     "sgpu_diff", "sgpu_diff_dev", "sgpu_fastq_ids_shard_dev", "sgpu_idset_export", "sgpu_idset_import",
-    "sgpu_idset_keys_dev", "sgpu_idset_from_bam",
+    "sgpu_idset_keys_dev", "sgpu_idset_from_bam", "sgpu_idset_partition_txt_dev", "sgpu_idset_assemble_dev",
 ]
 
 _lib = None
@@ -117,5 +118,7 @@ def load():
     L.sgpu_idset_export.argtypes = [vp, P(IdSetImage)]
     L.sgpu_idset_import.argtypes = [vp, P(IdSetImage), P(vp)]
     L.sgpu_idset_keys_dev.argtypes = [vp, vp, vp, sz, P(sz)]
+    L.sgpu_idset_partition_txt_dev.argtypes = [vp, vp, sz, sz, i32, i32, C.c_uint32, vp, sz, vp, P(u64), P(u64)]
+    L.sgpu_idset_assemble_dev.argtypes = [vp, i32, P(vp), P(vp), C.c_uint32, P(vp)]
     _lib = L
     return L

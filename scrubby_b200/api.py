@@ -342,6 +342,35 @@ def clean_fastq_shard_host(ctx: Context, ids: IdSet, h_in, n_in: int, own_len: i
                           bool(c.speculated), c.own_newlines, c.lead_newlines)
 
 
+def idset_partition_txt_dev(ctx: Context, d_buf, n: int, own_len: int, starts_line: bool, is_last: bool, log2_vpages: int,
+                            d_recs, d_vstart):
+    """sgpu_idset_partition_txt_dev (sharded set build, step 1): this rank's id-list shard -> slot images grouped by
+    virtual page in d_recs (uint8 tensor, 16 bytes per record) / d_vstart (int64 tensor of 2^log2_vpages + 2).
+    Returns the number of records, or None when the evidence cannot take the sharded build."""
+    n_recs, err = C.c_uint64(), C.c_uint64()
+    rc = ctx.L.sgpu_idset_partition_txt_dev(ctx.h, C.c_void_p(d_buf.data_ptr()), n, own_len, int(starts_line), int(is_last),
+                                            log2_vpages, C.c_void_p(d_recs.data_ptr()), d_recs.numel() // 16,
+                                            C.c_void_p(d_vstart.data_ptr()), C.byref(n_recs), C.byref(err))
+    if rc in (_lib.SGPU_ERR_NOT_SHARDABLE, _lib.SGPU_ERR_CAPACITY):
+        return None
+    _check(rc, err.value, "idset_partition_txt_dev")
+    return int(n_recs.value)
+
+
+def idset_assemble_dev(ctx: Context, recs, vstarts, log2_vpages: int):
+    """sgpu_idset_assemble_dev (step 2): the whole table from every rank's list (device tensors valid on this device:
+    pulled copies or mapped peer memory).  Returns an IdSet, or None (fall back to the replicated build)."""
+    n = len(recs)
+    a = (C.c_void_p * n)(*[t.data_ptr() for t in recs])
+    b = (C.c_void_p * n)(*[t.data_ptr() for t in vstarts])
+    h = C.c_void_p()
+    rc = ctx.L.sgpu_idset_assemble_dev(ctx.h, n, a, b, log2_vpages, C.byref(h))
+    if rc == _lib.SGPU_ERR_NOT_SHARDABLE:
+        return None
+    _check(rc, 0, "idset_assemble_dev")
+    return IdSet(ctx, h)
+
+
 def count_newlines_dev(ctx: Context, d_buf, n: int) -> int:
     out = C.c_uint64()
     _check(ctx.L.sgpu_count_newlines_dev(ctx.h, C.c_void_p(d_buf.data_ptr()), n, C.byref(out)))

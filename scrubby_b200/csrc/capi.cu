@@ -224,6 +224,7 @@ const char *sgpu_strerror(int s) {
     case SGPU_ERR_HALO: return "shard halo too small: last owned record does not end inside the buffer";
     case SGPU_ERR_SAM_RECORD: return "failed to parse a SAM record";
     case SGPU_ERR_BAM_RECORD: return "failed to read a BAM header or record";
+    case SGPU_ERR_NOT_SHARDABLE: return "evidence cannot take the sharded set build (long ids, or too many keys): replicate it";
     case SGPU_ERR_PHASE_UNKNOWN: return "shard needs the exact newlines_before / crlf (speculation not applicable)";
     default: return "unknown status";
     }

@@ -354,6 +354,12 @@ struct SpanStats {
 sgpu_status idset_insert_spans(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src, const uint64_t *d_off,
                                const uint32_t *d_len, const uint8_t *d_sel, size_t n, const SpanStats *known = nullptr);
 
+// idset_build.cu: the sharded build (slot images grouped by virtual page per rank, assembled from all ranks' lists)
+sgpu_status idset_partition(sgpu_ctx *c, const uint8_t *d_src, const uint64_t *d_off, const uint32_t *d_len, size_t n,
+                            uint32_t log2_v, ulonglong2 *d_recs, size_t cap_recs, uint64_t *d_vstart, uint64_t flags);
+sgpu_status idset_assemble(sgpu_ctx *c, int n_parts, const ulonglong2 *const *recs, const uint64_t *const *vstart,
+                           uint32_t log2_v, sgpu_idset *s);
+
 // fastq.cu
 struct FastqIndex;  // per-record metadata produced by the general path
 

@@ -532,6 +532,10 @@ struct TileOut {
     unsigned long long *dense;    // a tile with more than LT_LMAX lines: use the indexed path
     unsigned long long *stats;    // [0] bytes of candidates longer than 15, [1] an empty candidate, [2] one of >= 16 MiB:
                                   // what idset_measure_kernel would find, so the set build can skip that pass
+    // a SHARD of an evidence file (sharded set build): only the lines that START before own_end are this shard's; the
+    // buffer carries a halo behind own_end, and a line of the shard that does not end inside it is SGPU_ERR_HALO
+    uint64_t own_begin, own_end;  // 0, ~0: the whole buffer
+    int not_last;                 // the buffer does not end at the end of the file
 };
 
 // one line [s, e_raw) of the buffer (e_raw = position of its '\n', or n for an unterminated last line):
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(LT_NT)
             const int pi = (int)q - (first_ok ? 1 : 0);  // which newline precedes the line, -1: it starts the tile
             const int i0 = pi >= 0 ? (int)nl_idx[pi] : -1;  // its list index
             const uint32_t s = pi >= 0 ? ((uint32_t)seps[i0] & 0x7FFFu) + 1u : 0u;
-            if (s < tile_len) {
+            if (s < tile_len && g0 + s >= O.own_begin && g0 + s < O.own_end) {
                 // the line's own newline: the next newline entry of the list
                 bool fast = !high;
                 uint32_t e_nl = 0;  // tile offset of the line's '\n'
@@ -932,7 +936,8 @@ __global__ void __launch_bounds__(LT_NT)
                     // scanning routine over the buffer: non-ASCII tile, or a line that leaves the halo
                     uint64_t e = g0 + s;
                     while (e < n && in[e] != '\n') e++;
-                    if (mode == 2) sel = paf_line_scan(in, g0 + s, e, e < n, F, &koff, &klen, O.err_word);
+                    if (e == n && O.not_last) report_error(O.err_word, g0 + s, SGPU_ERR_HALO);  // the halo is too short
+                    else if (mode == 2) sel = paf_line_scan(in, g0 + s, e, e < n, F, &koff, &klen, O.err_word);
                     else sel = evidence_line(in, g0 + s, e, e < n, mode, T, need_fields, &koff, &klen, O.err_word, 0);
                 }
             }
@@ -1002,7 +1007,7 @@ static sgpu_status evidence_to_set(sgpu_ctx *c, EvidenceKind kind, const uint8_t
                 memcpy(c->h_pinned + 40, init, sizeof(init));
                 cudaMemcpyAsync(ctr.p, c->h_pinned + 40, sizeof(init), cudaMemcpyHostToDevice, st);
                 TileOut O{cand_off.p, cand_len.p, cap, (unsigned long long *)ctr.p, (unsigned long long *)ctr.p + 1,
-                          (unsigned long long *)ctr.p + 2, (unsigned long long *)ctr.p + 3};
+                          (unsigned long long *)ctr.p + 2, (unsigned long long *)ctr.p + 3, 0ull, ~0ull, 0};
                 lines_tile_kernel<<<(unsigned)ceil_div(n, (size_t)LT_TILE), LT_NT, 0, st>>>(
                     d_buf, (uint64_t)n, T ? *T : none, need_fields, kind == EV_TXT ? 1 : kind == EV_PAF ? 2 : 0, F, O);
                 SGPU_LAUNCH(c);
@@ -1334,6 +1339,99 @@ sgpu_status sgpu_idset_from_txt(sgpu_ctx *c, const uint8_t *buf, size_t n, sgpu_
     sgpu_status rc = sgpu_idset_from_txt_dev(c, d.p, n, out, err_line);
     cudaStreamSynchronize(c->stream);
     return rc;
+}
+
+// position of the first '\n' of buf[0..n), or ~0: one warp
+__global__ void first_newline_kernel(const uint8_t *buf, uint64_t n, unsigned long long *out) {
+    const int lane = threadIdx.x;
+    for (uint64_t base = 0; base < n; base += 512) {
+        const uint64_t pos = base + (uint64_t)lane * 16;
+        uint32_t m = 0;
+        if (pos < n) {
+            m = nl_mask16(ld_nc_u4(buf + pos));
+            if (n - pos < 16) m &= (1u << (n - pos)) - 1u;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, m != 0);
+        if (b) {
+            const int first = __ffs(b) - 1;
+            if (lane == first) *out = pos + (uint64_t)(__ffs(m) - 1);
+            return;
+        }
+    }
+}
+
+sgpu_status sgpu_idset_partition_txt_dev(sgpu_ctx *c, const uint8_t *d_buf, size_t n, size_t own_len, int starts_line,
+                                         int is_last, uint32_t log2_vpages, void *d_recs, size_t cap_recs,
+                                         uint64_t *d_vstart, uint64_t *n_recs, uint64_t *err_line) {
+    if (!c || !d_recs || !d_vstart || !n_recs || (n && !d_buf) || own_len > n || (is_last && own_len != n) ||
+        log2_vpages < 1 || log2_vpages > 30 || ((uintptr_t)d_buf & 15))
+        return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    SGPU_CUDA(cudaStreamSynchronize(st));  // (scratch comes from the stream-ordered pool: see evidence_to_set)
+    if (err_line) *err_line = 0;
+    *n_recs = 0;
+    // the first line this shard owns: a partial first line is the previous shard's
+    uint64_t own_begin = 0;
+    if (!starts_line) {
+        DevBuf<unsigned long long> pos;
+        SGPU_TRY(pos.alloc(1, st));
+        SGPU_CUDA(cudaMemsetAsync(pos.p, 0xFF, 8, st));
+        first_newline_kernel<<<1, 32, 0, st>>>(d_buf, own_len, pos.p);
+        SGPU_LAUNCH(c);
+        uint64_t p;
+        SGPU_TRY(read_u64s(c, pos.p, &p, 1));
+        own_begin = p == ~0ull ? (uint64_t)own_len : p + 1;
+    }
+    DevBuf<uint64_t> cand_off, ctr;
+    DevBuf<uint32_t> cand_len;
+    uint64_t cap = n / 8 + 4096, h[6] = {0, 0, 0, 0, 0, 0};
+    const TaxSet none{nullptr, 0, nullptr, nullptr, 0};
+    for (int attempt = 0; attempt < 2; attempt++) {
+        SGPU_TRY(cand_off.alloc(cap, st));
+        SGPU_TRY(cand_len.alloc(cap, st));
+        SGPU_TRY(ctr.alloc(6, st));
+        const uint64_t init[6] = {0, ~0ull, 0, 0, 0, 0};
+        memcpy(c->h_pinned + 40, init, sizeof(init));
+        SGPU_CUDA(cudaMemcpyAsync(ctr.p, c->h_pinned + 40, sizeof(init), cudaMemcpyHostToDevice, st));
+        TileOut O{cand_off.p, cand_len.p, cap, (unsigned long long *)ctr.p, (unsigned long long *)ctr.p + 1,
+                  (unsigned long long *)ctr.p + 2, (unsigned long long *)ctr.p + 3, own_begin, (uint64_t)own_len, is_last ? 0 : 1};
+        if (is_last) O.own_end = ~0ull;
+        if (n) {
+            lines_tile_kernel<<<(unsigned)ceil_div(n, (size_t)LT_TILE), LT_NT, 0, st>>>(d_buf, (uint64_t)n, none, 0, 1,
+                                                                                       PafParams{0, 0.0, 0}, O);
+            SGPU_LAUNCH(c);
+        }
+        SGPU_TRY(read_u64s(c, ctr.p, h, 6));
+        if (h[0] <= cap) break;
+        cap = h[0];
+    }
+    // anything out of the ordinary (a parse error, pathological line density, a line past the halo): the replicated build
+    // reports it exactly as the unsharded call would
+    if (h[2] || h[1] != ~0ull) return SGPU_ERR_NOT_SHARDABLE;
+    const uint64_t flags = ((h[3] || h[5]) ? 1ull : 0ull) | (h[4] ? 2ull : 0ull);
+    SGPU_TRY(idset_partition(c, d_buf, cand_off.p, cand_len.p, (size_t)h[0], log2_vpages, (ulonglong2 *)d_recs, cap_recs, d_vstart,
+                             flags));
+    *n_recs = (flags & 1) ? 0 : h[0];
+    return SGPU_OK;
+}
+
+sgpu_status sgpu_idset_assemble_dev(sgpu_ctx *c, int n_parts, const void *const *d_recs, const uint64_t *const *d_vstart,
+                                    uint32_t log2_vpages, sgpu_idset **out) {
+    if (!c || !out || !d_recs || !d_vstart) return SGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SGPU_CUDA(cudaSetDevice(c->device));
+    SGPU_CUDA(cudaStreamSynchronize(c->stream));
+    sgpu_idset *set = nullptr;
+    SGPU_TRY(idset_create(c, &set));
+    const sgpu_status rc = idset_assemble(c, n_parts, (const ulonglong2 *const *)d_recs, d_vstart, log2_vpages, set);
+    if (rc != SGPU_OK) {
+        sgpu_idset_free(set);
+        return rc;
+    }
+    *out = set;
+    return SGPU_OK;
 }
 
 sgpu_status sgpu_idset_from_reads_dev(sgpu_ctx *c, const uint8_t *d_buf, size_t n, int style,

@@ -154,6 +154,50 @@ struct PageSmem {
     uint32_t fresh;
 };
 __device__ __forceinline__ uint32_t page_slot(uint32_t b, uint32_t q) { return b * IDSET_BUCKET + ((q + b) & (IDSET_BUCKET - 1)); }
+// one slot image into the shared-memory page: one bucket at a time under its lock, so that the occupied slots stay a
+// prefix of every bucket and duplicates are seen exactly.  arena_shift: added to a long id's arena offset (the sharded
+// build concatenates the ranks' arenas)
+__device__ __forceinline__ void page_insert(PageSmem *S, ulonglong2 r, const uint8_t *arena, uint64_t arena_shift, uint32_t *fresh) {
+    const bool is_long = (r.x & 0xFF) == 0x80;
+    if (is_long) r.y += arena_shift << 24;
+    uint32_t b = (uint32_t)(slot_home(r.x, r.y) & (IDSET_PAGE_BUCKETS - 1));
+    bool done = false;
+    while (!done) {
+        if (atomicCAS(&S->lock[b], 0u, 1u) == 0u) {
+            __threadfence_block();
+            bool full = true;
+            for (uint32_t q = 0; q < IDSET_BUCKET; q++) {
+                volatile ulonglong2 *sp = &S->slot[page_slot(b, q)];
+                const uint64_t olo = sp->x, ohi = sp->y;
+                if ((olo | ohi) == 0) {
+                    sp->x = r.x;
+                    sp->y = r.y;
+                    (*fresh)++;
+                    done = true;
+                    full = false;
+                    break;
+                }
+                if (olo == r.x) {
+                    bool same;
+                    if (!is_long) same = ohi == r.y;
+                    else same = (ohi & 0xFFFFFFull) == (r.y & 0xFFFFFFull) &&
+                                arena_equal_words(arena + (ohi >> 24),
+                                                  GlobalKeyWords(arena + (r.y >> 24), (uint32_t)(r.y & 0xFFFFFFull)),
+                                                  (uint32_t)(r.y & 0xFFFFFFull));
+                    if (same) {
+                        done = true;
+                        full = false;
+                        break;
+                    }
+                }
+            }
+            __threadfence_block();
+            atomicExch(&S->lock[b], 0u);
+            if (full) b = (b + 1) & (uint32_t)(IDSET_PAGE_BUCKETS - 1);
+        }
+    }
+}
+
 #ifndef SGPU_PAGE_THREADS
 #define SGPU_PAGE_THREADS 256
 #endif
@@ -178,47 +222,7 @@ __global__ void __launch_bounds__(PAGE_THREADS)
         for (uint32_t i = threadIdx.x; i < SLOTS; i += blockDim.x) S->slot[i] = make_ulonglong2(0ull, 0ull);
         for (uint32_t i = threadIdx.x; i < IDSET_PAGE_BUCKETS; i += blockDim.x) S->lock[i] = 0;
         __syncthreads();
-        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const ulonglong2 r = recs[i];
-            const bool is_long = (r.x & 0xFF) == 0x80;
-            uint32_t b = (uint32_t)(slot_home(r.x, r.y) & (IDSET_PAGE_BUCKETS - 1));
-            bool done = false;
-            while (!done) {
-                // one bucket at a time under its lock: occupied slots stay a prefix, duplicates are seen exactly
-                if (atomicCAS(&S->lock[b], 0u, 1u) == 0u) {
-                    __threadfence_block();
-                    bool full = true;
-                    for (uint32_t q = 0; q < IDSET_BUCKET; q++) {
-                        volatile ulonglong2 *sp = &S->slot[page_slot(b, q)];
-                        const uint64_t olo = sp->x, ohi = sp->y;
-                        if ((olo | ohi) == 0) {
-                            sp->x = r.x;
-                            sp->y = r.y;
-                            fresh++;
-                            done = true;
-                            full = false;
-                            break;
-                        }
-                        if (olo == r.x) {
-                            bool same;
-                            if (!is_long) same = ohi == r.y;
-                            else same = (ohi & 0xFFFFFFull) == (r.y & 0xFFFFFFull) &&
-                                        arena_equal_words(arena + (ohi >> 24),
-                                                          GlobalKeyWords(arena + (r.y >> 24), (uint32_t)(r.y & 0xFFFFFFull)),
-                                                          (uint32_t)(r.y & 0xFFFFFFull));
-                            if (same) {
-                                done = true;
-                                full = false;
-                                break;
-                            }
-                        }
-                    }
-                    __threadfence_block();
-                    atomicExch(&S->lock[b], 0u);
-                    if (full) b = (b + 1) & (uint32_t)(IDSET_PAGE_BUCKETS - 1);
-                }
-            }
-        }
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) page_insert(S, recs[i], arena, 0, &fresh);
         __syncthreads();
         ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(table) + page * SLOTS;
         for (uint32_t i = threadIdx.x; i < SLOTS; i += blockDim.x) dst[i] = S->slot[page_slot(i >> 3, i & 7u)];
@@ -231,6 +235,143 @@ __global__ void __launch_bounds__(PAGE_THREADS)
     if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&S->fresh, fresh);
     __syncthreads();
     if (threadIdx.x == 0 && S->fresh) atomicAdd(&st->inserted, (unsigned long long)S->fresh);
+}
+
+// The same assembly from SEVERAL page-sorted lists (the sharded build: one list per rank).  A list is sorted by VIRTUAL
+// page (2^log2_v of them, page = top bits of the home hash); a table of n_pages = 2^(log2_v - shift) real pages takes the
+// records of virtual pages [p << shift, (p + 1) << shift) of every list -- one contiguous segment per list.
+constexpr int MAX_PARTS = 8;
+struct PartLists {
+    const ulonglong2 *recs[MAX_PARTS];
+    const uint64_t *vstart[MAX_PARTS];  // [V] exclusive starts, [V] = records of the list
+    int n;
+    uint32_t shift;
+};
+__global__ void __launch_bounds__(PAGE_THREADS)
+    idset_page_multi_kernel(PartLists L, uint64_t n_pages, Slot *table, BuildStats *st) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    PageSmem *S = reinterpret_cast<PageSmem *>(smem_raw);
+    constexpr uint32_t SLOTS = IDSET_PAGE_BUCKETS * IDSET_BUCKET;
+    uint32_t fresh = 0;
+    for (uint64_t page = blockIdx.x; page < n_pages; page += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < SLOTS; i += blockDim.x) S->slot[i] = make_ulonglong2(0ull, 0ull);
+        for (uint32_t i = threadIdx.x; i < IDSET_PAGE_BUCKETS; i += blockDim.x) S->lock[i] = 0;
+        __syncthreads();
+        for (int q = 0; q < L.n; q++) {
+            const uint64_t a = L.vstart[q][page << L.shift], b = L.vstart[q][(page + 1) << L.shift];
+            const ulonglong2 *recs = L.recs[q] + a;
+            for (uint64_t i = threadIdx.x; i < b - a; i += blockDim.x) page_insert(S, recs[i], nullptr, 0, &fresh);
+        }
+        __syncthreads();
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(table) + page * SLOTS;
+        for (uint32_t i = threadIdx.x; i < SLOTS; i += blockDim.x) dst[i] = S->slot[page_slot(i >> 3, i & 7u)];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S->fresh = 0;
+    __syncthreads();
+    for (int d = 16; d; d >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&S->fresh, fresh);
+    __syncthreads();
+    if (threadIdx.x == 0 && S->fresh) atomicAdd(&st->inserted, (unsigned long long)S->fresh);
+}
+
+static sgpu_status page_kernel_attr(sgpu_ctx *c) {
+    static bool attr_done[64] = {false};
+    if (!attr_done[c->device & 63]) {
+        SGPU_CUDA(cudaFuncSetAttribute(idset_page_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PageSmem)));
+        SGPU_CUDA(cudaFuncSetAttribute(idset_page_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PageSmem)));
+        attr_done[c->device & 63] = true;
+    }
+    return SGPU_OK;
+}
+
+// Sharded build, step 1 (every rank, on the candidates of ITS evidence shard): slot images grouped by virtual page into
+// caller-owned buffers (symmetric memory: the other ranks pull them).  d_vstart: V exclusive starts, [V] = records,
+// [V + 1] = flags (1: ids of 16 bytes and more / too long: not shardable, 2: the empty id was offered).
+sgpu_status idset_partition(sgpu_ctx *c, const uint8_t *d_src, const uint64_t *d_off, const uint32_t *d_len, size_t n,
+                            uint32_t log2_v, ulonglong2 *d_recs, size_t cap_recs, uint64_t *d_vstart, uint64_t flags) {
+    cudaStream_t st = c->stream;
+    const uint64_t V = 1ull << log2_v;
+    if (n > cap_recs) return SGPU_ERR_CAPACITY;
+    DevBuf<uint32_t> page_of, counts;
+    DevBuf<uint64_t> arena_at;
+    DevBuf<BuildStats> stats;
+    SGPU_TRY(page_of.alloc(n ? n : 1, st));
+    SGPU_TRY(counts.alloc(2 * V, st));
+    SGPU_TRY(arena_at.alloc(1, st));
+    SGPU_TRY(stats.alloc(1, st));
+    SGPU_CUDA(cudaMemsetAsync(counts.p, 0, 2 * V * 4, st));
+    SGPU_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(BuildStats), st));
+    c->h_pinned[48] = flags;
+    SGPU_CUDA(cudaMemcpyAsync(d_vstart + V + 1, c->h_pinned + 48, 8, cudaMemcpyHostToDevice, st));
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(ceil_div(n, (size_t)256), (size_t)c->sm_count * 16));
+    if (n && !(flags & 1)) {
+        idset_count_kernel<<<grid, 256, 0, st>>>(d_src, d_off, d_len, nullptr, n, V, 0, page_of.p, arena_at.p, counts.p, stats.p);
+        SGPU_LAUNCH(c);
+    }
+    SGPU_TRY(exclusive_scan_u32_to_u64(c, counts.p, d_vstart, V, d_vstart + V));
+    if (n && !(flags & 1)) {
+        idset_scatter_kernel<<<grid, 256, 0, st>>>(d_src, d_off, d_len, n, page_of.p, arena_at.p, d_vstart, counts.p + V, d_recs);
+        SGPU_LAUNCH(c);
+    }
+    SGPU_CUDA(cudaGetLastError());
+    SGPU_CUDA(cudaStreamSynchronize(st));  // the lists are final when this returns: the caller signals the other ranks
+    return SGPU_OK;
+}
+
+// Sharded build, step 2 (every rank, on ALL ranks' lists -- pulled into local memory or mapped peer memory)
+sgpu_status idset_assemble(sgpu_ctx *c, int n_parts, const ulonglong2 *const *recs, const uint64_t *const *vstart,
+                           uint32_t log2_v, sgpu_idset *s) {
+    cudaStream_t st = c->stream;
+    if (n_parts < 1 || n_parts > MAX_PARTS || log2_v > 30) return SGPU_ERR_INVALID_ARG;
+    const uint64_t V = 1ull << log2_v;
+    for (int q = 0; q < n_parts; q++)
+        SGPU_CUDA(cudaMemcpyAsync(c->h_pinned + 2 * q, vstart[q] + V, 16, cudaMemcpyDeviceToHost, st));
+    SGPU_CUDA(cudaStreamSynchronize(st));
+    uint64_t total = 0, flags = 0;
+    for (int q = 0; q < n_parts; q++) {
+        total += c->h_pinned[2 * q];
+        flags |= c->h_pinned[2 * q + 1];
+    }
+    if (flags & 1) return SGPU_ERR_NOT_SHARDABLE;
+    if (flags & 2) s->has_empty = true;
+    if (total == 0) return SGPU_OK;
+    // pages: a power of two (a merge of virtual pages), load <= 0.2 -- or up to 0.5 when the keys outgrow the virtual pages
+    uint64_t need = idset_buckets_for(total) / IDSET_PAGE_BUCKETS, n_pages = 1;
+    while (n_pages < need && n_pages < V) n_pages <<= 1;
+    if (total * 2 > n_pages * IDSET_PAGE_BUCKETS * IDSET_BUCKET) return SGPU_ERR_NOT_SHARDABLE;
+    uint32_t shift = 0;
+    while ((n_pages << shift) < V) shift++;
+    Slot *nt = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&nt, n_pages * IDSET_PAGE_BUCKETS * IDSET_BUCKET * sizeof(Slot), st);
+    if (e != cudaSuccess) {
+        set_cuda_error(e, __FILE__, __LINE__);
+        return SGPU_ERR_NOMEM;
+    }
+    if (s->d_table) SGPU_CUDA(cudaFreeAsync(s->d_table, st));
+    s->d_table = nt;
+    s->n_buckets = n_pages * IDSET_PAGE_BUCKETS;
+    DevBuf<BuildStats> stats;
+    SGPU_TRY(stats.alloc(1, st));
+    SGPU_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(BuildStats), st));
+    SGPU_TRY(page_kernel_attr(c));
+    PartLists L;
+    memset(&L, 0, sizeof(L));
+    for (int q = 0; q < n_parts; q++) {
+        L.recs[q] = recs[q];
+        L.vstart[q] = vstart[q];
+    }
+    L.n = n_parts;
+    L.shift = shift;
+    const unsigned per_sm = (unsigned)std::min<size_t>(16, (size_t)(220 * 1024) / (sizeof(PageSmem) + 1024));
+    const unsigned g3 = (unsigned)std::min<uint64_t>(n_pages, (uint64_t)c->sm_count * per_sm);
+    idset_page_multi_kernel<<<g3, PAGE_THREADS, sizeof(PageSmem), st>>>(L, n_pages, s->d_table, stats.p);
+    SGPU_LAUNCH(c);
+    SGPU_CUDA(cudaGetLastError());
+    BuildStats h;
+    SGPU_TRY(read_u64s(c, stats.p, (uint64_t *)&h, sizeof(BuildStats) / 8));
+    s->count = h.inserted;
+    return SGPU_OK;
 }
 
 // Builds the WHOLE table of an empty set from the selected candidates (the table and the arena are allocated, n_buckets
@@ -259,11 +400,7 @@ sgpu_status idset_build_paged(sgpu_ctx *c, sgpu_idset *s, const uint8_t *d_src, 
     SGPU_TRY(arena_at.alloc(any_long ? n : 1, st));
     SGPU_CUDA(cudaMemsetAsync(counts.p, 0, 2 * n_pages * 4, st));
     SGPU_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(BuildStats), st));
-    static bool attr_done[64] = {false};
-    if (!attr_done[c->device & 63]) {
-        SGPU_CUDA(cudaFuncSetAttribute(idset_page_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PageSmem)));
-        attr_done[c->device & 63] = true;
-    }
+    SGPU_TRY(page_kernel_attr(c));
     const unsigned grid = (unsigned)std::min<size_t>(ceil_div(n, (size_t)256), (size_t)c->sm_count * 16);
     idset_count_kernel<<<grid, 256, 0, st>>>(d_src, d_off, d_len, d_sel, n, n_pages, s->arena_used, page_of.p, arena_at.p,
                                              counts.p, stats.p);

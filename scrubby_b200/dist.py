@@ -433,6 +433,96 @@ class PeerFile:
         return out[:total]
 
 
+def evidence_shard_with_halo(full, rank: int, world: int, per: int, halo: int = 1 << 16):
+    """this rank's byte range of a line-oriented evidence file plus a halo (the start of the next range: a line of this
+    range may end there), as (device tensor padded by 16 readable bytes, n, own_len, starts_line, is_last).  `full` is
+    any 1-D uint8 tensor holding the file (each rank only touches its range, the halo and the byte before its range)."""
+    import torch
+
+    total = int(full.numel())
+    a, b = min(total, rank * per), min(total, (rank + 1) * per)
+    e = min(total, b + halo)
+    buf = torch.zeros(e - a + 16, dtype=torch.uint8, device=full.device)
+    buf[: e - a] = full[a:e]
+    starts_line = a == 0 or int(full[a - 1]) == 10
+    return buf, e - a, b - a, starts_line, b == total and e == total
+
+
+class ShardedTxtSet:
+    """Sharded build of the id set of a one-column id list (ReadAlignment::from_txt, alignment.rs:60-82) across the ranks.
+    Replicating the evidence makes every rank parse, hash and partition ALL keys; here every rank does that for ITS byte
+    range only (sgpu_idset_partition_txt_dev: slot images grouped by virtual page, in symmetric memory), one barrier says
+    "lists final", and every rank assembles the whole table from all ranks' lists (sgpu_idset_assemble_dev) -- read
+    straight out of the peers' memory over NVLink (`direct`), or pulled into local buffers first.  Only 16-byte images
+    travel; the result is the same exact set on every rank (cleaner.rs:236-254: one global set).  The symmetric
+    buffers are double-buffered: a rank may start its next partition while a peer still reads the previous lists."""
+
+    def __init__(self, api, ctx, dist, ev_total: int, per: int, device, direct: bool = True):
+        import math
+
+        import torch
+        import torch.distributed._symmetric_memory as symm
+
+        self.api, self.ctx, self.dist, self.direct = api, ctx, dist, direct
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        # virtual pages: the same on every rank; sized for lines of >= 8 bytes at ~410 keys (load 0.2) per page
+        self.log2_v = max(8, int(math.ceil(math.log2(max(1.0, ev_total / 8 / 410)))))
+        V = 1 << self.log2_v
+        self.cap = per // 6 + 65536  # records per rank (lines of >= 6 bytes on average; else the replicated build)
+        self.step = 0
+        self.recs, self.vs, self.p_recs, self.p_vs = [], [], [], []
+        for _ in range(2):
+            r = symm.empty(self.cap * 16, dtype=torch.uint8, device=device)
+            v = symm.empty(V + 2, dtype=torch.int64, device=device)
+            hr, hv = symm.rendezvous(r, dist.group.WORLD), symm.rendezvous(v, dist.group.WORLD)
+            self.recs.append(r)
+            self.vs.append(v)
+            self.p_recs.append([hr.get_buffer(q, (self.cap * 16,), torch.uint8) for q in range(self.world)])
+            self.p_vs.append([hv.get_buffer(q, (V + 2,), torch.int64) for q in range(self.world)])
+        self.l_vs = [torch.empty(V + 2, dtype=torch.int64, device=device) for _ in range(self.world)]
+        self.l_recs = None if direct else [torch.empty(self.cap * 16, dtype=torch.uint8, device=device)
+                                           for _ in range(self.world)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(min(4, self.world - 1))]
+        self.ready = torch.cuda.Event()
+
+    def build(self, d_buf, n: int, own_len: int, starts_line: bool, is_last: bool, mark=None):
+        """-> IdSet, or None on every rank when the evidence cannot take this path (decided collectively).
+        `mark` (optional) is called between the exchange and the assembly (bench.py's phase boundary)."""
+        import torch
+
+        k = self.step & 1
+        self.step += 1
+        V = 1 << self.log2_v
+        got = self.api.idset_partition_txt_dev(self.ctx, d_buf, n, own_len, starts_line, is_last, self.log2_v, self.recs[k],
+                                               self.vs[k])
+        if got is None:  # flag it for the others: they read it with the counts
+            self.vs[k][V + 1] = 1
+            self.vs[k][V] = 0
+            torch.cuda.current_stream().synchronize()
+        self.dist.barrier()  # every rank's lists are final
+        cur = torch.cuda.current_stream()
+        # the offset tables are small: always pulled (the page kernel looks two of them up per page and rank)
+        for q in range(self.world):
+            self.l_vs[q].copy_(self.p_vs[k][q], non_blocking=True)
+        if self.direct:
+            recs = self.p_recs[k]
+        else:
+            tail = torch.stack([v[V] for v in self.l_vs]).tolist()
+            self.ready.record(cur)
+            for j in range(1, self.world):
+                q = (self.rank + j) % self.world
+                st = self.streams[(j - 1) % len(self.streams)]
+                st.wait_event(self.ready)
+                with torch.cuda.stream(st):
+                    self.l_recs[q][: tail[q] * 16].copy_(self.p_recs[k][q][: tail[q] * 16], non_blocking=True)
+            for st in self.streams:
+                cur.wait_stream(st)
+            recs = [self.recs[k] if q == self.rank else self.l_recs[q] for q in range(self.world)]
+        if mark is not None:
+            mark()
+        return self.api.idset_assemble_dev(self.ctx, recs, self.l_vs, self.log2_v)
+
+
 def _gather_rows(dist, vals, world, device):
     """all_gather of a short int64 row per rank, on the device the ranks compute on"""
     import torch

@@ -101,6 +101,27 @@ for host in (False, True):
             print(f"one-pass {'host' if host else 'device'} buffers, mate {k + 1}: world {world} reads_in {r.reads_in} "
                   f"reads_out {r.reads_out} one_pass {r.one_pass} -> {'identical' if good else 'MISMATCH'}")
             ok = ok and good
+# ---- sharded set build (ShardedTxtSet): every rank partitions its byte range of the id list by virtual page, the lists
+#      are read over NVLink (directly, or pulled first), every rank assembles the same table: == from_txt on the whole file
+want_ids = ids2.sorted_ids()
+for direct in (True, False):
+    for lst, name in ((txt, "inline ids"), (synth.gen_txt_ids_illumina(20000, device=dev), "long ids (falls back)")):
+        tot = int(lst.numel())
+        per2 = sdist.evidence_shard_len(tot, world)
+        sh = sdist.ShardedTxtSet(api, ctx, dist, tot, per2, dev, direct=direct)
+        for rep in range(3):  # the symmetric buffers are double-buffered: several builds in a row
+            buf, nb, own, starts, last = sdist.evidence_shard_with_halo(lst, rank, world, per2, halo=4096)
+            got = sh.build(buf, nb, own, starts, last)
+            if name == "inline ids":
+                good = got is not None and got.sorted_ids() == want_ids
+            else:
+                good = got is None
+            if rank == 0 and rep == 0:
+                print(f"sharded set build ({'direct peer reads' if direct else 'pulled lists'}), {name}: world {world} "
+                      f"-> {'identical' if good else 'MISMATCH'}")
+            t = torch.tensor([1 if good else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = ok and bool(int(t))
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
