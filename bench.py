@@ -702,18 +702,20 @@ def run_e2e(args, torch, dist, D, api, sdist, ctx, dev, world, rank, c4, pairs, 
         if c4 and world > 1 and sharded_ev is not None:
             d_evs.copy_(h_evs, non_blocking=True)
             ids = sharded.build(d_evs, *evs[1:])
+            assert ids is not None, "the synthetic id list is inline-only: the sharded build must not decline it"
         elif c4 and world > 1:
             d_ev2[:per].copy_(h_k[:per], non_blocking=True)
             ev = sdist.replicate_file_dev(d_ev2, per, ev_total, D, d_ev_all)
             ids = api.IdSet.from_txt(ctx, ev)
-            r = sdist.clean_files_sharded_host(api, ctx, ids, [(h_r[i], shards[i], h_out[i], h_oth[i]) for i in range(2)], D)
-            assert all(x.one_pass for x in r), "speculated line phase refuted on canonical input"
         elif c4:
             ids = api.IdSet.from_txt(ctx, h_k[:n_k])
             r = [api.clean_fastq_host(ctx, ids, h_r[i], e_n[i], h_out[i], h_oth[i]) for i in range(2)]
         else:
             ids = api.IdSet.from_reads(ctx, h_k[:n_k], 0, taxids)
             r = [api.clean_fastq_host(ctx, ids, h_r[i], e_n[i], h_out[i], h_oth[i]) for i in range(2)]
+        if c4 and world > 1:
+            r = sdist.clean_files_sharded_host(api, ctx, ids, [(h_r[i], shards[i], h_out[i], h_oth[i]) for i in range(2)], D)
+            assert all(x.one_pass for x in r), "speculated line phase refuted on canonical input"
         ids.free()
         return r
 

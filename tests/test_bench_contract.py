@@ -80,3 +80,36 @@ def test_committed_bench_lines_carry_the_contract_keys():
             "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         c = j["cpu_baseline"]
         assert c["kind"] == "port" and c["cores"] == 2 and c["value"] > 0 and c["sample"]
+
+
+def test_committed_round2_bench_lines():
+    """profiles/r02_bench_c4_n*.json (the round's evidence): C4, strong scaling, every contract key, consistent derived
+    numbers, the per-phase breakdown adds up to the step, e2e counted from real bytes and below the box's copy ceiling"""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_c4_n[1248].json")))
+    assert files
+    for f in files:
+        j = json.load(open(f))
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks",
+                  "phases_ms"):
+            assert k in j, (f, k)
+        assert j["metric"] == "reads_per_s_depleted" and j["unit"] == "reads/s" and j["dtype"] == "u8"
+        assert j["scaling"] == "strong" and j["vs_baseline"] is None and j["data"] == "synthetic" and j["warmup"] >= 3
+        assert j["config"]["workload"].startswith("C4: 100M 2x150 pairs") and j["config"]["pairs_total"] == 100_000_000
+        assert abs(j["value"] - 2 * 100_000_000 / (j["ms_per_step"] * 1e-3)) / j["value"] < 1e-6
+        ph = j["phases_ms"]
+        assert set(ph) == {"evidence", "set_build", "filter", "exchange"}
+        assert sum(ph.values()) <= j["ms_per_step"] * 1.15 and ph["filter"] > 0.3 * j["ms_per_step"]
+        r = j["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["avg_ms"] * 1e-3) / 1e9) / r["achieved"] < 1e-6
+        e = j["e2e"]
+        assert e["h2d_bytes_per_step"] > j["config"]["fastq_bytes_total"] and e["d2h_bytes_per_step"] > 0
+        assert e["value"] < j["value"] and abs(e["value"] - 2 * e["pairs"] / (e["ms_per_step"] * 1e-3)) / e["value"] < 1e-6
+        c = e["host_copy_ceiling_all_ranks"]
+        assert e["h2d_bytes_per_step"] / (e["ms_per_step"] * 1e-3) / 1e9 <= 1.05 * c["h2d_gb_per_s"]
+        assert j["gpu_launches"] > 0 and j["clocks"]["sm_mhz"] and not set(j["clocks"]["reasons"]) & {
+            "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] == 2

@@ -14,7 +14,20 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit", "smsp__issue_active.avg.pct", "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "launch__block_size"]
-if len(sys.argv) > 4:  # python tools/ncu_summary.py rep top_n traffic.json pairs [split]: DRAM bytes of the launch
+if len(sys.argv) > 4 and sys.argv[4] in ("c4", "c2"):  # python tools/ncu_summary.py rep top_n traffic.json c4|c2 n_gpus [split]
+    import json
+
+    v = rows[2]
+    def _bytes(name):
+        i = hdr.index(name)
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        return float(v[i].replace(",", "")) * scale
+    with open(sys.argv[3], "w") as f:
+        json.dump({"kernel": v[hdr.index("Kernel Name")], "config": sys.argv[4], "n_gpus": int(sys.argv[5]),
+                   "split": len(sys.argv) > 6, "dram_bytes_read": _bytes("dram__bytes_read.sum"),
+                   "dram_bytes_write": _bytes("dram__bytes_write.sum"),
+                   "gpu_time_us_under_ncu": v[hdr.index("gpu__time_duration.sum")], "source": rep}, f, indent=1)
+elif len(sys.argv) > 4:  # (round 1 form) python tools/ncu_summary.py rep top_n traffic.json pairs [split]
     import json
 
     v = rows[2]
