@@ -391,7 +391,7 @@ def run_ours(args):
         # sharded set build (N > 1): this rank's byte range + a halo; every rank parses / hashes / partitions only its own
         # range, the page-sorted slot images are read over NVLink, every rank assembles the whole table
         sharded = None
-        if world > 1 and args.setbuild == "sharded":
+        if world > 1 and args.setbuild in ("auto", "sharded"):
             try:
                 evs = sdist.evidence_shard_with_halo(ev_full, rank, world, per)
                 sharded = sdist.ShardedTxtSet(api, ctx, dist, ev_total, per, dev, direct=not args.pull_lists)
@@ -403,10 +403,7 @@ def run_ours(args):
         # per step); --gather nccl keeps the NCCL all-gather
         peer_ev = None
         gather_how = "nccl all-gather"
-        if sharded is not None:
-            gather_how = ("sharded set build: page-sorted slot images " +
-                          ("read from peer memory by the page kernel" if not args.pull_lists else "pulled over NVLink"))
-        elif world > 1 and args.gather == "pull":
+        if world > 1 and args.gather == "pull" and (sharded is None or args.setbuild == "auto"):
             try:
                 peer_ev = sdist.PeerFile(per, dist, dev)
                 peer_ev.local[: per + 16].copy_(d_ev)
@@ -416,6 +413,46 @@ def run_ours(args):
                 sys.stderr.write(f"[bench] rank {rank}: symmetric memory unavailable ({type(e).__name__}: {e}); NCCL all-gather\n")
                 peer_ev = None
         del ev_full
+        # --setbuild auto (N > 1): the three ways to get the same set onto every rank are timed during setup (device
+        # events, max over ranks, so every rank picks the same one) and the fastest runs in the timed steps:
+        #   direct     sharded build, the page kernel reads the peers' lists in place over NVLink
+        #   pulled     sharded build, the peers' lists are first copied over NVLink in bulk
+        #   replicated the id list itself is replicated and every rank builds the whole set alone
+        tuned = None
+        if world > 1 and args.setbuild == "auto" and sharded is not None:
+            def one_build(mode):
+                if mode == "replicated":
+                    ev = peer_ev.pull(ev_total, d_ev_all) if peer_ev is not None else \
+                        sdist.replicate_file_dev(d_ev, per, ev_total, D, d_ev_all)
+                    api.IdSet.from_txt(ctx, ev).free()
+                else:
+                    sharded.direct = mode == "direct"
+                    got = sharded.build(*evs)
+                    assert got is not None, "the id list of this workload takes the sharded build"
+                    got.free()
+            tuned = {}
+            for mode in ("direct", "pulled", "replicated"):
+                for _ in range(2):
+                    one_build(mode)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    one_build(mode)
+                e1.record()
+                torch.cuda.synchronize()
+                t_m = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+                dist.all_reduce(t_m, op=dist.ReduceOp.MAX)
+                tuned[mode] = round(float(t_m[0]), 3)
+            best = min(tuned, key=tuned.get)
+            sys.stderr.write(f"[bench] rank {rank}: set build candidates (ms, max over ranks) {tuned} -> {best}\n")
+            if best == "replicated":
+                sharded = None
+            else:
+                sharded.direct = best == "direct"
+        if sharded is not None:
+            gather_how = ("sharded set build: page-sorted slot images " +
+                          ("read from peer memory by the page kernel" if sharded.direct else "pulled over NVLink"))
         taxids = None
         n_k = per if world > 1 else ev_total
         # a depleted file is smaller than its input: the outputs are sized for the expected kept fraction + slack
@@ -574,9 +611,13 @@ def run_ours(args):
                 "fastq_bytes_total": bytes_all, "evidence_bytes": ev_total if c4 else n_k * world,
                 "outputs": "kept+removed" if args.split else "kept (reference-equivalent single output)",
                 "fraction_kept": kept_all / reads_all,
-                "parallelism": (f"byte-range shards x{world}; id list replicated by {gather_how}, set built on every rank; "
+                "parallelism": (f"byte-range shards x{world}; " +
+                                ("id set built once on the GPU; " if world == 1 else
+                                 f"{gather_how}, the whole table assembled on every rank; " if sharded is not None else
+                                 f"id list replicated by {gather_how}, set built on every rank; ") +
                                 "one-pass filter with speculated line phase; counters all-reduced (NCCL)") if c4
                 else f"chunk-sharded x{world} (co-partitioned evidence, no collective in the step)",
+                "setbuild_candidates_ms": tuned if c4 else None,
                 "host_cpus_rank0": cpulist, "setup_s_rank0": round(t_setup, 1),
                 "l2": "inputs (>= 8 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
                 "fastq_gb_per_s": bytes_all / (ms * 1e-3) / 1e9,
@@ -775,7 +816,7 @@ def main():
                     help="c4: 100M pairs + 50M-id list, strong scaling (BASELINE configs[3]); c2: classifier, 10M pairs per GPU")
     ap.add_argument("--pairs", type=int, default=0, help="c4: pairs of the whole job (default 100M); c2: pairs per GPU (10M)")
     ap.add_argument("--halo", type=int, default=1 << 20, help="c4: bytes of halo after a shard's own range")
-    ap.add_argument("--setbuild", default="sharded", choices=["sharded", "replicated"],
+    ap.add_argument("--setbuild", default="auto", choices=["auto", "sharded", "replicated"],
                     help="c4, N > 1: every rank partitions its own byte range of the id list and all ranks assemble the table "
                          "from everybody's lists (sharded), or the id list is replicated and every rank builds alone")
     ap.add_argument("--pull-lists", action="store_true", help="sharded set build: pull the other ranks' lists into local "

@@ -480,8 +480,8 @@ class ShardedTxtSet:
             self.p_recs.append([hr.get_buffer(q, (self.cap * 16,), torch.uint8) for q in range(self.world)])
             self.p_vs.append([hv.get_buffer(q, (V + 2,), torch.int64) for q in range(self.world)])
         self.l_vs = [torch.empty(V + 2, dtype=torch.int64, device=device) for _ in range(self.world)]
-        self.l_recs = None if direct else [torch.empty(self.cap * 16, dtype=torch.uint8, device=device)
-                                           for _ in range(self.world)]
+        self.device = device
+        self.l_recs = None  # local copies of the peers' lists: allocated by the first pulled build
         self.streams = [torch.cuda.Stream(device=device) for _ in range(min(4, self.world - 1))]
         self.ready = torch.cuda.Event()
 
@@ -507,6 +507,9 @@ class ShardedTxtSet:
         if self.direct:
             recs = self.p_recs[k]
         else:
+            if self.l_recs is None:
+                self.l_recs = [None if q == self.rank else torch.empty(self.cap * 16, dtype=torch.uint8, device=self.device)
+                               for q in range(self.world)]
             tail = torch.stack([v[V] for v in self.l_vs]).tolist()
             self.ready.record(cur)
             for j in range(1, self.world):
