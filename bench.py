@@ -339,6 +339,9 @@ class Phases:
         e.record()
         return e
 
+    def each_ms(self):
+        return [[round(s[k].elapsed_time(s[k + 1]), 3) for k in range(len(self.names))] for s in self.steps]
+
     def mean_ms(self):
         out = {}
         for k, name in enumerate(self.names):
@@ -558,6 +561,7 @@ def run_ours(args):
     f_ms, f_n, f_bytes = ctx.fused_stats()
     ctx.set_profiling(False)
     phases = ph.mean_ms()
+    sys.stderr.write(f"[bench] rank {rank}: phases of every timed step (ms; {', '.join(names)}) {ph.each_ms()}\n")
     if c4:
         reads_job, kept_job, written_job = tot  # whole job (summed over ranks by the exchange)
     else:
