@@ -216,6 +216,11 @@ sgpu_status sgpu_clean_fastq_dev(sgpu_ctx *, const sgpu_idset *, const uint8_t *
  * the file before this shard (allgathered by the caller), `crlf` the file-level line ending
  * (decided by the first record, i.e. by shard 0), `is_last` marks the shard that holds EOF.
  * Concatenating the shards' outputs in order is byte-identical to the unsharded call.
+ * Only the is_last shard applies the end-of-file rules (a last record without a newline, a tail of blank lines); any
+ * other shard that finds fewer than four newlines after a record start it owns reports SGPU_ERR_HALO.  A caller must
+ * therefore never hand a buffer that reaches EOF to a shard that is not the last one: when own range + halo would reach
+ * EOF, that shard owns the rest of the file (own_len = n_in, is_last = 1) and the later ranks own nothing
+ * (scrubby_b200/dist.py: plan_shards does exactly that).
  *
  * One pass without a prior newline count (round 2): pass newlines_before = SGPU_NEWLINES_UNKNOWN (and crlf = -1) on
  * every shard but the first.  The shard then SPECULATES its line phase from the first "\n+\n" among its first four

@@ -34,8 +34,12 @@ class Shard:
 def plan_shards(n_bytes: int, world: int, halo: int = 1 << 20, align: int = 16) -> list[Shard]:
     """`world` contiguous ranges covering [0, n_bytes); cuts are multiples of `align` so that every shard
     buffer keeps the 16-byte alignment the kernels want when it is a view of one device buffer.
-    A shard may be empty (tiny files); the last shard always ends at EOF and carries no halo."""
+    A shard may be empty (tiny files); the last shard always ends at EOF and carries no halo.
+    A shard whose halo would reach EOF owns the rest of the file and IS the last shard (the C ABI's contract: only the
+    shard that holds EOF may apply the end-of-file rules -- a last record without a newline, a tail of blank lines --
+    and a buffer that ends at EOF without being that shard would have to call a short tail a halo problem)."""
     assert world >= 1 and n_bytes >= 0
+    assert halo > 0 or world == 1, "a record that starts exactly at a cut is owned by the shard before it: halo >= 1"
     per = -(-n_bytes // world)
     per = max(align, -(-per // align) * align)
     out, eof_seen = [], False
@@ -45,6 +49,8 @@ def plan_shards(n_bytes: int, world: int, halo: int = 1 << 20, align: int = 16) 
         if eof_seen:  # ranks after the one that reaches EOF own nothing
             out.append(Shard(r, n_bytes, 0, 0, False, False))
             continue
+        if b + halo >= n_bytes:
+            b = n_bytes
         is_last = b == n_bytes
         eof_seen = is_last
         end = n_bytes if is_last else min(n_bytes, b + halo)

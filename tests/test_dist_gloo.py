@@ -191,6 +191,46 @@ def test_plan_shards_covers_file_exactly():
             pos += s.own_len
 
 
+def test_plan_shards_buffer_at_eof_is_the_last_shard():
+    """ADVICE r01 (fastq_records.cuh:53): a buffer that ends at EOF must belong to the shard that applies the end-of-file
+    rules -- no non-last shard's halo reaches EOF, the shard whose halo would owns the rest of the file"""
+    for n, w, halo in [(1000, 4, 10), (1000, 4, 300), (1000, 4, 2000), (4096, 8, 512), (33, 2, 64), (1 << 20, 8, 1 << 17)]:
+        sh = plan_shards(n, w, halo=halo)
+        assert sum(s.own_len for s in sh) == n and sum(s.is_last for s in sh) == 1
+        for s in sh:
+            if s.own_len and not s.is_last:
+                assert s.start + s.buf_len < n
+            if s.is_last:
+                assert s.start + s.buf_len == n and s.buf_len == s.own_len
+
+
+@pytest.mark.parametrize("tail", ["no_final_newline", "blank_lines_at_cut", "blank_lines"])
+def test_sharded_clean_tail_straddles_the_last_cut(tail):
+    """the two inputs of ADVICE r01's HALO finding: a last record without a trailing newline that straddles the last
+    cut, and trailing blank lines that start exactly at a cut -- accepted by the unsharded path, so by the sharded one"""
+    from oracle import oracle as orc
+
+    recs = [b"@t.%d x\n" % i + b"ACGT" * 10 + b"\n+\n" + b"IIII" * 10 + b"\n" for i in range(60)]
+    fq = b"".join(recs)
+    cases = ((2, 64), (3, 16), (3, 4096))
+    if tail == "no_final_newline":  # ... on a last record that starts before the last cut and runs to EOF
+        fq = b"".join(b"@t%d\nAC\n+\nII\n" % i for i in range(5)) + b"@t.8 x\n" + b"A" * 200 + b"\n+\n" + b"I" * 200
+        cases = ((2, 64), (3, 16), (3, 4096), (4, 8))
+    elif tail == "blank_lines":
+        fq += b"\n\n"
+    else:  # 96 bytes of records + three blank lines on three ranks: cuts at 48 and 96, the last range is the blank tail
+        fq = b"".join(b"@t%d\nAC\n+\nII\n" % i for i in range(8)) + b"\n\n"
+        assert len(fq) == 98 and plan_shards(98, 3, 1)[2].start == 96
+        cases = ((3, 16), (3, 2), (2, 8))
+    ids_txt = b"".join(b"t.%d\nt%d\n" % (i, i) for i in range(0, 60, 2))
+    whole = orc.clean_fastq(fq, orc.set_from_txt(ids_txt))
+    assert whole.reads_in in (6, 8, 60) and 0 < whole.reads_out < whole.reads_in
+    for world, halo in cases:
+        res = _run(world, fq, ids_txt, halo=halo)
+        assert b"".join(r[1] for r in res) == whole.written
+        assert res[0][7] == whole.reads_in and res[0][8] == whole.reads_out
+
+
 @pytest.mark.parametrize("world,reverse", [(2, False), (2, True), (3, False)])
 def test_sharded_clean_matches_unsharded(world, reverse):
     from oracle import oracle as orc
