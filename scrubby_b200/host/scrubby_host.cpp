@@ -12,6 +12,11 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <future>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -275,66 +280,312 @@ std::vector<uint8_t> read_file(const std::string &path, size_t *raw_size) {
     return raw;
 }
 
+// Host stage: output bytes are deflated in independent 4 MiB blocks on all host threads, each block a
+// complete gzip member (as pigz -i / bgzip do).  The concatenation is a valid gzip file whose DEcompressed bytes equal
+// the reference's output; the compressed bytes differ (they depend on flate2's backend in the reference and are not
+// part of the parity contract).  n == 0 writes one empty member.
+static void deflate_members(FILE *f, const uint8_t *data, size_t n, int gz_level, const std::string &path) {
+    const size_t BLOCK = (size_t)4 << 20;
+    const size_t nb = n ? (n + BLOCK - 1) / BLOCK : 1;
+    std::vector<std::vector<uint8_t>> parts(nb);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    auto work = [&]() {
+        for (size_t b = next.fetch_add(1); b < nb && !failed; b = next.fetch_add(1)) {
+            const size_t a = b * BLOCK, len = std::min(BLOCK, n - a);
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (deflateInit2(&zs, gz_level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+                failed = true;
+                return;
+            }
+            std::vector<uint8_t> &o = parts[b];
+            o.resize(deflateBound(&zs, (uLong)len) + 64);
+            zs.next_in = const_cast<Bytef *>(data + a);
+            zs.avail_in = (uInt)len;
+            zs.next_out = o.data();
+            zs.avail_out = (uInt)o.size();
+            const int rc = deflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END) failed = true;
+            o.resize(o.size() - zs.avail_out);
+            deflateEnd(&zs);
+        }
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), nb);
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < nt; i++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (failed) throw ScrubbyError(ScrubbyError::NifflerError, "deflate failed: " + path);
+    for (auto &o : parts) {
+        if (!o.empty() && fwrite(o.data(), 1, o.size(), f) != o.size())
+            throw ScrubbyError(ScrubbyError::IoError, "write failed: " + path);
+    }
+}
+
 void write_file(const std::string &path, const uint8_t *data, size_t n, int gz_level) {
+    OutSink sink(path, gz_level);
+    sink.append(data, n);
+    sink.close();
+}
+
+// get_fastx_writer (utils.rs:38-74) as a sink that takes the output piece by piece: the file is created by the first
+// append (or by close), gz output gets its members appended as they are produced
+OutSink::OutSink(const std::string &path, int gz_level) : path_(path), level_(gz_level) {
     Compression c = compression_from_path(path);
     if (c == Compression::Bzip || c == Compression::Lzma)
         throw ScrubbyError(ScrubbyError::NifflerError, "bzip2/xz output: feature disabled in this build: " + path);
-    if (c == Compression::Gzip) {
-        // Host stage: the output is deflated in independent 4 MiB blocks on all host threads,
-        // each block a complete gzip member (as pigz -i / bgzip do).  The concatenation is a valid gzip file
-        // whose DEcompressed bytes equal the reference's output; the compressed bytes differ (they depend on
-        // flate2's backend in the reference and are not part of the parity contract).
-        const size_t BLOCK = (size_t)4 << 20;
-        const size_t nb = n ? (n + BLOCK - 1) / BLOCK : 1;
-        std::vector<std::vector<uint8_t>> parts(nb);
-        std::atomic<size_t> next{0};
-        std::atomic<bool> failed{false};
-        auto work = [&]() {
-            for (size_t b = next.fetch_add(1); b < nb && !failed; b = next.fetch_add(1)) {
-                const size_t a = b * BLOCK, len = std::min(BLOCK, n - a);
-                z_stream zs;
-                memset(&zs, 0, sizeof(zs));
-                if (deflateInit2(&zs, gz_level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
-                    failed = true;
-                    return;
+    gz_ = c == Compression::Gzip;
+}
+
+OutSink::~OutSink() {
+    if (f_) fclose((FILE *)f_);
+}
+
+void OutSink::open() {
+    if (f_) return;
+    f_ = fopen(path_.c_str(), "wb");
+    if (!f_) throw ScrubbyError(ScrubbyError::IoError, "cannot create " + path_);
+}
+
+void OutSink::append(const uint8_t *data, size_t n) {
+    open();
+    if (!n) return;
+    if (gz_)
+        deflate_members((FILE *)f_, data, n, level_, path_);
+    else if (fwrite(data, 1, n, (FILE *)f_) != n)
+        throw ScrubbyError(ScrubbyError::IoError, "write failed: " + path_);
+    total_ += n;
+}
+
+void OutSink::close() {
+    open();
+    if (gz_ && total_ == 0) deflate_members((FILE *)f_, nullptr, 0, level_, path_);  // an empty gzip member, as the writer leaves
+    const int rc = fclose((FILE *)f_);
+    f_ = nullptr;
+    if (rc != 0) throw ScrubbyError(ScrubbyError::IoError, "write failed: " + path_);
+}
+
+// ------------------------------------------------------------------------------------------ gzip input as a stream
+// a plain (non-BGZF) gzip FASTQ is inflated by ONE thread at a few hundred MB/s -- the slowest stage of
+// the whole tool.  Instead of inflating the file, then filtering it, then deflating the output, the three stages run
+// concurrently: a producer thread inflates into a bounded queue of blocks, the calling thread feeds the filter chunk by
+// chunk through the shard entry point of the C ABI (own range + halo, running newline count, the first chunk's CRLF
+// decision), and the previous chunk's output is deflated / written behind it.  Host memory: a few chunks instead of the
+// whole file and its output.
+namespace {
+
+class GzSource {  // serial inflate of a (multi-member) gzip file, pulled piece by piece
+  public:
+    explicit GzSource(const std::string &path) : path_(path), in_(1 << 20) {
+        f_ = fopen(path.c_str(), "rb");
+        if (!f_) throw ScrubbyError(ScrubbyError::IoError, "No such file or directory: " + path);
+        memset(&zs_, 0, sizeof(zs_));
+        if (inflateInit2(&zs_, 15 + 32) != Z_OK) {
+            fclose(f_);
+            throw ScrubbyError(ScrubbyError::NifflerError, "zlib init failed");
+        }
+    }
+    ~GzSource() {
+        inflateEnd(&zs_);
+        fclose(f_);
+    }
+    GzSource(const GzSource &) = delete;
+    GzSource &operator=(const GzSource &) = delete;
+    // up to `cap` decompressed bytes into dst; fewer than cap only at the end of the stream (a truncated last member
+    // ends the stream quietly, bytes that are not a gzip member after one are an error: as read_file has it)
+    size_t read(uint8_t *dst, size_t cap) {
+        size_t got = 0;
+        while (got < cap && !done_) {
+            if (zs_.avail_in == 0) {
+                const size_t r = fread(in_.data(), 1, in_.size(), f_);
+                if (r == 0) {
+                    done_ = true;
+                    break;
                 }
-                std::vector<uint8_t> &o = parts[b];
-                o.resize(deflateBound(&zs, (uLong)len) + 64);
-                zs.next_in = const_cast<Bytef *>(data + a);
-                zs.avail_in = (uInt)len;
-                zs.next_out = o.data();
-                zs.avail_out = (uInt)o.size();
-                const int rc = deflate(&zs, Z_FINISH);
-                if (rc != Z_STREAM_END) failed = true;
-                o.resize(o.size() - zs.avail_out);
-                deflateEnd(&zs);
+                zs_.next_in = in_.data();
+                zs_.avail_in = (uInt)r;
+                if (member_done_) {  // a further member starts here
+                    inflateReset(&zs_);
+                    member_done_ = false;
+                }
             }
-        };
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), nb);
-        std::vector<std::thread> th;
-        for (size_t i = 1; i < nt; i++) th.emplace_back(work);
-        work();
-        for (auto &t : th) t.join();
-        if (failed) throw ScrubbyError(ScrubbyError::NifflerError, "deflate failed: " + path);
-        FILE *f = fopen(path.c_str(), "wb");
-        if (!f) throw ScrubbyError(ScrubbyError::IoError, "cannot create " + path);
-        for (auto &o : parts) {
-            if (!o.empty() && fwrite(o.data(), 1, o.size(), f) != o.size()) {
-                fclose(f);
-                throw ScrubbyError(ScrubbyError::IoError, "write failed: " + path);
+            zs_.next_out = dst + got;
+            zs_.avail_out = (uInt)std::min<size_t>(cap - got, 0x40000000);
+            const int rc = inflate(&zs_, Z_NO_FLUSH);
+            got = (size_t)(zs_.next_out - dst);
+            if (rc == Z_STREAM_END) {
+                member_done_ = true;
+                if (zs_.avail_in) {
+                    inflateReset(&zs_);
+                    member_done_ = false;
+                }
+            } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+                throw ScrubbyError(ScrubbyError::IoError, "corrupt gzip stream: " + path_);
             }
         }
-        fclose(f);
-        return;
+        return got;
     }
-    FILE *f = fopen(path.c_str(), "wb");
-    if (!f) throw ScrubbyError(ScrubbyError::IoError, "cannot create " + path);
-    if (n && fwrite(data, 1, n, f) != n) {
-        fclose(f);
-        throw ScrubbyError(ScrubbyError::IoError, "write failed: " + path);
+
+  private:
+    std::string path_;
+    FILE *f_ = nullptr;
+    z_stream zs_;
+    std::vector<uint8_t> in_;
+    bool done_ = false, member_done_ = false;
+};
+
+class BlockQueue {  // producer: the inflating thread; consumer: the thread that owns the GPU context
+  public:
+    BlockQueue(const std::string &path, size_t block, size_t max_blocks) : block_(block), max_(max_blocks) {
+        th_ = std::thread([this, path] { produce(path); });
     }
-    fclose(f);
+    ~BlockQueue() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            cancel_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    // the next block (empty at the end of the stream); rethrows the producer's error
+    std::vector<uint8_t> pop() {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [this] { return !q_.empty() || finished_; });
+        if (q_.empty()) {
+            if (err_) std::rethrow_exception(err_);
+            return {};
+        }
+        std::vector<uint8_t> b = std::move(q_.front());
+        q_.pop_front();
+        l.unlock();
+        cv_.notify_all();
+        return b;
+    }
+
+  private:
+    void produce(const std::string &path) {
+        try {
+            GzSource src(path);
+            while (true) {
+                std::vector<uint8_t> b(block_);
+                const size_t n = src.read(b.data(), block_);
+                if (!n) break;
+                b.resize(n);
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [this] { return q_.size() < max_ || cancel_; });
+                if (cancel_) break;
+                q_.push_back(std::move(b));
+                l.unlock();
+                cv_.notify_all();
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> l(m_);
+            err_ = std::current_exception();
+        }
+        {
+            std::lock_guard<std::mutex> l(m_);
+            finished_ = true;
+        }
+        cv_.notify_all();
+    }
+    size_t block_, max_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::vector<uint8_t>> q_;
+    bool finished_ = false, cancel_ = false;
+    std::exception_ptr err_;
+    std::thread th_;
+};
+
+size_t env_size(const char *name, size_t dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? (size_t)strtoull(v, nullptr, 10) : dflt;
+}
+
+}  // namespace
+
+bool clean_fastq_gz_stream(const std::string &input, const std::string &output, const ShardFn &shard, size_t chunk, size_t halo) {
+    {   // only plain gzip goes this way: BGZF is inflated on all threads at once (read_file), everything else is not gzip
+        FILE *f = fopen(input.c_str(), "rb");
+        if (!f) throw ScrubbyError(ScrubbyError::IoError, "No such file or directory: " + input);
+        uint8_t h[18];
+        const size_t r = fread(h, 1, sizeof(h), f);
+        fclose(f);
+        if (r < 5 || h[0] != 0x1f || h[1] != 0x8b) return false;
+        if (r >= 16 && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C') return false;
+    }
+    chunk = std::max<size_t>(chunk, 16);
+    halo = std::max<size_t>(halo, 1);
+    const size_t BLOCK = std::min<size_t>((size_t)4 << 20, std::max<size_t>(chunk / 4, 64));
+    BlockQueue q(input, BLOCK, 24);
+    std::vector<uint8_t> win;
+    bool src_end = false;
+    auto fill = [&](size_t want) {
+        while (!src_end && win.size() < want) {
+            std::vector<uint8_t> b = q.pop();
+            if (b.empty())
+                src_end = true;
+            else
+                win.insert(win.end(), b.begin(), b.end());
+        }
+    };
+    fill(chunk + halo);
+    // nothing inside, FASTA, or not a sequence file: the whole-file path reports those exactly as before
+    if (win.empty() || win[0] != '@') return false;
+
+    OutSink sink(output, 6);  // niffler::compression::Level::Six
+    std::vector<uint8_t> out[2];
+    std::future<void> writing;
+    auto settle = [&] {
+        if (writing.valid()) writing.get();
+    };
+    uint64_t nlb = 0, reads_before = 0;
+    int crlf = -1;
+    bool first = true;
+    for (unsigned turn = 0;; turn ^= 1) {
+        fill(chunk + halo);
+        const bool last = src_end;  // the buffer reaches EOF: this chunk owns the rest and applies the end-of-file rules
+        const size_t own = last ? win.size() : chunk;
+        std::vector<uint8_t> &o = out[turn];
+        size_t cap = win.size() + win.size() / 16 + 4096;
+        size_t n_out = 0;
+        sgpu_counts counts;
+        int st;
+        while (true) {
+            if (o.size() < cap) o.resize(cap);
+            memset(&counts, 0, sizeof(counts));
+            st = shard(win.data(), win.size(), own, nlb, first ? 1 : 0, last ? 1 : 0, crlf, o.data(), o.size(), &n_out, &counts);
+            if (st != SGPU_ERR_CAPACITY || cap >= 2 * win.size() + 64) break;
+            cap = 2 * win.size() + 64;
+        }
+        if (st == SGPU_ERR_HALO && !last) {  // a record longer than the halo: look further ahead and run the chunk again
+            halo *= 2;
+            turn ^= 1;
+            continue;
+        }
+        const bool parse_error = st >= SGPU_ERR_FASTQ_INVALID_START && st <= SGPU_ERR_FASTQ_HEADER;
+        if (st == SGPU_OK || parse_error) {  // (on a parse error the reference has written the records before it)
+            settle();
+            const uint8_t *data = o.data();
+            writing = std::async(std::launch::async, [&sink, data, n_out] { sink.append(data, n_out); });
+        }
+        if (st != SGPU_OK) {
+            settle();
+            if (parse_error) sink.close();
+            check(st, reads_before + counts.error_record, "clean_reads");
+        }
+        if (first) crlf = counts.crlf ? 1 : 0;
+        first = false;
+        if (last) break;
+        nlb += (uint64_t)std::count(win.begin(), win.begin() + (ptrdiff_t)own, (uint8_t)'\n');
+        reads_before += counts.reads_in;
+        win.erase(win.begin(), win.begin() + (ptrdiff_t)own);
+    }
+    settle();
+    sink.close();
+    return true;
 }
 
 static bool file_exists(const std::string &p) {
@@ -604,6 +855,16 @@ ReadIdSet get_taxid_reads_metabuli(const GpuContext &g, const std::vector<std::s
 
 // ------------------------------------------------------------------------------------------ cleaner.rs
 void FastqCleaner::clean_reads(const GpuContext &g, const ReadIdSet &read_ids, bool reverse) const {
+    if (!getenv("SCRUBBY_NO_GZ_STREAM")) {  // plain gzip FASTQ: inflate, filter and deflate as one pipeline
+        ShardFn shard = [&](const uint8_t *in, size_t n_in, size_t own_len, uint64_t newlines_before, int is_first, int is_last,
+                            int crlf, uint8_t *out, size_t cap, size_t *n_out, sgpu_counts *counts) {
+            return (int)sgpu_clean_fastq_shard(g.get(), read_ids.get(), in, n_in, own_len, newlines_before, is_first, is_last, crlf,
+                                               reverse ? 1 : 0, out, cap, n_out, nullptr, 0, nullptr, counts);
+        };
+        if (clean_fastq_gz_stream(input, output, shard, env_size("SCRUBBY_STREAM_CHUNK", (size_t)64 << 20),
+                                  env_size("SCRUBBY_STREAM_HALO", (size_t)8 << 20)))
+            return;
+    }
     bool empty = false;
     std::vector<uint8_t> in = read_file(input, &empty);
     if (empty) {  // parse_fastx_file_with_check => None: warn, create nothing (cleaner.rs:755-757)
@@ -1219,6 +1480,23 @@ int scrubby_host_read_file(const char *path, uint8_t **out, size_t *out_n) {
         *out_n = v.size();
         return 0;
     } catch (const scrubby::ScrubbyError &e) {
+        return 100 + (int)e.kind;
+    }
+}
+
+// FastqCleaner::clean_reads' gzip pipeline (clean_fastq_gz_stream) with the shard call supplied by the caller: the CPU
+// tests pass a stand-in built on the oracle, so the chunking, the newline / CRLF bookkeeping, the halo growth, the error
+// indices and both writers are exercised without a GPU.  *handled = 0: the input is not a plain-gzip FASTQ.
+typedef int (*scrubby_shard_cb)(const uint8_t *in, size_t n_in, size_t own_len, uint64_t newlines_before, int is_first,
+                                int is_last, int crlf, uint8_t *out, size_t cap, size_t *n_out, sgpu_counts *counts);
+int scrubby_host_stream_clean(const char *input, const char *output, size_t chunk, size_t halo, scrubby_shard_cb cb,
+                              int *handled, uint64_t *err_index) {
+    try {
+        scrubby::ShardFn fn = cb;
+        *handled = scrubby::clean_fastq_gz_stream(input, output, fn, chunk, halo) ? 1 : 0;
+        return 0;
+    } catch (const scrubby::ScrubbyError &e) {
+        if (err_index) *err_index = e.index;
         return 100 + (int)e.kind;
     }
 }

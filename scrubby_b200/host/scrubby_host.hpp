@@ -16,6 +16,7 @@
 //   Scrubby / ScrubbyConfig / enums  scrubby.rs:32-309            -> scrubby::Scrubby, Aligner, Classifier, Preset
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <optional>
 #include <set>
@@ -136,6 +137,28 @@ Compression compression_from_path(const std::string &path);         // utils.rs:
 std::vector<uint8_t> read_file(const std::string &path, size_t *raw_size = nullptr);  // magic-byte sniffing + inflate (niffler::get_reader)
 std::vector<uint8_t> read_file(const std::string &path, bool *empty);  // + is_file_empty (utils.rs:359-375)
 void write_file(const std::string &path, const uint8_t *data, size_t n, int gz_level);  // get_fastx_writer
+// get_fastx_writer as a sink fed piece by piece (gz output: independent members deflated on all host threads)
+class OutSink {
+  public:
+    OutSink(const std::string &path, int gz_level);
+    ~OutSink();
+    OutSink(const OutSink &) = delete;
+    OutSink &operator=(const OutSink &) = delete;
+    void append(const uint8_t *data, size_t n);  // creates the file on first use
+    void close();                                // creates it when nothing was appended (an empty gzip member for .gz)
+  private:
+    void open();
+    std::string path_;
+    int level_;
+    bool gz_ = false;
+    void *f_ = nullptr;
+    size_t total_ = 0;
+};
+// a plain-gzip FASTQ as a pipeline inflate -> filter -> deflate.  `shard` has sgpu_clean_fastq_shard's
+// contract (minus context, set, mode and the second output).  false: not a plain-gzip FASTQ, nothing was done.
+using ShardFn = std::function<int(const uint8_t *in, size_t n_in, size_t own_len, uint64_t newlines_before, int is_first,
+                                  int is_last, int crlf, uint8_t *out, size_t cap, size_t *n_out, sgpu_counts *counts)>;
+bool clean_fastq_gz_stream(const std::string &input, const std::string &output, const ShardFn &shard, size_t chunk, size_t halo);
 
 // ---------------------------------------------------------------- alignment.rs
 struct ReadAlignment {

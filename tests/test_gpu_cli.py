@@ -321,3 +321,66 @@ def test_cli_tiny_gz_id_list_is_not_empty(cli, data, tmp_path):
     raw3 = _write(tmp_path / "tiny.txt", b"s\n")  # raw file of 2 bytes: empty by the FileTooShort rule
     _run(cli, "alignment", "-i", data["r1"], "-o", o1, "-a", raw3, "--format", "txt", "-j", js)
     assert open(o1, "rb").read() == data["fq"][0]
+
+
+@pytest.mark.parametrize("chunk,halo", [(300_000, 20_000), (1 << 20, 1 << 16), (4000, 700)])
+def test_cli_gzip_input_streams_through_the_shard_entry_point(cli, data, chunk, halo):
+    """a plain-gzip FASTQ goes inflate -> sgpu_clean_fastq_shard chunk by chunk -> deflate as a pipeline
+    (scrubby_host.cpp: clean_fastq_gz_stream); small chunks force many shard calls, paired files run two pipelines at once.
+    SCRUBBY_NO_GZ_STREAM takes the whole-file path: the same bytes either way."""
+    d = data["d"]
+    want = [orc.clean_fastq(f, orc.set_from_paf(data["paf"], 50, 0.5, 50), False).written for f in data["fq"]]
+    n_in = 20_000 if chunk > 4000 else 600
+    ins = []
+    for m in (0, 1):
+        g = d / f"s{m}_{chunk}.fq.gz"
+        src = data["fq"][m] if chunk > 4000 else data["fq"][m][: data["fq"][m].index(b"\n@syn.%d " % n_in) + 1]
+        with open(g, "wb") as f:  # two members, cut inside a record
+            f.write(gzip.compress(src[: len(src) // 3], 1) + gzip.compress(src[len(src) // 3:], 1))
+        ins.append(g)
+    if chunk <= 4000:
+        want = [orc.clean_fastq(gzip.open(g).read(), orc.set_from_paf(data["paf"], 50, 0.5, 50), False).written for g in ins]
+    for stream in (True, False):
+        env = dict(os.environ, SCRUBBY_STREAM_CHUNK=str(chunk), SCRUBBY_STREAM_HALO=str(halo))
+        if not stream:
+            env["SCRUBBY_NO_GZ_STREAM"] = "1"
+        o = [str(d / f"so{m}_{chunk}_{stream}.fq") + (".gz" if m else "") for m in (0, 1)]
+        js = d / f"s_{chunk}_{stream}.json"
+        _run(cli, "alignment", "-i", *ins, "-o", *o, "-a", data["paf_p"], "--min-len", 50, "--min-cov", 0.5, "--min-mapq", 50,
+             "-j", js, env=env)
+        assert open(o[0], "rb").read() == want[0]
+        assert gzip.open(o[1], "rb").read() == want[1]
+        rep = json.load(open(js))
+        assert rep["reads_in"] == 2 * n_in
+
+
+def test_cli_gzip_stream_parse_error_and_crlf(cli, data, tmp_path):
+    """a parse error in a later chunk of the stream: exit status and message as on the whole-file path, the records before
+    it are in the output; a CRLF file keeps the first record's line ending decision across chunks"""
+    fq = bytearray(data["fq"][0][: data["fq"][0].index(b"\n@syn.900 ") + 1])
+    at = fq.index(b"\n+\n", fq.index(b"@syn.700 ")) + 1
+    fq[at] = ord("-")
+    bad = tmp_path / "bad.fq.gz"
+    bad.write_bytes(gzip.compress(bytes(fq), 1))
+    want = orc.clean_fastq(bytes(fq), orc.set_from_paf(data["paf"], 50, 0.5, 50), False, raise_on_error=False)
+    assert want.error == 4 and want.error_record == 700
+    outs = []
+    for stream in (True, False):
+        env = dict(os.environ, SCRUBBY_STREAM_CHUNK="50000", SCRUBBY_STREAM_HALO="4000")
+        if not stream:
+            env["SCRUBBY_NO_GZ_STREAM"] = "1"
+        o = tmp_path / f"bad_{stream}.fq"
+        r = _run(cli, "alignment", "-i", bad, "-o", o, "-a", data["paf_p"], "--min-len", 50, "--min-cov", 0.5, "--min-mapq", 50,
+                 ok=False, env=env)
+        outs.append((r.returncode, r.stderr.strip().split("\n")[-1], open(o, "rb").read()))
+        assert outs[-1][2] == want.written
+    assert outs[0] == outs[1]
+    crlf = data["fq"][1][: data["fq"][1].index(b"\n@syn.1500 ") + 1].replace(b"\n", b"\r\n")
+    src = tmp_path / "crlf.fq.gz"
+    src.write_bytes(gzip.compress(crlf, 1))
+    wantc = orc.clean_fastq(crlf, orc.set_from_paf(data["paf"], 50, 0.5, 50), False)
+    assert wantc.crlf
+    env = dict(os.environ, SCRUBBY_STREAM_CHUNK="70000", SCRUBBY_STREAM_HALO="5000")
+    o = tmp_path / "crlf_out.fq"
+    _run(cli, "alignment", "-i", src, "-o", o, "-a", data["paf_p"], "--min-len", 50, "--min-cov", 0.5, "--min-mapq", 50, env=env)
+    assert open(o, "rb").read() == wantc.written
