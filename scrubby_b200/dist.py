@@ -463,14 +463,18 @@ class ShardedTxtSet:
     travel; the result is the same exact set on every rank (cleaner.rs:236-254: one global set).  The symmetric
     buffers are double-buffered: a rank may start its next partition while a peer still reads the previous lists."""
 
-    def __init__(self, api, ctx, dist, ev_total: int, per: int, device, direct: bool = True):
+    def __init__(self, api, ctx, dist, ev_total: int, per: int, device, direct: bool | None = None):
         import math
 
         import torch
         import torch.distributed._symmetric_memory as symm
 
-        self.api, self.ctx, self.dist, self.direct = api, ctx, dist, direct
+        self.api, self.ctx, self.dist = api, ctx, dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        # measured on C4 (DESIGN.md 5): reading the peers' lists in place wins on two GPUs (3.5 vs 3.9 ms); from four on
+        # a page's list on one peer is a few hundred bytes and the bulk pull is faster (4.4 vs 5.1 ms at N = 4, 5.9 vs
+        # 8.5 ms at N = 8).  `direct` may be flipped between builds (bench.py times both).
+        self.direct = (self.world <= 2) if direct is None else direct
         # virtual pages: the same on every rank; sized for lines of >= 8 bytes at ~410 keys (load 0.2) per page
         self.log2_v = max(8, int(math.ceil(math.log2(max(1.0, ev_total / 8 / 410)))))
         V = 1 << self.log2_v
