@@ -376,23 +376,37 @@ void OutSink::close() {
 // whole file and its output.
 namespace {
 
-class GzSource {  // serial inflate of a (multi-member) gzip file, pulled piece by piece
+struct ByteSource {  // decompressed bytes of a file, block by block
+    virtual ~ByteSource() {}
+    virtual bool next(std::vector<uint8_t> &block) = 0;  // false (and an empty block) at the end of the stream
+};
+
+class GzSource : public ByteSource {  // serial inflate of a (multi-member) gzip file, pulled piece by piece
   public:
-    explicit GzSource(const std::string &path) : path_(path), in_(1 << 20) {
+    GzSource(const std::string &path, size_t block) : path_(path), block_(block), in_(1 << 20) {
         f_ = fopen(path.c_str(), "rb");
         if (!f_) throw ScrubbyError(ScrubbyError::IoError, "No such file or directory: " + path);
-        memset(&zs_, 0, sizeof(zs_));
-        if (inflateInit2(&zs_, 15 + 32) != Z_OK) {
-            fclose(f_);
-            throw ScrubbyError(ScrubbyError::NifflerError, "zlib init failed");
-        }
+        init();
     }
-    ~GzSource() {
+    // continues a file another reader has opened: `pending` are the raw bytes it had read but not consumed
+    GzSource(const std::string &path, size_t block, FILE *f, const uint8_t *pending, size_t n_pending)
+        : path_(path), block_(block), f_(f), in_(std::max<size_t>(1 << 20, n_pending)) {
+        init();
+        if (n_pending) memcpy(in_.data(), pending, n_pending);
+        zs_.next_in = in_.data();
+        zs_.avail_in = (uInt)n_pending;
+    }
+    ~GzSource() override {
         inflateEnd(&zs_);
         fclose(f_);
     }
     GzSource(const GzSource &) = delete;
     GzSource &operator=(const GzSource &) = delete;
+    bool next(std::vector<uint8_t> &block) override {
+        block.resize(block_);
+        block.resize(read(block.data(), block_));
+        return !block.empty();
+    }
     // up to `cap` decompressed bytes into dst; fewer than cap only at the end of the stream (a truncated last member
     // ends the stream quietly, bytes that are not a gzip member after one are an error: as read_file has it)
     size_t read(uint8_t *dst, size_t cap) {
@@ -429,17 +443,172 @@ class GzSource {  // serial inflate of a (multi-member) gzip file, pulled piece 
     }
 
   private:
+    void init() {
+        memset(&zs_, 0, sizeof(zs_));
+        if (inflateInit2(&zs_, 15 + 32) != Z_OK) {
+            fclose(f_);
+            throw ScrubbyError(ScrubbyError::NifflerError, "zlib init failed");
+        }
+    }
     std::string path_;
+    size_t block_;
     FILE *f_ = nullptr;
     z_stream zs_;
     std::vector<uint8_t> in_;
     bool done_ = false, member_done_ = false;
 };
 
+// BGZF (bgzip): every member names its compressed size (BSIZE in the "BC" extra field) and its inflated size (ISIZE), so
+// a batch of members is cut out of the raw bytes without inflating and inflated on all host threads, each member into
+// its own slice of the block.  The first member that is not a BGZF block (a plain gzip member appended to the file, a
+// truncated tail) hands the rest of the file to the serial reader.
+class BgzfSource : public ByteSource {
+  public:
+    BgzfSource(const std::string &path, size_t block) : path_(path), block_(std::max<size_t>(block, 1 << 16)) {
+        const char *pc = getenv("SCRUBBY_BGZF_PIECE");  // (tests: raw bytes read per refill)
+        if (pc && *pc) piece_ = std::max<size_t>((size_t)strtoull(pc, nullptr, 10), 1 << 10);
+        f_ = fopen(path.c_str(), "rb");
+        if (!f_) throw ScrubbyError(ScrubbyError::IoError, "No such file or directory: " + path);
+    }
+    ~BgzfSource() override {
+        if (f_) fclose(f_);
+    }
+    BgzfSource(const BgzfSource &) = delete;
+    BgzfSource &operator=(const BgzfSource &) = delete;
+    bool next(std::vector<uint8_t> &block) override {
+        block.clear();
+        while (block.empty()) {
+            if (serial_) return serial_->next(block);
+            if (!batch(block)) return false;
+        }
+        return true;
+    }
+
+  private:
+    struct Blk {
+        size_t src, clen, dst;
+        uint32_t isize, crc;
+    };
+    // 1: a complete BGZF member at p (b filled, *size = its length); 0: more raw bytes needed; -1: not a BGZF member
+    static int member(const uint8_t *p, size_t avail, Blk &b, size_t *size) {
+        if (avail < 18) return 0;
+        if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return -1;
+        const size_t xlen = p[10] | (p[11] << 8);
+        if (avail < 12 + xlen) return 0;
+        size_t bsize = 0;
+        for (size_t q = 12; q + 4 <= 12 + xlen;) {
+            const size_t sl = p[q + 2] | (p[q + 3] << 8);
+            if (p[q] == 'B' && p[q + 1] == 'C' && sl == 2 && q + 6 <= 12 + xlen) bsize = (p[q + 4] | (p[q + 5] << 8)) + 1;
+            q += 4 + sl;
+        }
+        if (bsize < 12 + xlen + 8) return -1;
+        if (avail < bsize) return 0;
+        const uint8_t *t = p + bsize - 4;
+        b.isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        b.crc = (uint32_t)t[-4] | ((uint32_t)t[-3] << 8) | ((uint32_t)t[-2] << 16) | ((uint32_t)t[-1] << 24);
+        if (b.isize > 65536) return -1;  // the specification's cap: a member that claims more is not BGZF
+        b.src = 12 + xlen;
+        b.clen = bsize - 12 - xlen - 8;
+        *size = bsize;
+        return 1;
+    }
+    // one batch: the complete members at hand, up to about block_ bytes of output; false at the end of the file
+    bool batch(std::vector<uint8_t> &out) {
+        std::vector<Blk> blks;
+        size_t total = 0, p = pos_;
+        bool not_bgzf = false;
+        while (total < block_) {
+            Blk b;
+            size_t size = 0;
+            const int rc = member(raw_.data() + p, raw_.size() - p, b, &size);
+            if (rc == 0) {  // the member at p is not complete yet
+                if (!blks.empty()) break;  // inflate what is at hand first; the next call reads on
+                const bool more = refill();  // (drops the consumed bytes: offsets restart at 0)
+                p = pos_;
+                if (!more) {  // end of the file: leftover bytes are a truncated member (the serial reader's case)
+                    not_bgzf = raw_.size() > pos_;
+                    break;
+                }
+                continue;
+            }
+            if (rc < 0) {
+                not_bgzf = true;
+                break;
+            }
+            b.src += p;
+            b.dst = total;
+            total += b.isize;
+            blks.push_back(b);
+            p += size;
+        }
+        if (!blks.empty()) inflate_all(blks, total, out);
+        pos_ = p;
+        if (not_bgzf) {  // the serial reader takes the file from here
+            serial_.reset(new GzSource(path_, block_, f_, raw_.data() + pos_, raw_.size() - pos_));
+            f_ = nullptr;
+            raw_.clear();
+            pos_ = 0;
+            return true;
+        }
+        return !blks.empty();
+    }
+    // drops the consumed raw bytes and appends the next piece of the file; false at the end of the file
+    bool refill() {
+        raw_.erase(raw_.begin(), raw_.begin() + (ptrdiff_t)pos_);
+        pos_ = 0;
+        const size_t old = raw_.size();
+        raw_.resize(old + piece_);
+        const size_t r = fread(raw_.data() + old, 1, piece_, f_);
+        raw_.resize(old + r);
+        return r > 0;
+    }
+    void inflate_all(const std::vector<Blk> &blks, size_t total, std::vector<uint8_t> &out) {
+        out.resize(std::max<size_t>(total, 1));  // (a batch of empty members -- the EOF marker -- still needs a valid pointer)
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, blks.size() / 8));
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        const uint8_t *raw = raw_.data();
+        auto work = [&] {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) {
+                bad = true;
+                return;
+            }
+            for (size_t i; (i = next.fetch_add(1)) < blks.size() && !bad;) {
+                const Blk &b = blks[i];
+                inflateReset(&zs);
+                zs.next_in = const_cast<uint8_t *>(raw + b.src);
+                zs.avail_in = (uInt)b.clen;
+                zs.next_out = out.data() + b.dst;
+                zs.avail_out = b.isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.avail_out != 0 || zs.avail_in != 0 ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + b.dst, b.isize) != b.crc)
+                    bad = true;
+            }
+            inflateEnd(&zs);
+        };
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < nt; k++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        if (bad) throw ScrubbyError(ScrubbyError::IoError, "corrupt gzip stream: " + path_);
+        out.resize(total);
+    }
+    std::string path_;
+    size_t block_;
+    FILE *f_ = nullptr;
+    std::vector<uint8_t> raw_;
+    size_t pos_ = 0, piece_ = (size_t)8 << 20;
+    std::unique_ptr<GzSource> serial_;
+};
+
 class BlockQueue {  // producer: the inflating thread; consumer: the thread that owns the GPU context
   public:
-    BlockQueue(const std::string &path, size_t block, size_t max_blocks) : block_(block), max_(max_blocks) {
-        th_ = std::thread([this, path] { produce(path); });
+    BlockQueue(std::function<std::unique_ptr<ByteSource>()> make, size_t max_blocks) : max_(max_blocks) {
+        th_ = std::thread([this, make] { produce(make); });
     }
     ~BlockQueue() {
         {
@@ -465,14 +634,12 @@ class BlockQueue {  // producer: the inflating thread; consumer: the thread that
     }
 
   private:
-    void produce(const std::string &path) {
+    void produce(const std::function<std::unique_ptr<ByteSource>()> &make) {
         try {
-            GzSource src(path);
+            std::unique_ptr<ByteSource> src = make();
             while (true) {
-                std::vector<uint8_t> b(block_);
-                const size_t n = src.read(b.data(), block_);
-                if (!n) break;
-                b.resize(n);
+                std::vector<uint8_t> b;
+                if (!src->next(b)) break;
                 std::unique_lock<std::mutex> l(m_);
                 cv_.wait(l, [this] { return q_.size() < max_ || cancel_; });
                 if (cancel_) break;
@@ -490,7 +657,7 @@ class BlockQueue {  // producer: the inflating thread; consumer: the thread that
         }
         cv_.notify_all();
     }
-    size_t block_, max_;
+    size_t max_;
     std::mutex m_;
     std::condition_variable cv_;
     std::deque<std::vector<uint8_t>> q_;
@@ -507,19 +674,24 @@ size_t env_size(const char *name, size_t dflt) {
 }  // namespace
 
 bool clean_fastq_gz_stream(const std::string &input, const std::string &output, const ShardFn &shard, size_t chunk, size_t halo) {
-    {   // only plain gzip goes this way: BGZF is inflated on all threads at once (read_file), everything else is not gzip
+    bool bgzf = false;
+    {   // gzip only (by magic bytes, as niffler sniffs): plain members are inflated serially, BGZF members in parallel
         FILE *f = fopen(input.c_str(), "rb");
         if (!f) throw ScrubbyError(ScrubbyError::IoError, "No such file or directory: " + input);
         uint8_t h[18];
         const size_t r = fread(h, 1, sizeof(h), f);
         fclose(f);
         if (r < 5 || h[0] != 0x1f || h[1] != 0x8b) return false;
-        if (r >= 16 && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C') return false;
+        bgzf = r >= 16 && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+        if (bgzf && getenv("SCRUBBY_NO_BGZF_STREAM")) return false;
     }
     chunk = std::max<size_t>(chunk, 16);
     halo = std::max<size_t>(halo, 1);
     const size_t BLOCK = std::min<size_t>((size_t)4 << 20, std::max<size_t>(chunk / 4, 64));
-    BlockQueue q(input, BLOCK, 24);
+    BlockQueue q([&input, bgzf, BLOCK]() -> std::unique_ptr<ByteSource> {
+        if (bgzf) return std::unique_ptr<ByteSource>(new BgzfSource(input, 4 * BLOCK));
+        return std::unique_ptr<ByteSource>(new GzSource(input, BLOCK));
+    }, bgzf ? 8 : 24);
     std::vector<uint8_t> win;
     bool src_end = false;
     auto fill = [&](size_t want) {

@@ -178,14 +178,11 @@ def test_gz_stream_parse_error_in_a_later_chunk(tmp_path):
 
 
 def test_gz_stream_leaves_other_inputs_to_the_whole_file_path(tmp_path):
-    from bam_build import bgzf
-
     fq = synth.gen_fastq(50, 1).numpy().tobytes()
     ids = _ids(50)
     cases = {
         "plain.fastq": fq,                                          # not gzip
         "fasta.fa.gz": gzip.compress(b">a\nACGT\n>b\nAC\nGT\n"),    # FASTA: no shard entry point
-        "bgzf.fastq.gz": bgzf(fq),                                  # BGZF: inflated on all threads at once
         "empty.fastq.gz": gzip.compress(b""),                       # nothing inside: the empty-input rule
         "tiny.gz": b"\x1f\x8b\x08",                                 # niffler: FileTooShort
         "junk.fastq.gz": gzip.compress(b"hello\n"),                 # neither '@' nor '>': UnknownFormat, no output file
@@ -214,3 +211,54 @@ def test_gz_stream_corrupt_member(tmp_path):
     src.write_bytes(gzip.compress(fq) + b"garbage-after-the-member")
     rc, handled, _, _ = _stream(src, tmp_path / "o2.fastq", _ids(300), 2000, 500)
     assert rc == 100 + hostlib.KIND_IO
+
+
+@pytest.mark.parametrize("kind", ["bgzf", "bgzf_small_blocks", "bgzf_then_gzip", "gzip_then_bgzf", "bgzf_truncated", "bgzf_corrupt"])
+def test_bgzf_stream(tmp_path, monkeypatch, kind):
+    """BGZF input (bgzip): members cut out by BSIZE and inflated batch by batch on all threads; a member that is not BGZF
+    (appended plain gzip, a truncated tail) hands the rest of the file to the serial reader -- the same bytes as the
+    whole-file reader (scrubby::read_file) gives, through the same chunked shard calls"""
+    from bam_build import bgzf
+    from oracle import oracle as orc
+
+    n = 2500
+    fq = synth.gen_fastq(n, 1).numpy().tobytes()
+    ids = _ids(n)
+    cut = len(fq) // 2 + 77
+    raw = {"bgzf": bgzf(fq), "bgzf_small_blocks": bgzf(fq, 700),
+           "bgzf_then_gzip": bgzf(fq[:cut])[:-28] + gzip.compress(fq[cut:]),     # (without the EOF marker in between)
+           "gzip_then_bgzf": gzip.compress(fq[:cut]) + bgzf(fq[cut:]),
+           "bgzf_truncated": bgzf(fq)[: len(bgzf(fq)) * 2 // 3],
+           "bgzf_corrupt": bgzf(fq)}[kind]
+    if kind == "bgzf_corrupt":
+        b = bytearray(raw)
+        b[len(b) // 2] ^= 0x55
+        raw = bytes(b)
+    src = tmp_path / "in.fastq.gz"
+    src.write_bytes(raw)
+    try:
+        whole = hostlib.read_file(str(src))   # what the whole-file path would filter
+    except hostlib.HostError:
+        whole = None
+    assert (whole is None) == (kind == "bgzf_corrupt")
+    if kind in ("bgzf", "bgzf_small_blocks", "bgzf_then_gzip", "gzip_then_bgzf"):
+        assert whole == fq
+    for piece, chunk, halo in ((1 << 14, 30_000, 2000), (1 << 23, 1 << 18, 1 << 14), (1 << 12, 5000, 800)):
+        monkeypatch.setenv("SCRUBBY_BGZF_PIECE", str(piece))
+        dst = tmp_path / f"out_{piece}.fastq"
+        rc, handled, err, log = _stream(src, dst, ids, chunk, halo)
+        assert handled == 1 or rc
+        if whole is None:
+            assert rc == 100 + hostlib.KIND_IO or rc >= 100
+            continue
+        want = orc.clean_fastq(whole, ids, raise_on_error=False)
+        if want.error:
+            assert rc >= 100 and err == want.error_record
+        else:
+            assert rc == 0
+        assert _read_out(dst) == want.written
+        assert len([c for c in log if c["rc"] == 0]) > 1
+    monkeypatch.setenv("SCRUBBY_NO_BGZF_STREAM", "1")
+    rc, handled, _, log = _stream(src, tmp_path / "no.fastq", ids, 30_000, 2000)
+    if kind != "gzip_then_bgzf":  # (that one starts with a plain member: it is the plain-gzip stream's case)
+        assert (rc, handled) == (0, 0) and not log
